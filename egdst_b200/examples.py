@@ -1,0 +1,218 @@
+"""The reference's example models, transcribed property-for-property.
+
+Sources: egdst_examples/model_{deaton1,deaton2,retirement1,retirement2,occ3,cake1,cake2}.m and
+lecture_code/model2.m.  Only the model definitions are transcribed (the ``.m`` scripts also
+compile/solve/plot); sizes and parameters can be overridden by keyword, which is how the scaled
+BASELINE configs (S1, S1b, S5) are built.
+"""
+from __future__ import annotations
+
+from .model import EgdstModel
+
+
+def _common(m: EgdstModel, T, mmax, ngridmax, ngridm, nthrhmax, ny):
+    m.t0 = 1
+    m.T = T
+    m.mmax = mmax
+    m.ngridmax = ngridmax
+    m.ngridm = ngridm
+    m.nthrhmax = nthrhmax
+    m.ny = ny
+
+
+def _singleton(m: EgdstModel):
+    m.s = ("Singleton state", [0, "dummy state"])
+    m.trpr = ("true", [[1]])
+    m.feasible = ("defaultfeasible", True)
+
+
+def _log_utility(m: EgdstModel, util="log(consumption)"):
+    m.u = ("utility", util)
+    m.u = ("marginal", "1/consumption")
+    m.u = ("marginalinverse", "1/mutility")
+    m.u = ("extrap", "log(x)")
+
+
+def deaton(label="deaton1", a0=0.0, sigma="0", mu="0", mmax=50, ny=2, T=25, ngridm=100, ngridmax=1000,
+           interest=0.01, income=1.25) -> EgdstModel:
+    """egdst_examples/model_deaton1.m:6-46 (and model_deaton2.m with a0=-25, sigma=0.75, mmax=100, ny=10)."""
+    m = EgdstModel(label)
+    _common(m, T, mmax, ngridmax, ngridm, 10, ny)
+    _singleton(m)
+    m.d = ("Dummy decision", [0, "dummy decision"])
+    m.choiceset = ("defaultallow", True)
+    _log_utility(m)
+    m.budget = ("cashinhand", "savings*(1+interest)+income_level")
+    m.budget = ("marginal", "1+interest")
+    m.discount = "1/(1+interest)"
+    m.param = ("interest", "return on savings", interest)
+    m.eq = ("income_level", "Realized income", "income*shock", "next")
+    m.param = ("income", "income (times multiplicator shock)", income)
+    m.a0 = a0
+    m.shock = "lognormal"
+    m.shock = ("sigma", sigma)
+    m.shock = ("mu", mu)
+    return m
+
+
+def deaton1(**kw) -> EgdstModel:
+    return deaton("deaton1", **kw)
+
+
+def deaton2(**kw) -> EgdstModel:
+    args = dict(a0=-25.0, sigma="0.75", mu="-0.5*sigma*sigma", mmax=100, ny=10)
+    args.update(kw)
+    return deaton("deaton2", **args)
+
+
+def retirement(label="retire2", sigma="0.25", mu="-0.5*sigma*sigma", T=25, ngridm=100, ngridmax=1000, nthrhmax=10,
+               ny=10, interest=0.045, mmax=10, a0=-5.0, duw=0.5, wage=1.05) -> EgdstModel:
+    """egdst_examples/model_retirement2.m:6-46 (model_retirement1.m is the sigma=0 case)."""
+    m = EgdstModel(label)
+    _common(m, T, mmax, ngridmax, ngridm, nthrhmax, ny)
+    _singleton(m)
+    m.d = ("Labour supply", [0, "retire", 1, "work"])
+    m.choiceset = ("defaultallow", True)
+    m.u = ("utility", "log(consumption)+duw*(id==0)")
+    m.param = ("duw", "disutility of work", duw)
+    m.u = ("marginal", "1/consumption")
+    m.u = ("marginalinverse", "1/mutility")
+    m.u = ("extrap", "log(x)")
+    m.budget = ("cashinhand", "savings+wage_income*(id!=0)")
+    m.budget = ("marginal", "1+interest")
+    m.discount = "1/(1+interest)"
+    m.param = ("interest", "return on savings", interest)
+    m.eq = ("wage_income", "Realized wage income", "wage*shock", "next")
+    m.param = ("wage", "wage (times multiplicator shock)", wage)
+    m.a0 = a0
+    m.shock = "lognormal"
+    m.shock = ("sigma", sigma)
+    m.shock = ("mu", mu)
+    return m
+
+
+def retirement1(**kw) -> EgdstModel:
+    args = dict(label="retire1", sigma="0", mu="0")
+    args.update(kw)
+    return retirement(**args)
+
+
+def retirement2(**kw) -> EgdstModel:
+    return retirement(**kw)
+
+
+def retirement2_scaled(T=50, ngridm=10000, ny=100, interest=0.02) -> EgdstModel:
+    """S1 of SURVEY 8(d): retirement2 at 10k grid x 100 nodes x 50 periods; ``interest=0.02`` because the
+    reference itself aborts at this size with the shipped 0.045; nthrhmax=ngridm (fact 8)."""
+    return retirement(T=T, ngridm=ngridm, ngridmax=2 * ngridm, nthrhmax=ngridm, ny=ny, interest=interest)
+
+
+def occ3(ngridm=50, ngridmax=100, ny=10, T=40) -> EgdstModel:
+    """egdst_examples/model_occ3.m:3-44."""
+    m = EgdstModel("occ3")
+    m.t0 = 0
+    m.T = T
+    m.s = ("Dummy state", [0, "dummy"])
+    m.trpr = ("true", [[1]])
+    m.feasible = ("defaultfeasible", True)
+    m.d = ("Occupational choice", [0, "public sector (lower pay, secure)", 1, "private sector (hight pay, less secure)",
+                                   2, "entrepreneurship"])
+    m.choiceset = ("defaultallow", True)
+    m.u = ("utility", "(pow(consumption,1-crra)-1)/(1-crra) - coefleisure*disutility[1][(int)dc1+1]")
+    m.coef = ("disutility", "Disutility of work", [0.0, 1.0, 0.75])
+    m.param = ("crra", "CRRA coefficient in utility", 1.2)
+    m.param = ("coefleisure", "Weight with leisure in utility", 0.2)
+    m.u = ("marginal", "pow(consumption,-crra)")
+    m.u = ("marginalinverse", "pow(mutility,-1/crra)")
+    m.u = ("extrap", "pow(x,1-crra)")
+    m.discount = "0.93"
+    m.shock = "lognormal"
+    m.shock = ("sigma", "sigs[1][(int)dc1+1]")
+    m.coef = ("sigs", "Sigmas for different occupations", [0.15, 0.35, 0.75])
+    m.shock = ("mu", "-0.5*sigs[1][(int)dc1+1]*sigs[1][(int)dc1+1]")
+    m.eq = ("wage1", "Realized wage in the public sector", "max(ssinc,shock*0.5)", "next")
+    m.eq = ("wage2", "Realized wage in the private sector", "max(ssinc,shock*0.5*wagegap)", "next")
+    m.param = ("ssinc", "Guaranteed social security income", 0.01)
+    m.param = ("wagegap", "Wage gap between public and private sector", 1.35)
+    m.eq = ("entrep", "Entrepreneurial income (realized)", "max(ssinc,log(savings+1)*entrkap*shock)", "next")
+    m.param = ("entrkap", "Return on capital", 0.56)
+    m.budget = ("cashinhand", "savings*(1+interest)+(dc1==0)*wage1+(dc1==1)*wage2+(dc1==2)*entrep")
+    m.budget = ("marginal", "1+interest+(dc1==2)*max(0,entrkap*shock/(savings+1))")
+    m.param = ("interest", "return on savings", 0.05)
+    m.a0 = 0.0
+    m.mmax = 5
+    m.ngridm = ngridm
+    m.ngridmax = ngridmax
+    m.nthrhmax = 100
+    m.ny = ny
+    return m
+
+
+def cake(label="cake1", discount="1", T=25, ngridm=100) -> EgdstModel:
+    """egdst_examples/model_cake1.m:6-41 (cake2: discount='.75')."""
+    m = EgdstModel(label)
+    _common(m, T, 10, 1000, ngridm, 10, 2)
+    _singleton(m)
+    m.d = ("Dummy decision", [0, "dummy decision"])
+    m.choiceset = ("defaultallow", True)
+    _log_utility(m)
+    m.budget = ("cashinhand", "savings")
+    m.budget = ("marginal", "1")
+    m.discount = discount
+    m.a0 = 0.0
+    m.shock = "normal"
+    m.shock = ("sigma", "0")
+    m.shock = ("mu", "0")
+    return m
+
+
+def cake1(**kw) -> EgdstModel:
+    return cake("cake1", "1", **kw)
+
+
+def cake2(**kw) -> EgdstModel:
+    return cake("cake2", ".75", **kw)
+
+
+def model2(T=3, ngridm=100, nquad=10, mmax=100, cc=0.0, df=1.0, rho=0.0, r=0.0, sigma=0.0, duw=1.0, wage=5.0) -> EgdstModel:
+    """lecture_code/model2.m:1-77 -- the only shipped model with more than one state (absorbing retirement)."""
+    m = EgdstModel("model2")
+    m.t0 = 1
+    m.T = T
+    m.mmax = mmax
+    m.ngridmax = 10 * ngridm
+    m.ngridm = ngridm
+    m.nthrhmax = ngridm
+    m.ny = nquad
+    m.a0 = 0.0
+    m.s = ("Labour market state", [0, "retired", 1, "working"])
+    m.d = ("Retirement decision", [0, "Retirement", 1, "Work"])
+    m.feasible = ("defaultfeasible", True)
+    m.trpr = ("dc1==0", [[1, 0], [1, 0]])
+    m.trpr = ("dc1==1", [[0, 1], [0, 1]])
+    m.choiceset = ("defaultallow", True)
+    m.choiceset = ("ist==0 && id==1", "Retirement is absorbing")
+    m.u = ("utility", "(fabs(rho)<1e-10?log(consumption):(pow(consumption,rho)-1)/rho)  - (id?duw:0.0)")
+    m.u = ("marginal", "pow(consumption,rho-1)")
+    m.u = ("marginalinverse", "pow(mutility,1/(rho-1))")
+    m.param = ("rho", "1-crra parameter", rho)
+    m.param = ("duw", "scale parameter for disutility of work", duw)
+    m.u = ("extrap", "pow(x,rho)")
+    m.budget = ("cashinhand", "savings*(1+r)*shock  + (id?wage:0.0)")
+    m.budget = ("marginal", "(1+r)*shock")
+    m.param = ("r", "risk free return", r)
+    m.discount = "df"
+    m.param = ("df", "discount factor", df)
+    m.param = ("wage", "Workers wage", wage)
+    m.a0 = cc
+    m.shock = "lognormal"
+    m.shock = ("sigma", "sig")
+    m.shock = ("mu", "-sigma*sigma/2")
+    m.param = ("sig", "sigma parameter in lognormal return", sigma)
+    return m
+
+
+ALL = {
+    "deaton1": deaton1, "deaton2": deaton2, "retirement1": retirement1, "retirement2": retirement2,
+    "occ3": occ3, "cake1": cake1, "cake2": cake2, "model2": model2,
+}
