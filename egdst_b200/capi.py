@@ -1,0 +1,299 @@
+"""ctypes binding of the C ABI in include/egdst_b200.h (the same entry points the MEX stubs bind).
+
+No torch types cross this boundary: plain pointers and sizes.  A missing library raises -- there is
+no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Optional
+
+import numpy as np
+
+from .quadrature import model_quadrature
+
+ABI_VERSION = 1
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+
+class EgdstDesc(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int),
+        ("t0", C.c_int), ("T", C.c_int), ("ngridm", C.c_int), ("ngridmax", C.c_int), ("nthrhmax", C.c_int),
+        ("ny", C.c_int), ("nd", C.c_int), ("nnd", C.c_int), ("nst", C.c_int), ("nnst", C.c_int),
+        ("mmax", C.c_double), ("a0", C.c_double),
+        ("optim_UasD", C.c_int), ("optim_MUnoD", C.c_int), ("optim_UnoD", C.c_int), ("optim_TRPRnoSH", C.c_int),
+        ("tolerance", C.c_double), ("zeroconsumption", C.c_double), ("doublepoint_delta", C.c_double),
+        ("stm", _dp), ("states", _dp), ("decisions", _dp), ("params", _dp), ("nparam", C.c_int),
+        ("quadrature", _dp), ("neq", C.c_int), ("device", C.c_int),
+    ]
+
+
+class EgdstError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(msg)
+        self.code = code
+
+
+class EgdstWarning(UserWarning):
+    pass
+
+
+def _arr(a) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return a.ctypes.data_as(_dp) if a is not None and a.size else None
+
+
+class Desc:
+    """Keeps the numpy buffers alive next to the ctypes struct."""
+
+    def __init__(self, model, device: Optional[int] = None):
+        m = model
+        self.stm = _arr(m.stm)
+        self.states = _arr(np.asfortranarray(m.states).ravel(order="F"))
+        self.decisions = _arr(np.asfortranarray(m.decisions).ravel(order="F"))
+        self.params = _arr(m.param_vector())
+        self.quadrature = _arr(model_quadrature(m.ny)) if m.ny > 1 else None
+        d = EgdstDesc()
+        d.abi_version = ABI_VERSION
+        d.t0, d.T, d.ngridm, d.ngridmax, d.nthrhmax = int(m.t0), int(m.T), int(m.ngridm), int(m.ngridmax), int(m.nthrhmax)
+        d.ny, d.nd, d.nnd, d.nst, d.nnst = int(m.ny), int(m.nd), int(m.nnd), int(m.nst), int(m.nnst)
+        d.mmax, d.a0 = float(m.mmax), float(m.a0)
+        o = m.optim
+        d.optim_UasD, d.optim_MUnoD, d.optim_UnoD, d.optim_TRPRnoSH = (int(bool(o["optim_UasD"])), int(bool(o["optim_MUnoD"])),
+                                                                      int(bool(o["optim_UnoD"])), int(bool(o["optim_TRPRnoSH"])))
+        d.tolerance = float(m.cflags["TOLERANCE"])
+        d.zeroconsumption = float(m.cflags["ZEROCONSUMPTION"])
+        d.doublepoint_delta = float(m.cflags["DOUBLEPOINT_DELTA"])
+        d.stm, d.states, d.decisions, d.params = _ptr(self.stm), _ptr(self.states), _ptr(self.decisions), _ptr(self.params)
+        d.nparam = len(m.param)
+        d.quadrature = _ptr(self.quadrature)
+        d.neq = len(m.eq)
+        d.device = int(m.device if device is None else device)
+        self.c = d
+
+
+class Solution:
+    """Handle of a device-resident solution; ``M``/``D`` are exported lazily as nst x nt nested lists."""
+
+    def __init__(self, lib: "ModelLibrary", handle, model, nvec: int = 1):
+        self.lib, self.handle, self.nvec = lib, handle, nvec
+        self.nst, self.nt = model.nst, model.nt
+        self._cells = None
+        self.warning: Optional[str] = None
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.lib.L.egdst_free_solution(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def sizes(self):
+        n = self.nvec * self.nt * self.nst
+        mlen = np.zeros(n, dtype=np.int32)
+        thlen = np.zeros(n, dtype=np.int32)
+        rc = self.lib.L.egdst_solution_sizes(self.handle, mlen.ctypes.data_as(_ip), thlen.ctypes.data_as(_ip))
+        if rc == 2:
+            self.lib._raise(rc)
+        return mlen, thlen
+
+    def export(self):
+        """Returns (mlen, thlen, Mbuf, Dbuf): the packed host copy (saveoutput layouts)."""
+        mlen, thlen = self.sizes()
+        Mbuf = np.empty(4 * int(mlen.sum()), dtype=np.float64)
+        Dbuf = np.empty(2 * int(thlen.sum()), dtype=np.float64)
+        rc = self.lib.L.egdst_solution_export(self.handle, Mbuf.ctypes.data_as(_dp), Dbuf.ctypes.data_as(_dp))
+        if rc:
+            self.lib._raise(rc)
+        return mlen, thlen, Mbuf, Dbuf
+
+    def cells(self, ivec: int = 0):
+        """(M, D) nested lists [ist][it] of (mlen x 4) / (thlen x 2) arrays for parameter vector ``ivec``."""
+        if self._cells is None:
+            self._cells = self.export()
+        mlen, thlen, Mbuf, Dbuf = self._cells
+        moff = np.concatenate([[0], np.cumsum(mlen)]) * 4
+        toff = np.concatenate([[0], np.cumsum(thlen)]) * 2
+        M = [[None] * self.nt for _ in range(self.nst)]
+        D = [[None] * self.nt for _ in range(self.nst)]
+        for it in range(self.nt):
+            for ist in range(self.nst):
+                c = (ivec * self.nt + it) * self.nst + ist
+                if mlen[c] > 0:
+                    M[ist][it] = Mbuf[moff[c]:moff[c + 1]].reshape((mlen[c], 4), order="F")
+                    D[ist][it] = Dbuf[toff[c]:toff[c + 1]].reshape((thlen[c], 2), order="F")
+        return M, D
+
+    @property
+    def M(self):
+        return self.cells(0)[0]
+
+    @property
+    def D(self):
+        return self.cells(0)[1]
+
+    def status(self, ivec: int = 0):
+        it, ist, idd = C.c_int(0), C.c_int(0), C.c_int(0)
+        code = self.lib.L.egdst_solution_status(self.handle, ivec, C.byref(it), C.byref(ist), C.byref(idd))
+        return code, it.value, ist.value, idd.value
+
+    def units(self) -> int:
+        return int(self.lib.L.egdst_solution_units(self.handle))
+
+
+class ModelLibrary:
+    """One loaded model image (libegdst_b200_<key>.so)."""
+
+    EXPORTS = ["egdst_abi_version", "egdst_model_key", "egdst_model_nparam", "egdst_model_neq", "egdst_last_error",
+               "egdst_set_stream", "egdst_solve", "egdst_solve_batch", "egdst_resolve", "egdst_solution_sizes",
+               "egdst_solution_export", "egdst_solution_status", "egdst_solution_nvec", "egdst_solution_units",
+               "egdst_free_solution", "egdst_solution_import", "egdst_simulate", "egdst_simulate_philox",
+               "egdst_simulate_device", "egdst_call"]
+
+    def __init__(self, path: str):
+        if not os.path.isfile(path):
+            raise FileNotFoundError("egdst_b200 model library not found: %s (run model.compile(); there is no CPU path)" % path)
+        self.path = path
+        self.L = L = C.CDLL(path)
+        vp = C.c_void_p
+        L.egdst_abi_version.restype = C.c_int
+        L.egdst_model_key.restype = C.c_char_p
+        L.egdst_last_error.restype = C.c_char_p
+        L.egdst_set_stream.argtypes = [vp]
+        L.egdst_solve.argtypes = [C.POINTER(EgdstDesc), C.POINTER(vp)]
+        L.egdst_solve_batch.argtypes = [C.POINTER(EgdstDesc), _dp, C.c_int, C.POINTER(vp)]
+        L.egdst_resolve.argtypes = [vp, C.POINTER(EgdstDesc), _dp]
+        L.egdst_solution_sizes.argtypes = [vp, _ip, _ip]
+        L.egdst_solution_export.argtypes = [vp, _dp, _dp]
+        L.egdst_solution_status.argtypes = [vp, C.c_int, _ip, _ip, _ip]
+        L.egdst_solution_nvec.argtypes = [vp]
+        L.egdst_solution_units.argtypes = [vp]
+        L.egdst_solution_units.restype = C.c_longlong
+        L.egdst_free_solution.argtypes = [vp]
+        L.egdst_free_solution.restype = None
+        L.egdst_solution_import.argtypes = [C.POINTER(EgdstDesc), _ip, _ip, _dp, _dp, C.POINTER(vp)]
+        L.egdst_simulate.argtypes = [C.POINTER(EgdstDesc), vp, C.c_int, _dp, C.c_int, _dp, C.c_longlong, C.c_int, _dp]
+        L.egdst_simulate_philox.argtypes = [C.POINTER(EgdstDesc), vp, C.c_int, _dp, C.c_int, C.c_longlong, C.c_ulonglong, _dp, _dp]
+        L.egdst_simulate_device.argtypes = [C.POINTER(EgdstDesc), vp, C.c_int, vp, C.c_int, C.c_longlong, C.c_ulonglong,
+                                            vp, C.c_int, vp, vp]
+        L.egdst_call.argtypes = [C.POINTER(EgdstDesc), vp, C.c_int, _dp, C.c_int, C.c_int, _dp]
+        if L.egdst_abi_version() != ABI_VERSION:
+            raise RuntimeError("ABI version mismatch in %s" % path)
+
+    def last_error(self) -> str:
+        return self.L.egdst_last_error().decode(errors="replace")
+
+    def _raise(self, rc: int):
+        raise EgdstError(rc, self.last_error())
+
+    def set_stream(self, stream_ptr: int):
+        self.L.egdst_set_stream(C.c_void_p(stream_ptr))
+
+    # -- solve
+    def solve(self, model, device: Optional[int] = None, strict: bool = False) -> Solution:
+        d = Desc(model, device)
+        h = C.c_void_p()
+        rc = self.L.egdst_solve(C.byref(d.c), C.byref(h))
+        if rc == 2 or (rc and strict):
+            if h:
+                self.L.egdst_free_solution(h)
+            self._raise(rc)
+        sol = Solution(self, h, model)
+        if rc == 1:  # soft error: partial result kept, like mexWarnMsgTxt(err) (egdst_solver.c:237)
+            import warnings
+            sol.warning = self.last_error()
+            warnings.warn(sol.warning, EgdstWarning)
+        return sol
+
+    def solve_batch(self, model, params: np.ndarray, device: Optional[int] = None) -> Solution:
+        d = Desc(model, device)
+        p = _arr(params)
+        if p.ndim != 2 or p.shape[1] != len(model.param):
+            raise ValueError("params must be [nvec, nparam]")
+        h = C.c_void_p()
+        rc = self.L.egdst_solve_batch(C.byref(d.c), _ptr(p), p.shape[0], C.byref(h))
+        if rc == 2:
+            self._raise(rc)
+        sol = Solution(self, h, model, nvec=p.shape[0])
+        if rc == 1:
+            sol.warning = self.last_error()
+        return sol
+
+    def resolve(self, sol: Solution, model, params: Optional[np.ndarray] = None, device: Optional[int] = None):
+        d = Desc(model, device)
+        p = _arr(params) if params is not None else None
+        rc = self.L.egdst_resolve(sol.handle, C.byref(d.c), _ptr(p))
+        if rc:
+            self._raise(rc)
+        sol._cells = None
+
+    def import_solution(self, model, M, D, device: Optional[int] = None) -> Solution:
+        d = Desc(model, device)
+        nst, nt = model.nst, model.nt
+        mlen = np.zeros(nt * nst, dtype=np.int32)
+        thlen = np.zeros(nt * nst, dtype=np.int32)
+        mb: List[np.ndarray] = []
+        db: List[np.ndarray] = []
+        for it in range(nt):
+            for ist in range(nst):
+                c = it * nst + ist
+                if M[ist][it] is not None and M[ist][it].size:
+                    mlen[c] = M[ist][it].shape[0]
+                    thlen[c] = D[ist][it].shape[0]
+                    mb.append(np.asarray(M[ist][it], dtype=np.float64).ravel(order="F"))
+                    db.append(np.asarray(D[ist][it], dtype=np.float64).ravel(order="F"))
+        Mbuf = _arr(np.concatenate(mb)) if mb else np.zeros(1)
+        Dbuf = _arr(np.concatenate(db)) if db else np.zeros(1)
+        h = C.c_void_p()
+        rc = self.L.egdst_solution_import(C.byref(d.c), mlen.ctypes.data_as(_ip), thlen.ctypes.data_as(_ip), _ptr(Mbuf), _ptr(Dbuf), C.byref(h))
+        if rc:
+            self._raise(rc)
+        return Solution(self, h, model)
+
+    # -- simulate
+    def simulate(self, model, sol: Solution, init, randstream, rndtype: int = 0, ivec: int = 0) -> np.ndarray:
+        """[nsim, nt, nsimout] (already permuted as egdstmodel.m:1270 does)."""
+        d = Desc(model)
+        init = np.atleast_2d(np.asarray(init, dtype=np.float64))
+        nsim = init.shape[0]
+        initf = _arr(init.ravel(order="F"))
+        rs = _arr(np.asarray(randstream, dtype=np.float64).ravel())
+        nso, nt = model.nsimout(), model.nt
+        sims = np.empty(nso * nt * nsim, dtype=np.float64)
+        rc = self.L.egdst_simulate(C.byref(d.c), sol.handle, ivec, _ptr(initf), nsim, _ptr(rs), rs.size, rndtype, _ptr(sims))
+        if rc:
+            self._raise(rc)
+        return np.transpose(sims.reshape((nso, nt, nsim), order="F"), (2, 1, 0))
+
+    def simulate_philox(self, model, sol: Solution, init, seed: int, agent0: int = 0, ivec: int = 0, want_sims=True, want_moments=False):
+        d = Desc(model)
+        init = np.atleast_2d(np.asarray(init, dtype=np.float64))
+        nsim = init.shape[0]
+        initf = _arr(init.ravel(order="F"))
+        nso, nt = model.nsimout(), model.nt
+        sims = np.empty(nso * nt * nsim, dtype=np.float64) if want_sims else None
+        mom = np.zeros(3 * nso * nt, dtype=np.float64) if want_moments else None
+        rc = self.L.egdst_simulate_philox(C.byref(d.c), sol.handle, ivec, _ptr(initf), nsim, agent0, seed, _ptr(sims), _ptr(mom))
+        if rc:
+            self._raise(rc)
+        out_s = np.transpose(sims.reshape((nso, nt, nsim), order="F"), (2, 1, 0)) if want_sims else None
+        out_m = mom.reshape((3, nso, nt), order="F") if want_moments else None
+        return out_s, out_m
+
+    def call(self, model, sol: Solution, sw: int, args: np.ndarray) -> np.ndarray:
+        d = Desc(model)
+        a = np.atleast_2d(np.asarray(args, dtype=np.float64))
+        narg, k = a.shape
+        af = _arr(a.ravel(order="F"))
+        res = np.empty(narg, dtype=np.float64)
+        rc = self.L.egdst_call(C.byref(d.c), sol.handle, sw, _ptr(af), narg, k, _ptr(res))
+        if rc == 2:
+            self._raise(rc)
+        return res

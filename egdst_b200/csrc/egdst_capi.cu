@@ -1,0 +1,409 @@
+// egdst_capi.cu -- host orchestration and the C ABI (include/egdst_b200.h).
+//
+// Replaces the reference's MEX gateways and driver loops:
+//   mexFunction/solver()      egdst_solver.c:143-339   -> egdst_solve / egdst_resolve (period loop of kernel launches)
+//   saveoutput/swappointers   egdst_solver.c:917-952,342 -> the device arena (next period reads the cells in place)
+//   parseModel/loadparameters egdst_lib.c:34-62          -> egdst_desc
+// There is no host arithmetic on the data path: even the cdfni transform of the quadrature abscissas
+// (egdst_solver.c:162-164) runs on the device.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "egdst_b200.h"
+#include "egdst_envelope.cuh"
+#include "egdst_simulator.cuh"
+#include "egdst_solver.cuh"
+
+#ifndef EGDST_MODEL_KEY
+#define EGDST_MODEL_KEY "unknown"
+#endif
+
+static thread_local std::string g_err;
+static thread_local cudaStream_t g_stream = 0;
+
+static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+
+#define CK(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess) return fail(2, std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #call); \
+    } while (0)
+
+static const char *status_text(int code) {
+    switch (code) {  // wording of the reference's error() sites
+    case EGDST_ERR_CHECKSUM: return "Transition probabilities don't sum up! Check model specification!";
+    case EGDST_ERR_NOSAVINGS: return "Failed to find any value of savings to result in positive consumption next period! Increase mmax.";
+    case EGDST_ERR_GRIDSPACE: return "Not enough space for endogenous grid. Increase max number of grid points for M!";
+    case EGDST_ERR_EMPTYCHOICE: return "Empty choiceset encountered! Check model specifications!";
+    case EGDST_ERR_ALLINF: return "All of the choices lead to -inf value functions for all values of money-at-hand!";
+    case EGDST_ERR_ENVELOPE: return "Failed to compute upper envelope, most likely individual grids don't overlap!";
+    case EGDST_ERR_ADRAW_INIT: return "Could not complete initial stage in adraw()..\nSeems like M(a0)>mmax! Increase mmax!";
+    case EGDST_ERR_ADRAW_LOOP: return "Emergiency exit from adraw, possibly infinite loop! Check model specifications!";
+    case EGDST_ERR_THRSPACE: return "Not enough space for thresholds. Increase max number of threshold points!";
+    case EGDST_ERR_TWO_ANALYTIC: return "Fatal error in threshold module. Two analytical value functions seem to intersect. Utility is not additively separable in consumption and discrete choices.";
+    case EGDST_ERR_BRACKET: return "Fatal error in braketing module! Solution is outside of brackets.";
+    case EGDST_ERR_CASHINVERSE: return "Did not manage to invert the intertemporal budget (cashinhand) after performing many-many iterations!";
+    case EGDST_ERR_INTERP2PT: return "Error: At least two points are required for interpolation!";
+    case EGDST_ERR_ENV2SPACE: return "Not enough space for endogenous grid in envelop2()";
+    case EGDST_ERR_RESEND_LATE: return "Zero-consumption re-send requested after the seed stage of the savings grid (not supported by the parallel grid)";
+    case EGDST_ERR_TRPR_INDEX: return "Error in trpr: unknown index of the state variable";
+    case EGDST_ERR_TRPR_CASES: return "Error in trpr: unknown combination of current state and decision (the set of cases is not complete)!";
+    default: return "unknown error";
+    }
+}
+
+struct egdst_solution {
+    EgdstDev P;
+    int device;
+    std::vector<void *> owned;  // device allocations
+    double *d_qraw;             // quadrature as passed (weights, abscissas)
+    double *d_stm, *d_states, *d_decisions, *d_bparams, *d_q;
+    int nsd, ncell, nslot;
+    std::vector<int> h_mlen, h_thlen, h_status;
+    bool sizes_valid;
+    double *d_pack;  // export staging
+    size_t pack_cap;
+    int *d_moff, *d_toff;
+    int neq;
+};
+
+template <class T>
+static cudaError_t dalloc(egdst_solution *s, T **p, size_t n) {
+    cudaError_t e = cudaMalloc((void **)p, (n ? n : 1) * sizeof(T));
+    if (e == cudaSuccess) s->owned.push_back((void *)*p);
+    return e;
+}
+
+// quadrature abscissas -> standard normal quantiles (egdst_solver.c:162-164), on the device
+__global__ void egdst_k_quadrature(const double *qraw, double *q, int ny) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < ny) { q[i] = qraw[i]; q[ny + i] = egdst_cdfni(qraw[ny + i]); }
+}
+
+// mark infeasible (it,ist) cells as empty and detect empty choice sets (egdst_solver.c:294-300, 694-702)
+__global__ void egdst_k_cells(EgdstDev P, int it) {
+    const int ivec = blockIdx.x, ist = threadIdx.x;
+    if (ist >= P.cx.nst) return;
+    egdst_ctx cx; egdst_load_ctx(P, ivec, cx);
+    PeriodVars curr; curr.it = it; curr.ist = ist; curr.id = 0; curr.cash = 0; curr.savings = 0; curr.shock = 0;
+    const int cell = egdst_cell(P, ivec, it, ist);
+    if (feasible(&cx, &curr) != 1) { P.mlen[cell] = 0; P.thlen[cell] = 0; return; }
+    int any = 0;
+    for (curr.id = 0; curr.id < cx.nd; curr.id++) any |= (inchoiceset(&cx, &curr) == 1);
+    if (!any) { P.mlen[cell] = 0; P.thlen[cell] = 0; egdst_fail(P, ivec, EGDST_ERR_EMPTYCHOICE, it, ist, -1); }
+}
+
+// after the per-id EGM: "all choices produced empty grids" (egdst_solver.c:704-710)
+__global__ void egdst_k_checkempty(EgdstDev P, int it) {
+    const int ivec = blockIdx.x, ist = threadIdx.x;
+    if (ist >= P.cx.nst) return;
+    const int sd0 = egdst_sd(P, ivec, ist, 0);
+    int any = 0, tot = 0;
+    for (int id = 0; id < P.cx.nd; id++) { any |= P.active[sd0 + id]; tot += P.ptN[sd0 + id]; }
+    if (any && tot == 0) egdst_fail(P, ivec, EGDST_ERR_ALLINF, it, ist, -1);
+}
+
+static int fill_ctx(const egdst_desc *d, egdst_ctx *cx) {
+    if (!d) return fail(2, "null descriptor");
+    if (d->abi_version != EGDST_ABI_VERSION) return fail(2, "egdst_desc.abi_version mismatch");
+    if (d->nparam != EGDST_NPARAM) return fail(2, "number of parameters does not match the compiled model image");
+    if (d->nnst > EGDST_NNST || d->nnd > EGDST_NND) return fail(2, "state/decision vector size does not match the compiled model image");
+    if (d->ngridm < 2 || d->ngridmax <= d->ngridm || d->T < d->t0 || d->nst < 1 || d->nd < 1 || d->ny < 1 || d->nthrhmax < 2)
+        return fail(2, "invalid model dimensions");
+    if (d->ny > 1 && !d->quadrature) return fail(2, "quadrature missing");
+    memset(cx, 0, sizeof(*cx));
+    cx->t0 = d->t0; cx->T = d->T; cx->ngridm = d->ngridm; cx->ngridmax = d->ngridmax; cx->nthrhmax = d->nthrhmax;
+    cx->ny = d->ny; cx->nd = d->nd; cx->nnd = d->nnd; cx->nst = d->nst; cx->nnst = d->nnst;
+    cx->optim_UasD = d->optim_UasD; cx->optim_MUnoD = d->optim_MUnoD; cx->optim_UnoD = d->optim_UnoD; cx->optim_TRPRnoSH = d->optim_TRPRnoSH;
+    cx->byval = 0;
+    cx->mmax = d->mmax; cx->a0 = d->a0;
+    cx->tolerance = d->tolerance; cx->zeroconsumption = d->zeroconsumption; cx->doublepoint_delta = d->doublepoint_delta;
+    for (int i = 0; i < EGDST_NPARAM; i++) cx->param[i] = d->params[i];
+    return 0;
+}
+
+static int check_device(int device) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) return fail(2, "no CUDA device: egdst_b200 has no CPU path");
+    if (device < 0 || device >= n) return fail(2, "invalid CUDA device ordinal");
+    if (cudaSetDevice(device) != cudaSuccess) return fail(2, "cudaSetDevice failed");
+    return 0;
+}
+
+static int create_solution(const egdst_desc *d, int nvec, egdst_solution **out) {
+    egdst_ctx cx;
+    int rc = fill_ctx(d, &cx);
+    if (rc) return rc;
+    if ((rc = check_device(d->device))) return rc;
+    egdst_solution *s = new egdst_solution();
+    s->device = d->device; s->sizes_valid = false; s->d_pack = 0; s->pack_cap = 0; s->neq = d->neq;
+    EgdstDev &P = s->P;
+    memset(&P, 0, sizeof(P));
+    P.cx = cx;
+    P.NT = d->T - d->t0 + 1; P.nvec = nvec; P.rowcap = d->ngridmax + 2; P.gcap = d->ngridmax; P.N = d->ngridm;
+    const int nst = d->nst, nd = d->nd;
+    s->ncell = nvec * P.NT * nst; s->nsd = nvec * nst * nd; s->nslot = s->nsd + nvec * nst;
+    P.envcap = (nd > 2 ? nd : 2) * P.gcap + 2;
+#define DA(ptr, n) do { cudaError_t e_ = dalloc(s, &(ptr), (size_t)(n)); if (e_ != cudaSuccess) { egdst_free_solution(s); return fail(2, std::string("cudaMalloc failed: ") + cudaGetErrorString(e_)); } } while (0)
+    DA(s->d_stm, 2 * d->nnst); DA(s->d_states, nst * d->nnst); DA(s->d_decisions, nd * d->nnd);
+    DA(s->d_bparams, (size_t)nvec * EGDST_NPARAM_); DA(s->d_qraw, 2 * d->ny); DA(s->d_q, 2 * d->ny);
+    DA(P.arena, (size_t)s->ncell * 4 * P.rowcap); DA(P.mlen, s->ncell); DA(P.thlen, s->ncell); DA(P.evf, s->ncell);
+    DA(P.thD, (size_t)s->ncell * d->nthrhmax); DA(P.thTH, (size_t)s->ncell * d->nthrhmax);
+    DA(P.active, s->nsd); DA(P.seed, (size_t)s->nsd * 8); DA(P.evfa0, s->nsd);
+    DA(P.rawM, (size_t)s->nsd * P.N); DA(P.rawC, (size_t)s->nsd * P.N); DA(P.rawV, (size_t)s->nsd * P.N); DA(P.rawStop, (size_t)s->nsd * P.N);
+    DA(P.rawFlag, (size_t)s->nsd * P.N);
+    DA(P.ptX, (size_t)s->nsd * P.gcap); DA(P.ptC, (size_t)s->nsd * P.gcap); DA(P.ptV, (size_t)s->nsd * P.gcap);
+    DA(P.ptN, s->nsd); DA(P.nfold, s->nsd); DA(P.runStart, (size_t)s->nsd * (P.gcap + 1));
+    DA(P.mgX, (size_t)s->nslot * P.envcap); DA(P.mgF, (size_t)s->nslot * P.envcap); DA(P.mgK, (size_t)s->nslot * P.envcap); DA(P.mgA, (size_t)s->nslot * P.envcap);
+    DA(P.outX, (size_t)s->nsd * P.envcap); DA(P.outC, (size_t)s->nsd * P.envcap); DA(P.outV, (size_t)s->nsd * P.envcap);
+    DA(P.status, 4 * nvec); DA(s->d_moff, s->ncell + 1); DA(s->d_toff, s->ncell + 1);
+#undef DA
+    P.cx.stm = s->d_stm; P.cx.states = s->d_states; P.cx.decisions = s->d_decisions;
+    P.qw = s->d_q; P.qz = s->d_q + d->ny;
+    s->h_mlen.assign(s->ncell, 0); s->h_thlen.assign(s->ncell, 0); s->h_status.assign(4 * nvec, 0);
+    *out = s;
+    return 0;
+}
+
+// one backward-induction pass; asynchronous
+static int run_solve(egdst_solution *s, const egdst_desc *d, const double *params) {
+    EgdstDev &P = s->P;
+    egdst_ctx cx;
+    int rc = fill_ctx(d, &cx);
+    if (rc) return rc;
+    if (d->ngridm != P.N || d->ngridmax != P.gcap || d->T - d->t0 + 1 != P.NT || d->nst != P.cx.nst || d->nd != P.cx.nd ||
+        d->ny != P.cx.ny || d->nthrhmax != P.cx.nthrhmax)
+        return fail(2, "egdst_resolve: dimensions differ from the solution object");
+    CK(cudaSetDevice(s->device));
+    cx.stm = s->d_stm; cx.states = s->d_states; cx.decisions = s->d_decisions;
+    P.cx = cx;
+    cudaStream_t st = g_stream;
+    CK(cudaMemcpyAsync(s->d_stm, d->stm, sizeof(double) * 2 * d->nnst, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(s->d_states, d->states, sizeof(double) * d->nst * d->nnst, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(s->d_decisions, d->decisions, sizeof(double) * d->nd * d->nnd, cudaMemcpyHostToDevice, st));
+    if (params) {
+        CK(cudaMemcpyAsync(s->d_bparams, params, sizeof(double) * (size_t)P.nvec * EGDST_NPARAM, cudaMemcpyHostToDevice, st));
+        P.bparams = s->d_bparams;
+    } else {
+        P.bparams = 0;
+    }
+    if (d->ny > 1) {
+        CK(cudaMemcpyAsync(s->d_qraw, d->quadrature, sizeof(double) * 2 * d->ny, cudaMemcpyHostToDevice, st));
+        EGDST_LAUNCH(egdst_k_quadrature, dim3((d->ny + 127) / 128), dim3(128), 0, st, s->d_qraw, s->d_q, d->ny);
+    }
+    CK(cudaMemsetAsync(P.status, 0, sizeof(int) * 4 * P.nvec, st));
+    CK(cudaMemsetAsync(P.mlen, 0, sizeof(int) * s->ncell, st));
+    CK(cudaMemsetAsync(P.thlen, 0, sizeof(int) * s->ncell, st));
+    const int nst = P.cx.nst, nd = P.cx.nd, nvec = P.nvec, N = P.N, B = EGDST_BLOCK;
+    const int cellthreads = ((nst + 31) / 32) * 32;
+    for (int it = P.NT - 1; it >= 0; it--) {
+        EGDST_LAUNCH(egdst_k_cells, dim3(nvec), dim3(cellthreads), 0, st, P, it);
+        if (it == P.NT - 1) {
+            EGDST_LAUNCH(egdst_k_terminal, dim3((N + B - 1) / B, nst * nd, nvec), dim3(B), 0, st, P, it);
+        } else {
+            EGDST_LAUNCH(egdst_k_seed, dim3(nd, nst, nvec), dim3(B), 0, st, P, it);
+            EGDST_LAUNCH(egdst_k_egm, dim3((N - 1 + 31) / 32, nst * nd, nvec), dim3(32, EGDST_EGM_SPLIT), 0, st, P, it);
+            EGDST_LAUNCH(egdst_k_compact, dim3(nd, nst, nvec), dim3(B), 0, st, P, it);
+            // secondary envelope (no-op for (ist,id) without folds)
+            EGDST_LAUNCH(egdst_k_envA<1>, dim3((2 * P.gcap + B - 1) / B, nst * nd, nvec), dim3(B), 0, st, P, it);
+            EGDST_LAUNCH(egdst_k_envBC<1>, dim3(1, nst * nd, nvec), dim3(B), 0, st, P, it);
+            EGDST_LAUNCH(egdst_k_checkempty, dim3(nvec), dim3(cellthreads), 0, st, P, it);
+        }
+        EGDST_LAUNCH(egdst_k_envA<0>, dim3((nd * P.gcap + B - 1) / B, nst, nvec), dim3(B), 0, st, P, it);
+        EGDST_LAUNCH(egdst_k_envBC<0>, dim3(1, nst, nvec), dim3(B), 0, st, P, it);
+    }
+    s->sizes_valid = false;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static int fetch_sizes(egdst_solution *s) {
+    if (s->sizes_valid) return 0;
+    CK(cudaSetDevice(s->device));
+    cudaStream_t st = g_stream;
+    CK(cudaMemcpyAsync(s->h_mlen.data(), s->P.mlen, sizeof(int) * s->ncell, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(s->h_thlen.data(), s->P.thlen, sizeof(int) * s->ncell, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(s->h_status.data(), s->P.status, sizeof(int) * 4 * s->P.nvec, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    s->sizes_valid = true;
+    return 0;
+}
+
+static int status_rc(egdst_solution *s) {
+    for (int v = 0; v < s->P.nvec; v++) {
+        const int code = s->h_status[4 * v];
+        if (code) {
+            char buf[512];
+            snprintf(buf, sizeof(buf), "Error:\n%s\n(vector %d, period it=%d, ist=%d, id=%d)", status_text(code), v, s->h_status[4 * v + 1],
+                     s->h_status[4 * v + 2], s->h_status[4 * v + 3]);
+            return fail(code >= 100 ? 2 : 1, buf);
+        }
+    }
+    return 0;
+}
+
+// gather the ragged cells into the packed export layout
+__global__ void egdst_k_pack(EgdstDev P, const int *moff, const int *toff, double *Mbuf, double *Dbuf, int ncell) {
+    const int cell = blockIdx.x;
+    if (cell >= ncell) return;
+    const int n = P.mlen[cell], nth = P.thlen[cell];
+    const double *src = P.arena + (size_t)cell * 4 * P.rowcap;
+    double *dst = Mbuf + (size_t)4 * moff[cell];
+    for (int i = threadIdx.x; i < 4 * n; i += blockDim.x) dst[i] = src[(size_t)(i / n) * P.rowcap + (i % n)];
+    double *dd = Dbuf + (size_t)2 * toff[cell];
+    for (int i = threadIdx.x; i < nth; i += blockDim.x) {
+        dd[i] = P.thD[(size_t)cell * P.cx.nthrhmax + i];
+        dd[nth + i] = P.thTH[(size_t)cell * P.cx.nthrhmax + i];
+    }
+}
+
+// scatter host cells into the arena (egdst_solution_import)
+__global__ void egdst_k_unpack(EgdstDev P, const int *moff, const int *toff, const double *Mbuf, const double *Dbuf, int ncell) {
+    const int cell = blockIdx.x;
+    if (cell >= ncell) return;
+    const int n = P.mlen[cell], nth = P.thlen[cell];
+    double *dst = P.arena + (size_t)cell * 4 * P.rowcap;
+    const double *src = Mbuf + (size_t)4 * moff[cell];
+    for (int i = threadIdx.x; i < 4 * n; i += blockDim.x) dst[(size_t)(i / n) * P.rowcap + (i % n)] = src[i];
+    const double *dd = Dbuf + (size_t)2 * toff[cell];
+    for (int i = threadIdx.x; i < nth; i += blockDim.x) {
+        P.thD[(size_t)cell * P.cx.nthrhmax + i] = dd[i];
+        P.thTH[(size_t)cell * P.cx.nthrhmax + i] = dd[nth + i];
+    }
+    if (threadIdx.x == 0 && n > 0) P.evf[cell] = src[3 * n];
+}
+
+extern "C" {
+
+int egdst_abi_version(void) { return EGDST_ABI_VERSION; }
+const char *egdst_model_key(void) { return EGDST_MODEL_KEY; }
+int egdst_model_nparam(void) { return EGDST_NPARAM; }
+int egdst_model_neq(void) { return EGDST_NREQ; }
+const char *egdst_last_error(void) { return g_err.c_str(); }
+void egdst_set_stream(void *cuda_stream) { g_stream = (cudaStream_t)cuda_stream; }
+
+int egdst_solve_batch(const egdst_desc *d, const double *params, int nvec, egdst_solution **out) {
+    if (!out || nvec < 1) return fail(2, "invalid arguments");
+    *out = 0;
+    egdst_solution *s = 0;
+    int rc = create_solution(d, nvec, &s);
+    if (rc) return rc;
+    rc = run_solve(s, d, params);
+    if (rc) { egdst_free_solution(s); return rc; }
+    rc = fetch_sizes(s);
+    if (rc) { egdst_free_solution(s); return rc; }
+    *out = s;
+    rc = status_rc(s);
+    if (rc == 2) { egdst_free_solution(s); *out = 0; }
+    return rc;
+}
+
+int egdst_solve(const egdst_desc *d, egdst_solution **out) { return egdst_solve_batch(d, 0, 1, out); }
+
+int egdst_resolve(egdst_solution *s, const egdst_desc *d, const double *params) {
+    if (!s) return fail(2, "null solution");
+    return run_solve(s, d, params);
+}
+
+int egdst_solution_sizes(egdst_solution *s, int *mlen, int *thlen) {
+    if (!s) return fail(2, "null solution");
+    int rc = fetch_sizes(s);
+    if (rc) return rc;
+    if (mlen) memcpy(mlen, s->h_mlen.data(), sizeof(int) * s->ncell);
+    if (thlen) memcpy(thlen, s->h_thlen.data(), sizeof(int) * s->ncell);
+    return status_rc(s) == 2 ? 2 : 0;
+}
+
+int egdst_solution_export(egdst_solution *s, double *Mbuf, double *Dbuf) {
+    if (!s || !Mbuf || !Dbuf) return fail(2, "invalid arguments");
+    int rc = fetch_sizes(s);
+    if (rc) return rc;
+    std::vector<int> moff(s->ncell + 1, 0), toff(s->ncell + 1, 0);
+    for (int c = 0; c < s->ncell; c++) { moff[c + 1] = moff[c] + s->h_mlen[c]; toff[c + 1] = toff[c] + s->h_thlen[c]; }
+    const size_t nm = (size_t)4 * moff[s->ncell], nd2 = (size_t)2 * toff[s->ncell];
+    cudaStream_t st = g_stream;
+    if (nm + nd2 > s->pack_cap) {
+        if (s->d_pack) cudaFree(s->d_pack);
+        s->d_pack = 0; s->pack_cap = 0;
+        CK(cudaMalloc((void **)&s->d_pack, sizeof(double) * (nm + nd2 + 1)));
+        s->pack_cap = nm + nd2;
+    }
+    CK(cudaMemcpyAsync(s->d_moff, moff.data(), sizeof(int) * (s->ncell + 1), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(s->d_toff, toff.data(), sizeof(int) * (s->ncell + 1), cudaMemcpyHostToDevice, st));
+    EGDST_LAUNCH(egdst_k_pack, dim3(s->ncell), dim3(EGDST_BLOCK), 0, st, s->P, s->d_moff, s->d_toff, s->d_pack, s->d_pack + nm, s->ncell);
+    CK(cudaMemcpyAsync(Mbuf, s->d_pack, sizeof(double) * nm, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(Dbuf, s->d_pack + nm, sizeof(double) * nd2, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int egdst_solution_status(egdst_solution *s, int ivec, int *it, int *ist, int *id) {
+    if (!s || ivec < 0 || ivec >= s->P.nvec) return -1;
+    if (fetch_sizes(s)) return -1;
+    if (it) *it = s->h_status[4 * ivec + 1];
+    if (ist) *ist = s->h_status[4 * ivec + 2];
+    if (id) *id = s->h_status[4 * ivec + 3];
+    const int code = s->h_status[4 * ivec];
+    if (code) status_rc(s);
+    return code;
+}
+
+int egdst_solution_nvec(const egdst_solution *s) { return s ? s->P.nvec : 0; }
+
+long long egdst_solution_units(egdst_solution *s) {
+    // the solve work unit: every (it, ist, id in choice set) contributes its EGM grid points.
+    // Counted from the final cells as rows excluding the a0 row -- a lower bound on the stored quadruples.
+    if (!s || fetch_sizes(s)) return -1;
+    long long u = 0;
+    for (int c = 0; c < s->ncell; c++) u += s->h_mlen[c] > 0 ? s->h_mlen[c] - 1 : 0;
+    return u;
+}
+
+void egdst_free_solution(egdst_solution *s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    for (void *p : s->owned) cudaFree(p);
+    if (s->d_pack) cudaFree(s->d_pack);
+    delete s;
+}
+
+int egdst_solution_import(const egdst_desc *d, const int *mlen, const int *thlen, const double *Mbuf, const double *Dbuf, egdst_solution **out) {
+    if (!out || !mlen || !thlen || !Mbuf || !Dbuf) return fail(2, "invalid arguments");
+    *out = 0;
+    egdst_solution *s = 0;
+    int rc = create_solution(d, 1, &s);
+    if (rc) return rc;
+    std::vector<int> moff(s->ncell + 1, 0), toff(s->ncell + 1, 0);
+    for (int c = 0; c < s->ncell; c++) {
+        if (mlen[c] > s->P.rowcap || thlen[c] > d->nthrhmax) { egdst_free_solution(s); return fail(2, "imported cell exceeds ngridmax/nthrhmax"); }
+        moff[c + 1] = moff[c] + mlen[c]; toff[c + 1] = toff[c] + thlen[c];
+    }
+    const size_t nm = (size_t)4 * moff[s->ncell], nd2 = (size_t)2 * toff[s->ncell];
+    cudaStream_t st = g_stream;
+    if (cudaMalloc((void **)&s->d_pack, sizeof(double) * (nm + nd2 + 1)) != cudaSuccess) { egdst_free_solution(s); return fail(2, "cudaMalloc failed"); }
+    s->pack_cap = nm + nd2;
+    cudaMemcpyAsync(s->d_pack, Mbuf, sizeof(double) * nm, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(s->d_pack + nm, Dbuf, sizeof(double) * nd2, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(s->P.mlen, mlen, sizeof(int) * s->ncell, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(s->P.thlen, thlen, sizeof(int) * s->ncell, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(s->d_moff, moff.data(), sizeof(int) * (s->ncell + 1), cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(s->d_toff, toff.data(), sizeof(int) * (s->ncell + 1), cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(s->d_stm, d->stm, sizeof(double) * 2 * d->nnst, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(s->d_states, d->states, sizeof(double) * d->nst * d->nnst, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(s->d_decisions, d->decisions, sizeof(double) * d->nd * d->nnd, cudaMemcpyHostToDevice, st);
+    cudaMemsetAsync(s->P.status, 0, sizeof(int) * 4, st);
+    EGDST_LAUNCH(egdst_k_unpack, dim3(s->ncell), dim3(EGDST_BLOCK), 0, st, s->P, s->d_moff, s->d_toff, s->d_pack, s->d_pack + nm, s->ncell);
+    if (cudaStreamSynchronize(st) != cudaSuccess) { egdst_free_solution(s); return fail(2, "import failed"); }
+    memcpy(s->h_mlen.data(), mlen, sizeof(int) * s->ncell);
+    memcpy(s->h_thlen.data(), thlen, sizeof(int) * s->ncell);
+    s->sizes_valid = true;
+    *out = s;
+    return 0;
+}
+
+#include "egdst_capi_sim.inc"
+
+}  // extern "C"

@@ -1,0 +1,109 @@
+// egdst_common.cuh -- device-side problem descriptor, launch macro and block/warp collectives.
+#pragma once
+
+#include "egdst_numerics.cuh"
+
+#ifdef EGDST_HOSTEMU
+// tools/hostemu: the kernels are compiled by g++ against an emulation of the CUDA execution model so that
+// their logic can be debugged without a GPU.  Development aid only -- never loaded by the product.
+#include "cuda_emul.h"
+#define EGDST_BLOCK 64
+#else
+#include <cuda_runtime.h>
+#define EGDST_BLOCK 256
+#define EGDST_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
+
+#ifdef __CUDACC__
+#define EGDST_DEV_M __device__ __forceinline__
+#else
+#define EGDST_DEV_M inline
+#endif
+
+#define EGDST_FULL 0xffffffffu
+#define EGDST_MAXCAND 72   /* stage-0 bisection candidates: (mmax-a0)/2^k < TOLERANCE well before 72 halvings */
+#define EGDST_ENV_STACK 24 /* crossing-chain stack (thresholds() recursion depth) */
+#define EGDST_ENV_MARKW 32 /* 32*32 = 1024 functions (envelope2 runs) can be marked */
+
+// raw-point flags written by the seed/EGM kernels
+enum { EGDST_PT_OK = 0, EGDST_PT_C1NEG = 1, EGDST_PT_EVFINF = 2, EGDST_PT_CHECKSUM = 3, EGDST_PT_NONFINITE = 4, EGDST_PT_NONE = 5 };
+
+// Everything a kernel needs.  Leading dimension of every array is the parameter-vector index `ivec`
+// (batched solves; nvec=1 for a single model).
+struct EgdstDev {
+    egdst_ctx cx;
+    int NT, nvec, rowcap, gcap, N;  // rowcap = ngridmax+2 rows per arena column; gcap = ngridmax; N = ngridm
+    const double *bparams;          // [nvec*NPARAM] or null
+    const double *qw, *qz;          // quadrature weights, std-normal abscissas (cdfni applied) [ny]
+    // solution arena
+    double *arena;                  // [(nvec*NT*nst) * 4 * rowcap]  columns M,C,A,V
+    int *mlen;                      // [nvec*NT*nst] rows incl. the a0 row (0 = no solution)
+    double *thD, *thTH;             // [nvec*NT*nst * nthrhmax]
+    int *thlen;                     // [nvec*NT*nst]
+    double *evf;                    // [nvec*NT*nst]
+    // per-period workspace, indexed by sd = (ivec*nst+ist)*nd+id
+    int *active;                    // 1 if feasible(ist) && inchoiceset(id)
+    double *seed;                   // [nsd*8]: lim1,lim2,lim3,lim3p,k3,A0,-,-
+    double *rawM, *rawC, *rawV, *rawStop;  // [nsd*N]
+    int *rawFlag;                   // [nsd*N]
+    double *evfa0;                  // [nsd]
+    double *ptX, *ptC, *ptV;        // [nsd*gcap] per-id point lists
+    int *ptN, *nfold, *runStart;    // [nsd], [nsd], [nsd*(gcap+1)]
+    // envelope scratch: secondary jobs use slot sd, primary jobs use slot nsd_total + (ivec*nst+ist)
+    double *mgX; int *mgF, *mgK, *mgA;     // merged order, capacity envcap per slot
+    double *outX, *outC, *outV;            // per-slot output staging, capacity envcap
+    int envcap;
+    int *status;                    // [nvec*4]: code, it, ist, id of the first error
+};
+
+EGDST_DEV int egdst_cell(const EgdstDev &P, int ivec, int it, int ist) { return (ivec * P.NT + it) * P.cx.nst + ist; }
+EGDST_DEV int egdst_sd(const EgdstDev &P, int ivec, int ist, int id) { return (ivec * P.cx.nst + ist) * P.cx.nd + id; }
+EGDST_DEV double *egdst_colM(const EgdstDev &P, int cell) { return P.arena + (size_t)cell * 4 * P.rowcap; }
+EGDST_DEV double *egdst_colC(const EgdstDev &P, int cell) { return P.arena + ((size_t)cell * 4 + 1) * P.rowcap; }
+EGDST_DEV double *egdst_colA(const EgdstDev &P, int cell) { return P.arena + ((size_t)cell * 4 + 2) * P.rowcap; }
+EGDST_DEV double *egdst_colV(const EgdstDev &P, int cell) { return P.arena + ((size_t)cell * 4 + 3) * P.rowcap; }
+
+EGDST_DEV void egdst_load_ctx(const EgdstDev &P, int ivec, egdst_ctx &cx) {
+    cx = P.cx;
+    if (P.bparams) for (int i = 0; i < EGDST_NPARAM; i++) cx.param[i] = P.bparams[(size_t)ivec * EGDST_NPARAM + i];
+    cx.status = P.status ? P.status + 4 * ivec : 0;
+}
+
+// first error wins (soft errors keep the partial solution, like err[300] in the reference)
+EGDST_DEV void egdst_fail(const EgdstDev &P, int ivec, int code, int it, int ist, int id) {
+    int *s = P.status + 4 * ivec;
+    if (atomicCAS(s, 0, code) == 0) { s[1] = it; s[2] = ist; s[3] = id; }
+}
+
+// ---- warp / block collectives (shuffle based) -------------------------------------------------
+EGDST_DEV double egdst_warp_sum(double v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(EGDST_FULL, v, o);
+    return v;
+}
+EGDST_DEV int egdst_warp_min(int v) {
+    for (int o = 16; o > 0; o >>= 1) { int w = __shfl_down_sync(EGDST_FULL, v, o); v = w < v ? w : v; }
+    return v;
+}
+EGDST_DEV int egdst_warp_incl_scan(int v, int lane) {
+    for (int o = 1; o < 32; o <<= 1) { int w = __shfl_up_sync(EGDST_FULL, v, o); if (lane >= o) v += w; }
+    return v;
+}
+// exclusive block scan of one int per thread; returns the exclusive prefix, *total gets the block sum.
+// `sh` must hold blockDim.x/32+1 ints.  Contains two __syncthreads().
+EGDST_DEV int egdst_block_excl_scan(int v, int *sh, int *total) {
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    int inc = egdst_warp_incl_scan(v, lane);
+    if (lane == 31) sh[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        int s = lane < nw ? sh[lane] : 0;
+        int si = egdst_warp_incl_scan(s, lane);
+        if (lane < nw) sh[lane] = si - s;
+        if (lane == nw - 1) sh[nw] = si;
+    }
+    __syncthreads();
+    int res = inc - v + sh[w];
+    *total = sh[nw];
+    __syncthreads();
+    return res;
+}

@@ -1,0 +1,381 @@
+// egdst_envelope.cuh -- upper envelope of tabulated value functions, thresholds and double points.
+//
+// Parallel restatement of the reference's serial sweep:
+//   envelop      egdst_solver.c:1165-1550   (qsort + sweep with cases 0/1/2)
+//   funcvalue    egdst_solver.c:1553-1567   linter2 :1585-1593   comp1 :1570-1582
+//   thresholds   egdst_solver.c:1596-1915   brsolve :1918-1968
+//   envelope2    egdst_solver.c:776-913     (same routine, the "functions" are monotone runs of one id)
+//
+// The serial sweep visits the union of all points in (x asc, V desc, index asc) order, keeps a point
+// when its own function is the maximum there, and inserts the crossing(s) of the previous and the new
+// maximal function whenever the argmax changes.  Between two consecutive points of the union every
+// function is a single linear piece (or its analytic credit-constrained branch), therefore
+//   (A) every point can find its rank in the union and the argmax at its abscissa independently
+//       (binary searches into the other functions' lists -- no sort, no sweep state), and
+//   (B) the crossings belong to the boundaries r-1|r of the union where argmax(r-1) != argmax(r); the
+//       chain of switches inside one boundary is found with the reference's own recursion rule.
+// Output order is restored with block-wide prefix sums (warp shuffles).  In generic position this
+// produces the same grid, values, thresholds and double points as the sweep; in exact ties it may
+// differ by which of two coincident points is kept (the functions agree).
+#pragma once
+
+#include "egdst_common.cuh"
+
+// ---- views over the input functions ---------------------------------------------------------
+// MODE 0: primary envelope, function f = decision id f of state ist (lists ptX/ptC/ptV of sd0+f)
+// MODE 1: secondary envelope of one (ist,id): function f = f-th monotone run; every run but the last is
+//         extended by the constant-extrapolation sentinel (1.5*mmax, C_last, V_last) (egdst_solver.c:824-827)
+template <int MODE>
+struct EgdstEnvView {
+    int F;
+    const double *X, *C, *V;  // MODE 0: base of decision 0 (stride gcap); MODE 1: the id's list
+    const int *n;             // MODE 0: ptN + sd0 ; MODE 1: runStart
+    const double *evfa0;      // MODE 0: evfa0 + sd0 ; MODE 1: &evfa0[sd]
+    int gcap, id;
+    double sentinel;
+
+    EGDST_DEV_M int npts(int f) const {
+        if (MODE == 0) return n[f];
+        return n[f + 1] - n[f] + (f < F - 1 ? 1 : 0);
+    }
+    EGDST_DEV_M int pstart(int f) const {  // offset of function f in the flattened point order
+        if (MODE == 0) { int s = 0; for (int g = 0; g < f; g++) s += n[g]; return s; }
+        return n[f] + f;
+    }
+    EGDST_DEV_M double x(int f, int k) const {
+        if (MODE == 0) return X[(size_t)f * gcap + k];
+        const int real = n[f + 1] - n[f];
+        return k < real ? X[n[f] + k] : sentinel;
+    }
+    EGDST_DEV_M double c(int f, int k) const {
+        if (MODE == 0) return C[(size_t)f * gcap + k];
+        const int real = n[f + 1] - n[f];
+        return C[n[f] + (k < real ? k : real - 1)];
+    }
+    EGDST_DEV_M double v(int f, int k) const {
+        if (MODE == 0) return V[(size_t)f * gcap + k];
+        const int real = n[f + 1] - n[f];
+        return V[n[f] + (k < real ? k : real - 1)];
+    }
+    EGDST_DEV_M double evf(int f) const {
+        if (MODE == 0) return evfa0[f];
+        return f == 0 ? evfa0[0] : -EGDST_INF;
+    }
+    EGDST_DEV_M int fid(int f) const { return MODE == 0 ? f : id; }
+};
+
+// linter2 (egdst_solver.c:1585-1593): no extrapolation
+EGDST_DEV double egdst_linter2(double x, double g0, double g1, double f0, double f1) {
+    if (x == g0) return f0;
+    if (x < g0) return -EGDST_INF;
+    if (x > g1) return -EGDST_INF;
+    return f1 * (x - g0) / (g1 - g0) + f0 * (g1 - x) / (g1 - g0);
+}
+
+// number of points of function g that precede the point (x, v, f, k) in the sweep order
+// (x asc, V desc, function asc -- comp1, egdst_solver.c:1570-1582; k breaks ties inside one function)
+template <class View>
+EGDST_DEV int egdst_env_count_before(const View &E, int g, double x, double v, int f, int k) {
+    const int ng = E.npts(g);
+    int lo = 0, hi = ng;  // lower bound: first index with x_g >= x
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (E.x(g, mid) < x) lo = mid + 1; else hi = mid; }
+    int cnt = lo;
+    for (int j = lo; j < ng && E.x(g, j) == x; j++) {
+        const double vj = E.v(g, j);
+        if (vj > v || (vj == v && (g < f || (g == f && j < k)))) cnt++;
+    }
+    return cnt;
+}
+
+// segment index of function g "current" at a sweep position: min(#processed-1, n-2) (egdst_solver.c:1524)
+EGDST_DEV int egdst_env_cur(int cnt, int ng) { int c = cnt - 1; return c < ng - 2 ? c : ng - 2; }
+
+template <class View>
+EGDST_DEV double egdst_env_analytic(const egdst_ctx *cx, const View &E, int it, int ist, int g, double x) {
+    PeriodVars cu; cu.it = it; cu.ist = ist; cu.id = E.fid(g); cu.cash = 0; cu.savings = 0; cu.shock = 0;
+    return utility(cx, &cu, x - cx->a0) + discount(cx, &cu) * E.evf(g);
+}
+
+// funcvalue (egdst_solver.c:1553-1567)
+template <class View>
+EGDST_DEV double egdst_env_value(const egdst_ctx *cx, const View &E, int it, int ist, int g, int cur, double x) {
+    if (cur >= 0) return egdst_linter2(x, E.x(g, cur), E.x(g, cur + 1), E.v(g, cur), E.v(g, cur + 1));
+    if (E.evf(g) == -EGDST_INF) return -EGDST_INF;
+    return egdst_env_analytic(cx, E, it, ist, g, x);
+}
+// the second tabulated function (consumption) of g at x, with the credit-constrained branch
+template <class View>
+EGDST_DEV double egdst_env_value2(const egdst_ctx *cx, const View &E, int g, int cur, double x) {
+    if (cur >= 0) return egdst_linter2(x, E.x(g, cur), E.x(g, cur + 1), E.c(g, cur), E.c(g, cur + 1));
+    if (E.evf(g) == -EGDST_INF) return cx->zeroconsumption;
+    return x - cx->a0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Step A: one thread per input point: rank in the union, argmax at its abscissa.
+// grid (ceil(maxP/B), njobs_y, nvec)
+// ---------------------------------------------------------------------------------------------
+template <int MODE>
+EGDST_DEV bool egdst_env_job(const EgdstDev &P, int ivec, int jy, int &ist, int &id, int &slot, EgdstEnvView<MODE> &E) {
+    if (MODE == 0) {
+        ist = jy; id = 0;
+        const int sd0 = egdst_sd(P, ivec, ist, 0);
+        int any = 0;
+        for (int f = 0; f < P.cx.nd; f++) any |= P.active[sd0 + f];
+        if (!any) return false;
+        E.F = P.cx.nd; E.X = P.ptX + (size_t)sd0 * P.gcap; E.C = P.ptC + (size_t)sd0 * P.gcap; E.V = P.ptV + (size_t)sd0 * P.gcap;
+        E.n = P.ptN + sd0; E.evfa0 = P.evfa0 + sd0; E.gcap = P.gcap; E.id = 0; E.sentinel = 0;
+        slot = P.nvec * P.cx.nst * P.cx.nd + ivec * P.cx.nst + ist;
+        return true;
+    } else {
+        ist = jy / P.cx.nd; id = jy % P.cx.nd;
+        const int sd = egdst_sd(P, ivec, ist, id);
+        if (!P.active[sd] || P.nfold[sd] == 0) return false;
+        E.F = P.nfold[sd] + 1; E.X = P.ptX + (size_t)sd * P.gcap; E.C = P.ptC + (size_t)sd * P.gcap; E.V = P.ptV + (size_t)sd * P.gcap;
+        E.n = P.runStart + (size_t)sd * (P.gcap + 1); E.evfa0 = P.evfa0 + sd; E.gcap = P.gcap; E.id = id; E.sentinel = 1.5 * P.cx.mmax;
+        slot = sd;
+        return true;
+    }
+}
+
+template <int MODE>
+__global__ void egdst_k_envA(EgdstDev P, int it) {
+    const int ivec = blockIdx.z;
+    int ist, id, slot;
+    EgdstEnvView<MODE> E;
+    if (!egdst_env_job<MODE>(P, ivec, blockIdx.y, ist, id, slot, E)) return;
+    egdst_ctx cx; egdst_load_ctx(P, ivec, cx);
+    const int Ptot = E.pstart(E.F - 1) + E.npts(E.F - 1);
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    // grid bound: min over functions of the last abscissa (egdst_solver.c:1266-1271)
+    double grb = EGDST_INF;
+    for (int g = 0; g < E.F; g++) { const int ng = E.npts(g); if (ng > 0) { const double xl = E.x(g, ng - 1); if (xl < grb) grb = xl; } }
+    if (p >= Ptot) return;
+    // flattened index -> (f,k)
+    int f = 0;
+    if (MODE == 0) { int s = 0; while (f < E.F - 1 && p >= s + E.npts(f)) { s += E.npts(f); f++; } }
+    else { int lo = 0, hi = E.F - 1; while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (E.pstart(mid) <= p) lo = mid; else hi = mid - 1; } f = lo; }
+    const int k = p - E.pstart(f);
+    const double x = E.x(f, k), v = E.v(f, k);
+    int rank = 0, best = f;
+    double bestv = v;
+    for (int g = 0; g < E.F; g++) {
+        const int ng = E.npts(g);
+        if (ng <= 0) continue;
+        const int cnt = egdst_env_count_before(E, g, x, v, f, k);
+        rank += cnt;
+        if (g == f) continue;
+        const double val = egdst_env_value(&cx, E, it, ist, g, egdst_env_cur(cnt, ng), x);
+        if (val > bestv || (val == bestv && g < best)) { bestv = val; best = g; }
+    }
+    size_t o = (size_t)slot * P.envcap + rank;
+    P.mgX[o] = x; P.mgF[o] = f; P.mgK[o] = k; P.mgA[o] = best;
+    (void)grb;
+}
+
+// ---------------------------------------------------------------------------------------------
+// crossing chain on the boundary before sweep position (xr,vr,fr,kr): thresholds() restated with an
+// explicit stack.  Counts (write==false) or writes the grid points / thresholds it produces.
+// ---------------------------------------------------------------------------------------------
+template <class View>
+EGDST_DEV double egdst_env_brsolve(const egdst_ctx *cx, const View &E, int it, int ist, int ga, double br0, double br1,
+                                   double g0, double g1, double f0, double f1, int *err) {
+    const double dd = cx->doublepoint_delta;
+    for (int iter = 0; iter < 400; iter++) {
+        const double fa0 = egdst_env_analytic(cx, E, it, ist, ga, br0), fa1 = egdst_env_analytic(cx, E, it, ist, ga, br1);
+        const double s0 = (fa0 - egdst_linter2(br0, g0, g1, f0, f1)) > 0 ? 1.0 : -1.0;
+        const double s1 = (fa1 - egdst_linter2(br1, g0, g1, f0, f1)) > 0 ? 1.0 : -1.0;
+        if (s0 == s1 || br0 > br1) { *err = EGDST_ERR_BRACKET; return br0; }
+        if (fabs(br0 - br1) < 2 * dd || fabs(fa0 - fa1) < dd) return (br0 + br1) / 2;
+        const double mid = (br0 + br1) / 2;
+        const double sm = (egdst_env_analytic(cx, E, it, ist, ga, mid) - egdst_linter2(mid, g0, g1, f0, f1)) > 0 ? 1.0 : -1.0;
+        if (s0 == sm) br0 = mid; else if (s1 == sm) br1 = mid; else return br0;
+    }
+    return (br0 + br1) / 2;
+}
+
+template <class View>
+EGDST_DEV void egdst_env_chain(const egdst_ctx *cx, const View &E, int it, int ist, double xr, double vr, int fr, int kr,
+                               int pri0, int nwi0, bool write, double *gx, double *gv, double *gc, int gleft,
+                               double *tth, double *tdd, int tleft, int &ng, int &nt, int *err) {
+    unsigned marks[EGDST_ENV_MARKW];
+    for (int w = 0; w < EGDST_ENV_MARKW; w++) marks[w] = 0u;
+    if (E.F > 32 * EGDST_ENV_MARKW) { *err = EGDST_ERR_ENV2SPACE; ng = 0; nt = 0; return; }
+    short sp_p[EGDST_ENV_STACK], sp_q[EGDST_ENV_STACK];
+    int sp = 0;
+    sp_p[0] = (short)pri0; sp_q[0] = (short)nwi0; sp = 1;
+    ng = 0; nt = 0;
+    while (sp > 0) {
+        sp--;
+        const int p = sp_p[sp], q = sp_q[sp];
+        marks[p >> 5] |= 1u << (p & 31);
+        marks[q >> 5] |= 1u << (q & 31);
+        const int np = E.npts(p), nq = E.npts(q);
+        const int cp = egdst_env_cur(egdst_env_count_before(E, p, xr, vr, fr, kr), np);
+        const int cq = egdst_env_cur(egdst_env_count_before(E, q, xr, vr, fr, kr), nq);
+        double newpoint, cmax;
+        if (cp == -1 && cq != -1) {  // pri analytic, nwi linear
+            const double g0 = E.x(q, cq), g1 = E.x(q, cq + 1), f0 = E.v(q, cq), f1 = E.v(q, cq + 1);
+            if (E.evf(p) == -EGDST_INF) newpoint = E.x(p, 0);
+            else newpoint = egdst_env_brsolve(cx, E, it, ist, p, g0, MIN(E.x(p, 0), g1), g0, g1, f0, f1, err);
+            cmax = egdst_linter2(newpoint, g0, g1, f0, f1);
+        } else if (cp != -1 && cq == -1) {  // nwi analytic, pri linear
+            const double g0 = E.x(p, cp), g1 = E.x(p, cp + 1), f0 = E.v(p, cp), f1 = E.v(p, cp + 1);
+            if (E.evf(q) == -EGDST_INF) newpoint = E.x(q, 0);
+            else newpoint = egdst_env_brsolve(cx, E, it, ist, q, g0, MIN(E.x(q, 0), g1), g0, g1, f0, f1, err);
+            cmax = egdst_linter2(newpoint, g0, g1, f0, f1);
+        } else if (cp == -1 && cq == -1) {
+            *err = EGDST_ERR_TWO_ANALYTIC;
+            return;
+        } else {
+            const double pg0 = E.x(p, cp), pg1 = E.x(p, cp + 1), pf0 = E.v(p, cp), pf1 = E.v(p, cp + 1);
+            const double qg0 = E.x(q, cq), qg1 = E.x(q, cq + 1), qf0 = E.v(q, cq), qf1 = E.v(q, cq + 1);
+            const double sq = (qf1 - qf0) / (qg1 - qg0), iq = (qf0 * qg1 - qf1 * qg0) / (qg1 - qg0);
+            const double spp = (pf1 - pf0) / (pg1 - pg0), ip = (pf0 * pg1 - pf1 * pg0) / (pg1 - pg0);
+            if (pg1 == pg0) { newpoint = pg0; cmax = newpoint * sq + iq; }
+            else if (qg1 == qg0) { newpoint = qg0; cmax = newpoint * spp + ip; }
+            else if (sq == spp) { newpoint = (pg0 + pg1 + qg0 + qg1) / 4; cmax = newpoint * sq + iq; }
+            else { newpoint = (ip - iq) / (sq - spp); cmax = newpoint * sq + iq; }
+        }
+        // is a third, not yet visited function above at the crossing? (egdst_solver.c:1807-1845, mode 1)
+        int optk = -1;
+        for (int k = 0; k < E.F; k++) {
+            if (marks[k >> 5] & (1u << (k & 31))) continue;
+            const int nk = E.npts(k);
+            if (nk <= 0) continue;
+            const int ck = egdst_env_cur(egdst_env_count_before(E, k, xr, vr, fr, kr), nk);
+            const double tmax = (ck >= 0) ? egdst_linter2(newpoint, E.x(k, ck), E.x(k, ck + 1), E.v(k, ck), E.v(k, ck + 1))
+                                          : egdst_env_analytic(cx, E, it, ist, k, newpoint);
+            if (cmax < tmax) { cmax = tmax; optk = k; }
+        }
+        if (optk != -1) {
+            if (sp + 2 > EGDST_ENV_STACK) { *err = EGDST_ERR_ENV2SPACE; return; }
+            sp_p[sp] = (short)optk; sp_q[sp] = (short)q; sp++;  // right part, processed second
+            sp_p[sp] = (short)p; sp_q[sp] = (short)optk; sp++;  // left part, processed first
+            continue;
+        }
+        const double c_left = egdst_env_value2(cx, E, p, cp, newpoint), c_right = egdst_env_value2(cx, E, q, cq, newpoint);
+        const bool single = (E.evf(q) == -EGDST_INF && cq == -1);  // egdst_solver.c:1892-1896
+        if (write) {
+            if (ng < gleft) { gx[ng] = single ? newpoint - cx->tolerance : newpoint; gv[ng] = cmax; gc[ng] = c_left; }
+            if (nt < tleft) { tth[nt] = newpoint; tdd[nt] = (double)q; }
+            if (!single && ng + 1 < gleft) { gx[ng + 1] = newpoint + cx->doublepoint_delta; gv[ng + 1] = cmax; gc[ng + 1] = c_right; }
+        }
+        ng += single ? 1 : 2;
+        nt += 1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Step B/C: one CTA per job walks the union in order, chunk by chunk; block-wide scans place the kept
+// points, the crossing double points and the thresholds.
+// MODE 0 writes the period's solution cell (rows 1.., thresholds, evf, row 0); MODE 1 rewrites the id's list.
+// grid (1, njobs_y, nvec)
+// ---------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void egdst_k_envBC(EgdstDev P, int it) {
+    __shared__ int sh[40];
+    __shared__ int s_gbase, s_tbase;
+    const int ivec = blockIdx.z;
+    int ist, id, slot;
+    EgdstEnvView<MODE> E;
+    if (!egdst_env_job<MODE>(P, ivec, blockIdx.y, ist, id, slot, E)) return;
+    egdst_ctx cx; egdst_load_ctx(P, ivec, cx);
+    const double *mgX = P.mgX + (size_t)slot * P.envcap;
+    const int *mgF = P.mgF + (size_t)slot * P.envcap, *mgK = P.mgK + (size_t)slot * P.envcap, *mgA = P.mgA + (size_t)slot * P.envcap;
+    double *ox, *oc, *ov, *oth = 0, *odd = 0;
+    int gcapacity, tcapacity = 0, cell = 0;
+    if (MODE == 0) {
+        cell = egdst_cell(P, ivec, it, ist);
+        ox = egdst_colM(P, cell) + 1; oc = egdst_colC(P, cell) + 1; ov = egdst_colV(P, cell) + 1;
+        oth = P.thTH + (size_t)cell * cx.nthrhmax; odd = P.thD + (size_t)cell * cx.nthrhmax;
+        gcapacity = P.rowcap - 1; tcapacity = cx.nthrhmax;
+    } else {
+        ox = P.outX + (size_t)slot * P.envcap; oc = P.outC + (size_t)slot * P.envcap; ov = P.outV + (size_t)slot * P.envcap;
+        gcapacity = P.envcap;
+    }
+    if (threadIdx.x == 0) { s_gbase = 0; s_tbase = 0; }
+    __syncthreads();
+    // unified grid bound = min over functions of the last abscissa (egdst_solver.c:1266-1271); the union is
+    // sorted, so the active positions are the prefix with x<=grb
+    double grb = EGDST_INF;
+    for (int g = 0; g < E.F; g++) { const int ng_ = E.npts(g); if (ng_ > 0) { const double xl = E.x(g, ng_ - 1); if (xl < grb) grb = xl; } }
+    const int Ptot = E.pstart(E.F - 1) + E.npts(E.F - 1);
+    int nact;
+    { int lo = 0, hi = Ptot; while (lo < hi) { int mid = (lo + hi) >> 1; if (mgX[mid] <= grb) lo = mid + 1; else hi = mid; } nact = lo; }
+    int err = 0;
+    for (int base = 0; base < nact; base += blockDim.x) {
+        const int r = base + threadIdx.x;
+        int ng = 0, nt = 0, emit = 0, chain = 0;
+        double x = 0, v = 0, c = 0; int f = 0, k = 0, a = 0, aprev = 0;
+        if (r < nact) {
+            x = mgX[r]; f = mgF[r]; k = mgK[r]; a = mgA[r];
+            v = E.v(f, k);
+            const bool newx = (r == 0) || (mgX[r - 1] < x);
+            if (r == 0) nt = 1;  // (a0, argmax at the first point)  egdst_solver.c:1321-1325
+            else if (newx) { aprev = mgA[r - 1]; if (aprev != a) chain = 1; }
+            if (chain) {
+                int cg, ct;
+                egdst_env_chain(&cx, E, it, ist, x, v, f, k, aprev, a, false, (double *)0, (double *)0, (double *)0, 0, (double *)0, (double *)0, 0, cg, ct, &err);
+                ng += cg; nt += ct;
+            }
+            if (newx) {
+                if (a == f) { emit = 1; c = E.c(f, k); }
+                else if (x == grb) {  // last abscissa of the unified grid: keep the interpolated maximum
+                    const int na = E.npts(a);
+                    const int ca = egdst_env_cur(egdst_env_count_before(E, a, x, v, f, k), na);
+                    emit = 1;
+                    v = egdst_env_value(&cx, E, it, ist, a, ca, x);
+                    c = egdst_env_value2(&cx, E, a, ca, x);
+                }
+            }
+            ng += emit;
+        }
+        int gtot, ttot;
+        const int goff = s_gbase + egdst_block_excl_scan(ng, sh, &gtot);
+        const int toff = s_tbase + egdst_block_excl_scan(nt, sh, &ttot);
+        if (r < nact) {
+            int gpos = goff, tpos = toff;
+            if (r == 0 && MODE == 0 && tpos < tcapacity) { oth[tpos] = cx.a0; odd[tpos] = (double)a; }
+            if (r == 0) tpos += 1;
+            if (chain) {
+                int cg, ct;
+                egdst_env_chain(&cx, E, it, ist, x, E.v(f, k), f, k, aprev, a, true, ox + gpos, ov + gpos, oc + gpos, gcapacity - gpos,
+                                MODE == 0 ? oth + tpos : (double *)0, MODE == 0 ? odd + tpos : (double *)0, MODE == 0 ? tcapacity - tpos : 0, cg, ct, &err);
+                gpos += cg;
+            }
+            if (emit && gpos < gcapacity) { ox[gpos] = x; ov[gpos] = v; oc[gpos] = c; }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { s_gbase += gtot; s_tbase += ttot; }
+        __syncthreads();
+    }
+    if (err) egdst_fail(P, ivec, err, it, ist, id);
+    const int nout = s_gbase, nth = s_tbase;
+    if (MODE == 0) {
+        if (threadIdx.x == 0) {
+            if (nout >= cx.ngridmax) egdst_fail(P, ivec, EGDST_ERR_GRIDSPACE, it, ist, -1);
+            if (nth >= cx.nthrhmax) egdst_fail(P, ivec, EGDST_ERR_THRSPACE, it, ist, -1);
+            if (nout == 0 || nth == 0) egdst_fail(P, ivec, EGDST_ERR_ENVELOPE, it, ist, -1);
+            const int n = nout < gcapacity ? nout : gcapacity;
+            const int d0 = nact > 0 ? mgA[0] : 0;
+            const double e = E.evf(d0);  // egdst_solver.c:730
+            P.evf[cell] = e;
+            P.mlen[cell] = n + 1;
+            P.thlen[cell] = nth < tcapacity ? nth : tcapacity;
+            egdst_colM(P, cell)[0] = cx.a0; egdst_colC(P, cell)[0] = 0.0; egdst_colV(P, cell)[0] = e;  // saveoutput :931-941
+        }
+        __syncthreads();
+        const int n = nout < gcapacity ? nout : gcapacity;
+        double *Mc = egdst_colM(P, cell), *Cc = egdst_colC(P, cell), *Ac = egdst_colA(P, cell);
+        for (int i = threadIdx.x; i <= n; i += blockDim.x) Ac[i] = Mc[i] - Cc[i];
+    } else {
+        const int sd = slot;
+        if (threadIdx.x == 0 && nout >= cx.ngridmax) egdst_fail(P, ivec, EGDST_ERR_ENV2SPACE, it, ist, id);
+        const int n = nout < P.gcap ? nout : P.gcap;
+        double *X = P.ptX + (size_t)sd * P.gcap, *Cc = P.ptC + (size_t)sd * P.gcap, *V = P.ptV + (size_t)sd * P.gcap;
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) { X[i] = ox[i]; Cc[i] = oc[i]; V[i] = ov[i]; }
+        if (threadIdx.x == 0) P.ptN[sd] = n;
+    }
+}

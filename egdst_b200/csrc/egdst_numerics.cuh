@@ -1,0 +1,146 @@
+// egdst_numerics.cuh -- device numerics shared by the solver and simulator kernels.
+//
+// Device restatement of the reference's shared numerics (@egdstmodel/egdst_lib.c):
+//   bracket search      egdst_lib.c:123-165  (bxsearch / bxsearch_common / optimd)
+//   linter              egdst_lib.c:168-176
+//   linter_extrap       egdst_lib.c:179-206
+//   cdfni (Acklam)      egdst_lib.c:435-519
+//   cdfinv/rescale/expectation per DISTRIB   egdst_lib.c:66-101
+//   cashinhandinverse   egdst_lib.c:275-296
+// All FP64.  Nothing here allocates; tables are read through plain pointers so the same code
+// serves global memory, shared memory (TMA-staged) and the host emulator used for debugging.
+#pragma once
+
+#include "modelspec_dev.h"
+
+#ifndef EGDST_DEV
+#ifdef __CUDACC__
+#define EGDST_DEV static __device__ __forceinline__
+#else
+#define EGDST_DEV static inline
+#endif
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// bracket search: index i of the interval [grid[i], grid[i+1]] used for interpolation.
+// Reference semantics (egdst_lib.c:138-165): 0 if x<grid[1]; n-2 if x>=grid[n-2] (type 0) or n-1 if
+// x>=grid[n-1] (type 1); otherwise the largest interior i with grid[i]<=x.  For a strictly increasing
+// grid that is "largest i with grid[i]<=x, clamped", which is what is computed here (branch-free
+// bisection over the same interior range, so the visiting order of the reference is kept).
+// ---------------------------------------------------------------------------------------------
+EGDST_DEV int egdst_bracket(double x, const double *__restrict__ grid, int n, int type) {
+    if (x < grid[1]) return 0;
+    if (type == 0 && x >= grid[n - 2]) return n - 2;
+    if (type == 1 && x >= grid[n - 1]) return n - 1;
+    int lo = 1, hi = n - 2;
+    while (hi - lo > 1) {
+        int mid = (hi + lo) >> 1;
+        if (grid[mid] > x) hi = mid; else lo = mid;
+    }
+    return lo;
+}
+
+// optimal discrete decision from the threshold table (egdst_lib.c:129-132)
+EGDST_DEV int egdst_optimd(double m, const double *__restrict__ th, const double *__restrict__ dd, int nth) {
+    if (nth <= 1) return (int)dd[0];  // the reference reads grid[1] here; one threshold => one choice
+    return (int)dd[egdst_bracket(m, th, nth, 1)];
+}
+
+// linear interpolation / extrapolation on interval i (egdst_lib.c:175)
+EGDST_DEV double egdst_lerp(double x, double g0, double g1, double f0, double f1) {
+    double w = g1 - g0;
+    return f1 * (x - g0) / w + f0 * (g1 - x) / w;
+}
+
+EGDST_DEV double egdst_linter(double x, int n, const double *__restrict__ grid, const double *__restrict__ fun) {
+    int i = egdst_bracket(x, grid, n, 0);
+    return egdst_lerp(x, grid[i], grid[i + 1], fun[i], fun[i + 1]);
+}
+
+// interpolation with transform-weighted extrapolation outside the grid (egdst_lib.c:179-206)
+EGDST_DEV double egdst_linter_extrap_at(const egdst_ctx *cx, const PeriodVars *prd, double x, int i, int n,
+                                         const double *__restrict__ grid, const double *__restrict__ fun) {
+    double f0 = fun[i], f1 = fun[i + 1];
+    if (!isfinite(f0)) return f0;
+    if (!isfinite(f1)) return f1;
+    double g0 = grid[i], g1 = grid[i + 1];
+    if (x > cx->a0 && (x > grid[n - 1] || x < grid[0])) {
+        double tx = tr(cx, prd, x - cx->a0), t0 = tr(cx, prd, g0 - cx->a0), t1 = tr(cx, prd, g1 - cx->a0);
+        return f1 * (tx - t0) / (t1 - t0) + f0 * (t1 - tx) / (t1 - t0);
+    }
+    return egdst_lerp(x, g0, g1, f0, f1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Acklam's rational approximation of the standard normal quantile (egdst_lib.c:435-519).
+// Parity at 1e-9 needs this polynomial, not normcdfinv.
+// ---------------------------------------------------------------------------------------------
+EGDST_DEV double egdst_cdfni(double p) {
+    const double a0 = -3.969683028665376e+01, a1 = 2.209460984245205e+02, a2 = -2.759285104469687e+02,
+                 a3 = 1.383577518672690e+02, a4 = -3.066479806614716e+01, a5 = 2.506628277459239e+00;
+    const double b0 = -5.447609879822406e+01, b1 = 1.615858368580409e+02, b2 = -1.556989798598866e+02,
+                 b3 = 6.680131188771972e+01, b4 = -1.328068155288572e+01;
+    const double c0 = -7.784894002430293e-03, c1 = -3.223964580411365e-01, c2 = -2.400758277161838e+00,
+                 c3 = -2.549732539343734e+00, c4 = 4.374664141464968e+00, c5 = 2.938163982698783e+00;
+    const double d0 = 7.784695709041462e-03, d1 = 3.224671290700398e-01, d2 = 2.445134137142996e+00,
+                 d3 = 3.754408661907416e+00;
+    if (p < 0 || p > 1) return 0.0;
+    if (p == 0) return -EGDST_INF;
+    if (p == 1) return EGDST_INF;
+    if (p < 0.02425) {
+        double q = sqrt(-2 * log(p));
+        return (((((c0 * q + c1) * q + c2) * q + c3) * q + c4) * q + c5) / ((((d0 * q + d1) * q + d2) * q + d3) * q + 1);
+    }
+    if (p > 0.97575) {
+        double q = sqrt(-2 * log(1 - p));
+        return -(((((c0 * q + c1) * q + c2) * q + c3) * q + c4) * q + c5) / ((((d0 * q + d1) * q + d2) * q + d3) * q + 1);
+    }
+    double q = p - 0.5, r = q * q;
+    return (((((a0 * r + a1) * r + a2) * r + a3) * r + a4) * r + a5) * q /
+           (((((b0 * r + b1) * r + b2) * r + b3) * r + b4) * r + 1);
+}
+
+// shock distribution helpers (egdst_lib.c:66-101); DISTRIB 1 = lognormal, 2 = normal
+EGDST_DEV double egdst_cdfinv(double p, double mu, double sigma) {
+#if EGDST_DISTRIB == 1
+    return exp(sigma * egdst_cdfni(p) + mu);
+#else
+    return sigma * egdst_cdfni(p) + mu;
+#endif
+}
+EGDST_DEV double egdst_expectation(const egdst_ctx *cx, const PeriodVars *curr, const PeriodVars *next) {
+#if EGDST_DISTRIB == 1
+    double s = sigma_param(cx, curr, next);
+    return exp(mu_param(cx, curr, next) + s * s / 2);
+#else
+    return mu_param(cx, curr, next);
+#endif
+}
+EGDST_DEV double egdst_rescale(const egdst_ctx *cx, const PeriodVars *curr, const PeriodVars *next, double z) {
+#if EGDST_DISTRIB == 1
+    return exp(mu_param(cx, curr, next) + z * sigma_param(cx, curr, next));
+#else
+    return mu_param(cx, curr, next) + z * sigma_param(cx, curr, next);
+#endif
+}
+
+// Newton inversion of the budget: a such that cashinhand(a)=arg (egdst_lib.c:275-296).
+// Returns the number of iterations through *fail (>=100 => EGDST_ERR_CASHINVERSE).
+EGDST_DEV double egdst_cashinhandinverse(const egdst_ctx *cx, const PeriodVars *curr, PeriodVars next, double arg, int *fail) {
+    int cnt = 0;
+    next.savings = arg;
+    while (fabs(cashinhand(cx, curr, &next) - arg) > cx->zeroconsumption / 10) {
+        next.savings -= (cashinhand(cx, curr, &next) - arg) / cashinhand_marginal(cx, curr, &next);
+        if (++cnt >= 100) { *fail = 1; return -1.0; }
+    }
+    return next.savings;
+}
+
+// fill the value-coded parts of a PeriodVars (only read when byval>0, i.e. never in the solver;
+// kept so that generated code that references curr->st/dc is always initialised)
+EGDST_DEV void egdst_fill_state(const egdst_ctx *cx, PeriodVars *p) {
+    for (int i = 0; i < cx->nnst; i++) p->st[i] = cx->states[i * cx->nst + p->ist];
+}
+EGDST_DEV void egdst_fill_decision(const egdst_ctx *cx, PeriodVars *p) {
+    for (int i = 0; i < cx->nnd; i++) p->dc[i] = cx->decisions[i * cx->nd + p->id];
+}

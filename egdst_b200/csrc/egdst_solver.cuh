@@ -1,0 +1,451 @@
+// egdst_solver.cuh -- backward-induction kernels for one period (all states, all decisions, all
+// parameter vectors of a batch at once).
+//
+// Restates the reference's egmbellman (egdst_solver.c:370-752) in parallel form:
+//   k_terminal   terminal-period closed-form grid                     egdst_solver.c:452-475
+//   k_seed       adraw stage 0/1 + ZEROCONSUMPTION feedback            egdst_solver.c:955-1099, 583-627
+//   k_egm        expectation over (ist1, iy) + Euler inversion         egdst_solver.c:490-665
+//   k_compact    adraw stop rule, drop rules, fold detection           egdst_solver.c:1100-1152, 640-664, 819
+// The upper envelopes are in egdst_envelope.cuh.
+//
+// Parallel decomposition (hard part 1): the A-grid is sequential in the reference only
+// through (i) the stage-0 bisection, whose candidates mmax, (mmax+a0)/2, ... are known in advance and
+// are evaluated concurrently, (ii) the a0 point and its re-sends (serial, a handful of evaluations),
+// and (iii) the stop rule, which is applied after all N-1 closed-form grid points were evaluated.
+#pragma once
+
+#include "egdst_common.cuh"
+
+// next-period tables of one state ist1
+struct EgdstNext {
+    const double *M, *C, *V;  // rows 0..n1 (row 0 = a0 row)
+    const double *th, *dd;
+    int n1, nth;              // n1 = egdims (rows excluding the a0 row)
+    double evf;
+};
+
+EGDST_DEV EgdstNext egdst_next_tables(const EgdstDev &P, int ivec, int it1, int ist1) {
+    int cell = egdst_cell(P, ivec, it1, ist1);
+    EgdstNext t;
+    t.M = egdst_colM(P, cell);
+    t.C = egdst_colC(P, cell);
+    t.V = egdst_colV(P, cell);
+    t.n1 = P.mlen[cell] - 1;
+    t.th = P.thTH + (size_t)cell * P.cx.nthrhmax;
+    t.dd = P.thD + (size_t)cell * P.cx.nthrhmax;
+    t.nth = P.thlen[cell];
+    t.evf = P.evf[cell];
+    return t;
+}
+
+// accumulator of one Euler evaluation (possibly a partial one: a strided subset of the nodes)
+struct EgdstAcc {
+    double rhs, evf, checksum;
+    int badq;        // smallest flattened node index ist1*ny+iy that aborted the evaluation, or INT_MAX
+    int badtype;     // EGDST_PT_C1NEG or EGDST_PT_EVFINF
+    double badcash, badshock;
+};
+#define EGDST_NOBAD 0x7fffffff
+
+// Evaluate nodes q = part, part+nparts, ... of the expectation at end-of-period savings A
+// (egdst_solver.c:494-574).  keep==0 skips the value function (adraw seed phase).
+EGDST_DEV void egdst_eval_nodes(const egdst_ctx *cx, const EgdstDev &P, int ivec, const PeriodVars *curr, double A, int keep,
+                                int part, int nparts, EgdstAcc &acc) {
+    const int ny = cx->ny, nst = cx->nst;
+    acc.rhs = 0.0; acc.evf = 0.0; acc.checksum = 0.0; acc.badq = EGDST_NOBAD; acc.badtype = 0; acc.badcash = 0.0; acc.badshock = 0.0;
+    PeriodVars next;
+    next.it = curr->it + 1;
+    next.savings = A;
+    next.id = 0;
+    next.cash = 0.0;
+    next.shock = 0.0;
+    for (int ist1 = 0; ist1 < nst; ist1++) {
+        next.ist = ist1;
+        if (feasible(cx, &next) != 1) continue;
+        double pr1pre = 0.0;
+        if (cx->optim_TRPRnoSH == 1) {
+            pr1pre = trpr(cx, curr, &next, 1);
+            if (pr1pre == 0.0) continue;
+        }
+        const int niy = (sigma_param(cx, curr, &next) <= 0 || ny == 1) ? 1 : ny;
+        const EgdstNext t = egdst_next_tables(P, ivec, next.it, ist1);
+        for (int iy = part; iy < niy; iy += nparts) {
+            double pr1;
+            if (niy == 1) {
+                next.shock = egdst_expectation(cx, curr, &next);
+                pr1 = (cx->optim_TRPRnoSH != 1) ? trpr(cx, curr, &next, 1) : pr1pre;
+            } else {
+                next.shock = egdst_rescale(cx, curr, &next, P.qz[iy]);
+                pr1 = (cx->optim_TRPRnoSH != 1) ? trpr(cx, curr, &next, 1) : pr1pre;
+                pr1 *= P.qw[iy];
+            }
+            if (pr1 == 0.0) continue;
+            const int q = ist1 * ny + iy;
+            if (q > acc.badq) break;  // the reference would have stopped before this node
+            acc.checksum += pr1;
+            next.cash = cashinhand(cx, curr, &next);
+            // one bracket search serves consumption (rows 0..n1) and value (rows 1..n1): the second
+            // bracket of the reference is max(i,1) of the first (same strictly increasing grid).
+            const int i = egdst_bracket(next.cash, t.M, t.n1 + 1, 0);
+            double c1 = egdst_lerp(next.cash, t.M[i], t.M[i + 1], t.C[i], t.C[i + 1]);
+            if (next.cash > t.M[t.n1]) c1 = MAX(c1, t.C[t.n1]);  // constant extrapolation guard (egdst_solver.c:554)
+            if (c1 <= 0) {
+                acc.badq = q; acc.badtype = EGDST_PT_C1NEG; acc.badcash = next.cash; acc.badshock = next.shock;
+                break;
+            }
+            if (cx->optim_MUnoD != 1 || (cx->optim_UnoD != 1 && keep == 1 && next.cash < t.M[1]))
+                next.id = egdst_optimd(next.cash, t.th, t.dd, t.nth);
+            else
+                next.id = 0;
+            acc.rhs += pr1 * utility_marginal(cx, &next, c1) * cashinhand_marginal(cx, curr, &next);
+            if (keep == 1) {
+                double v1;
+                if (next.cash < t.M[1] && t.evf > -EGDST_INF) {
+                    v1 = utility(cx, &next, next.cash - cx->a0) + discount(cx, &next) * t.evf;  // egdst_solver.c:763
+                } else {
+                    const int j = i < 1 ? 1 : i;
+                    v1 = egdst_linter_extrap_at(cx, &next, next.cash, j - 1, t.n1, t.M + 1, t.V + 1);
+                }
+                const double term = pr1 * v1;
+                acc.evf += term;
+                if (term == -EGDST_INF) {
+                    acc.badq = q; acc.badtype = EGDST_PT_EVFINF; acc.badcash = next.cash; acc.badshock = next.shock;
+                    break;
+                }
+            }
+        }
+    }
+}
+
+// combine partial accumulators across a warp; every lane ends with the full result
+EGDST_DEV void egdst_warp_combine(EgdstAcc &a) {
+    const int minq = __shfl_sync(EGDST_FULL, egdst_warp_min(a.badq), 0);
+    const unsigned owner = __ballot_sync(EGDST_FULL, a.badq == minq && minq != EGDST_NOBAD);
+    a.rhs = __shfl_sync(EGDST_FULL, egdst_warp_sum(a.rhs), 0);
+    a.evf = __shfl_sync(EGDST_FULL, egdst_warp_sum(a.evf), 0);
+    a.checksum = __shfl_sync(EGDST_FULL, egdst_warp_sum(a.checksum), 0);
+    if (minq != EGDST_NOBAD) {
+        const int src = __ffs(owner) - 1;
+        a.badtype = __shfl_sync(EGDST_FULL, a.badtype, src);
+        a.badcash = __shfl_sync(EGDST_FULL, a.badcash, src);
+        a.badshock = __shfl_sync(EGDST_FULL, a.badshock, src);
+    }
+    a.badq = minq;
+}
+
+// ---------------------------------------------------------------------------------------------
+// terminal period: M_i = trinv(m1 + i (m2-m1)/(N-1)), C = M, V = u(C); evfa0 = -inf   (END2, A0T = 0)
+// grid (ceil(N/B), nst*nd, nvec)
+// ---------------------------------------------------------------------------------------------
+__global__ void egdst_k_terminal(EgdstDev P, int it) {
+    const int ivec = blockIdx.z, ist = blockIdx.y / P.cx.nd, id = blockIdx.y % P.cx.nd;
+    egdst_ctx cx; egdst_load_ctx(P, ivec, cx);
+    const int sd = egdst_sd(P, ivec, ist, id);
+    PeriodVars curr; curr.it = it; curr.ist = ist; curr.id = id; curr.cash = 0; curr.savings = 0; curr.shock = 0;
+    const int act = (feasible(&cx, &curr) == 1) && (inchoiceset(&cx, &curr) == 1);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        P.active[sd] = act;
+        P.evfa0[sd] = -EGDST_INF;
+        P.ptN[sd] = act ? P.N : 0;
+        P.nfold[sd] = 0;
+    }
+    if (!act || i >= P.N) return;
+    const double m1 = tr(&cx, &curr, cx.zeroconsumption - 0.0), m2 = tr(&cx, &curr, cx.mmax - 0.0);
+    const double m = trinv(&cx, &curr, m1 + i * (m2 - m1) / (P.N - 1)) + 0.0;
+    const double c = m - 0.0;
+    P.ptX[(size_t)sd * P.gcap + i] = m;
+    P.ptC[(size_t)sd * P.gcap + i] = c;
+    P.ptV[(size_t)sd * P.gcap + i] = utility(&cx, &curr, c);
+}
+
+// ---------------------------------------------------------------------------------------------
+// seed: one CTA per (ist,id,ivec).  Warps evaluate the stage-0 candidates concurrently; the whole CTA
+// evaluates A=a0 and any re-sent point; thread 0 runs the adraw state machine.
+// ---------------------------------------------------------------------------------------------
+struct EgdstSeedShared {
+    double candA[EGDST_MAXCAND], candM[EGDST_MAXCAND];
+    int candBad[EGDST_MAXCAND];
+    double wr[32], we[32], wc[32], wcash[32], wshock[32];
+    int wq[32], wt[32];
+    double A, rhs, evf, checksum, badcash, badshock;
+    int ncand, badq, badtype, go, nresend;
+};
+
+EGDST_DEV void egdst_block_eval(const egdst_ctx *cx, const EgdstDev &P, int ivec, const PeriodVars *curr, double A, int keep,
+                                EgdstSeedShared &S) {
+    EgdstAcc a;
+    egdst_eval_nodes(cx, P, ivec, curr, A, keep, threadIdx.x, blockDim.x, a);
+    egdst_warp_combine(a);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if (lane == 0) { S.wr[w] = a.rhs; S.we[w] = a.evf; S.wc[w] = a.checksum; S.wq[w] = a.badq; S.wt[w] = a.badtype; S.wcash[w] = a.badcash; S.wshock[w] = a.badshock; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double r = 0, e = 0, c = 0; int bq = EGDST_NOBAD, bw = 0;
+        for (int k = 0; k < nw; k++) { r += S.wr[k]; e += S.we[k]; c += S.wc[k]; if (S.wq[k] < bq) { bq = S.wq[k]; bw = k; } }
+        S.rhs = r; S.evf = e; S.checksum = c; S.badq = bq; S.badtype = S.wt[bw]; S.badcash = S.wcash[bw]; S.badshock = S.wshock[bw];
+    }
+    __syncthreads();
+}
+
+__global__ void egdst_k_seed(EgdstDev P, int it) {
+    __shared__ EgdstSeedShared S;
+    const int ivec = blockIdx.z, ist = blockIdx.y, id = blockIdx.x;
+    egdst_ctx cx; egdst_load_ctx(P, ivec, cx);
+    const int sd = egdst_sd(P, ivec, ist, id);
+    PeriodVars curr; curr.it = it; curr.ist = ist; curr.id = id; curr.cash = 0; curr.savings = 0; curr.shock = 0;
+    const int act = (feasible(&cx, &curr) == 1) && (inchoiceset(&cx, &curr) == 1);
+    const int N = P.N;
+    double *rawM = P.rawM + (size_t)sd * N, *rawC = P.rawC + (size_t)sd * N, *rawV = P.rawV + (size_t)sd * N, *rawStop = P.rawStop + (size_t)sd * N;
+    int *rawFlag = P.rawFlag + (size_t)sd * N;
+    double *seed = P.seed + (size_t)sd * 8;
+    if (threadIdx.x == 0) {
+        P.active[sd] = act;
+        P.evfa0[sd] = 0.0;
+        P.ptN[sd] = 0;
+        P.nfold[sd] = 0;
+        rawFlag[0] = EGDST_PT_NONE;
+        rawStop[0] = EGDST_INF;  // "stop": no grid points unless the seed succeeds
+        // stage-0 candidates (egdst_solver.c:979-1027): mmax, then halfway to a0 until A-a0<TOLERANCE
+        int n = 0; double A = cx.mmax;
+        while (n < EGDST_MAXCAND) { S.candA[n++] = A; if (A - cx.a0 < cx.tolerance) break; A = (A + cx.a0) / 2; }
+        S.ncand = n;
+    }
+    __syncthreads();
+    if (!act) return;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const double beta = discount(&cx, &curr);
+    for (int k = w; k < S.ncand; k += nw) {
+        EgdstAcc a;
+        egdst_eval_nodes(&cx, P, ivec, &curr, S.candA[k], 0, lane, 32, a);
+        egdst_warp_combine(a);
+        if (lane == 0) {
+            int bad = 0;
+            if (a.badq != EGDST_NOBAD) bad = EGDST_PT_C1NEG;
+            else if (fabs(a.checksum - 1) > cx.tolerance) bad = EGDST_PT_CHECKSUM;
+            S.candBad[k] = bad;
+            S.candM[k] = S.candA[k] + utility_marginal_inverse(&cx, &curr, beta * a.rhs);
+        }
+    }
+    __syncthreads();
+    // thread 0: first candidate with M<=mmax is the base point
+    double baseA = 0, baseM = 0;
+    if (threadIdx.x == 0) {
+        S.go = 0;
+        int k = 0;
+        for (; k < S.ncand; k++) {
+            if (S.candBad[k] == EGDST_PT_C1NEG) { egdst_fail(P, ivec, EGDST_ERR_NOSAVINGS, it, ist, id); break; }
+            if (S.candBad[k] == EGDST_PT_CHECKSUM) { egdst_fail(P, ivec, EGDST_ERR_CHECKSUM, it, ist, id); break; }
+            if (S.candM[k] <= cx.mmax) { baseA = S.candA[k]; baseM = S.candM[k]; S.go = 1; break; }
+            if (S.candA[k] - cx.a0 < cx.tolerance) { egdst_fail(P, ivec, EGDST_ERR_ADRAW_INIT, it, ist, id); break; }
+        }
+        if (k == S.ncand && !S.go) egdst_fail(P, ivec, EGDST_ERR_ADRAW_INIT, it, ist, id);
+        S.A = cx.a0;
+        S.nresend = S.ncand;  // used as the adraw call counter (loop guard, egdst_solver.c:963)
+    }
+    __syncthreads();
+    if (!S.go) return;
+    // stage 1 (+ re-sends): serial in A, parallel over nodes
+    double lim1 = 0, lim2 = 0, lim3 = 0, lim2p = 0, lim3p = 0, k3 = 0, lastA = cx.a0, aM = 0, evfa0 = 0.0;
+    int stored = 0;
+    while (true) {
+        egdst_block_eval(&cx, P, ivec, &curr, S.A, 1, S);
+        if (threadIdx.x == 0) {
+            lastA = S.A;
+            int resend = 0, fatal = 0;
+            if (S.badq == EGDST_NOBAD && fabs(S.checksum - 1) > cx.tolerance) {
+                egdst_fail(P, ivec, EGDST_ERR_CHECKSUM, it, ist, id); fatal = 1;
+            } else if (S.badq != EGDST_NOBAD) {
+                evfa0 = -EGDST_INF;
+                aM = S.badcash;
+                if (S.badtype == EGDST_PT_C1NEG) {
+                    aM = cx.a0 - 1;
+                    PeriodVars next; next.it = it + 1; next.ist = S.badq / cx.ny; next.id = 0; next.savings = lastA; next.shock = S.badshock; next.cash = S.badcash;
+                    const EgdstNext t = egdst_next_tables(P, ivec, it + 1, next.ist);
+                    const double target = (t.evf > -EGDST_INF) ? cx.a0 : t.M[1];
+                    int fail = 0;
+                    lastA = egdst_cashinhandinverse(&cx, &curr, next, target, &fail) + cx.zeroconsumption;
+                    if (fail) { egdst_fail(P, ivec, EGDST_ERR_CASHINVERSE, it, ist, id); fatal = 1; }
+                }
+            } else {
+                aM = lastA + utility_marginal_inverse(&cx, &curr, beta * S.rhs);
+                if (isfinite(aM)) {
+                    if (fabs(lastA - cx.a0) < cx.tolerance && evfa0 > -EGDST_INF) evfa0 = S.evf;
+                    rawM[0] = aM; rawC[0] = aM - lastA; rawV[0] = utility(&cx, &curr, aM - lastA) + beta * S.evf;
+                    rawFlag[0] = EGDST_PT_OK; stored = 1;
+                }
+            }
+            if (!fatal) {
+                // adraw, ngenerated==1 branch (egdst_solver.c:1032-1099)
+                double aa = (aM - baseM) / (lastA - baseA), bb = baseM - aa * baseA;
+                if (k3 == 0) {
+                    lim2p = MIN(cx.mmax, (cx.mmax - bb) / aa);
+                    lim3p = -bb / aa;
+                    if (cx.a0 < 0 && cx.a0 < lim3p) k3 = MAX(floor(N * (lim3p - cx.a0) / (lim2p - cx.a0)), 2.0);
+                    else { lim3p = cx.a0; k3 = 1.0; }
+                    lim1 = tr(&cx, &curr, lim3p - cx.a0); lim2 = tr(&cx, &curr, lim2p - lim3p); lim3 = tr(&cx, &curr, 0);
+                }
+                if (aM <= cx.a0 - 1 + cx.tolerance) {
+                    aa = (cx.a0 - baseM) / (cx.a0 - baseA); bb = baseM - aa * baseA;
+                    lim2p = MIN(cx.mmax, (cx.mmax - bb) / aa);
+                    lim3p = lastA - cx.zeroconsumption;
+                    k3 = 1.0;
+                    lim1 = tr(&cx, &curr, lim3p - cx.a0); lim2 = tr(&cx, &curr, lim2p - lim3p); lim3 = tr(&cx, &curr, 0);
+                    resend = 1;
+                    if (++S.nresend + 1 >= cx.ngridmax) { egdst_fail(P, ivec, EGDST_ERR_ADRAW_LOOP, it, ist, id); resend = 0; fatal = 1; }
+                }
+            }
+            S.A = lastA;
+            S.go = fatal ? -1 : resend;
+        }
+        __syncthreads();
+        if (S.go != 1) break;
+    }
+    if (threadIdx.x == 0) {
+        P.evfa0[sd] = evfa0;
+        if (S.go == 0) {
+            seed[0] = lim1; seed[1] = lim2; seed[2] = lim3; seed[3] = lim3p; seed[4] = k3; seed[5] = lastA;
+            rawStop[0] = aM;
+            if (!stored) rawFlag[0] = EGDST_PT_EVFINF;
+        }
+    }
+}
+
+// closed-form A-grid after the seed (egdst_solver.c:1104-1136); n = 1..N-1
+EGDST_DEV double egdst_agrid_target(const egdst_ctx *cx, const PeriodVars *curr, const double *seed, int n, int N) {
+    const double lim1 = seed[0], lim2 = seed[1], lim3 = seed[2], lim3p = seed[3], k3 = seed[4];
+    if (n < (int)k3 - 1) return -trinv(cx, curr, lim3 + (k3 - 1 - n) * (lim1 - lim3) / (k3 - 1)) + lim3p;
+    return trinv(cx, curr, lim3 + (n - k3 + 1) * (lim2 - lim3) / (N - k3)) + lim3p;
+}
+EGDST_DEV double egdst_agrid(const egdst_ctx *cx, const PeriodVars *curr, const double *seed, int n, int N) {
+    const double t = egdst_agrid_target(cx, curr, seed, n, N);
+    const double prev = (n == 1) ? seed[5] : egdst_agrid_target(cx, curr, seed, n - 1, N);
+    return (t - prev < 0) ? prev + 1e-5 : t;  // astep<0 rule (egdst_solver.c:1120-1133)
+}
+
+// ---------------------------------------------------------------------------------------------
+// EGM step for grid points n=1..N-1.  blockDim = (32, SPLIT): lanes are 32 consecutive A points (their
+// next-period cash values are neighbours, so the table searches of a warp stay coherent), the SPLIT
+// warps of a CTA share the quadrature nodes of the same 32 points and combine through shared memory.
+// grid (ceil((N-1)/32), nst*nd, nvec)
+// ---------------------------------------------------------------------------------------------
+#ifndef EGDST_EGM_SPLIT
+#ifdef EGDST_HOSTEMU
+#define EGDST_EGM_SPLIT 2
+#else
+#define EGDST_EGM_SPLIT 8
+#endif
+#endif
+
+__global__ void egdst_k_egm(EgdstDev P, int it) {
+    __shared__ double s_rhs[EGDST_EGM_SPLIT][32], s_evf[EGDST_EGM_SPLIT][32], s_chk[EGDST_EGM_SPLIT][32], s_cash[EGDST_EGM_SPLIT][32];
+    __shared__ int s_q[EGDST_EGM_SPLIT][32], s_t[EGDST_EGM_SPLIT][32];
+    const int ivec = blockIdx.z, ist = blockIdx.y / P.cx.nd, id = blockIdx.y % P.cx.nd;
+    const int sd = egdst_sd(P, ivec, ist, id);
+    const int lane = threadIdx.x, part = threadIdx.y;
+    const int N = P.N;
+    const int n = 1 + blockIdx.x * 32 + lane;
+    if (!P.active[sd] || P.rawFlag[(size_t)sd * N] == EGDST_PT_NONE) return;  // uniform per CTA
+    egdst_ctx cx; egdst_load_ctx(P, ivec, cx);
+    PeriodVars curr; curr.it = it; curr.ist = ist; curr.id = id; curr.cash = 0; curr.savings = 0; curr.shock = 0;
+    const double *seed = P.seed + (size_t)sd * 8;
+    double A = 0.0;
+    EgdstAcc a; a.rhs = 0; a.evf = 0; a.checksum = 0; a.badq = EGDST_NOBAD; a.badtype = 0; a.badcash = 0; a.badshock = 0;
+    if (n < N) {
+        A = egdst_agrid(&cx, &curr, seed, n, N);
+        egdst_eval_nodes(&cx, P, ivec, &curr, A, 1, part, EGDST_EGM_SPLIT, a);
+    }
+    s_rhs[part][lane] = a.rhs; s_evf[part][lane] = a.evf; s_chk[part][lane] = a.checksum;
+    s_q[part][lane] = a.badq; s_t[part][lane] = a.badtype; s_cash[part][lane] = a.badcash;
+    __syncthreads();
+    if (part != 0 || n >= N) return;
+    double rhs = 0, evf = 0, chk = 0, badcash = 0; int bq = EGDST_NOBAD, bt = 0;
+    for (int k = 0; k < EGDST_EGM_SPLIT; k++) {
+        rhs += s_rhs[k][lane]; evf += s_evf[k][lane]; chk += s_chk[k][lane];
+        if (s_q[k][lane] < bq) { bq = s_q[k][lane]; bt = s_t[k][lane]; badcash = s_cash[k][lane]; }
+    }
+    const size_t o = (size_t)sd * N + n;
+    if (bq != EGDST_NOBAD) {
+        P.rawFlag[o] = bt;
+        P.rawStop[o] = (bt == EGDST_PT_C1NEG) ? cx.a0 - 1 : badcash;
+        return;
+    }
+    if (fabs(chk - 1) > cx.tolerance) { P.rawFlag[o] = EGDST_PT_CHECKSUM; P.rawStop[o] = EGDST_INF; return; }
+    const double beta = discount(&cx, &curr);
+    const double M = A + utility_marginal_inverse(&cx, &curr, beta * rhs);
+    P.rawStop[o] = M;
+    if (!isfinite(M)) { P.rawFlag[o] = EGDST_PT_NONFINITE; return; }
+    const double c = M - A;
+    P.rawM[o] = M; P.rawC[o] = c; P.rawV[o] = utility(&cx, &curr, c) + beta * evf;
+    P.rawFlag[o] = EGDST_PT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// stop rule + compaction + fold detection: one CTA per (ist,id,ivec).
+// The reference generates point n only while every earlier returned M was < mmax
+// (egdst_solver.c:1100); stored points are those with a finite M and no abort (:640-664).
+// Folds (M or V decreasing, :819) split the list into runs for the secondary envelope.
+// ---------------------------------------------------------------------------------------------
+__global__ void egdst_k_compact(EgdstDev P, int it) {
+    __shared__ int sh[40];
+    __shared__ int s_stop, s_base, s_fbase, s_late;
+    __shared__ double s_lastX, s_lastV;
+    const int ivec = blockIdx.z, ist = blockIdx.y, id = blockIdx.x;
+    const int sd = egdst_sd(P, ivec, ist, id);
+    if (!P.active[sd]) return;
+    const int N = P.N;
+    const double *rawM = P.rawM + (size_t)sd * N, *rawC = P.rawC + (size_t)sd * N, *rawV = P.rawV + (size_t)sd * N, *rawStop = P.rawStop + (size_t)sd * N;
+    const int *rawFlag = P.rawFlag + (size_t)sd * N;
+    double *X = P.ptX + (size_t)sd * P.gcap, *Cc = P.ptC + (size_t)sd * P.gcap, *V = P.ptV + (size_t)sd * P.gcap;
+    int *runStart = P.runStart + (size_t)sd * (P.gcap + 1);
+    if (threadIdx.x == 0) { s_stop = N - 1; s_base = 0; s_fbase = 0; s_late = N; s_lastX = -EGDST_INF; s_lastV = -EGDST_INF; }
+    __syncthreads();
+    if (rawFlag[0] == EGDST_PT_NONE) { if (threadIdx.x == 0) { P.ptN[sd] = 0; P.nfold[sd] = 0; } return; }
+    // first n whose returned M fails "M<mmax" ends the sequence (that point itself is kept)
+    int mystop = N - 1;
+    for (int n = threadIdx.x; n < N; n += blockDim.x)
+        if (!(rawStop[n] < P.cx.mmax)) { mystop = n; break; }
+    mystop = egdst_warp_min(mystop);
+    if ((threadIdx.x & 31) == 0) atomicMin(&s_stop, mystop);
+    __syncthreads();
+    const int nstop = s_stop;
+    // compaction in chunks of blockDim
+    for (int base = 0; base <= nstop; base += blockDim.x) {
+        const int n = base + threadIdx.x;
+        const int f = (n <= nstop) ? rawFlag[n] : EGDST_PT_NONE;
+        const int keep = (f == EGDST_PT_OK);
+        if (n <= nstop && f == EGDST_PT_C1NEG && n > 0) atomicMin(&s_late, n);
+        if (n <= nstop && f == EGDST_PT_CHECKSUM) egdst_fail(P, ivec, EGDST_ERR_CHECKSUM, it, ist, id);
+        int total;
+        const int off = egdst_block_excl_scan(keep, sh, &total);
+        const int dst = s_base + off;
+        if (keep && dst < P.gcap) { X[dst] = rawM[n]; Cc[dst] = rawC[n]; V[dst] = rawV[n]; }
+        __syncthreads();
+        if (threadIdx.x == 0) s_base += total;
+        __syncthreads();
+    }
+    const int nvd = s_base < P.gcap ? s_base : P.gcap;
+    if (threadIdx.x == 0) {
+        if (s_base >= P.cx.ngridmax) egdst_fail(P, ivec, EGDST_ERR_GRIDSPACE, it, ist, id);
+        if (s_late < N) egdst_fail(P, ivec, EGDST_ERR_RESEND_LATE, it, ist, id);
+        runStart[0] = 0;
+    }
+    __syncthreads();
+    // fold detection over the compacted list
+    for (int base = 0; base < nvd; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        int fold = 0;
+        if (i > 0 && i < nvd) fold = (X[i - 1] > X[i] || V[i - 1] > V[i]) ? 1 : 0;
+        int total;
+        const int off = egdst_block_excl_scan(fold, sh, &total);
+        if (fold) runStart[s_fbase + off + 1] = i;
+        __syncthreads();
+        if (threadIdx.x == 0) s_fbase += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        P.ptN[sd] = nvd;
+        P.nfold[sd] = s_fbase;
+        runStart[s_fbase + 1] = nvd;
+    }
+}

@@ -1,0 +1,109 @@
+/* egdst_b200.h -- C ABI of the B200-native egdst solver / simulator library.
+ *
+ * One shared library is built per generated model image (libegdst_b200_<key>.so: the user's exec
+ * strings compiled into the sm_100a kernels).  Its entry points are what the reference's three MEX
+ * gateways bind (INTEGRATION.md shows the MEX stubs):
+ *
+ *   egdst_solve        replaces  [M,D,dbg] = egdst_solver(model)      @egdstmodel/egdst_solver.c:143-239
+ *   egdst_simulate     replaces  sims = egdst_simulator(model,rnd)    @egdstmodel/egdst_simulator.c:47-117
+ *   egdst_call         replaces  res  = egdst_call(model,sw,args)     @egdstmodel/egdst_call.c:17-125
+ *   egdst_desc         replaces  parseModel()/loadparameters()        @egdstmodel/egdst_lib.c:34-62, compile.m:469-474
+ *   egdst_last_error   replaces  err[300] / mexWarnMsgTxt / mexErrMsgTxt  egdst_lib.c:299-302, egdst_solver.c:237
+ *
+ * plus the multi-GPU / batched entry points the reference does not have (egdst_solve_batch,
+ * egdst_sim_moments, Philox-driven simulation).
+ *
+ * Conventions: plain pointers and sizes, caller owns every input and output buffer, the library owns
+ * egdst_solution objects until egdst_free_solution.  Return codes: 0 ok; 1 soft error (partial result
+ * kept, message available -- the reference warns and returns partial M,D, egdst_solver.c:237); 2 hard
+ * error (mexErrMsgTxt in the reference).  All device work runs on the stream set with egdst_set_stream
+ * (default: the legacy default stream).  There is no CPU path: without a CUDA device every compute
+ * entry point returns 2 with "no CUDA device".
+ */
+#ifndef EGDST_B200_H
+#define EGDST_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EGDST_ABI_VERSION 1
+
+/* The model object flattened to a POD: exactly the properties the reference reads across the MEX
+ * boundary (egdst_lib.c:37-55, compile.m:472, egdst_solver.c:162) plus the -D flags of compile.m:757-777. */
+typedef struct egdst_desc {
+    int abi_version;
+    int t0, T, ngridm, ngridmax, nthrhmax, ny, nd, nnd, nst, nnst;
+    double mmax, a0;
+    int optim_UasD, optim_MUnoD, optim_UnoD, optim_TRPRnoSH;
+    double tolerance, zeroconsumption, doublepoint_delta; /* cflags TOLERANCE, ZEROCONSUMPTION, DOUBLEPOINT_DELTA */
+    const double *stm;        /* [2*nnst]                                       */
+    const double *states;     /* [nst*nnst] column-major                        */
+    const double *decisions;  /* [nd*nnd]  column-major                         */
+    const double *params;     /* [nparam] param(i).value                        */
+    int nparam;
+    const double *quadrature; /* [2*ny] weights then abscissas in (0,1), as model.quadrature (may be NULL if ny==1) */
+    int neq;                  /* numel(model.eq)                                 */
+    int device;               /* CUDA device ordinal                             */
+} egdst_desc;
+
+typedef struct egdst_solution egdst_solution;
+
+/* library / model-image introspection */
+int egdst_abi_version(void);
+const char *egdst_model_key(void);   /* key of the model image compiled into this library */
+int egdst_model_nparam(void);
+int egdst_model_neq(void);
+const char *egdst_last_error(void);  /* per-thread message of the last non-zero return */
+void egdst_set_stream(void *cuda_stream);
+
+/* ---- solve ------------------------------------------------------------------------------- */
+/* Backward induction for one model.  *out receives a new solution object (device resident). */
+int egdst_solve(const egdst_desc *d, egdst_solution **out);
+/* nvec parameter vectors of the same model solved in one pass (params: [nvec*nparam], row = vector). */
+int egdst_solve_batch(const egdst_desc *d, const double *params, int nvec, egdst_solution **out);
+/* Re-run the solve into an existing solution object (same dimensions; new parameter values allowed).
+ * Asynchronous on the library stream: no host synchronisation, no allocation. */
+int egdst_resolve(egdst_solution *s, const egdst_desc *d, const double *params);
+/* Rows per cell.  mlen/thlen: [nvec*NT*nst], index (ivec*NT+it)*nst+ist; 0 rows = infeasible (it,ist). */
+int egdst_solution_sizes(egdst_solution *s, int *mlen, int *thlen);
+/* Packed copy-out in cell order: M cell = mlen x 4 column-major (M,C,A,V; row 0 = a0,0,a0,evf(a0)),
+ * D cell = thlen x 2 column-major (decision index, threshold) -- the layouts of saveoutput,
+ * egdst_solver.c:917-951.  Mbuf holds 4*sum(mlen) doubles, Dbuf 2*sum(thlen). */
+int egdst_solution_export(egdst_solution *s, double *Mbuf, double *Dbuf);
+/* status of the last (re)solve of vector ivec: returns the code, fills it/ist/id of the first failure */
+int egdst_solution_status(egdst_solution *s, int ivec, int *it, int *ist, int *id);
+int egdst_solution_nvec(const egdst_solution *s);
+/* total number of EGM grid points kept over all (it,ist,id) of the last solve (the solve work unit) */
+long long egdst_solution_units(egdst_solution *s);
+void egdst_free_solution(egdst_solution *s);
+/* Build a solution object from host M/D cells (the MEX simulator receives model.M, model.D). */
+int egdst_solution_import(const egdst_desc *d, const int *mlen, const int *thlen, const double *Mbuf, const double *Dbuf,
+                          egdst_solution **out);
+
+/* ---- simulate ---------------------------------------------------------------------------- */
+/* sims: [nsimout, nt, nsim] column-major doubles, nsimout = 11+nnst+nnd+neq, NaN after death
+ * (egdst_simulator.c:95-143).  init: [nsim*2] column-major (1-based ist0, m0).  randstream: U(0,1),
+ * 4 slots per agent-period; rndtype 0 = own shocks, 1 = same shocks (egdst_simulator.c:71-75,109-114). */
+int egdst_simulate(const egdst_desc *d, egdst_solution *s, int ivec, const double *init, int nsim,
+                   const double *randstream, long long nrand, int rndtype, double *sims);
+/* Same simulation with counter-based Philox4x32-10 uniforms generated on the device (no randstream).
+ * agent0 = global index of the first agent (results do not depend on how agents are sharded).
+ * sims may be NULL (moments only).  moments: [3, nsimout, nt] = sum x, sum x^2, alive count. */
+int egdst_simulate_philox(const egdst_desc *d, egdst_solution *s, int ivec, const double *init, int nsim,
+                          long long agent0, unsigned long long seed, double *sims, double *moments);
+/* device-resident variants for sharded multi-GPU runs: d_init [nsim*2], d_sims / d_moments device pointers
+ * (either may be NULL); asynchronous on the library stream. */
+int egdst_simulate_device(const egdst_desc *d, egdst_solution *s, int ivec, const double *d_init, int nsim,
+                          long long agent0, unsigned long long seed, const double *d_randstream, int rndtype,
+                          double *d_sims, double *d_moments);
+
+/* ---- call -------------------------------------------------------------------------------- */
+/* sw: 1 utility, 2 marginal utility, 3 discount, 4 budget, 5 marginal budget, 6 value function;
+ * args: [narg*k] column-major with k = 4,4,2,6,6,3 (egdst_call.c:45-58); res: [narg]. */
+int egdst_call(const egdst_desc *d, egdst_solution *s, int sw, const double *args, int narg, int k, double *res);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
