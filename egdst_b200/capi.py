@@ -152,7 +152,8 @@ class ModelLibrary:
     """One loaded model image (libegdst_b200_<key>.so)."""
 
     EXPORTS = ["egdst_abi_version", "egdst_model_key", "egdst_model_nparam", "egdst_model_neq", "egdst_last_error",
-               "egdst_set_stream", "egdst_solve", "egdst_solve_batch", "egdst_resolve", "egdst_solution_sizes",
+               "egdst_set_stream", "egdst_launch_count", "egdst_profile_classes", "egdst_profile_class_name",
+               "egdst_profile_enable", "egdst_profile_read", "egdst_solve", "egdst_solve_batch", "egdst_resolve", "egdst_solution_sizes",
                "egdst_solution_export", "egdst_solution_status", "egdst_solution_nvec", "egdst_solution_units",
                "egdst_free_solution", "egdst_solution_import", "egdst_simulate", "egdst_simulate_philox",
                "egdst_simulate_device", "egdst_call"]
@@ -167,6 +168,11 @@ class ModelLibrary:
         L.egdst_model_key.restype = C.c_char_p
         L.egdst_last_error.restype = C.c_char_p
         L.egdst_set_stream.argtypes = [vp]
+        L.egdst_launch_count.restype = C.c_longlong
+        L.egdst_profile_class_name.restype = C.c_char_p
+        L.egdst_profile_class_name.argtypes = [C.c_int]
+        L.egdst_profile_enable.argtypes = [C.c_int]
+        L.egdst_profile_read.argtypes = [_dp, C.POINTER(C.c_longlong)]
         L.egdst_solve.argtypes = [C.POINTER(EgdstDesc), C.POINTER(vp)]
         L.egdst_solve_batch.argtypes = [C.POINTER(EgdstDesc), _dp, C.c_int, C.POINTER(vp)]
         L.egdst_resolve.argtypes = [vp, C.POINTER(EgdstDesc), _dp]
@@ -195,6 +201,30 @@ class ModelLibrary:
 
     def set_stream(self, stream_ptr: int):
         self.L.egdst_set_stream(C.c_void_p(stream_ptr))
+
+    def launch_count(self) -> int:
+        return int(self.L.egdst_launch_count())
+
+    def profile_enable(self, on: bool):
+        self.L.egdst_profile_enable(1 if on else 0)
+
+    def profile_read(self):
+        """{class name: (total ms, launches)} accumulated since profile_enable(True)."""
+        n = self.L.egdst_profile_classes()
+        ms = (C.c_double * n)()
+        cnt = (C.c_longlong * n)()
+        self.L.egdst_profile_read(ms, cnt)
+        return {self.L.egdst_profile_class_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n)}
+
+    def simulate_device(self, model, sol: "Solution", d_init: int, nsim: int, agent0: int, seed: int, d_sims: int = 0,
+                        d_moments: int = 0, d_randstream: int = 0, rndtype: int = 0, ivec: int = 0, desc: "Desc" = None):
+        """Asynchronous launch on the library stream; all pointers are device addresses (ints)."""
+        d = desc or Desc(model)
+        rc = self.L.egdst_simulate_device(C.byref(d.c), sol.handle, ivec, C.c_void_p(d_init), nsim, agent0, seed,
+                                          C.c_void_p(d_randstream or None), rndtype, C.c_void_p(d_sims or None),
+                                          C.c_void_p(d_moments or None))
+        if rc:
+            self._raise(rc)
 
     # -- solve
     def solve(self, model, device: Optional[int] = None, strict: bool = False) -> Solution:

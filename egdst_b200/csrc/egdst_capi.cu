@@ -24,6 +24,40 @@
 static thread_local std::string g_err;
 static thread_local cudaStream_t g_stream = 0;
 
+// ---- launch counter and optional per-kernel-class event timing (bench.py's roofline leg) --------------
+enum { KC_SETUP = 0, KC_TERMINAL, KC_SEED, KC_EGM, KC_COMPACT, KC_ENV2, KC_ENV, KC_SIM, KC_OTHER, KC_COUNT };
+static const char *const g_kc_names[KC_COUNT] = {"setup", "terminal", "seed", "egm", "compact", "envelope2", "envelope", "simulate", "other"};
+static long long g_launches = 0;
+static bool g_prof_on = false;
+struct ProfRec { int cls; cudaEvent_t a, b; };
+static std::vector<ProfRec> g_prof_pending;
+static double g_prof_ms[KC_COUNT];
+static long long g_prof_n[KC_COUNT];
+static void prof_begin(int cls, cudaStream_t st) {
+    g_launches++;
+    if (!g_prof_on) return;
+    ProfRec r; r.cls = cls;
+    cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, st);
+    g_prof_pending.push_back(r);
+}
+static void prof_end(cudaStream_t st) {
+    if (!g_prof_on) return;
+    cudaEventRecord(g_prof_pending.back().b, st);
+}
+static void prof_collect() {
+    for (ProfRec &r : g_prof_pending) {
+        float ms = 0.f;
+        cudaEventSynchronize(r.b);
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        g_prof_ms[r.cls] += ms; g_prof_n[r.cls]++;
+        cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    }
+    g_prof_pending.clear();
+}
+#define KLAUNCH(cls, kernel, grid, block, smem, stream, ...) \
+    do { prof_begin(cls, stream); EGDST_LAUNCH(kernel, grid, block, smem, stream, __VA_ARGS__); prof_end(stream); } while (0)
+
 static int fail(int code, const std::string &msg) { g_err = msg; return code; }
 
 #define CK(call)                                                                                       \
@@ -159,8 +193,9 @@ static int create_solution(const egdst_desc *d, int nvec, egdst_solution **out) 
     DA(P.ptN, s->nsd); DA(P.nfold, s->nsd); DA(P.runStart, (size_t)s->nsd * (P.gcap + 1));
     DA(P.mgX, (size_t)s->nslot * P.envcap); DA(P.mgF, (size_t)s->nslot * P.envcap); DA(P.mgK, (size_t)s->nslot * P.envcap); DA(P.mgA, (size_t)s->nslot * P.envcap);
     DA(P.outX, (size_t)s->nsd * P.envcap); DA(P.outC, (size_t)s->nsd * P.envcap); DA(P.outV, (size_t)s->nsd * P.envcap);
-    DA(P.status, 4 * nvec); DA(s->d_moff, s->ncell + 1); DA(s->d_toff, s->ncell + 1);
+    DA(P.status, 4 * nvec); DA(P.units, nvec); DA(s->d_moff, s->ncell + 1); DA(s->d_toff, s->ncell + 1);
 #undef DA
+    cudaMemset(P.units, 0, sizeof(unsigned long long) * nvec);
     P.cx.stm = s->d_stm; P.cx.states = s->d_states; P.cx.decisions = s->d_decisions;
     P.qw = s->d_q; P.qz = s->d_q + d->ny;
     s->h_mlen.assign(s->ncell, 0); s->h_thlen.assign(s->ncell, 0); s->h_status.assign(4 * nvec, 0);
@@ -192,28 +227,29 @@ static int run_solve(egdst_solution *s, const egdst_desc *d, const double *param
     }
     if (d->ny > 1) {
         CK(cudaMemcpyAsync(s->d_qraw, d->quadrature, sizeof(double) * 2 * d->ny, cudaMemcpyHostToDevice, st));
-        EGDST_LAUNCH(egdst_k_quadrature, dim3((d->ny + 127) / 128), dim3(128), 0, st, s->d_qraw, s->d_q, d->ny);
+        KLAUNCH(KC_SETUP, egdst_k_quadrature, dim3((d->ny + 127) / 128), dim3(128), 0, st, s->d_qraw, s->d_q, d->ny);
     }
     CK(cudaMemsetAsync(P.status, 0, sizeof(int) * 4 * P.nvec, st));
+    CK(cudaMemsetAsync(P.units, 0, sizeof(unsigned long long) * P.nvec, st));
     CK(cudaMemsetAsync(P.mlen, 0, sizeof(int) * s->ncell, st));
     CK(cudaMemsetAsync(P.thlen, 0, sizeof(int) * s->ncell, st));
     const int nst = P.cx.nst, nd = P.cx.nd, nvec = P.nvec, N = P.N, B = EGDST_BLOCK;
     const int cellthreads = ((nst + 31) / 32) * 32;
     for (int it = P.NT - 1; it >= 0; it--) {
-        EGDST_LAUNCH(egdst_k_cells, dim3(nvec), dim3(cellthreads), 0, st, P, it);
+        KLAUNCH(KC_SETUP, egdst_k_cells, dim3(nvec), dim3(cellthreads), 0, st, P, it);
         if (it == P.NT - 1) {
-            EGDST_LAUNCH(egdst_k_terminal, dim3((N + B - 1) / B, nst * nd, nvec), dim3(B), 0, st, P, it);
+            KLAUNCH(KC_TERMINAL, egdst_k_terminal, dim3((N + B - 1) / B, nst * nd, nvec), dim3(B), 0, st, P, it);
         } else {
-            EGDST_LAUNCH(egdst_k_seed, dim3(nd, nst, nvec), dim3(B), 0, st, P, it);
-            EGDST_LAUNCH(egdst_k_egm, dim3((N - 1 + 31) / 32, nst * nd, nvec), dim3(32, EGDST_EGM_SPLIT), 0, st, P, it);
-            EGDST_LAUNCH(egdst_k_compact, dim3(nd, nst, nvec), dim3(B), 0, st, P, it);
+            KLAUNCH(KC_SEED, egdst_k_seed, dim3(nd, nst, nvec), dim3(B), 0, st, P, it);
+            KLAUNCH(KC_EGM, egdst_k_egm, dim3((N - 1 + 31) / 32, nst * nd, nvec), dim3(32, EGDST_EGM_SPLIT), 0, st, P, it);
+            KLAUNCH(KC_COMPACT, egdst_k_compact, dim3(nd, nst, nvec), dim3(B), 0, st, P, it);
             // secondary envelope (no-op for (ist,id) without folds)
-            EGDST_LAUNCH(egdst_k_envA<1>, dim3((2 * P.gcap + B - 1) / B, nst * nd, nvec), dim3(B), 0, st, P, it);
-            EGDST_LAUNCH(egdst_k_envBC<1>, dim3(1, nst * nd, nvec), dim3(B), 0, st, P, it);
-            EGDST_LAUNCH(egdst_k_checkempty, dim3(nvec), dim3(cellthreads), 0, st, P, it);
+            KLAUNCH(KC_ENV2, egdst_k_envA<1>, dim3((2 * P.gcap + B - 1) / B, nst * nd, nvec), dim3(B), 0, st, P, it);
+            KLAUNCH(KC_ENV2, egdst_k_envBC<1>, dim3(1, nst * nd, nvec), dim3(B), 0, st, P, it);
+            KLAUNCH(KC_SETUP, egdst_k_checkempty, dim3(nvec), dim3(cellthreads), 0, st, P, it);
         }
-        EGDST_LAUNCH(egdst_k_envA<0>, dim3((nd * P.gcap + B - 1) / B, nst, nvec), dim3(B), 0, st, P, it);
-        EGDST_LAUNCH(egdst_k_envBC<0>, dim3(1, nst, nvec), dim3(B), 0, st, P, it);
+        KLAUNCH(KC_ENV, egdst_k_envA<0>, dim3((nd * P.gcap + B - 1) / B, nst, nvec), dim3(B), 0, st, P, it);
+        KLAUNCH(KC_ENV, egdst_k_envBC<0>, dim3(1, nst, nvec), dim3(B), 0, st, P, it);
     }
     s->sizes_valid = false;
     CK(cudaGetLastError());
@@ -284,6 +320,19 @@ int egdst_model_nparam(void) { return EGDST_NPARAM; }
 int egdst_model_neq(void) { return EGDST_NREQ; }
 const char *egdst_last_error(void) { return g_err.c_str(); }
 void egdst_set_stream(void *cuda_stream) { g_stream = (cudaStream_t)cuda_stream; }
+long long egdst_launch_count(void) { return g_launches; }
+int egdst_profile_classes(void) { return KC_COUNT; }
+const char *egdst_profile_class_name(int cls) { return (cls >= 0 && cls < KC_COUNT) ? g_kc_names[cls] : ""; }
+void egdst_profile_enable(int on) {
+    prof_collect();
+    g_prof_on = on != 0;
+    if (on) for (int i = 0; i < KC_COUNT; i++) { g_prof_ms[i] = 0.0; g_prof_n[i] = 0; }
+}
+int egdst_profile_read(double *ms, long long *count) {
+    prof_collect();
+    for (int i = 0; i < KC_COUNT; i++) { if (ms) ms[i] = g_prof_ms[i]; if (count) count[i] = g_prof_n[i]; }
+    return KC_COUNT;
+}
 
 int egdst_solve_batch(const egdst_desc *d, const double *params, int nvec, egdst_solution **out) {
     if (!out || nvec < 1) return fail(2, "invalid arguments");
@@ -333,7 +382,7 @@ int egdst_solution_export(egdst_solution *s, double *Mbuf, double *Dbuf) {
     }
     CK(cudaMemcpyAsync(s->d_moff, moff.data(), sizeof(int) * (s->ncell + 1), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(s->d_toff, toff.data(), sizeof(int) * (s->ncell + 1), cudaMemcpyHostToDevice, st));
-    EGDST_LAUNCH(egdst_k_pack, dim3(s->ncell), dim3(EGDST_BLOCK), 0, st, s->P, s->d_moff, s->d_toff, s->d_pack, s->d_pack + nm, s->ncell);
+    KLAUNCH(KC_OTHER, egdst_k_pack, dim3(s->ncell), dim3(EGDST_BLOCK), 0, st, s->P, s->d_moff, s->d_toff, s->d_pack, s->d_pack + nm, s->ncell);
     CK(cudaMemcpyAsync(Mbuf, s->d_pack, sizeof(double) * nm, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(Dbuf, s->d_pack + nm, sizeof(double) * nd2, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -354,12 +403,16 @@ int egdst_solution_status(egdst_solution *s, int ivec, int *it, int *ist, int *i
 int egdst_solution_nvec(const egdst_solution *s) { return s ? s->P.nvec : 0; }
 
 long long egdst_solution_units(egdst_solution *s) {
-    // the solve work unit: every (it, ist, id in choice set) contributes its EGM grid points.
-    // Counted from the final cells as rows excluding the a0 row -- a lower bound on the stored quadruples.
-    if (!s || fetch_sizes(s)) return -1;
-    long long u = 0;
-    for (int c = 0; c < s->ncell; c++) u += s->h_mlen[c] > 0 ? s->h_mlen[c] - 1 : 0;
-    return u;
+    // the solve work unit: every EGM grid point stored for an (it, ist, id) -- the mgridvecs
+    // quadruples of egdst_solver.c:646-650, terminal period included; counted on the device by the kernels.
+    if (!s) return -1;
+    if (cudaSetDevice(s->device) != cudaSuccess) return -1;
+    std::vector<unsigned long long> u(s->P.nvec, 0ULL);
+    if (cudaMemcpyAsync(u.data(), s->P.units, sizeof(unsigned long long) * s->P.nvec, cudaMemcpyDeviceToHost, g_stream) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(g_stream) != cudaSuccess) return -1;
+    long long tot = 0;
+    for (unsigned long long x : u) tot += (long long)x;
+    return tot;
 }
 
 void egdst_free_solution(egdst_solution *s) {
@@ -395,7 +448,7 @@ int egdst_solution_import(const egdst_desc *d, const int *mlen, const int *thlen
     cudaMemcpyAsync(s->d_states, d->states, sizeof(double) * d->nst * d->nnst, cudaMemcpyHostToDevice, st);
     cudaMemcpyAsync(s->d_decisions, d->decisions, sizeof(double) * d->nd * d->nnd, cudaMemcpyHostToDevice, st);
     cudaMemsetAsync(s->P.status, 0, sizeof(int) * 4, st);
-    EGDST_LAUNCH(egdst_k_unpack, dim3(s->ncell), dim3(EGDST_BLOCK), 0, st, s->P, s->d_moff, s->d_toff, s->d_pack, s->d_pack + nm, s->ncell);
+    KLAUNCH(KC_OTHER, egdst_k_unpack, dim3(s->ncell), dim3(EGDST_BLOCK), 0, st, s->P, s->d_moff, s->d_toff, s->d_pack, s->d_pack + nm, s->ncell);
     if (cudaStreamSynchronize(st) != cudaSuccess) { egdst_free_solution(s); return fail(2, "import failed"); }
     memcpy(s->h_mlen.data(), mlen, sizeof(int) * s->ncell);
     memcpy(s->h_thlen.data(), thlen, sizeof(int) * s->ncell);

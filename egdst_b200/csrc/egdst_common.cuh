@@ -54,6 +54,7 @@ struct EgdstDev {
     double *outX, *outC, *outV;            // per-slot output staging, capacity envcap
     int envcap;
     int *status;                    // [nvec*4]: code, it, ist, id of the first error
+    unsigned long long *units;      // [nvec] EGM grid points stored over all (it,ist,id): the solve work unit
 };
 
 EGDST_DEV int egdst_cell(const EgdstDev &P, int ivec, int it, int ist) { return (ivec * P.NT + it) * P.cx.nst + ist; }

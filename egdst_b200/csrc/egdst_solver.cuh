@@ -149,6 +149,7 @@ __global__ void egdst_k_terminal(EgdstDev P, int it) {
         P.evfa0[sd] = -EGDST_INF;
         P.ptN[sd] = act ? P.N : 0;
         P.nfold[sd] = 0;
+        if (act) atomicAdd(P.units + ivec, (unsigned long long)P.N);
     }
     if (!act || i >= P.N) return;
     const double m1 = tr(&cx, &curr, cx.zeroconsumption - 0.0), m2 = tr(&cx, &curr, cx.mmax - 0.0);
@@ -447,5 +448,6 @@ __global__ void egdst_k_compact(EgdstDev P, int it) {
         P.ptN[sd] = nvd;
         P.nfold[sd] = s_fbase;
         runStart[s_fbase + 1] = nvd;
+        atomicAdd(P.units + ivec, (unsigned long long)nvd);
     }
 }

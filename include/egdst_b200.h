@@ -56,6 +56,14 @@ int egdst_model_nparam(void);
 int egdst_model_neq(void);
 const char *egdst_last_error(void);  /* per-thread message of the last non-zero return */
 void egdst_set_stream(void *cuda_stream);
+/* measurement aids: number of kernels launched by this library so far; optional CUDA-event timing of
+ * every launch, accumulated per kernel class (setup, terminal, seed, egm, compact, envelope2, envelope,
+ * simulate, other).  Profiling adds two event records per launch -- never enable it in a timed region. */
+long long egdst_launch_count(void);
+int egdst_profile_classes(void);
+const char *egdst_profile_class_name(int cls);
+void egdst_profile_enable(int on);
+int egdst_profile_read(double *ms, long long *count); /* arrays of egdst_profile_classes() entries */
 
 /* ---- solve ------------------------------------------------------------------------------- */
 /* Backward induction for one model.  *out receives a new solution object (device resident). */
