@@ -102,6 +102,11 @@ struct egdst_solution {
     size_t pack_cap;
     int *d_moff, *d_toff;
     int neq;
+    // simulator acceleration structure (egdst_k_simtab), rebuilt lazily after every (re)solve / import
+    double4 *d_simrows;
+    double *d_simcoarse;
+    int sim_rowcap, sim_ccap, sim_cstep;
+    bool sim_valid;
 };
 
 template <class T>
@@ -147,7 +152,6 @@ static int fill_ctx(const egdst_desc *d, egdst_ctx *cx) {
     if (d->nnst > EGDST_NNST || d->nnd > EGDST_NND) return fail(2, "state/decision vector size does not match the compiled model image");
     if (d->ngridm < 2 || d->ngridmax <= d->ngridm || d->T < d->t0 || d->nst < 1 || d->nd < 1 || d->ny < 1 || d->nthrhmax < 2)
         return fail(2, "invalid model dimensions");
-    if (d->ny > 1 && !d->quadrature) return fail(2, "quadrature missing");
     memset(cx, 0, sizeof(*cx));
     cx->t0 = d->t0; cx->T = d->T; cx->ngridm = d->ngridm; cx->ngridmax = d->ngridmax; cx->nthrhmax = d->nthrhmax;
     cx->ny = d->ny; cx->nd = d->nd; cx->nnd = d->nnd; cx->nst = d->nst; cx->nnst = d->nnst;
@@ -173,7 +177,7 @@ static int create_solution(const egdst_desc *d, int nvec, egdst_solution **out) 
     if (rc) return rc;
     if ((rc = check_device(d->device))) return rc;
     egdst_solution *s = new egdst_solution();
-    s->device = d->device; s->sizes_valid = false; s->d_pack = 0; s->pack_cap = 0; s->neq = d->neq;
+    s->device = d->device; s->sizes_valid = false; s->d_simrows = 0; s->d_simcoarse = 0; s->sim_rowcap = 0; s->sim_ccap = 0; s->sim_cstep = 8; s->sim_valid = false; s->d_pack = 0; s->pack_cap = 0; s->neq = d->neq;
     EgdstDev &P = s->P;
     memset(&P, 0, sizeof(P));
     P.cx = cx;
@@ -209,6 +213,7 @@ static int run_solve(egdst_solution *s, const egdst_desc *d, const double *param
     egdst_ctx cx;
     int rc = fill_ctx(d, &cx);
     if (rc) return rc;
+    if (d->ny > 1 && !d->quadrature) return fail(2, "quadrature missing");
     if (d->ngridm != P.N || d->ngridmax != P.gcap || d->T - d->t0 + 1 != P.NT || d->nst != P.cx.nst || d->nd != P.cx.nd ||
         d->ny != P.cx.ny || d->nthrhmax != P.cx.nthrhmax)
         return fail(2, "egdst_resolve: dimensions differ from the solution object");
@@ -252,6 +257,7 @@ static int run_solve(egdst_solution *s, const egdst_desc *d, const double *param
         KLAUNCH(KC_ENV, egdst_k_envBC<0>, dim3(1, nst, nvec), dim3(B), 0, st, P, it);
     }
     s->sizes_valid = false;
+    s->sim_valid = false;
     CK(cudaGetLastError());
     return 0;
 }
@@ -420,6 +426,8 @@ void egdst_free_solution(egdst_solution *s) {
     cudaSetDevice(s->device);
     for (void *p : s->owned) cudaFree(p);
     if (s->d_pack) cudaFree(s->d_pack);
+    if (s->d_simrows) cudaFree(s->d_simrows);
+    if (s->d_simcoarse) cudaFree(s->d_simcoarse);
     delete s;
 }
 

@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 #define EGDST_BLOCK 256
 #define EGDST_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define EGDST_DYN_SMEM(type, name) extern __shared__ __align__(16) type name[]
 #endif
 
 #ifdef __CUDACC__

@@ -87,13 +87,12 @@ EGDST_DEV double egdst_cdfni(double p) {
     if (p < 0 || p > 1) return 0.0;
     if (p == 0) return -EGDST_INF;
     if (p == 1) return EGDST_INF;
-    if (p < 0.02425) {
-        double q = sqrt(-2 * log(p));
-        return (((((c0 * q + c1) * q + c2) * q + c3) * q + c4) * q + c5) / ((((d0 * q + d1) * q + d2) * q + d3) * q + 1);
-    }
-    if (p > 0.97575) {
-        double q = sqrt(-2 * log(1 - p));
-        return -(((((c0 * q + c1) * q + c2) * q + c3) * q + c4) * q + c5) / ((((d0 * q + d1) * q + d2) * q + d3) * q + 1);
+    if (p < 0.02425 || p > 0.97575) {
+        // both tails share one code path (less divergence): the upper tail is -f(1-p) (egdst_lib.c:506-511)
+        const bool upper = p > 0.97575;
+        const double q = sqrt(-2 * log(upper ? 1 - p : p));
+        const double v = (((((c0 * q + c1) * q + c2) * q + c3) * q + c4) * q + c5) / ((((d0 * q + d1) * q + d2) * q + d3) * q + 1);
+        return upper ? -v : v;
     }
     double q = p - 0.5, r = q * q;
     return (((((a0 * r + a1) * r + a2) * r + a3) * r + a4) * r + a5) * q /
@@ -139,8 +138,10 @@ EGDST_DEV double egdst_cashinhandinverse(const egdst_ctx *cx, const PeriodVars *
 // fill the value-coded parts of a PeriodVars (only read when byval>0, i.e. never in the solver;
 // kept so that generated code that references curr->st/dc is always initialised)
 EGDST_DEV void egdst_fill_state(const egdst_ctx *cx, PeriodVars *p) {
-    for (int i = 0; i < cx->nnst; i++) p->st[i] = cx->states[i * cx->nst + p->ist];
+#pragma unroll
+    for (int i = 0; i < EGDST_NNST; i++) p->st[i] = cx->states[i * cx->nst + p->ist];
 }
 EGDST_DEV void egdst_fill_decision(const egdst_ctx *cx, PeriodVars *p) {
-    for (int i = 0; i < cx->nnd; i++) p->dc[i] = cx->decisions[i * cx->nd + p->id];
+#pragma unroll
+    for (int i = 0; i < EGDST_NND; i++) p->dc[i] = cx->decisions[i * cx->nd + p->id];
 }

@@ -21,9 +21,13 @@
 #else
 #define EGDST_SIM_BLOCK 128
 #endif
+#ifndef EGDST_SIM_MINBLOCKS
+#define EGDST_SIM_MINBLOCKS 6
+#endif
 
 // Philox4x32-10 (Salmon et al. 2011); counter = (c0,c1,c2,c3), key = (k0,k1)
-EGDST_DEV void egdst_philox4x32(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1, unsigned out[4]) {
+EGDST_DEV void egdst_philox4x32(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1,
+                                unsigned &o0, unsigned &o1, unsigned &o2, unsigned &o3) {
     for (int r = 0; r < 10; r++) {
         const unsigned long long p0 = (unsigned long long)0xD2511F53u * c0, p1 = (unsigned long long)0xCD9E8D57u * c2;
         const unsigned hi0 = (unsigned)(p0 >> 32), lo0 = (unsigned)p0, hi1 = (unsigned)(p1 >> 32), lo1 = (unsigned)p1;
@@ -31,9 +35,19 @@ EGDST_DEV void egdst_philox4x32(unsigned c0, unsigned c1, unsigned c2, unsigned 
         c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
         k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
-    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+    o0 = c0; o1 = c1; o2 = c2; o3 = c3;
 }
 EGDST_DEV double egdst_u01(unsigned x) { return ((double)x + 0.5) * (1.0 / 4294967296.0); }
+
+// Per-solution acceleration structure of the simulator (built once per solve by egdst_k_simtab):
+//   rows   [ncell][rowcap] double4 (M, C, V, -)  one 32-byte sector per grid row: the two rows of a bracket
+//                                                are 64 contiguous bytes
+//   coarse [ncell][ccap]   every cstep-th M      the top of the bracket search: ~10 KB per period, L1-resident
+struct EgdstSimTab {
+    const double4 *rows;
+    const double *coarse;
+    int rowcap, ccap, cstep;
+};
 
 struct EgdstSimArgs {
     const double *init;        // [nsim*2] column-major: 1-based ist0, m0
@@ -46,27 +60,65 @@ struct EgdstSimArgs {
     double *sims;              // [nsimout, nt, nsim] or null
     double *moments;           // [3, nsimout, nt] or null
     int nsimout;
+    int mom_smem;              // 1: per-CTA moment accumulators for all periods live in shared memory
+    EgdstSimTab tab;
 };
 
-__global__ void egdst_k_simulate(EgdstDev P, EgdstSimArgs S) {
-    __shared__ double tile[EGDST_SIM_BLOCK / 32][32 * (EGDST_NSIMOUT_MAX | 1)];
-    __shared__ double mom[3][EGDST_NSIMOUT_MAX];
+// one CTA per cell: AoS copy of the policy/value table and its coarse search index
+__global__ void egdst_k_simtab(EgdstDev P, double4 *rows, double *coarse, int rowcap, int ccap, int cstep) {
+    const int cell = blockIdx.x;
+    const int n = P.mlen[cell];
+    const double *M = egdst_colM(P, cell), *C = egdst_colC(P, cell), *V = egdst_colV(P, cell);
+    double4 *r = rows + (size_t)cell * rowcap;
+    for (int i = threadIdx.x; i < n && i < rowcap; i += blockDim.x) { double4 v; v.x = M[i]; v.y = C[i]; v.z = V[i]; v.w = 0.0; r[i] = v; }
+    for (int k = threadIdx.x; k * cstep < n && k < ccap; k += blockDim.x) coarse[(size_t)cell * ccap + k] = M[k * cstep];
+}
+
+// Bracket search through the coarse index, then inside one cstep-row window of the AoS table.
+// Same result as egdst_bracket(x, M, n, 0) on a strictly increasing grid: (#rows <= x) - 1 clamped to [0, n-2].
+EGDST_DEV int egdst_bracket_tab(double x, const double4 *__restrict__ rows, int n, const double *__restrict__ cs, int step) {
+    const int nc = (n + step - 1) / step;
+    int lo = 0, hi = nc;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (cs[mid] <= x) lo = mid + 1; else hi = mid; }
+    int cnt = 0;
+    if (lo > 0) {
+        int l = (lo - 1) * step + 1, h = lo * step < n ? lo * step : n;
+        while (l < h) { const int mid = (l + h) >> 1; if (rows[mid].x <= x) l = mid + 1; else h = mid; }
+        cnt = l;
+    }
+    int i = cnt - 1;
+    if (i > n - 2) i = n - 2;
+    return i < 0 ? 0 : i;
+}
+
+// Dynamic shared memory layout of egdst_k_simulate:
+//   tile[warps][32*TS]                one staged record per agent of the warp's tile (TS = nso|1, odd)
+//   mom[nt][nso][3]   (mom_smem)      per-CTA moment accumulators, flushed once at the end
+__global__ void __launch_bounds__(EGDST_SIM_BLOCK, EGDST_SIM_MINBLOCKS) egdst_k_simulate(EgdstDev P, EgdstSimArgs S) {
+    EGDST_DYN_SMEM(double, egdst_sim_smem);
+    constexpr int NSO = EGDST_NSIMOUT_MAX;   // the model image fixes nsimout (checked on the host)
+    constexpr int TS = NSO | 1;              // odd record stride: conflict-free staging and column walks
+    constexpr int WPB = EGDST_SIM_BLOCK / 32;
     egdst_ctx cx; egdst_load_ctx(P, S.ivec, cx);
     cx.status = 0;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int nt = P.NT, nso = S.nsimout, tstride = nso | 1;  // odd stride: conflict-free record rows
+    const int nt = P.NT;
+    double *tile = egdst_sim_smem + (size_t)w * 32 * TS;
+    double *mom = egdst_sim_smem + (size_t)WPB * 32 * TS;
     const double NaN = EGDST_NAN;
     const int ntiles = (S.nsim + 31) / 32;
-    const int wpb = blockDim.x >> 5;
-    // persistent: every warp strides over tiles of 32 agents; all warps of the CTA run the same number of
-    // rounds so that the per-period moment flush can use block barriers
-    const int rounds = (ntiles + gridDim.x * wpb - 1) / (gridDim.x * wpb);
-    for (int round = 0; round < rounds; round++) {
-        const int tileidx = (round * gridDim.x + blockIdx.x) * wpb + w;
+    if (S.moments && S.mom_smem) {
+        for (int i = threadIdx.x; i < nt * NSO * 3; i += blockDim.x) mom[i] = 0.0;
+        __syncthreads();
+    }
+    // persistent: every warp strides over tiles of 32 agents and walks each tile through all periods
+    for (int tileidx = blockIdx.x * WPB + w; tileidx < ntiles; tileidx += gridDim.x * WPB) {
         const int isim = tileidx * 32 + lane;
-        const bool live_lane = tileidx < ntiles && isim < S.nsim;
+        const bool live_lane = isim < S.nsim;
         PeriodVars cur; cur.it = 0; cur.ist = 0; cur.id = 0; cur.cash = 0; cur.savings = 0; cur.shock = NaN;
+#pragma unroll
         for (int i = 0; i < EGDST_NNST; i++) cur.st[i] = 0;
+#pragma unroll
         for (int i = 0; i < EGDST_NND; i++) cur.dc[i] = 0;
         double mu = NaN, sigma = NaN, c = 0, vf = 0;
         double eqs[EGDST_NREQ > 0 ? EGDST_NREQ : 1];
@@ -88,9 +140,9 @@ __global__ void egdst_k_simulate(EgdstDev P, EgdstSimArgs S) {
                     rrr = rs[0]; rrr1 = rs[1]; rrr2 = rs[2];
                 } else {
                     const unsigned long long g = (unsigned long long)(S.agent0 + isim);
-                    unsigned r4[4];
-                    egdst_philox4x32((unsigned)g, (unsigned)(g >> 32), (unsigned)it, 0u, (unsigned)S.seed, (unsigned)(S.seed >> 32), r4);
-                    rrr = egdst_u01(r4[0]); rrr1 = egdst_u01(r4[1]); rrr2 = egdst_u01(r4[2]);
+                    unsigned r0, r1, r2, r3;
+                    egdst_philox4x32((unsigned)g, (unsigned)(g >> 32), (unsigned)it, 0u, (unsigned)S.seed, (unsigned)(S.seed >> 32), r0, r1, r2, r3);
+                    rrr = egdst_u01(r0); rrr1 = egdst_u01(r1); rrr2 = egdst_u01(r2);
                 }
                 if (rrr2 > survival(&cx, &cur)) {
                     state = 1;  // death: the rest of the record stays NaN
@@ -131,9 +183,10 @@ __global__ void egdst_k_simulate(EgdstDev P, EgdstSimArgs S) {
                 const int nm = P.mlen[cell];
                 if (nm < 2) { state = 1; }
                 else {
-                    const double *Mg = egdst_colM(P, cell), *Cg = egdst_colC(P, cell), *Vg = egdst_colV(P, cell);
-                    const int i = egdst_bracket(cur.cash, Mg, nm, 0);
-                    c = egdst_lerp(cur.cash, Mg[i], Mg[i + 1], Cg[i], Cg[i + 1]);
+                    const double4 *rows = S.tab.rows + (size_t)cell * S.tab.rowcap;
+                    const int i = egdst_bracket_tab(cur.cash, rows, nm, S.tab.coarse + (size_t)cell * S.tab.ccap, S.tab.cstep);
+                    const double4 r0 = rows[i], r1 = rows[i + 1];
+                    c = egdst_lerp(cur.cash, r0.x, r1.x, r0.y, r1.y);
                     cur.savings = cur.cash - c;
                     const int nth = P.thlen[cell];
                     const double *th = P.thTH + (size_t)cell * cx.nthrhmax, *dd = P.thD + (size_t)cell * cx.nthrhmax;
@@ -141,49 +194,86 @@ __global__ void egdst_k_simulate(EgdstDev P, EgdstSimArgs S) {
                     while (ith < nth && cur.cash >= th[ith]) ith++;
                     cur.id = (int)dd[ith > 0 ? ith - 1 : 0];
                     egdst_fill_decision(&cx, &cur);
-                    const double evf = Vg[0];
-                    if (cur.cash < Mg[1] && evf > -EGDST_INF) vf = utility(&cx, &cur, c) + discount(&cx, &cur) * evf;
-                    else vf = egdst_lerp(cur.cash, Mg[i], Mg[i + 1], Vg[i], Vg[i + 1]);
+                    const double evf = P.evf[cell];  // == V(row 0)
+                    if (cur.cash < rows[1].x && evf > -EGDST_INF) vf = utility(&cx, &cur, c) + discount(&cx, &cur) * evf;
+                    else vf = egdst_lerp(cur.cash, r0.x, r1.x, r0.z, r1.z);
                 }
             }
             // stage the record of this period
-            double *rec = tile[w] + lane * tstride;
+            double *rec = tile + lane * TS;
             if (state == 0) {
                 rec[0] = cur.cash; rec[1] = c; rec[2] = cur.savings; rec[3] = vf; rec[4] = (double)cur.id; rec[5] = (double)cur.ist;
                 rec[6] = mu; rec[7] = sigma; rec[8] = cur.shock; rec[9] = utility(&cx, &cur, c); rec[10] = discount(&cx, &cur);
-                for (int i = 0; i < cx.nnst; i++) rec[11 + i] = cur.st[i];
-                for (int i = 0; i < cx.nnd; i++) rec[11 + cx.nnst + i] = cur.dc[i];
-                for (int i = 0; i < nso - 11 - cx.nnst - cx.nnd; i++) rec[11 + cx.nnst + cx.nnd + i] = eqs[i];
+#pragma unroll
+                for (int i = 0; i < EGDST_NNST; i++) rec[11 + i] = cur.st[i];
+#pragma unroll
+                for (int i = 0; i < EGDST_NND; i++) rec[11 + EGDST_NNST + i] = cur.dc[i];
+#pragma unroll
+                for (int i = 0; i < EGDST_NREQ; i++) rec[11 + EGDST_NNST + EGDST_NND + i] = eqs[i];
             } else {
-                for (int j = 0; j < nso; j++) rec[j] = NaN;
+#pragma unroll
+                for (int j = 0; j < NSO; j++) rec[j] = NaN;
             }
+            const bool clean = __all_sync(EGDST_FULL, state == 0) && it > 0;  // no NaN record in the tile
             __syncwarp();
-            if (S.sims && tileidx < ntiles) {
-                // cooperative write: element e of the tile belongs to agent e/nso, column e%nso
-                const int nvalid = (S.nsim - tileidx * 32 < 32 ? S.nsim - tileidx * 32 : 32) * nso;
-                for (int e = lane; e < nvalid; e += 32) {
-                    const int a = e / nso, j = e - a * nso;
-                    S.sims[((size_t)(tileidx * 32 + a) * nt + it) * nso + j] = tile[w][a * tstride + j];
+            if (S.sims) {
+                // cooperative write of the tile: the 32 records of this period, NSO contiguous doubles each
+                const int na = S.nsim - tileidx * 32 < 32 ? S.nsim - tileidx * 32 : 32;
+                double *dst = S.sims + ((size_t)tileidx * 32 * nt + it) * NSO;
+                if ((NSO & 1) == 0 && NSO <= 16 && (((size_t)S.sims & 15) == 0)) {
+                    // 16-byte pieces, 8 slots per agent (NSO/2 used): agent = 4*t + lane/8, piece = lane%8
+                    const int k = lane & 7, a0 = lane >> 3;
+                    if (k < NSO / 2) {
+#pragma unroll
+                        for (int t = 0; t < 8; t++) {
+                            const int a = 4 * t + a0;
+                            if (a < na) {
+                                const double2 v = make_double2(tile[a * TS + 2 * k], tile[a * TS + 2 * k + 1]);
+                                *reinterpret_cast<double2 *>(dst + (size_t)a * nt * NSO + 2 * k) = v;
+                            }
+                        }
+                    }
+                } else {
+                    for (int e = lane; e < na * NSO; e += 32) {
+                        const int a = e / NSO, j = e - a * NSO;
+                        dst[(size_t)a * nt * NSO + j] = tile[a * TS + j];
+                    }
                 }
             }
             if (S.moments) {
-                if (threadIdx.x < 3 * nso) (&mom[0][0])[(threadIdx.x / nso) * EGDST_NSIMOUT_MAX + threadIdx.x % nso] = 0.0;
-                __syncthreads();
-                // each lane reduces one column over the 32 agents of the tile (bank-conflict-free column walk)
-                for (int j = lane; j < nso; j += 32) {
-                    double s1 = 0, s2 = 0, n = 0;
-                    for (int a = 0; a < 32; a++) { const double x = tile[w][a * tstride + j]; if (x == x) { s1 += x; s2 += x * x; n += 1; } }
-                    atomicAdd(&mom[0][j], s1); atomicAdd(&mom[1][j], s2); atomicAdd(&mom[2][j], n);
+                // column sums over the tile: lanes split the NSO columns (two half-tiles when 2*NSO <= 32)
+                constexpr int HV = (2 * NSO <= 32) ? 2 : 1;
+                double s1 = 0, s2 = 0, n = 0;
+                if (lane < HV * NSO) {
+                    const int j = lane % NSO, h = lane / NSO;
+                    const double *col = tile + h * (32 / HV) * TS + j;
+                    if (clean && j != 6 && j != 7 && j != 8 && j < 11 + EGDST_NNST + EGDST_NND) {
+                        // every agent of the tile is alive and the column cannot hold NaN
+#pragma unroll 8
+                        for (int a = 0; a < 32 / HV; a++) { const double x = col[a * TS]; s1 += x; s2 = fma(x, x, s2); }
+                        n = 32 / HV;
+                    } else {
+                        for (int a = 0; a < 32 / HV; a++) { const double x = col[a * TS]; if (x == x) { s1 += x; s2 = fma(x, x, s2); n += 1; } }
+                    }
                 }
-                __syncthreads();
-                if (threadIdx.x < 3 * nso) {
-                    const int k = threadIdx.x / nso, j = threadIdx.x % nso;
-                    const double val = mom[k][j];
-                    if (val != 0.0) atomicAdd(&S.moments[((size_t)it * nso + j) * 3 + k], val);
+                if (HV == 2) {
+                    s1 += __shfl_down_sync(EGDST_FULL, s1, NSO);
+                    s2 += __shfl_down_sync(EGDST_FULL, s2, NSO);
+                    n += __shfl_down_sync(EGDST_FULL, n, NSO);
                 }
-                __syncthreads();
+                if (lane < NSO && n > 0) {
+                    double *dstm = S.mom_smem ? mom + ((size_t)it * NSO + lane) * 3 : S.moments + ((size_t)it * NSO + lane) * 3;
+                    atomicAdd(dstm + 0, s1); atomicAdd(dstm + 1, s2); atomicAdd(dstm + 2, n);
+                }
             }
             __syncwarp();
+        }
+    }
+    if (S.moments && S.mom_smem) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < nt * NSO * 3; i += blockDim.x) {
+            const double v = mom[i];
+            if (v != 0.0) atomicAdd(S.moments + i, v);
         }
     }
 }

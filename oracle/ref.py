@@ -102,8 +102,10 @@ class RefError(RuntimeError):
 class Reference:
     """Runs the reference gateways on an ``EgdstModel`` through the shim."""
 
-    def __init__(self, model, variant: str = "base"):
-        path = build(model, variant)
+    def __init__(self, model, variant: str = "base", libpath: Optional[str] = None):
+        # libpath: any library exporting the three gateways + the shim harness (tests/mexharness.py drives the
+        # product's own MEX gateways through the same fake model object)
+        path = libpath or build(model, variant)
         if path is None:
             raise FileNotFoundError("oracle/_ref library for this model is not built and /root/reference is absent")
         self.lib = L = C.CDLL(path)

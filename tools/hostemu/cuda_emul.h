@@ -26,6 +26,13 @@
 #define __forceinline__ inline
 #define __restrict__
 #define __shared__ static
+#define __launch_bounds__(...)
+struct double2 { double x, y; };
+struct double4 { double x, y, z, w; };
+inline bool __all_sync(unsigned, int pred);
+inline double2 make_double2(double x, double y) { double2 v; v.x = x; v.y = y; return v; }
+inline void *emu_dyn_smem = nullptr;
+#define EGDST_DYN_SMEM(type, name) type *name = (type *)emu_dyn_smem
 
 struct dim3 {
     unsigned x, y, z;
@@ -83,6 +90,7 @@ inline unsigned __ballot_sync(unsigned, int pred) {
     W.bar->arrive_and_wait();
     return r;
 }
+inline bool __all_sync(unsigned m, int pred) { return __ballot_sync(m, !pred) == 0; }
 inline int __ffs(unsigned v) { return v ? __builtin_ctz(v) + 1 : 0; }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 
@@ -98,7 +106,8 @@ inline int atomicMin(int *p, int v) {
 }
 
 // ---- launch ------------------------------------------------------------------------------------
-inline void emu_launch(dim3 grid, dim3 block, const std::function<void()> &body) {
+inline void emu_launch(dim3 grid, dim3 block, size_t smem, const std::function<void()> &body) {
+    std::vector<unsigned char> dyn(smem + 16);
     const int nthreads = (int)(block.x * block.y * block.z);
     const int nwarps = (nthreads + 31) / 32;
     for (unsigned bz = 0; bz < grid.z; bz++)
@@ -112,6 +121,7 @@ inline void emu_launch(dim3 grid, dim3 block, const std::function<void()> &body)
                     B.warps[w].bar = std::make_unique<std::barrier<>>(B.warps[w].nlanes);
                 }
                 emu_block = &B;
+                emu_dyn_smem = dyn.data();
                 std::vector<std::thread> ts;
                 ts.reserve(nthreads);
                 for (int t = 0; t < nthreads; t++)
@@ -128,7 +138,7 @@ inline void emu_launch(dim3 grid, dim3 block, const std::function<void()> &body)
                 emu_block = nullptr;
             }
 }
-#define EGDST_LAUNCH(kernel, grid, block, smem, stream, ...) emu_launch((grid), (block), [&] { kernel(__VA_ARGS__); })
+#define EGDST_LAUNCH(kernel, grid, block, smem, stream, ...) emu_launch((grid), (block), (size_t)(smem), [&] { kernel(__VA_ARGS__); })
 
 // ---- runtime API subset --------------------------------------------------------------------------
 typedef int cudaError_t;
@@ -140,6 +150,7 @@ inline cudaError_t cudaMalloc(void **p, size_t n) { *p = std::calloc(1, n ? n : 
 inline cudaError_t cudaFree(void *p) { std::free(p); return 0; }
 inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { std::memcpy(d, s, n); return 0; }
 inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t) { std::memcpy(d, s, n); return 0; }
+inline cudaError_t cudaMemset(void *d, int v, size_t n) { std::memset(d, v, n); return 0; }
 inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t) { std::memset(d, v, n); return 0; }
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
 inline cudaError_t cudaDeviceSynchronize() { return 0; }
