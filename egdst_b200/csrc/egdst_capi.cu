@@ -6,6 +6,7 @@
 //   parseModel/loadparameters egdst_lib.c:34-62          -> egdst_desc
 // There is no host arithmetic on the data path: even the cdfni transform of the quadrature abscissas
 // (egdst_solver.c:162-164) runs on the device.
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -104,8 +105,8 @@ struct egdst_solution {
     int neq;
     // simulator acceleration structure (egdst_k_simtab), rebuilt lazily after every (re)solve / import
     double4 *d_simrows;
-    double *d_simcoarse;
-    int sim_rowcap, sim_ccap, sim_cstep;
+    int *d_simlut;
+    int sim_rowcap, sim_lutcap, sim_mbits;
     bool sim_valid;
 };
 
@@ -177,7 +178,7 @@ static int create_solution(const egdst_desc *d, int nvec, egdst_solution **out) 
     if (rc) return rc;
     if ((rc = check_device(d->device))) return rc;
     egdst_solution *s = new egdst_solution();
-    s->device = d->device; s->sizes_valid = false; s->d_simrows = 0; s->d_simcoarse = 0; s->sim_rowcap = 0; s->sim_ccap = 0; s->sim_cstep = 8; s->sim_valid = false; s->d_pack = 0; s->pack_cap = 0; s->neq = d->neq;
+    s->device = d->device; s->sizes_valid = false; s->d_simrows = 0; s->d_simlut = 0; s->sim_rowcap = 0; s->sim_lutcap = 0; s->sim_mbits = 0; s->sim_valid = false; s->d_pack = 0; s->pack_cap = 0; s->neq = d->neq;
     EgdstDev &P = s->P;
     memset(&P, 0, sizeof(P));
     P.cx = cx;
@@ -427,7 +428,7 @@ void egdst_free_solution(egdst_solution *s) {
     for (void *p : s->owned) cudaFree(p);
     if (s->d_pack) cudaFree(s->d_pack);
     if (s->d_simrows) cudaFree(s->d_simrows);
-    if (s->d_simcoarse) cudaFree(s->d_simcoarse);
+    if (s->d_simlut) cudaFree(s->d_simlut);
     delete s;
 }
 

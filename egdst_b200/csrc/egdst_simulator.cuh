@@ -40,14 +40,32 @@ EGDST_DEV void egdst_philox4x32(unsigned c0, unsigned c1, unsigned c2, unsigned 
 EGDST_DEV double egdst_u01(unsigned x) { return ((double)x + 0.5) * (1.0 / 4294967296.0); }
 
 // Per-solution acceleration structure of the simulator (built once per solve by egdst_k_simtab):
-//   rows   [ncell][rowcap] double4 (M, C, V, -)  one 32-byte sector per grid row: the two rows of a bracket
-//                                                are 64 contiguous bytes
-//   coarse [ncell][ccap]   every cstep-th M      the top of the bracket search: ~10 KB per period, L1-resident
+//   rows [ncell][rowcap] double4 (M, C, V, -)  one 32-byte sector per grid row: the two rows of a bracket are
+//                                              64 contiguous bytes
+//   lut  [ncell][lutcap+1] int                 direct index into the rows by the leading bits of the IEEE
+//                                              representation of (x - a0 + 1): key = exponent and the top
+//                                              `mbits` mantissa bits, a piecewise-linear log2 -- the endogenous
+//                                              grids are (sym-)log spaced (egdst_solver.c:1104-1136), so the
+//                                              buckets hold a few rows each.  lut[b] = #rows with key < b, hence
+//                                              #rows <= x lies in [lut[key(x)], lut[key(x)+1]]: one table load
+//                                              and a 2-3 step bisection replace the 14-step bisection of
+//                                              bxsearch (egdst_lib.c:138-165).
 struct EgdstSimTab {
     const double4 *rows;
-    const double *coarse;
-    int rowcap, ccap, cstep;
+    const int *lut;
+    int rowcap, lutcap, mbits;
 };
+
+EGDST_DEV int egdst_lut_key(double x, double a0, int mbits) {
+    const double y = x - a0 + 1.0;
+#ifdef EGDST_HOSTEMU
+    long long bits; memcpy(&bits, &y, 8);
+    const int hi = (int)(bits >> 32);
+#else
+    const int hi = __double2hiint(y);
+#endif
+    return (hi >> (20 - mbits)) - (0x3FF00000 >> (20 - mbits));
+}
 
 struct EgdstSimArgs {
     const double *init;        // [nsim*2] column-major: 1-based ist0, m0
@@ -64,29 +82,32 @@ struct EgdstSimArgs {
     EgdstSimTab tab;
 };
 
-// one CTA per cell: AoS copy of the policy/value table and its coarse search index
-__global__ void egdst_k_simtab(EgdstDev P, double4 *rows, double *coarse, int rowcap, int ccap, int cstep) {
+// one CTA per cell: AoS copy of the policy/value table and its direct-index table
+__global__ void egdst_k_simtab(EgdstDev P, double4 *rows, int *lut, int rowcap, int lutcap, int mbits) {
     const int cell = blockIdx.x;
-    const int n = P.mlen[cell];
+    int n = P.mlen[cell];
+    if (n > rowcap) n = rowcap;
+    const double a0 = P.cx.a0;
     const double *M = egdst_colM(P, cell), *C = egdst_colC(P, cell), *V = egdst_colV(P, cell);
     double4 *r = rows + (size_t)cell * rowcap;
-    for (int i = threadIdx.x; i < n && i < rowcap; i += blockDim.x) { double4 v; v.x = M[i]; v.y = C[i]; v.z = V[i]; v.w = 0.0; r[i] = v; }
-    for (int k = threadIdx.x; k * cstep < n && k < ccap; k += blockDim.x) coarse[(size_t)cell * ccap + k] = M[k * cstep];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { double4 v; v.x = M[i]; v.y = C[i]; v.z = V[i]; v.w = 0.0; r[i] = v; }
+    int *L = lut + (size_t)cell * (lutcap + 1);
+    for (int b = threadIdx.x; b <= lutcap; b += blockDim.x) {
+        int lo = 0, hi = n;  // first row whose key is >= b (keys are non-decreasing along the grid)
+        if (b == lutcap) lo = n;
+        else while (lo < hi) { const int mid = (lo + hi) >> 1; if (egdst_lut_key(M[mid], a0, mbits) < b) lo = mid + 1; else hi = mid; }
+        L[b] = lo;
+    }
 }
 
-// Bracket search through the coarse index, then inside one cstep-row window of the AoS table.
-// Same result as egdst_bracket(x, M, n, 0) on a strictly increasing grid: (#rows <= x) - 1 clamped to [0, n-2].
-EGDST_DEV int egdst_bracket_tab(double x, const double4 *__restrict__ rows, int n, const double *__restrict__ cs, int step) {
-    const int nc = (n + step - 1) / step;
-    int lo = 0, hi = nc;
-    while (lo < hi) { const int mid = (lo + hi) >> 1; if (cs[mid] <= x) lo = mid + 1; else hi = mid; }
-    int cnt = 0;
-    if (lo > 0) {
-        int l = (lo - 1) * step + 1, h = lo * step < n ? lo * step : n;
-        while (l < h) { const int mid = (l + h) >> 1; if (rows[mid].x <= x) l = mid + 1; else h = mid; }
-        cnt = l;
-    }
-    int i = cnt - 1;
+// Bracket through the direct-index table.  Same result as egdst_bracket(x, M, n, 0) on a strictly increasing
+// grid: (#rows <= x) - 1 clamped to [0, n-2].
+EGDST_DEV int egdst_bracket_tab(double x, const double4 *__restrict__ rows, int n, const int *__restrict__ lut, int lutcap, int mbits, double a0) {
+    int b = egdst_lut_key(x, a0, mbits);
+    b = b < 0 ? 0 : (b > lutcap - 1 ? lutcap - 1 : b);
+    int l = lut[b], h = lut[b + 1];
+    while (l < h) { const int mid = (l + h) >> 1; if (rows[mid].x <= x) l = mid + 1; else h = mid; }
+    int i = l - 1;
     if (i > n - 2) i = n - 2;
     return i < 0 ? 0 : i;
 }
@@ -184,7 +205,7 @@ __global__ void __launch_bounds__(EGDST_SIM_BLOCK, EGDST_SIM_MINBLOCKS) egdst_k_
                 if (nm < 2) { state = 1; }
                 else {
                     const double4 *rows = S.tab.rows + (size_t)cell * S.tab.rowcap;
-                    const int i = egdst_bracket_tab(cur.cash, rows, nm, S.tab.coarse + (size_t)cell * S.tab.ccap, S.tab.cstep);
+                    const int i = egdst_bracket_tab(cur.cash, rows, nm, S.tab.lut + (size_t)cell * (S.tab.lutcap + 1), S.tab.lutcap, S.tab.mbits, cx.a0);
                     const double4 r0 = rows[i], r1 = rows[i + 1];
                     c = egdst_lerp(cur.cash, r0.x, r1.x, r0.y, r1.y);
                     cur.savings = cur.cash - c;
@@ -247,12 +268,15 @@ __global__ void __launch_bounds__(EGDST_SIM_BLOCK, EGDST_SIM_MINBLOCKS) egdst_k_
                 if (lane < HV * NSO) {
                     const int j = lane % NSO, h = lane / NSO;
                     const double *col = tile + h * (32 / HV) * TS + j;
-                    if (clean && j != 6 && j != 7 && j != 8 && j < 11 + EGDST_NNST + EGDST_NND) {
-                        // every agent of the tile is alive and the column cannot hold NaN
+                    if (clean) {
+                        // every agent of the tile is alive: sum without NaN tests (warp-uniform branch); a column that
+                        // holds a NaN after all (user equations) shows up as a NaN sum and is redone below
 #pragma unroll 8
                         for (int a = 0; a < 32 / HV; a++) { const double x = col[a * TS]; s1 += x; s2 = fma(x, x, s2); }
                         n = 32 / HV;
-                    } else {
+                    }
+                    if (!clean || s1 != s1 || s2 != s2) {
+                        s1 = 0; s2 = 0; n = 0;
                         for (int a = 0; a < 32 / HV; a++) { const double x = col[a * TS]; if (x == x) { s1 += x; s2 = fma(x, x, s2); n += 1; } }
                     }
                 }
