@@ -104,8 +104,8 @@ struct egdst_solution {
     int *d_moff, *d_toff;
     int neq;
     // simulator acceleration structure (egdst_k_simtab), rebuilt lazily after every (re)solve / import
-    double4 *d_simrows;
-    int *d_simlut;
+    EgdstInterval *d_simivl;
+    EgdstLutEntry *d_simlut;
     int sim_rowcap, sim_lutcap, sim_mbits;
     bool sim_valid;
 };
@@ -178,7 +178,7 @@ static int create_solution(const egdst_desc *d, int nvec, egdst_solution **out) 
     if (rc) return rc;
     if ((rc = check_device(d->device))) return rc;
     egdst_solution *s = new egdst_solution();
-    s->device = d->device; s->sizes_valid = false; s->d_simrows = 0; s->d_simlut = 0; s->sim_rowcap = 0; s->sim_lutcap = 0; s->sim_mbits = 0; s->sim_valid = false; s->d_pack = 0; s->pack_cap = 0; s->neq = d->neq;
+    s->device = d->device; s->sizes_valid = false; s->d_simivl = 0; s->d_simlut = 0; s->sim_rowcap = 0; s->sim_lutcap = 0; s->sim_mbits = 0; s->sim_valid = false; s->d_pack = 0; s->pack_cap = 0; s->neq = d->neq;
     EgdstDev &P = s->P;
     memset(&P, 0, sizeof(P));
     P.cx = cx;
@@ -427,7 +427,7 @@ void egdst_free_solution(egdst_solution *s) {
     cudaSetDevice(s->device);
     for (void *p : s->owned) cudaFree(p);
     if (s->d_pack) cudaFree(s->d_pack);
-    if (s->d_simrows) cudaFree(s->d_simrows);
+    if (s->d_simivl) cudaFree(s->d_simivl);
     if (s->d_simlut) cudaFree(s->d_simlut);
     delete s;
 }

@@ -75,15 +75,21 @@ EGDST_DEV double egdst_linter_extrap_at(const egdst_ctx *cx, const PeriodVars *p
 // Acklam's rational approximation of the standard normal quantile (egdst_lib.c:435-519).
 // Parity at 1e-9 needs this polynomial, not normcdfinv.
 // ---------------------------------------------------------------------------------------------
+// The 21 coefficients live in the constant bank: as literals every use costs two uniform moves (UMOV) to
+// materialise the 64-bit immediate; as c[bank][offset] they are direct DFMA operands.
+#ifdef __CUDACC__
+__constant__
+#else
+static const
+#endif
+double EGDST_CDFNI_K[21] = {
+    -3.969683028665376e+01, 2.209460984245205e+02, -2.759285104469687e+02, 1.383577518672690e+02, -3.066479806614716e+01, 2.506628277459239e+00,  // a0..a5
+    -5.447609879822406e+01, 1.615858368580409e+02, -1.556989798598866e+02, 6.680131188771972e+01, -1.328068155288572e+01,                        // b0..b4
+    -7.784894002430293e-03, -3.223964580411365e-01, -2.400758277161838e+00, -2.549732539343734e+00, 4.374664141464968e+00, 2.938163982698783e+00,  // c0..c5
+    7.784695709041462e-03, 3.224671290700398e-01, 2.445134137142996e+00, 3.754408661907416e+00};                                                // d0..d3
+
 EGDST_DEV double egdst_cdfni(double p) {
-    const double a0 = -3.969683028665376e+01, a1 = 2.209460984245205e+02, a2 = -2.759285104469687e+02,
-                 a3 = 1.383577518672690e+02, a4 = -3.066479806614716e+01, a5 = 2.506628277459239e+00;
-    const double b0 = -5.447609879822406e+01, b1 = 1.615858368580409e+02, b2 = -1.556989798598866e+02,
-                 b3 = 6.680131188771972e+01, b4 = -1.328068155288572e+01;
-    const double c0 = -7.784894002430293e-03, c1 = -3.223964580411365e-01, c2 = -2.400758277161838e+00,
-                 c3 = -2.549732539343734e+00, c4 = 4.374664141464968e+00, c5 = 2.938163982698783e+00;
-    const double d0 = 7.784695709041462e-03, d1 = 3.224671290700398e-01, d2 = 2.445134137142996e+00,
-                 d3 = 3.754408661907416e+00;
+    const double *K = EGDST_CDFNI_K;
     if (p < 0 || p > 1) return 0.0;
     if (p == 0) return -EGDST_INF;
     if (p == 1) return EGDST_INF;
@@ -91,12 +97,13 @@ EGDST_DEV double egdst_cdfni(double p) {
         // both tails share one code path (less divergence): the upper tail is -f(1-p) (egdst_lib.c:506-511)
         const bool upper = p > 0.97575;
         const double q = sqrt(-2 * log(upper ? 1 - p : p));
-        const double v = (((((c0 * q + c1) * q + c2) * q + c3) * q + c4) * q + c5) / ((((d0 * q + d1) * q + d2) * q + d3) * q + 1);
+        const double v = (((((K[11] * q + K[12]) * q + K[13]) * q + K[14]) * q + K[15]) * q + K[16]) /
+                         ((((K[17] * q + K[18]) * q + K[19]) * q + K[20]) * q + 1);
         return upper ? -v : v;
     }
-    double q = p - 0.5, r = q * q;
-    return (((((a0 * r + a1) * r + a2) * r + a3) * r + a4) * r + a5) * q /
-           (((((b0 * r + b1) * r + b2) * r + b3) * r + b4) * r + 1);
+    const double q = p - 0.5, r = q * q;
+    return (((((K[0] * r + K[1]) * r + K[2]) * r + K[3]) * r + K[4]) * r + K[5]) * q /
+           (((((K[6] * r + K[7]) * r + K[8]) * r + K[9]) * r + K[10]) * r + 1);
 }
 
 // shock distribution helpers (egdst_lib.c:66-101); DISTRIB 1 = lognormal, 2 = normal
