@@ -25,6 +25,14 @@
 #define EGDST_SIM_MINBLOCKS 4
 #endif
 
+// the sims array is written once and never re-read by the kernel: evict-first (st.global.cs) keeps the policy
+// tables resident in L2 instead of the output stream
+#ifdef EGDST_HOSTEMU
+#define EGDST_STREAM_STORE2(ptr, v) (*reinterpret_cast<double2 *>(ptr) = (v))
+#else
+#define EGDST_STREAM_STORE2(ptr, v) __stcs(reinterpret_cast<double2 *>(ptr), (v))
+#endif
+
 // Philox4x32-10 (Salmon et al. 2011); counter = (c0,c1,c2,c3), key = (k0,k1)
 EGDST_DEV void egdst_philox4x32(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1,
                                 unsigned &o0, unsigned &o1, unsigned &o2, unsigned &o3) {
@@ -278,10 +286,10 @@ __global__ void __launch_bounds__(EGDST_SIM_BLOCK, EGDST_SIM_MINBLOCKS) egdst_k_
                         if (na == 32) {
 #pragma unroll
                             for (int t = 0; t < 8; t++)
-                                *reinterpret_cast<double2 *>(d + t * dstride) = make_double2(src[t * 4 * TS], src[t * 4 * TS + 1]);
+                                EGDST_STREAM_STORE2(d + t * dstride, make_double2(src[t * 4 * TS], src[t * 4 * TS + 1]));
                         } else {
                             for (int t = 0; 4 * t + a0 < na; t++)
-                                *reinterpret_cast<double2 *>(d + t * dstride) = make_double2(src[t * 4 * TS], src[t * 4 * TS + 1]);
+                                EGDST_STREAM_STORE2(d + t * dstride, make_double2(src[t * 4 * TS], src[t * 4 * TS + 1]));
                         }
                     }
                 } else {
