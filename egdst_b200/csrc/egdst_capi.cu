@@ -248,14 +248,14 @@ static int run_solve(egdst_solution *s, const egdst_desc *d, const double *param
         } else {
             KLAUNCH(KC_SEED, egdst_k_seed, dim3(nd, nst, nvec), dim3(B), 0, st, P, it);
             KLAUNCH(KC_EGM, egdst_k_egm, dim3((N - 1 + 31) / 32, nst * nd, nvec), dim3(32, EGDST_EGM_SPLIT), 0, st, P, it);
-            KLAUNCH(KC_COMPACT, egdst_k_compact, dim3(nd, nst, nvec), dim3(B), 0, st, P, it);
+            KLAUNCH(KC_COMPACT, egdst_k_compact, dim3(nd, nst, nvec), dim3(EGDST_WIDE), 0, st, P, it);
             // secondary envelope (no-op for (ist,id) without folds)
             KLAUNCH(KC_ENV2, egdst_k_envA<1>, dim3((2 * P.gcap + B - 1) / B, nst * nd, nvec), dim3(B), 0, st, P, it);
-            KLAUNCH(KC_ENV2, egdst_k_envBC<1>, dim3(1, nst * nd, nvec), dim3(B), 0, st, P, it);
+            KLAUNCH(KC_ENV2, egdst_k_envBC<1>, dim3(1, nst * nd, nvec), dim3(EGDST_ENVW), 0, st, P, it);
             KLAUNCH(KC_SETUP, egdst_k_checkempty, dim3(nvec), dim3(cellthreads), 0, st, P, it);
         }
         KLAUNCH(KC_ENV, egdst_k_envA<0>, dim3((nd * P.gcap + B - 1) / B, nst, nvec), dim3(B), 0, st, P, it);
-        KLAUNCH(KC_ENV, egdst_k_envBC<0>, dim3(1, nst, nvec), dim3(B), 0, st, P, it);
+        KLAUNCH(KC_ENV, egdst_k_envBC<0>, dim3(1, nst, nvec), dim3(EGDST_ENVW), 0, st, P, it);
     }
     s->sizes_valid = false;
     s->sim_valid = false;

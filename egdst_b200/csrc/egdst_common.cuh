@@ -8,9 +8,13 @@
 // their logic can be debugged without a GPU.  Development aid only -- never loaded by the product.
 #include "cuda_emul.h"
 #define EGDST_BLOCK 64
+#define EGDST_WIDE 64
+#define EGDST_ENVW 64
 #else
 #include <cuda_runtime.h>
 #define EGDST_BLOCK 256
+#define EGDST_WIDE 1024  /* single-CTA scan/compaction kernels: one CTA owns a whole (state, decision) list */
+#define EGDST_ENVW 512   /* envelope merge kernels: 8 positions per thread, 128 registers available */
 #define EGDST_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #define EGDST_DYN_SMEM(type, name) extern __shared__ __align__(16) type name[]
 #endif
@@ -90,6 +94,39 @@ EGDST_DEV int egdst_warp_incl_scan(int v, int lane) {
     for (int o = 1; o < 32; o <<= 1) { int w = __shfl_up_sync(EGDST_FULL, v, o); if (lane >= o) v += w; }
     return v;
 }
+// 64-bit variant (two packed 32-bit counters share one scan): same barriers as egdst_block_excl_scan
+EGDST_DEV long long egdst_warp_incl_scan64(long long v, int lane) {
+    for (int o = 1; o < 32; o <<= 1) { long long w = __shfl_up_sync(EGDST_FULL, v, o); if (lane >= o) v += w; }
+    return v;
+}
+EGDST_DEV long long egdst_block_excl_scan64(long long v, long long *sh, long long *total) {
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    long long inc = egdst_warp_incl_scan64(v, lane);
+    if (lane == 31) sh[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        long long s = lane < nw ? sh[lane] : 0;
+        long long si = egdst_warp_incl_scan64(s, lane);
+        if (lane < nw) sh[lane] = si - s;
+        if (lane == nw - 1) sh[nw] = si;
+    }
+    __syncthreads();
+    long long res = inc - v + sh[w];
+    *total = sh[nw];
+    __syncthreads();
+    return res;
+}
+EGDST_DEV int egdst_block_min(int v, int *sh) {  // sh: 32 ints; every thread gets the block minimum
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = egdst_warp_min(v);
+    if (lane == 0) sh[w] = v;
+    __syncthreads();
+    int r = sh[0];
+    for (int k = 1; k < nw; k++) r = sh[k] < r ? sh[k] : r;
+    __syncthreads();
+    return r;
+}
+
 // exclusive block scan of one int per thread; returns the exclusive prefix, *total gets the block sum.
 // `sh` must hold blockDim.x/32+1 ints.  Contains two __syncthreads().
 EGDST_DEV int egdst_block_excl_scan(int v, int *sh, int *total) {

@@ -176,6 +176,7 @@ __global__ void egdst_k_envA(EgdstDev P, int it) {
 // ---------------------------------------------------------------------------------------------
 // crossing chain on the boundary before sweep position (xr,vr,fr,kr): thresholds() restated with an
 // explicit stack.  Counts (write==false) or writes the grid points / thresholds it produces.
+// WARP-COOPERATIVE: must be called by all 32 lanes of a warp with identical arguments (lane 0 writes).
 // ---------------------------------------------------------------------------------------------
 template <class View>
 EGDST_DEV double egdst_env_brsolve(const egdst_ctx *cx, const View &E, int it, int ist, int ga, double br0, double br1,
@@ -238,15 +239,27 @@ EGDST_DEV void egdst_env_chain(const egdst_ctx *cx, const View &E, int it, int i
             else { newpoint = (ip - iq) / (sq - spp); cmax = newpoint * sq + iq; }
         }
         // is a third, not yet visited function above at the crossing? (egdst_solver.c:1807-1845, mode 1)
+        // The candidates are split over the lanes of the warp (the secondary envelope can have ~10^2 runs);
+        // the serial rule "first strictly greater value wins" = maximum value, lowest index among ties.
         int optk = -1;
-        for (int k = 0; k < E.F; k++) {
-            if (marks[k >> 5] & (1u << (k & 31))) continue;
-            const int nk = E.npts(k);
-            if (nk <= 0) continue;
-            const int ck = egdst_env_cur(egdst_env_count_before(E, k, xr, vr, fr, kr), nk);
-            const double tmax = (ck >= 0) ? egdst_linter2(newpoint, E.x(k, ck), E.x(k, ck + 1), E.v(k, ck), E.v(k, ck + 1))
-                                          : egdst_env_analytic(cx, E, it, ist, k, newpoint);
-            if (cmax < tmax) { cmax = tmax; optk = k; }
+        {
+            const int lane_ = threadIdx.x & 31;
+            double lv = -EGDST_INF; int lk = 0x7fffffff;
+            for (int k = lane_; k < E.F; k += 32) {
+                if (marks[k >> 5] & (1u << (k & 31))) continue;
+                const int nk = E.npts(k);
+                if (nk <= 0) continue;
+                const int ck = egdst_env_cur(egdst_env_count_before(E, k, xr, vr, fr, kr), nk);
+                const double tmax = (ck >= 0) ? egdst_linter2(newpoint, E.x(k, ck), E.x(k, ck + 1), E.v(k, ck), E.v(k, ck + 1))
+                                              : egdst_env_analytic(cx, E, it, ist, k, newpoint);
+                if (tmax > lv) { lv = tmax; lk = k; }
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov_ = __shfl_xor_sync(EGDST_FULL, lv, o);
+                const int ok_ = __shfl_xor_sync(EGDST_FULL, lk, o);
+                if (ov_ > lv || (ov_ == lv && ok_ < lk)) { lv = ov_; lk = ok_; }
+            }
+            if (cmax < lv) { cmax = lv; optk = lk; }
         }
         if (optk != -1) {
             if (sp + 2 > EGDST_ENV_STACK) { *err = EGDST_ERR_ENV2SPACE; return; }
@@ -256,7 +269,7 @@ EGDST_DEV void egdst_env_chain(const egdst_ctx *cx, const View &E, int it, int i
         }
         const double c_left = egdst_env_value2(cx, E, p, cp, newpoint), c_right = egdst_env_value2(cx, E, q, cq, newpoint);
         const bool single = (E.evf(q) == -EGDST_INF && cq == -1);  // egdst_solver.c:1892-1896
-        if (write) {
+        if (write && (threadIdx.x & 31) == 0) {
             if (ng < gleft) { gx[ng] = single ? newpoint - cx->tolerance : newpoint; gv[ng] = cmax; gc[ng] = c_left; }
             if (nt < tleft) { tth[nt] = newpoint; tdd[nt] = (double)q; }
             if (!single && ng + 1 < gleft) { gx[ng + 1] = newpoint + cx->doublepoint_delta; gv[ng + 1] = cmax; gc[ng + 1] = c_right; }
@@ -267,14 +280,73 @@ EGDST_DEV void egdst_env_chain(const egdst_ctx *cx, const View &E, int it, int i
 }
 
 // ---------------------------------------------------------------------------------------------
-// Step B/C: one CTA per job walks the union in order, chunk by chunk; block-wide scans place the kept
-// points, the crossing double points and the thresholds.
+// Step B/C: one wide CTA per job walks the union in order, EGDST_ENV_IPT consecutive positions per thread
+// and pass; one block-wide scan per pass places the kept points, the crossing double points and the
+// thresholds (a 2*10^4-point union is five passes).
 // MODE 0 writes the period's solution cell (rows 1.., thresholds, evf, row 0); MODE 1 rewrites the id's list.
 // grid (1, njobs_y, nvec)
 // ---------------------------------------------------------------------------------------------
+#define EGDST_ENV_IPT 8
+
+// one position r of the union per lane: what it contributes (ng grid points, nt thresholds) and, when WRITE, the
+// output.  Called by all lanes of a warp (valid=false for lanes without a position): the rare crossing chains
+// are run one after the other by the whole warp.
+template <int MODE, bool WRITE>
+EGDST_DEV void egdst_env_item(const egdst_ctx *cx, const EgdstEnvView<MODE> &E, int it, int ist, const double *mgX, const int *mgF,
+                              const int *mgK, const int *mgA, bool valid, int r, double grb, double *ox, double *ov, double *oc, int gcapacity,
+                              double *oth, double *odd, int tcapacity, int gpos, int tpos, int &ng, int &nt, int *err) {
+    double x = 0, v = 0, c = 0;
+    int f = 0, k = 0, a = 0, aprev = 0;
+    bool newx = false, chain = false;
+    ng = 0; nt = 0;
+    if (valid) {
+        x = mgX[r]; f = mgF[r]; k = mgK[r]; a = mgA[r];
+        v = E.v(f, k);
+        newx = (r == 0) || (mgX[r - 1] < x);
+        if (r == 0) {
+            nt = 1;  // (a0, argmax at the first point)  egdst_solver.c:1321-1325
+            if (WRITE) { if (MODE == 0 && tpos < tcapacity) { oth[tpos] = cx->a0; odd[tpos] = (double)a; } tpos += 1; }
+        } else if (newx) { aprev = mgA[r - 1]; chain = aprev != a; }
+    }
+    unsigned need = __ballot_sync(EGDST_FULL, chain);
+    const int lane = threadIdx.x & 31;
+    while (need) {
+        const int src = __ffs(need) - 1;
+        need &= need - 1;
+        const double bx = __shfl_sync(EGDST_FULL, x, src), bv = __shfl_sync(EGDST_FULL, v, src);
+        const int bf = __shfl_sync(EGDST_FULL, f, src), bk = __shfl_sync(EGDST_FULL, k, src);
+        const int bp = __shfl_sync(EGDST_FULL, aprev, src), ba = __shfl_sync(EGDST_FULL, a, src);
+        const int bg = __shfl_sync(EGDST_FULL, gpos, src), bt = __shfl_sync(EGDST_FULL, tpos, src);
+        int cg, ct;
+        if (WRITE)
+            egdst_env_chain(cx, E, it, ist, bx, bv, bf, bk, bp, ba, true, ox + bg, ov + bg, oc + bg, gcapacity - bg,
+                            MODE == 0 ? oth + bt : (double *)0, MODE == 0 ? odd + bt : (double *)0, MODE == 0 ? tcapacity - bt : 0, cg, ct, err);
+        else
+            egdst_env_chain(cx, E, it, ist, bx, bv, bf, bk, bp, ba, false, (double *)0, (double *)0, (double *)0, 0, (double *)0, (double *)0, 0, cg, ct, err);
+        if (lane == src) { ng += cg; nt += ct; gpos += cg; }
+    }
+    if (valid && newx) {
+        bool emit = false;
+        if (a == f) { emit = true; if (WRITE) c = E.c(f, k); }
+        else if (x == grb) {  // last abscissa of the unified grid: keep the interpolated maximum
+            emit = true;
+            if (WRITE) {
+                const int na = E.npts(a);
+                const int ca = egdst_env_cur(egdst_env_count_before(E, a, x, v, f, k), na);
+                v = egdst_env_value(cx, E, it, ist, a, ca, x);
+                c = egdst_env_value2(cx, E, a, ca, x);
+            }
+        }
+        if (emit) {
+            if (WRITE && gpos < gcapacity) { ox[gpos] = x; ov[gpos] = v; oc[gpos] = c; }
+            ng += 1;
+        }
+    }
+}
+
 template <int MODE>
-__global__ void egdst_k_envBC(EgdstDev P, int it) {
-    __shared__ int sh[40];
+__global__ void __launch_bounds__(EGDST_ENVW) egdst_k_envBC(EgdstDev P, int it) {
+    __shared__ long long sh[40];
     __shared__ int s_gbase, s_tbase;
     const int ivec = blockIdx.z;
     int ist, id, slot;
@@ -304,50 +376,28 @@ __global__ void egdst_k_envBC(EgdstDev P, int it) {
     int nact;
     { int lo = 0, hi = Ptot; while (lo < hi) { int mid = (lo + hi) >> 1; if (mgX[mid] <= grb) lo = mid + 1; else hi = mid; } nact = lo; }
     int err = 0;
-    for (int base = 0; base < nact; base += blockDim.x) {
-        const int r = base + threadIdx.x;
-        int ng = 0, nt = 0, emit = 0, chain = 0;
-        double x = 0, v = 0, c = 0; int f = 0, k = 0, a = 0, aprev = 0;
-        if (r < nact) {
-            x = mgX[r]; f = mgF[r]; k = mgK[r]; a = mgA[r];
-            v = E.v(f, k);
-            const bool newx = (r == 0) || (mgX[r - 1] < x);
-            if (r == 0) nt = 1;  // (a0, argmax at the first point)  egdst_solver.c:1321-1325
-            else if (newx) { aprev = mgA[r - 1]; if (aprev != a) chain = 1; }
-            if (chain) {
-                int cg, ct;
-                egdst_env_chain(&cx, E, it, ist, x, v, f, k, aprev, a, false, (double *)0, (double *)0, (double *)0, 0, (double *)0, (double *)0, 0, cg, ct, &err);
-                ng += cg; nt += ct;
-            }
-            if (newx) {
-                if (a == f) { emit = 1; c = E.c(f, k); }
-                else if (x == grb) {  // last abscissa of the unified grid: keep the interpolated maximum
-                    const int na = E.npts(a);
-                    const int ca = egdst_env_cur(egdst_env_count_before(E, a, x, v, f, k), na);
-                    emit = 1;
-                    v = egdst_env_value(&cx, E, it, ist, a, ca, x);
-                    c = egdst_env_value2(&cx, E, a, ca, x);
-                }
-            }
-            ng += emit;
+    const int CH = blockDim.x * EGDST_ENV_IPT;
+    for (int base = 0; base < nact; base += CH) {
+        const int r0 = base + threadIdx.x * EGDST_ENV_IPT;
+        int ngj[EGDST_ENV_IPT], ntj[EGDST_ENV_IPT], ngs = 0, nts = 0;
+#pragma unroll
+        for (int j = 0; j < EGDST_ENV_IPT; j++) {
+            egdst_env_item<MODE, false>(&cx, E, it, ist, mgX, mgF, mgK, mgA, r0 + j < nact, r0 + j, grb, ox, ov, oc, gcapacity, oth, odd, tcapacity, 0, 0, ngj[j], ntj[j], &err);
+            ngs += ngj[j]; nts += ntj[j];
         }
-        int gtot, ttot;
-        const int goff = s_gbase + egdst_block_excl_scan(ng, sh, &gtot);
-        const int toff = s_tbase + egdst_block_excl_scan(nt, sh, &ttot);
-        if (r < nact) {
-            int gpos = goff, tpos = toff;
-            if (r == 0 && MODE == 0 && tpos < tcapacity) { oth[tpos] = cx.a0; odd[tpos] = (double)a; }
-            if (r == 0) tpos += 1;
-            if (chain) {
-                int cg, ct;
-                egdst_env_chain(&cx, E, it, ist, x, E.v(f, k), f, k, aprev, a, true, ox + gpos, ov + gpos, oc + gpos, gcapacity - gpos,
-                                MODE == 0 ? oth + tpos : (double *)0, MODE == 0 ? odd + tpos : (double *)0, MODE == 0 ? tcapacity - tpos : 0, cg, ct, &err);
-                gpos += cg;
-            }
-            if (emit && gpos < gcapacity) { ox[gpos] = x; ov[gpos] = v; oc[gpos] = c; }
+        long long tot;
+        const long long off = egdst_block_excl_scan64(((long long)nts << 32) | (long long)ngs, sh, &tot);
+        int gpos = s_gbase + (int)(off & 0xffffffffLL), tpos = s_tbase + (int)(off >> 32);
+#pragma unroll
+        for (int j = 0; j < EGDST_ENV_IPT; j++) {
+            int g2, t2;
+            // warp-uniform skip: nothing to write for this j anywhere in the warp
+            if (__ballot_sync(EGDST_FULL, (ngj[j] | ntj[j]) != 0))
+                egdst_env_item<MODE, true>(&cx, E, it, ist, mgX, mgF, mgK, mgA, r0 + j < nact, r0 + j, grb, ox, ov, oc, gcapacity, oth, odd, tcapacity, gpos, tpos, g2, t2, &err);
+            gpos += ngj[j]; tpos += ntj[j];
         }
         __syncthreads();
-        if (threadIdx.x == 0) { s_gbase += gtot; s_tbase += ttot; }
+        if (threadIdx.x == 0) { s_gbase += (int)(tot & 0xffffffffLL); s_tbase += (int)(tot >> 32); }
         __syncthreads();
     }
     if (err) egdst_fail(P, ivec, err, it, ist, id);

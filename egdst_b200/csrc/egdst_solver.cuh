@@ -216,36 +216,46 @@ __global__ void egdst_k_seed(EgdstDev P, int it) {
     if (!act) return;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const double beta = discount(&cx, &curr);
-    for (int k = w; k < S.ncand; k += nw) {
-        EgdstAcc a;
-        egdst_eval_nodes(&cx, P, ivec, &curr, S.candA[k], 0, lane, 32, a);
-        egdst_warp_combine(a);
-        if (lane == 0) {
-            int bad = 0;
-            if (a.badq != EGDST_NOBAD) bad = EGDST_PT_C1NEG;
-            else if (fabs(a.checksum - 1) > cx.tolerance) bad = EGDST_PT_CHECKSUM;
-            S.candBad[k] = bad;
-            S.candM[k] = S.candA[k] + utility_marginal_inverse(&cx, &curr, beta * a.rhs);
-        }
-    }
-    __syncthreads();
-    // thread 0: first candidate with M<=mmax is the base point
+    // stage 0 in waves of one candidate per warp: the base point is almost always among the first few
+    // candidates (mmax, (mmax+a0)/2, ...), so later waves rarely run
     double baseA = 0, baseM = 0;
-    if (threadIdx.x == 0) {
-        S.go = 0;
-        int k = 0;
-        for (; k < S.ncand; k++) {
-            if (S.candBad[k] == EGDST_PT_C1NEG) { egdst_fail(P, ivec, EGDST_ERR_NOSAVINGS, it, ist, id); break; }
-            if (S.candBad[k] == EGDST_PT_CHECKSUM) { egdst_fail(P, ivec, EGDST_ERR_CHECKSUM, it, ist, id); break; }
-            if (S.candM[k] <= cx.mmax) { baseA = S.candA[k]; baseM = S.candM[k]; S.go = 1; break; }
-            if (S.candA[k] - cx.a0 < cx.tolerance) { egdst_fail(P, ivec, EGDST_ERR_ADRAW_INIT, it, ist, id); break; }
+    if (threadIdx.x == 0) S.go = 0;
+    __syncthreads();
+    for (int k0 = 0; k0 < S.ncand; k0 += nw) {
+        const int kk = k0 + w;
+        if (kk < S.ncand) {
+            EgdstAcc a;
+            egdst_eval_nodes(&cx, P, ivec, &curr, S.candA[kk], 0, lane, 32, a);
+            egdst_warp_combine(a);
+            if (lane == 0) {
+                int bad = 0;
+                if (a.badq != EGDST_NOBAD) bad = EGDST_PT_C1NEG;
+                else if (fabs(a.checksum - 1) > cx.tolerance) bad = EGDST_PT_CHECKSUM;
+                S.candBad[kk] = bad;
+                S.candM[kk] = S.candA[kk] + utility_marginal_inverse(&cx, &curr, beta * a.rhs);
+            }
         }
-        if (k == S.ncand && !S.go) egdst_fail(P, ivec, EGDST_ERR_ADRAW_INIT, it, ist, id);
+        __syncthreads();
+        // thread 0: first candidate with M<=mmax is the base point (sequential semantics of adraw stage 0)
+        if (threadIdx.x == 0) {
+            const int kend = k0 + nw < S.ncand ? k0 + nw : S.ncand;
+            for (int k = k0; k < kend; k++) {
+                if (S.candBad[k] == EGDST_PT_C1NEG) { egdst_fail(P, ivec, EGDST_ERR_NOSAVINGS, it, ist, id); S.go = -1; break; }
+                if (S.candBad[k] == EGDST_PT_CHECKSUM) { egdst_fail(P, ivec, EGDST_ERR_CHECKSUM, it, ist, id); S.go = -1; break; }
+                if (S.candM[k] <= cx.mmax) { baseA = S.candA[k]; baseM = S.candM[k]; S.go = 1; break; }
+                if (S.candA[k] - cx.a0 < cx.tolerance) { egdst_fail(P, ivec, EGDST_ERR_ADRAW_INIT, it, ist, id); S.go = -1; break; }
+            }
+            if (kend == S.ncand && S.go == 0) { egdst_fail(P, ivec, EGDST_ERR_ADRAW_INIT, it, ist, id); S.go = -1; }
+        }
+        __syncthreads();
+        if (S.go != 0) break;
+    }
+    if (threadIdx.x == 0) {
         S.A = cx.a0;
         S.nresend = S.ncand;  // used as the adraw call counter (loop guard, egdst_solver.c:963)
     }
     __syncthreads();
-    if (!S.go) return;
+    if (S.go != 1) return;
     // stage 1 (+ re-sends): serial in A, parallel over nodes
     double lim1 = 0, lim2 = 0, lim3 = 0, lim2p = 0, lim3p = 0, k3 = 0, lastA = cx.a0, aM = 0, evfa0 = 0.0;
     int stored = 0;
@@ -387,10 +397,10 @@ __global__ void egdst_k_egm(EgdstDev P, int it) {
 // (egdst_solver.c:1100); stored points are those with a finite M and no abort (:640-664).
 // Folds (M or V decreasing, :819) split the list into runs for the secondary envelope.
 // ---------------------------------------------------------------------------------------------
-__global__ void egdst_k_compact(EgdstDev P, int it) {
+#define EGDST_CMP_IPT 8  /* consecutive items per thread: a 10^4-point list is two passes of a 1024-thread CTA */
+__global__ void __launch_bounds__(EGDST_WIDE) egdst_k_compact(EgdstDev P, int it) {
     __shared__ int sh[40];
-    __shared__ int s_stop, s_base, s_fbase, s_late;
-    __shared__ double s_lastX, s_lastV;
+    __shared__ int s_base, s_fbase, s_late;
     const int ivec = blockIdx.z, ist = blockIdx.y, id = blockIdx.x;
     const int sd = egdst_sd(P, ivec, ist, id);
     if (!P.active[sd]) return;
@@ -399,28 +409,43 @@ __global__ void egdst_k_compact(EgdstDev P, int it) {
     const int *rawFlag = P.rawFlag + (size_t)sd * N;
     double *X = P.ptX + (size_t)sd * P.gcap, *Cc = P.ptC + (size_t)sd * P.gcap, *V = P.ptV + (size_t)sd * P.gcap;
     int *runStart = P.runStart + (size_t)sd * (P.gcap + 1);
-    if (threadIdx.x == 0) { s_stop = N - 1; s_base = 0; s_fbase = 0; s_late = N; s_lastX = -EGDST_INF; s_lastV = -EGDST_INF; }
-    __syncthreads();
+    if (threadIdx.x == 0) { s_base = 0; s_fbase = 0; s_late = N; }
     if (rawFlag[0] == EGDST_PT_NONE) { if (threadIdx.x == 0) { P.ptN[sd] = 0; P.nfold[sd] = 0; } return; }
     // first n whose returned M fails "M<mmax" ends the sequence (that point itself is kept)
     int mystop = N - 1;
     for (int n = threadIdx.x; n < N; n += blockDim.x)
         if (!(rawStop[n] < P.cx.mmax)) { mystop = n; break; }
-    mystop = egdst_warp_min(mystop);
-    if ((threadIdx.x & 31) == 0) atomicMin(&s_stop, mystop);
-    __syncthreads();
-    const int nstop = s_stop;
-    // compaction in chunks of blockDim
-    for (int base = 0; base <= nstop; base += blockDim.x) {
-        const int n = base + threadIdx.x;
-        const int f = (n <= nstop) ? rawFlag[n] : EGDST_PT_NONE;
-        const int keep = (f == EGDST_PT_OK);
-        if (n <= nstop && f == EGDST_PT_C1NEG && n > 0) atomicMin(&s_late, n);
-        if (n <= nstop && f == EGDST_PT_CHECKSUM) egdst_fail(P, ivec, EGDST_ERR_CHECKSUM, it, ist, id);
+    const int nstop = egdst_block_min(mystop, sh);  // also orders the s_* initialisation
+    // compaction: every warp owns 32*EGDST_CMP_IPT consecutive points per pass (coalesced, lane-strided);
+    // positions come from ballots within the warp and one block scan of the warp totals per pass
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const unsigned ltmask = (1u << lane) - 1u;
+    const int WCH = 32 * EGDST_CMP_IPT, CH = nw * WCH;
+    for (int base = 0; base <= nstop; base += CH) {
+        const int wbase = base + w * WCH;
+        unsigned bal[EGDST_CMP_IPT];
+        int wtotal = 0;
+#pragma unroll
+        for (int j = 0; j < EGDST_CMP_IPT; j++) {
+            const int n = wbase + j * 32 + lane;
+            const int f = (n <= nstop) ? rawFlag[n] : EGDST_PT_NONE;
+            if (n <= nstop && f == EGDST_PT_C1NEG && n > 0) atomicMin(&s_late, n);
+            if (n <= nstop && f == EGDST_PT_CHECKSUM) egdst_fail(P, ivec, EGDST_ERR_CHECKSUM, it, ist, id);
+            bal[j] = __ballot_sync(EGDST_FULL, f == EGDST_PT_OK);
+            wtotal += __popc(bal[j]);
+        }
         int total;
-        const int off = egdst_block_excl_scan(keep, sh, &total);
-        const int dst = s_base + off;
-        if (keep && dst < P.gcap) { X[dst] = rawM[n]; Cc[dst] = rawC[n]; V[dst] = rawV[n]; }
+        int woff = egdst_block_excl_scan(lane == 0 ? wtotal : 0, sh, &total);
+        woff = __shfl_sync(EGDST_FULL, woff, 0) + s_base;
+#pragma unroll
+        for (int j = 0; j < EGDST_CMP_IPT; j++) {
+            const int n = wbase + j * 32 + lane;
+            if (bal[j] & (1u << lane)) {
+                const int dst = woff + __popc(bal[j] & ltmask);
+                if (dst < P.gcap) { X[dst] = rawM[n]; Cc[dst] = rawC[n]; V[dst] = rawV[n]; }
+            }
+            woff += __popc(bal[j]);
+        }
         __syncthreads();
         if (threadIdx.x == 0) s_base += total;
         __syncthreads();
@@ -432,14 +457,27 @@ __global__ void egdst_k_compact(EgdstDev P, int it) {
         runStart[0] = 0;
     }
     __syncthreads();
-    // fold detection over the compacted list
-    for (int base = 0; base < nvd; base += blockDim.x) {
-        const int i = base + threadIdx.x;
-        int fold = 0;
-        if (i > 0 && i < nvd) fold = (X[i - 1] > X[i] || V[i - 1] > V[i]) ? 1 : 0;
+    // fold detection over the compacted list (same scheme)
+    for (int base = 0; base < nvd; base += CH) {
+        const int wbase = base + w * WCH;
+        unsigned bal[EGDST_CMP_IPT];
+        int wtotal = 0;
+#pragma unroll
+        for (int j = 0; j < EGDST_CMP_IPT; j++) {
+            const int i = wbase + j * 32 + lane;
+            bool fold = false;
+            if (i > 0 && i < nvd) fold = X[i - 1] > X[i] || V[i - 1] > V[i];
+            bal[j] = __ballot_sync(EGDST_FULL, fold);
+            wtotal += __popc(bal[j]);
+        }
         int total;
-        const int off = egdst_block_excl_scan(fold, sh, &total);
-        if (fold) runStart[s_fbase + off + 1] = i;
+        int woff = egdst_block_excl_scan(lane == 0 ? wtotal : 0, sh, &total);
+        woff = __shfl_sync(EGDST_FULL, woff, 0) + s_fbase;
+#pragma unroll
+        for (int j = 0; j < EGDST_CMP_IPT; j++) {
+            if (bal[j] & (1u << lane)) runStart[woff + __popc(bal[j] & ltmask) + 1] = wbase + j * 32 + lane;
+            woff += __popc(bal[j]);
+        }
         __syncthreads();
         if (threadIdx.x == 0) s_fbase += total;
         __syncthreads();

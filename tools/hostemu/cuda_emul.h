@@ -79,6 +79,8 @@ inline T __shfl_sync(unsigned, T v, int src) { return emu_exchange(v, src & 31);
 template <class T>
 inline T __shfl_down_sync(unsigned, T v, int o) { const int lane = emu_lin & 31; return emu_exchange(v, lane + o < 32 ? lane + o : -1); }
 template <class T>
+inline T __shfl_xor_sync(unsigned, T v, int o) { const int lane = emu_lin & 31; return emu_exchange(v, lane ^ o); }
+template <class T>
 inline T __shfl_up_sync(unsigned, T v, int o) { const int lane = emu_lin & 31; return emu_exchange(v, lane - o); }
 inline unsigned __ballot_sync(unsigned, int pred) {
     EmuWarp &W = emu_warp();
