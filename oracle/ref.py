@@ -34,7 +34,7 @@ REFSRC = os.path.join(REFROOT, "@egdstmodel")
 OUTROOT = os.path.join(HERE, "_ref")
 
 BASE_FLAGS = ["-std=gnu99", "-O2", "-fno-inline", "-ffp-contract=off", "-include", "stdbool.h", "-fPIC", "-w"]
-NOISE_FLAGS = ["-std=gnu99", "-O2", "-fno-inline", "-march=native", "-ffp-contract=fast", "-include", "stdbool.h", "-fPIC", "-w"]
+NOISE_FLAGS = ["-std=gnu99", "-O2", "-fno-inline", "-march=x86-64-v3", "-ffp-contract=fast", "-include", "stdbool.h", "-fPIC", "-w"]
 
 
 def reference_available() -> bool:

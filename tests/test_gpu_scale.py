@@ -1,0 +1,151 @@
+"""GPU tests at BASELINE sizes and of the sharded / batched paths:
+S1 (retirement2 at 10k x 100 x 50) and S5 against the reference oracle, S1b under the oracle noise-floor mask,
+size-independent invariants, Philox sharding invariance, moments, and batched solves."""
+import numpy as np
+import pytest
+
+from egdst_b200 import distributed as D
+from egdst_b200 import examples
+from oracle import ref
+from tests.oracles import oracle_for
+from tests.parity import cell_errors, solution_errors
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+def _solve(m):
+    m.compile()
+    m.solve()
+    assert m._solution.status()[0] == 0, m._solution.status()
+    return m
+
+
+def _invariants(m):
+    for it in range(m.nt):
+        M = m.M[0][it]
+        assert np.all(np.diff(M[:, 0]) > 0), "M not strictly increasing at it=%d" % it
+        A = M[:, 0] - M[:, 1]
+        assert np.all(A >= m.a0 - 1e-12) and abs(A.min() - m.a0) < 1e-9
+        assert np.array_equal(M[:, 2], A)
+        D_ = m.D[0][it]
+        assert D_[0, 1] == m.a0 and np.all(np.diff(D_[:, 1]) > 0)
+        # every threshold but the first is the left member of a double point exactly DOUBLEPOINT_DELTA apart
+        for th in D_[1:, 1]:
+            j = np.searchsorted(M[:, 0], th)
+            assert M[j, 0] == th and abs(M[j + 1, 0] - th - 1e-10) < 1e-15
+
+
+@pytest.fixture(scope="module")
+def s1():
+    return _solve(examples.retirement2_scaled())
+
+
+def test_s1_full_size_matches_reference(s1):
+    orc = oracle_for(s1)
+    Mr, Dr = orc.solve()
+    e = solution_errors(s1.M, s1.D, Mr, Dr)
+    assert e["cells"] == 50
+    assert e["C"] < TOL and e["V"] < TOL and e["evf"] < TOL and e["TH"] < TOL and e["Dseq"], e
+    assert e["rowdiff"] <= 2
+    _invariants(s1)
+    # S2 parity sub-run: 10^4 agents on a shared host randstream
+    rng = np.random.default_rng(20141)
+    nsim = 10_000
+    init = np.column_stack([np.ones(nsim), s1.a0 + 0.5 * (s1.mmax - s1.a0) * rng.random(nsim)])
+    rs = rng.random(4 * nsim * s1.nt)
+    s1.sim(init, "own_shocks", randstream=rs)
+    sr = orc.simulate(Mr, Dr, init, rs, 0)
+    both = ~np.isnan(sr)
+    assert np.array_equal(np.isnan(s1.sims), np.isnan(sr))
+    # identical discrete choices except where cash is within 1e-9 of a threshold
+    diff = (s1.sims[:, :, 4] != sr[:, :, 4]) & both[:, :, 4]
+    for i, t in zip(*np.nonzero(diff)):
+        assert np.min(np.abs(Dr[0][t][:, 1] - sr[i, t, 0])) < 1e-9
+    ok = both & ~np.repeat(diff[:, :, None], sr.shape[2], axis=2)
+    fin = ok & np.isfinite(sr)
+    assert np.max(np.abs(s1.sims[fin] - sr[fin]) / np.maximum(1, np.abs(sr[fin]))) < TOL
+
+
+def test_s5_retirement1_2000_points(s1):
+    m = _solve(examples.retirement1(T=50, ngridm=2000, ngridmax=4000, nthrhmax=2000, interest=0.02))
+    Mr, Dr = oracle_for(m).solve()
+    e = solution_errors(m.M, m.D, Mr, Dr)
+    assert e["C"] < TOL and e["V"] < TOL and e["TH"] < TOL and e["Dseq"], e
+
+
+def test_s1b_shipped_parameters_under_noise_floor():
+    """Shipped interest=0.045 at T=40 sits next to the reference's own instability: parity is
+    asserted only in the cells where two differently rounded builds of the reference agree with each other."""
+    m = _solve(examples.retirement(T=40, ngridm=2000, ngridmax=4000, nthrhmax=2000, ny=20))
+    base = ref.Reference(m)
+    Mb, Db = base.solve()
+    noise = ref.Reference(m, variant="noise")
+    Mn, Dn = noise.solve()
+    checked = 0
+    for it in range(m.nt):
+        en = cell_errors(Mn[0][it], Dn[0][it], Mb[0][it], Db[0][it])
+        if max(en["C"], en["V"]) < 1e-11 and en["nth"][0] == en["nth"][1]:
+            eg = cell_errors(m.M[0][it], m.D[0][it], Mb[0][it], Db[0][it])
+            assert eg["C"] < TOL and eg["V"] < TOL, (it, eg, en)
+            checked += 1
+    assert checked >= m.nt // 2
+
+
+def test_philox_results_do_not_depend_on_sharding(s1):
+    lib = s1._capi()
+    sol = s1._solution
+    rng = np.random.default_rng(3)
+    n = 5000
+    init = np.column_stack([np.ones(n), s1.a0 + 0.5 * (s1.mmax - s1.a0) * rng.random(n)])
+    full, mom = lib.simulate_philox(s1, sol, init, 12345, want_sims=True, want_moments=True)
+    parts, moms = [], []
+    for world in (3,):
+        for r in range(world):
+            lo, hi = D.shard_range(n, r, world)
+            s_, m_ = lib.simulate_philox(s1, sol, init[lo:hi], 12345, agent0=lo, want_sims=True, want_moments=True)
+            parts.append(s_); moms.append(m_)
+    cat = np.concatenate(parts, axis=0)
+    assert np.array_equal(np.isnan(cat), np.isnan(full)) and np.array_equal(np.nan_to_num(cat), np.nan_to_num(full))
+    msum = sum(moms)
+    assert np.allclose(msum, mom, rtol=1e-12, atol=1e-9)
+    # moments against numpy on the full path array ([3, nsimout, nt])
+    alive = ~np.isnan(full)
+    s1_ = np.where(alive, full, 0.0).sum(axis=0).T
+    fin = np.isfinite(s1_)
+    assert np.allclose(mom[0][fin], s1_[fin], rtol=1e-11, atol=1e-9)
+    assert np.array_equal(mom[2], alive.sum(axis=0).T.astype(float))
+    # a different seed gives different shocks; same seed is reproducible
+    again, _ = lib.simulate_philox(s1, sol, init, 12345, want_sims=True)
+    other, _ = lib.simulate_philox(s1, sol, init, 54321, want_sims=True)
+    assert np.array_equal(np.nan_to_num(again), np.nan_to_num(full)) and not np.array_equal(np.nan_to_num(other), np.nan_to_num(full))
+    # uniforms are U(0,1): the lognormal shock column has mean ~ 1 (mu = -sigma^2/2)
+    assert abs(np.nanmean(full[:, 1:, 8]) - 1.0) < 0.01
+
+
+def test_batched_solve_matches_individual_solves_and_reference():
+    m = examples.deaton2()
+    m.compile()
+    lib = m._capi()
+    rng = np.random.default_rng(4096)
+    nvec = 24
+    params = np.column_stack([rng.uniform(0.0, 0.05, nvec), rng.uniform(0.75, 1.75, nvec)])  # (interest, income)
+    sol = lib.solve_batch(m, params)
+    assert sol.warning is None, sol.warning
+    for i in (0, 7, 23):
+        mi = examples.deaton2(interest=params[i, 0], income=params[i, 1])
+        mi.compile(); mi.solve()
+        Mb, Db = sol.cells(i)
+        for it in range(m.nt):
+            assert np.array_equal(Mb[0][it], mi.M[0][it]) and np.array_equal(Db[0][it], mi.D[0][it])
+        Mr, Dr = oracle_for(mi).solve()
+        e = solution_errors(Mb, Db, Mr, Dr)
+        assert e["C"] < TOL and e["V"] < TOL and e["Dseq"], (i, e)
+    # sweep: per-vector moments through the sharded entry point (world = 1 here)
+    init = np.column_stack([np.ones(256), np.full(256, 0.25)])
+    table, (lo, hi) = D.solve_batch_sharded(lib, m, params, init, seed=7)
+    assert (lo, hi) == (0, nvec) and table.shape == (nvec, 3, m.nsimout(), m.nt)
+    assert np.all(table[:, 2, 0, :] == 256)  # everybody alive (survival = 1)
+    # higher income => higher mean consumption in the first period, all else equal is not guaranteed across interest,
+    # so just check the moments are finite and differ across vectors
+    assert np.all(np.isfinite(table[:, 0, 1, :])) and np.ptp(table[:, 0, 1, 5]) > 0
