@@ -156,7 +156,7 @@ class ModelLibrary:
                "egdst_profile_enable", "egdst_profile_read", "egdst_solve", "egdst_solve_batch", "egdst_resolve", "egdst_solution_sizes",
                "egdst_solution_export", "egdst_solution_status", "egdst_solution_nvec", "egdst_solution_units",
                "egdst_free_solution", "egdst_solution_import", "egdst_simulate", "egdst_simulate_philox",
-               "egdst_simulate_device", "egdst_call"]
+               "egdst_simulate_device", "egdst_sim_moments", "egdst_sim_moments_device", "egdst_call"]
 
     def __init__(self, path: str):
         if not os.path.isfile(path):
@@ -190,6 +190,8 @@ class ModelLibrary:
         L.egdst_simulate_device.argtypes = [C.POINTER(EgdstDesc), vp, C.c_int, vp, C.c_int, C.c_longlong, C.c_ulonglong,
                                             vp, C.c_int, vp, vp]
         L.egdst_call.argtypes = [C.POINTER(EgdstDesc), vp, C.c_int, _dp, C.c_int, C.c_int, _dp]
+        L.egdst_sim_moments.argtypes = [C.POINTER(EgdstDesc), vp, C.c_int, C.c_int, _dp, C.c_int, C.c_longlong, C.c_ulonglong, _dp]
+        L.egdst_sim_moments_device.argtypes = [C.POINTER(EgdstDesc), vp, C.c_int, C.c_int, vp, C.c_int, C.c_longlong, C.c_ulonglong, vp]
         if L.egdst_abi_version() != ABI_VERSION:
             raise RuntimeError("ABI version mismatch in %s" % path)
 
@@ -316,6 +318,28 @@ class ModelLibrary:
         out_s = np.transpose(sims.reshape((nso, nt, nsim), order="F"), (2, 1, 0)) if want_sims else None
         out_m = mom.reshape((3, nso, nt), order="F") if want_moments else None
         return out_s, out_m
+
+    def sim_moments(self, model, sol: Solution, init, seed: int, agent0: int = 0, ivec0: int = 0, nvec: Optional[int] = None) -> np.ndarray:
+        """Moments [nvec, 3, nsimout, nt] of the same agents under parameter vectors ivec0.. of a batched solution."""
+        d = Desc(model)
+        init = np.atleast_2d(np.asarray(init, dtype=np.float64))
+        nsim = init.shape[0]
+        initf = _arr(init.ravel(order="F"))
+        nvec = sol.nvec - ivec0 if nvec is None else nvec
+        nso, nt = model.nsimout(), model.nt
+        mom = np.zeros(nvec * 3 * nso * nt, dtype=np.float64)
+        rc = self.L.egdst_sim_moments(C.byref(d.c), sol.handle, ivec0, nvec, _ptr(initf), nsim, agent0, seed, _ptr(mom))
+        if rc:
+            self._raise(rc)
+        return np.stack([mom[i * 3 * nso * nt:(i + 1) * 3 * nso * nt].reshape((3, nso, nt), order="F") for i in range(nvec)])
+
+    def sim_moments_device(self, model, sol: Solution, d_init: int, nsim: int, agent0: int, seed: int, d_moments: int,
+                           ivec0: int = 0, nvec: Optional[int] = None, desc: "Desc" = None):
+        d = desc or Desc(model)
+        nvec = sol.nvec - ivec0 if nvec is None else nvec
+        rc = self.L.egdst_sim_moments_device(C.byref(d.c), sol.handle, ivec0, nvec, C.c_void_p(d_init), nsim, agent0, seed, C.c_void_p(d_moments))
+        if rc:
+            self._raise(rc)
 
     def call(self, model, sol: Solution, sw: int, args: np.ndarray) -> np.ndarray:
         d = Desc(model)

@@ -149,10 +149,15 @@ __global__ void __launch_bounds__(EGDST_SIM_BLOCK, EGDST_SIM_MINBLOCKS) egdst_k_
     constexpr int NSO = EGDST_NSIMOUT_MAX;   // the model image fixes nsimout (checked on the host)
     constexpr int TS = NSO | 1;              // odd record stride: conflict-free staging and column walks
     constexpr int WPB = EGDST_SIM_BLOCK / 32;
-    egdst_ctx cx; egdst_load_ctx(P, S.ivec, cx);
+    // blockIdx.y walks the parameter vectors of a batched sweep: same agents and shocks under every vector,
+    // per-vector output blocks (sims [nvec][nsimout,nt,nsim], moments [nvec][3,nsimout,nt])
+    const int ivec = S.ivec + blockIdx.y;
+    egdst_ctx cx; egdst_load_ctx(P, ivec, cx);
     cx.status = 0;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int nt = P.NT;
+    if (S.sims) S.sims += (size_t)blockIdx.y * EGDST_NSIMOUT_MAX * nt * S.nsim;
+    if (S.moments) S.moments += (size_t)blockIdx.y * EGDST_NSIMOUT_MAX * nt * 3;
     double *tile = egdst_sim_smem + (size_t)w * 32 * TS;
     double *mom = egdst_sim_smem + (size_t)WPB * 32 * TS;
     const double NaN = EGDST_NAN;
@@ -229,7 +234,7 @@ __global__ void __launch_bounds__(EGDST_SIM_BLOCK, EGDST_SIM_MINBLOCKS) egdst_k_
             }
             if (state == 0) {
                 // policy (egdst_simulator.c:145-199)
-                const int cell = egdst_cell(P, S.ivec, it, cur.ist);
+                const int cell = egdst_cell(P, ivec, it, cur.ist);
                 const int nm = P.mlen[cell];
                 if (nm < 2) { state = 1; }
                 else {

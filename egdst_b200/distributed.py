@@ -97,12 +97,8 @@ def solve_batch_sharded(lib, model, params: np.ndarray, init: np.ndarray, seed: 
         if solve_sim_fn is None:
             def solve_sim_fn(pblock, first):
                 sol = lib.solve_batch(model, pblock)
-                out = np.zeros((pblock.shape[0], 3, nso, nt))
-                for i in range(pblock.shape[0]):
-                    # the same agents (global ids 0..nsim-1) and the same shocks under every parameter vector
-                    _, m = lib.simulate_philox(model, sol, init, seed, agent0=0, ivec=i, want_sims=False, want_moments=True)
-                    out[i] = m
-                return out
+                # the same agents (global ids 0..nsim-1) and the same shocks under every parameter vector, one launch
+                return lib.sim_moments(model, sol, init, seed, agent0=0)
         table[lo:hi] = solve_sim_fn(params[lo:hi], lo)
     flat = table.reshape(-1)
     all_reduce_moments(flat, group)

@@ -106,6 +106,15 @@ int egdst_simulate_device(const egdst_desc *d, egdst_solution *s, int ivec, cons
                           long long agent0, unsigned long long seed, const double *d_randstream, int rndtype,
                           double *d_sims, double *d_moments);
 
+/* Estimation sweeps: moments-only simulation of the same agents (and the same Philox shocks) under parameter
+ * vectors ivec0..ivec0+nvec-1 of a batched solution, in one launch.  moments: [nvec][3*nsimout*nt].
+ * The _device variant takes device pointers, is asynchronous on the library stream and accumulates into
+ * d_moments (the caller zeroes it), so a rank can all-reduce the buffer right after. */
+int egdst_sim_moments(const egdst_desc *d, egdst_solution *s, int ivec0, int nvec, const double *init, int nsim,
+                      long long agent0, unsigned long long seed, double *moments);
+int egdst_sim_moments_device(const egdst_desc *d, egdst_solution *s, int ivec0, int nvec, const double *d_init, int nsim,
+                             long long agent0, unsigned long long seed, double *d_moments);
+
 /* ---- call -------------------------------------------------------------------------------- */
 /* sw: 1 utility, 2 marginal utility, 3 discount, 4 budget, 5 marginal budget, 6 value function;
  * args: [narg*k] column-major with k = 4,4,2,6,6,3 (egdst_call.c:45-58); res: [narg]. */

@@ -146,6 +146,10 @@ def test_batched_solve_matches_individual_solves_and_reference():
     table, (lo, hi) = D.solve_batch_sharded(lib, m, params, init, seed=7)
     assert (lo, hi) == (0, nvec) and table.shape == (nvec, 3, m.nsimout(), m.nt)
     assert np.all(table[:, 2, 0, :] == 256)  # everybody alive (survival = 1)
+    # the one-launch batched moments equal the per-vector simulations
+    for i in (0, 7, 23):
+        _, mi_ = lib.simulate_philox(m, sol, init, 7, ivec=i, want_sims=False, want_moments=True)
+        assert np.allclose(table[i], mi_, rtol=1e-12, atol=1e-10)
     # higher income => higher mean consumption in the first period, all else equal is not guaranteed across interest,
     # so just check the moments are finite and differ across vectors
     assert np.all(np.isfinite(table[:, 0, 1, :])) and np.ptp(table[:, 0, 1, 5]) > 0
