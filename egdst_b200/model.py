@@ -449,6 +449,75 @@ class EgdstModel:
     def nsimout(self) -> int:
         return 11 + self.nnst + self.nnd + len(self.eq)
 
+    # ------------------------------------------------------------------ (de)serialisation of the public properties
+    _SCALARS = ("label", "t0", "T", "mmax", "ngridm", "ngridmax", "nthrhmax", "ny", "a0", "discount", "survival")
+
+    def to_dict(self) -> Dict[str, Any]:
+        """The public properties as plain data, in the shape ``jsonencode(struct(model))`` gives in MATLAB."""
+        d: Dict[str, Any] = {k: getattr(self, k) for k in self._SCALARS}
+        d["s"] = [{"name": v["name"], "values": [dict(x) for x in v["values"]]} for v in self.s]
+        d["d"] = [{"name": v["name"], "values": [dict(x) for x in v["values"]]} for v in self.d]
+        d["u"] = dict(self.u)
+        d["transform"] = dict(self.transform)
+        d["budget"] = dict(self.budget)
+        d["shock"] = dict(self.shock)
+        d["trpr"] = [{"varindex": t["varindex"], "cases": [dict(c) for c in t["cases"]]} for t in self.trpr]
+        d["choiceset"] = {"defaultallow": self.choiceset["defaultallow"], "rules": [dict(r) for r in self.choiceset["rules"]]}
+        d["feasible"] = {"defaultfeasible": self.feasible["defaultfeasible"], "rules": [dict(r) for r in self.feasible["rules"]]}
+        d["eq"] = [dict(e) for e in self.eq]
+        d["coef"] = [dict(c) for c in self.coef]
+        d["param"] = [dict(p) for p in self.param]
+        d["cflags"] = dict(self.cflags)
+        return d
+
+    @classmethod
+    def from_dict(cls, d: Dict[str, Any]) -> "EgdstModel":
+        def lst(x):  # jsonencode collapses 1-element struct arrays to a struct
+            return [] if x is None else (x if isinstance(x, list) else [x])
+        m = cls(d.get("label", "<no name>"))
+        m.t0, m.T, m.mmax = d["t0"], d["T"], d["mmax"]
+        m.ngridmax = d.get("ngridmax", 100)
+        m.ngridm = d.get("ngridm", 10)
+        m.nthrhmax, m.ny, m.a0 = d.get("nthrhmax", 100), d.get("ny", 1), d.get("a0", 0.0)
+        for kind in ("s", "d"):
+            for v in lst(d.get(kind)):
+                spec = []
+                for x in lst(v["values"]):
+                    spec += [x["value"], x["description"]]
+                setattr(m, kind, (v["name"], spec))
+        for k, v in d["u"].items():
+            if v:
+                m.u = (k, v)
+        if d.get("transform"):
+            m.transform = (d["transform"]["direct"], d["transform"]["inverse"])
+        for k in ("cashinhand", "marginal"):
+            m.budget = (k, d["budget"][k])
+        m.shock = d["shock"].get("type", "lognormal")
+        m.shock = ("mu", d["shock"]["mu"])
+        m.shock = ("sigma", d["shock"]["sigma"])
+        m.discount = d["discount"]
+        m.survival = d.get("survival", "1.0")
+        for p in lst(d.get("param")):
+            m.param = (p["ref"], p.get("description", ""), p["value"])
+        for c in lst(d.get("coef")):
+            m.coef = (c["ref"], c.get("description", ""), c["array"])
+        for e in lst(d.get("eq")):
+            m.eq = (e["ref"], e.get("description", ""), e["expression"], e.get("type", "current"))
+        for t in lst(d.get("trpr")):
+            for c in lst(t["cases"]):
+                m.trpr = (int(t["varindex"]), c["condition"], c["prob"])
+        cs = d.get("choiceset") or {}
+        m.choiceset = ("defaultallow", bool(cs.get("defaultallow", True)))
+        for r in lst(cs.get("rules")):
+            m.choiceset = (r["condition"], r.get("description", ""))
+        fs = d.get("feasible") or {}
+        m.feasible = ("defaultfeasible", bool(fs.get("defaultfeasible", True)))
+        for r in lst(fs.get("rules")):
+            m.feasible = (r["condition"], r.get("description", ""))
+        if d.get("cflags"):
+            m.cflags = {k: str(v) for k, v in d["cflags"].items()}
+        return m
+
 
 def env_dir(default: str) -> str:
     return os.environ.get("EGDST_B200_BUILD_DIR", default)

@@ -1,0 +1,107 @@
+"""Host-side logic that needs no GPU: code generation rules, quadrature, state enumeration, optim_* inference,
+model (de)serialisation, and the oracle (compiled reference) against the committed golden vectors."""
+import json
+
+import numpy as np
+import pytest
+
+from egdst_b200 import codegen, examples
+from egdst_b200.model import EgdstModel
+from egdst_b200.quadrature import model_quadrature, quadpoints
+from tests import goldens
+from tests.parity import solution_errors
+
+
+def test_quadrature_gauss_legendre_on_unit_interval():
+    for n in (1, 2, 10, 100):
+        x, w = quadpoints(n, 0.0, 1.0)
+        assert abs(w.sum() - 1.0) < 1e-13 and np.all((x > 0) & (x < 1)) and np.all(np.diff(x) > 0)
+        # exact for polynomials up to degree 2n-1
+        for k in range(0, min(2 * n, 12)):
+            assert abs((w * x ** k).sum() - 1.0 / (k + 1)) < 1e-12
+    q = model_quadrature(10)
+    assert q.shape == (20,) and abs(q[:10].sum() - 1) < 1e-13
+
+
+def test_state_enumeration_first_variable_slowest():
+    m = EgdstModel("t")
+    m.s = ("a", [0, "a0", 1, "a1"])
+    m.s = ("b", [10, "b0", 20, "b1", 30, "b2"])
+    assert m.nst == 6 and m.nnst == 2 and m.stm == [2, 3, 3, 1]
+    assert m.states.tolist() == [[0, 10], [0, 20], [0, 30], [1, 10], [1, 20], [1, 30]]
+
+
+def test_std_convert_rules_and_order():
+    m = examples.retirement2()
+    s = codegen.std_convert(m, "min(savings,cash)+wage_income*(id!=0)+age+dc1+st1")
+    assert "MIN(next->savings,curr->cash)" in s and "wage_income(curr,next)" in s and "(curr->it+t0)" in s
+    assert "decisions[curr->id+0*nd]" in s and "states[curr->ist+0*nst]" in s
+
+
+def test_optim_inference_matches_the_shipped_models():
+    want = {"retirement2": dict(optim_MUnoD=True, optim_UnoD=False), "deaton2": dict(optim_MUnoD=True, optim_UnoD=True),
+            "occ3": dict(optim_MUnoD=True, optim_UnoD=False)}
+    for name, w in want.items():
+        m = examples.ALL[name](); m.prepare()
+        for k, v in w.items():
+            assert bool(m.optim[k]) == v, (name, k, m.optim)
+
+
+def test_model_dict_roundtrip_preserves_the_generated_source():
+    for name in examples.ALL:
+        m = goldens.model_for(name); m.prepare()
+        m2 = EgdstModel.from_dict(json.loads(json.dumps(m.to_dict()))); m2.prepare()
+        assert codegen.emit_devspec(m) == codegen.emit_devspec(m2), name
+        assert codegen.model_key(m) == codegen.model_key(m2)
+        assert (m2.nst, m2.nd, m2.ngridm, m2.ngridmax, m2.ny) == (m.nst, m.nd, m.ngridm, m.ngridmax, m.ny)
+        assert np.array_equal(m.param_vector(), m2.param_vector())
+
+
+def test_duplicate_refs_and_reserved_words_are_rejected():
+    m = EgdstModel("t")
+    m.param = ("x", "", 1.0)
+    with pytest.raises(ValueError):
+        m.param = ("x", "", 2.0)
+    with pytest.raises(ValueError):
+        m.param = ("cash", "", 2.0)
+
+
+def test_setparam_getparam():
+    m = examples.deaton2()
+    m.setparam("interest", 0.03, 2, 1.5)
+    assert m.getparam("interest") == 0.03 and m.getparam(2) == 1.5
+    m.setparam([0.01, 1.0])
+    assert m.getparam().tolist() == [0.01, 1.0]
+    with pytest.raises(ValueError):
+        m.setparam([1.0])
+
+
+@pytest.mark.parametrize("name", ["cake1", "cake2", "deaton2", "retirement2", "model2"])
+def test_oracle_reproduces_golden_vectors(name):
+    """Pins the checker: the compiled reference (prebuilt oracle/_ref or built from /root/reference) against the
+    committed outputs of the reference on its own example models."""
+    from tests.oracles import oracle_for, ref_available
+    m = goldens.model_for(name)
+    if not ref_available(m):
+        pytest.skip("oracle/_ref not built and /root/reference absent")
+    g = goldens.load(name)
+    orc = oracle_for(m)
+    Mr, Dr = orc.solve()
+    e = solution_errors(Mr, Dr, g["M"], g["D"])
+    assert e["C"] < 1e-12 and e["V"] < 1e-12 and e["TH"] < 1e-12 and e["Dseq"] and e["rowdiff"] == 0, e
+    sims = orc.simulate(Mr, Dr, g["init"], g["randstream"], 0)
+    se = goldens.sims_errors(sims, g["sims"])
+    assert se["nan_mismatch"] == 0 and se["discrete_mismatch"] == 0 and se["max"] < 1e-12
+
+
+def test_cake_closed_forms_in_golden_vectors():
+    # cake1: c_t(M) = M/(T-t+1) with T=25 periods; cake2: c_t(M) = M(1-b)/(1-b^(T-t+1)), b=.75
+    g1, g2 = goldens.load("cake1"), goldens.load("cake2")
+    for it in (0, 5, 10, 24):
+        M = g1["M"][0][it]
+        ok = M[:, 0] > 1e-6
+        assert np.allclose(M[ok, 1], M[ok, 0] / (25 - it), rtol=1e-10)
+        M = g2["M"][0][it]
+        ok = M[:, 0] > 1e-6
+        b = 0.75
+        assert np.allclose(M[ok, 1], M[ok, 0] * (1 - b) / (1 - b ** (25 - it)), rtol=1e-10)
