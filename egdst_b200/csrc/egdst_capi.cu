@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -108,13 +109,29 @@ struct egdst_solution {
     EgdstLutEntry *d_simlut;
     int sim_rowcap, sim_lutcap, sim_mbits;
     bool sim_valid;
+    size_t bytes;   // device bytes owned (workspace cache policy)
+    int dims[12];   // shape signature for re-use
 };
 
 template <class T>
 static cudaError_t dalloc(egdst_solution *s, T **p, size_t n) {
     cudaError_t e = cudaMalloc((void **)p, (n ? n : 1) * sizeof(T));
-    if (e == cudaSuccess) s->owned.push_back((void *)*p);
+    if (e == cudaSuccess) { s->owned.push_back((void *)*p); s->bytes += (n ? n : 1) * sizeof(T); }
     return e;
+}
+
+// One released solution object is kept for re-use by the next egdst_solve of the same shape: the MEX gateway
+// solves, exports and frees on every call, and ~45 cudaMalloc/cudaFree pairs cost far more than the solve itself.
+static std::mutex g_cache_mu;
+static egdst_solution *g_cached = 0;
+static const size_t EGDST_CACHE_MAX_BYTES = (size_t)2 << 30;
+static void destroy_solution(egdst_solution *s) {
+    cudaSetDevice(s->device);
+    for (void *p : s->owned) cudaFree(p);
+    if (s->d_pack) cudaFree(s->d_pack);
+    if (s->d_simivl) cudaFree(s->d_simivl);
+    if (s->d_simlut) cudaFree(s->d_simlut);
+    delete s;
 }
 
 // quadrature abscissas -> standard normal quantiles (egdst_solver.c:162-164), on the device
@@ -177,7 +194,23 @@ static int create_solution(const egdst_desc *d, int nvec, egdst_solution **out) 
     int rc = fill_ctx(d, &cx);
     if (rc) return rc;
     if ((rc = check_device(d->device))) return rc;
+    const int dims[12] = {d->device, nvec, d->T - d->t0 + 1, d->nst, d->nd, d->ngridm, d->ngridmax, d->nthrhmax, d->ny, d->nnst, d->nnd, 0};
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        if (g_cached && memcmp(g_cached->dims, dims, sizeof(dims)) == 0) {
+            egdst_solution *s = g_cached;
+            g_cached = 0;
+            s->sizes_valid = false; s->sim_valid = false; s->neq = d->neq;
+            const double *stm = s->d_stm, *states = s->d_states, *decisions = s->d_decisions;
+            s->P.cx = cx; s->P.cx.stm = stm; s->P.cx.states = states; s->P.cx.decisions = decisions;
+            s->P.bparams = 0;
+            cudaMemset(s->P.units, 0, sizeof(unsigned long long) * nvec);
+            *out = s;
+            return 0;
+        }
+    }
     egdst_solution *s = new egdst_solution();
+    s->bytes = 0; memcpy(s->dims, dims, sizeof(dims));
     s->device = d->device; s->sizes_valid = false; s->d_simivl = 0; s->d_simlut = 0; s->sim_rowcap = 0; s->sim_lutcap = 0; s->sim_mbits = 0; s->sim_valid = false; s->d_pack = 0; s->pack_cap = 0; s->neq = d->neq;
     EgdstDev &P = s->P;
     memset(&P, 0, sizeof(P));
@@ -186,7 +219,7 @@ static int create_solution(const egdst_desc *d, int nvec, egdst_solution **out) 
     const int nst = d->nst, nd = d->nd;
     s->ncell = nvec * P.NT * nst; s->nsd = nvec * nst * nd; s->nslot = s->nsd + nvec * nst;
     P.envcap = (nd > 2 ? nd : 2) * P.gcap + 2;
-#define DA(ptr, n) do { cudaError_t e_ = dalloc(s, &(ptr), (size_t)(n)); if (e_ != cudaSuccess) { egdst_free_solution(s); return fail(2, std::string("cudaMalloc failed: ") + cudaGetErrorString(e_)); } } while (0)
+#define DA(ptr, n) do { cudaError_t e_ = dalloc(s, &(ptr), (size_t)(n)); if (e_ != cudaSuccess) { destroy_solution(s); return fail(2, std::string("cudaMalloc failed: ") + cudaGetErrorString(e_)); } } while (0)
     DA(s->d_stm, 2 * d->nnst); DA(s->d_states, nst * d->nnst); DA(s->d_decisions, nd * d->nnd);
     DA(s->d_bparams, (size_t)nvec * EGDST_NPARAM_); DA(s->d_qraw, 2 * d->ny); DA(s->d_q, 2 * d->ny);
     DA(P.arena, (size_t)s->ncell * 4 * P.rowcap); DA(P.mlen, s->ncell); DA(P.thlen, s->ncell); DA(P.evf, s->ncell);
@@ -424,13 +457,13 @@ long long egdst_solution_units(egdst_solution *s) {
 
 void egdst_free_solution(egdst_solution *s) {
     if (!s) return;
-    cudaSetDevice(s->device);
-    for (void *p : s->owned) cudaFree(p);
-    if (s->d_pack) cudaFree(s->d_pack);
-    if (s->d_simivl) cudaFree(s->d_simivl);
-    if (s->d_simlut) cudaFree(s->d_simlut);
-    delete s;
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        if (!g_cached && s->bytes <= EGDST_CACHE_MAX_BYTES) { g_cached = s; return; }
+    }
+    destroy_solution(s);
 }
+
 
 int egdst_solution_import(const egdst_desc *d, const int *mlen, const int *thlen, const double *Mbuf, const double *Dbuf, egdst_solution **out) {
     if (!out || !mlen || !thlen || !Mbuf || !Dbuf) return fail(2, "invalid arguments");
@@ -445,8 +478,12 @@ int egdst_solution_import(const egdst_desc *d, const int *mlen, const int *thlen
     }
     const size_t nm = (size_t)4 * moff[s->ncell], nd2 = (size_t)2 * toff[s->ncell];
     cudaStream_t st = g_stream;
-    if (cudaMalloc((void **)&s->d_pack, sizeof(double) * (nm + nd2 + 1)) != cudaSuccess) { egdst_free_solution(s); return fail(2, "cudaMalloc failed"); }
-    s->pack_cap = nm + nd2;
+    if (nm + nd2 > s->pack_cap || !s->d_pack) {
+        if (s->d_pack) cudaFree(s->d_pack);
+        s->d_pack = 0; s->pack_cap = 0;
+        if (cudaMalloc((void **)&s->d_pack, sizeof(double) * (nm + nd2 + 1)) != cudaSuccess) { egdst_free_solution(s); return fail(2, "cudaMalloc failed"); }
+        s->pack_cap = nm + nd2;
+    }
     cudaMemcpyAsync(s->d_pack, Mbuf, sizeof(double) * nm, cudaMemcpyHostToDevice, st);
     cudaMemcpyAsync(s->d_pack + nm, Dbuf, sizeof(double) * nd2, cudaMemcpyHostToDevice, st);
     cudaMemcpyAsync(s->P.mlen, mlen, sizeof(int) * s->ncell, cudaMemcpyHostToDevice, st);

@@ -78,7 +78,8 @@ EGDST_DEV int egdst_lut_key(double x, double a0, int mbits) {
 }
 
 struct EgdstSimArgs {
-    const double *init;        // [nsim*2] column-major: 1-based ist0, m0
+    const double *init;        // [nsim] 1-based ist0 of the agents of this launch
+    const double *init_m0;     // [nsim] m0 (the second column of the reference's init matrix)
     int nsim;
     int ivec;
     const double *randstream;  // reference layout, or null => Philox
@@ -180,7 +181,7 @@ __global__ void __launch_bounds__(EGDST_SIM_BLOCK, EGDST_SIM_MINBLOCKS) egdst_k_
         int state = live_lane ? 0 : 2;  // 0 alive, 1 dead/skipped (NaN rows), 2 no agent
         if (live_lane) {
             const int ist0 = (int)S.init[isim] - 1;
-            const double m0 = S.init[S.nsim + isim];
+            const double m0 = S.init_m0[isim];
             if (ist0 < 0 || ist0 >= cx.nst || m0 < cx.a0 || m0 > cx.mmax) state = 1;  // egdst_simulator.c:215-216
             else { cur.ist = ist0; cur.cash = m0; egdst_fill_state(&cx, &cur); if (!feasible(&cx, &cur)) state = 1; }
         }

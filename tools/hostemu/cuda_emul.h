@@ -155,6 +155,7 @@ inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyK
 inline cudaError_t cudaMemset(void *d, int v, size_t n) { std::memset(d, v, n); return 0; }
 inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t) { std::memset(d, v, n); return 0; }
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
+inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }
 inline cudaError_t cudaDeviceSynchronize() { return 0; }
 inline cudaError_t cudaGetLastError() { return 0; }
 inline const char *cudaGetErrorString(cudaError_t) { return "emulated"; }
