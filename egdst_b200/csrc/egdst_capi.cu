@@ -142,7 +142,18 @@ __global__ void egdst_k_quadrature(const double *qraw, double *q, int ny) {
 
 // mark infeasible (it,ist) cells as empty and detect empty choice sets (egdst_solver.c:294-300, 694-702)
 __global__ void egdst_k_cells(EgdstDev P, int it) {
-    const int ivec = blockIdx.x, ist = threadIdx.x;
+    const int ivec = blockIdx.x;
+    // reset the chained-scan state of this parameter vector's jobs for the coming period
+    const int nsdv = P.cx.nst * P.cx.nd, sd0 = ivec * nsdv;
+    for (int i = threadIdx.x; i < nsdv * P.chC; i += blockDim.x) P.scanC[(size_t)sd0 * P.chC + i] = 0ULL;
+    for (int i = threadIdx.x; i < nsdv * 2; i += blockDim.x) P.tickC[2 * sd0 + i] = 0;
+    for (int i = threadIdx.x; i < nsdv; i += blockDim.x) P.foldCnt[sd0 + i] = 0;
+    for (int i = threadIdx.x; i < nsdv * P.chE; i += blockDim.x) P.scanE[(size_t)sd0 * P.chE + i] = 0ULL;          // secondary slots
+    for (int i = threadIdx.x; i < nsdv * 2; i += blockDim.x) P.tickE[2 * sd0 + i] = 0;
+    const int ps0 = P.nvec * nsdv + ivec * P.cx.nst;                                                                // primary slots
+    for (int i = threadIdx.x; i < P.cx.nst * P.chE; i += blockDim.x) P.scanE[(size_t)ps0 * P.chE + i] = 0ULL;
+    for (int i = threadIdx.x; i < P.cx.nst * 2; i += blockDim.x) P.tickE[2 * ps0 + i] = 0;
+    const int ist = threadIdx.x;
     if (ist >= P.cx.nst) return;
     egdst_ctx cx; egdst_load_ctx(P, ivec, cx);
     PeriodVars curr; curr.it = it; curr.ist = ist; curr.id = 0; curr.cash = 0; curr.savings = 0; curr.shock = 0;
@@ -231,6 +242,10 @@ static int create_solution(const egdst_desc *d, int nvec, egdst_solution **out) 
     DA(P.ptN, s->nsd); DA(P.nfold, s->nsd); DA(P.runStart, (size_t)s->nsd * (P.gcap + 1));
     DA(P.mgX, (size_t)s->nslot * P.envcap); DA(P.mgF, (size_t)s->nslot * P.envcap); DA(P.mgK, (size_t)s->nslot * P.envcap); DA(P.mgA, (size_t)s->nslot * P.envcap);
     DA(P.outX, (size_t)s->nsd * P.envcap); DA(P.outC, (size_t)s->nsd * P.envcap); DA(P.outV, (size_t)s->nsd * P.envcap);
+    P.chC = (P.N + EGDST_CMP_CHUNK - 1) / EGDST_CMP_CHUNK + 1;
+    P.chE = (P.envcap + EGDST_ENV_CHUNK - 1) / EGDST_ENV_CHUNK + 1;
+    DA(P.scanC, (size_t)s->nsd * P.chC); DA(P.tickC, (size_t)2 * s->nsd); DA(P.foldList, (size_t)s->nsd * (P.gcap + 1)); DA(P.foldCnt, s->nsd);
+    DA(P.scanE, (size_t)s->nslot * P.chE); DA(P.tickE, (size_t)2 * s->nslot);
     DA(P.status, 4 * nvec); DA(P.units, nvec); DA(s->d_moff, s->ncell + 1); DA(s->d_toff, s->ncell + 1);
 #undef DA
     cudaMemset(P.units, 0, sizeof(unsigned long long) * nvec);
@@ -273,7 +288,7 @@ static int run_solve(egdst_solution *s, const egdst_desc *d, const double *param
     CK(cudaMemsetAsync(P.mlen, 0, sizeof(int) * s->ncell, st));
     CK(cudaMemsetAsync(P.thlen, 0, sizeof(int) * s->ncell, st));
     const int nst = P.cx.nst, nd = P.cx.nd, nvec = P.nvec, N = P.N, B = EGDST_BLOCK;
-    const int cellthreads = ((nst + 31) / 32) * 32;
+    const int cellthreads = ((nst + 31) / 32) * 32 < 128 ? 128 : ((nst + 31) / 32) * 32;
     for (int it = P.NT - 1; it >= 0; it--) {
         KLAUNCH(KC_SETUP, egdst_k_cells, dim3(nvec), dim3(cellthreads), 0, st, P, it);
         if (it == P.NT - 1) {
@@ -281,14 +296,14 @@ static int run_solve(egdst_solution *s, const egdst_desc *d, const double *param
         } else {
             KLAUNCH(KC_SEED, egdst_k_seed, dim3(nd, nst, nvec), dim3(B), 0, st, P, it);
             KLAUNCH(KC_EGM, egdst_k_egm, dim3((N - 1 + 31) / 32, nst * nd, nvec), dim3(32, EGDST_EGM_SPLIT), 0, st, P, it);
-            KLAUNCH(KC_COMPACT, egdst_k_compact, dim3(nd, nst, nvec), dim3(EGDST_WIDE), 0, st, P, it);
+            KLAUNCH(KC_COMPACT, egdst_k_compact, dim3(P.chC, nst * nd, nvec), dim3(EGDST_CMP_THREADS), 0, st, P, it);
             // secondary envelope (no-op for (ist,id) without folds)
             KLAUNCH(KC_ENV2, egdst_k_envA<1>, dim3((2 * P.gcap + B - 1) / B, nst * nd, nvec), dim3(B), 0, st, P, it);
-            KLAUNCH(KC_ENV2, egdst_k_envBC<1>, dim3(1, nst * nd, nvec), dim3(EGDST_ENVW), 0, st, P, it);
+            KLAUNCH(KC_ENV2, egdst_k_envBC<1>, dim3(P.chE, nst * nd, nvec), dim3(EGDST_ENVW), 0, st, P, it);
             KLAUNCH(KC_SETUP, egdst_k_checkempty, dim3(nvec), dim3(cellthreads), 0, st, P, it);
         }
         KLAUNCH(KC_ENV, egdst_k_envA<0>, dim3((nd * P.gcap + B - 1) / B, nst, nvec), dim3(B), 0, st, P, it);
-        KLAUNCH(KC_ENV, egdst_k_envBC<0>, dim3(1, nst, nvec), dim3(EGDST_ENVW), 0, st, P, it);
+        KLAUNCH(KC_ENV, egdst_k_envBC<0>, dim3(P.chE, nst, nvec), dim3(EGDST_ENVW), 0, st, P, it);
     }
     s->sizes_valid = false;
     s->sim_valid = false;

@@ -14,9 +14,10 @@
 #include <cuda_runtime.h>
 #define EGDST_BLOCK 256
 #define EGDST_WIDE 1024  /* single-CTA scan/compaction kernels: one CTA owns a whole (state, decision) list */
-#define EGDST_ENVW 512   /* envelope merge kernels: 8 positions per thread, 128 registers available */
+#define EGDST_ENVW 256   /* envelope merge kernels: 8 positions per thread, chained across CTAs */
 #define EGDST_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #define EGDST_DYN_SMEM(type, name) extern __shared__ __align__(16) type name[]
+#define EGDST_LDCG(p) __ldcg(p)
 #endif
 
 #ifdef __CUDACC__
@@ -60,6 +61,12 @@ struct EgdstDev {
     int envcap;
     int *status;                    // [nvec*4]: code, it, ist, id of the first error
     unsigned long long *units;      // [nvec] EGM grid points stored over all (it,ist,id): the solve work unit
+    // chained scans across CTAs (decoupled look-back): state words per chunk, [ticket, done] counters per job;
+    // zeroed at the start of every period by egdst_k_cells
+    unsigned long long *scanC, *scanE;  // [nsd*chC] compaction, [nslot*chE] envelope merge
+    int *tickC, *tickE;                 // [nsd*2], [nslot*2]
+    int chC, chE;                       // chunks per job
+    int *foldList, *foldCnt;            // [nsd*(gcap+1)] unordered fold positions, [nsd]
 };
 
 EGDST_DEV int egdst_cell(const EgdstDev &P, int ivec, int it, int ist) { return (ivec * P.NT + it) * P.cx.nst + ist; }
@@ -126,6 +133,56 @@ EGDST_DEV int egdst_block_min(int v, int *sh) {  // sh: 32 ints; every thread ge
     __syncthreads();
     return r;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Chained scan across the CTAs of one job (single-pass prefix sum with decoupled look-back, Merrill & Garland
+// 2016).  Chunk ids are handed out by an atomic ticket, so a CTA only ever waits on CTAs that are already running.
+// State word: bits 63..62 = 0 empty / 1 aggregate / 2 inclusive prefix; payload = two 31-bit fields (lo, hi).
+// KIND 0: both fields add (grid points, thresholds).  KIND 1: lo adds until hi ("the savings grid stopped
+// here", egdst_solver.c:1100) is set -- later chunks contribute nothing.  Polls are bounded: a protocol bug
+// shows up as an error status, never as a hung device.
+// ---------------------------------------------------------------------------------------------
+#define EGDST_SCAN_AGG (1ULL << 62)
+#define EGDST_SCAN_INC (2ULL << 62)
+#define EGDST_SCAN_MASK ((1ULL << 62) - 1ULL)
+#define EGDST_SCAN_POLLS (1 << 22)
+EGDST_DEV unsigned long long egdst_scan_pack(int lo, int hi) { return (unsigned long long)(unsigned)lo | ((unsigned long long)(unsigned)hi << 31); }
+EGDST_DEV int egdst_scan_lo(unsigned long long p) { return (int)(p & 0x7fffffffULL); }
+EGDST_DEV int egdst_scan_hi(unsigned long long p) { return (int)((p >> 31) & 0x7fffffffULL); }
+template <int KIND>
+EGDST_DEV unsigned long long egdst_scan_combine(unsigned long long earlier, unsigned long long later) {
+    if (KIND == 1) {
+        if (egdst_scan_hi(earlier)) return earlier;
+        return egdst_scan_pack(egdst_scan_lo(earlier) + egdst_scan_lo(later), egdst_scan_hi(later));
+    }
+    return egdst_scan_pack(egdst_scan_lo(earlier) + egdst_scan_lo(later), egdst_scan_hi(earlier) + egdst_scan_hi(later));
+}
+// Called by all 32 lanes of one warp.  Publishes this chunk's aggregate, returns the exclusive prefix over the
+// earlier chunks and publishes the inclusive prefix.
+template <int KIND>
+EGDST_DEV unsigned long long egdst_lookback(volatile unsigned long long *st, int chunk, unsigned long long agg, int *err) {
+    const int lane = threadIdx.x & 31;
+    if (lane == 0 && chunk > 0) st[chunk] = EGDST_SCAN_AGG | agg;
+    unsigned long long excl = 0ULL;
+    for (int base = chunk - 1; base >= 0; base -= 32) {
+        const int idx = base - lane;
+        unsigned long long w = EGDST_SCAN_INC;  // positions before chunk 0: inclusive prefix = identity
+        if (idx >= 0) {
+            int polls = 0;
+            do { w = st[idx]; } while ((w >> 62) == 0ULL && ++polls < EGDST_SCAN_POLLS);
+            if ((w >> 62) == 0ULL) { *err = 1; w = EGDST_SCAN_INC; }
+        }
+        const unsigned incmask = __ballot_sync(EGDST_FULL, (w >> 62) == 2ULL);
+        const int cut = incmask ? __ffs(incmask) - 1 : 31;  // nearest predecessor that already knows its prefix
+        unsigned long long acc = __shfl_sync(EGDST_FULL, w, cut) & EGDST_SCAN_MASK;
+        for (int l = cut - 1; l >= 0; l--) acc = egdst_scan_combine<KIND>(acc, __shfl_sync(EGDST_FULL, w, l) & EGDST_SCAN_MASK);
+        excl = egdst_scan_combine<KIND>(acc, excl);
+        if (incmask) break;
+    }
+    if (lane == 0) st[chunk] = EGDST_SCAN_INC | egdst_scan_combine<KIND>(excl, agg);
+    return excl;
+}
+EGDST_DEV unsigned long long egdst_scan_inclusive(const volatile unsigned long long *st, int chunk) { return st[chunk] & EGDST_SCAN_MASK; }
 
 // exclusive block scan of one int per thread; returns the exclusive prefix, *total gets the block sum.
 // `sh` must hold blockDim.x/32+1 ints.  Contains two __syncthreads().

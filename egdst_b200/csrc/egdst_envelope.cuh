@@ -344,10 +344,15 @@ EGDST_DEV void egdst_env_item(const egdst_ctx *cx, const EgdstEnvView<MODE> &E, 
     }
 }
 
+#define EGDST_ENV_CHUNK (EGDST_ENVW * EGDST_ENV_IPT)  /* union positions per CTA */
+// grid (chE, njobs_y, nvec): the CTAs of one job are chained by a decoupled look-back scan over
+// (grid points, thresholds) emitted so far; the last CTA to finish writes the cell header (MODE 0) or copies the
+// staged result back over the decision's point list (MODE 1).
 template <int MODE>
 __global__ void __launch_bounds__(EGDST_ENVW) egdst_k_envBC(EgdstDev P, int it) {
     __shared__ long long sh[40];
-    __shared__ int s_gbase, s_tbase;
+    __shared__ int s_chunk, s_last;
+    __shared__ unsigned long long s_excl;
     const int ivec = blockIdx.z;
     int ist, id, slot;
     EgdstEnvView<MODE> E;
@@ -355,6 +360,7 @@ __global__ void __launch_bounds__(EGDST_ENVW) egdst_k_envBC(EgdstDev P, int it) 
     egdst_ctx cx; egdst_load_ctx(P, ivec, cx);
     const double *mgX = P.mgX + (size_t)slot * P.envcap;
     const int *mgF = P.mgF + (size_t)slot * P.envcap, *mgK = P.mgK + (size_t)slot * P.envcap, *mgA = P.mgA + (size_t)slot * P.envcap;
+    volatile unsigned long long *st = P.scanE + (size_t)slot * P.chE;
     double *ox, *oc, *ov, *oth = 0, *odd = 0;
     int gcapacity, tcapacity = 0, cell = 0;
     if (MODE == 0) {
@@ -366,8 +372,6 @@ __global__ void __launch_bounds__(EGDST_ENVW) egdst_k_envBC(EgdstDev P, int it) 
         ox = P.outX + (size_t)slot * P.envcap; oc = P.outC + (size_t)slot * P.envcap; ov = P.outV + (size_t)slot * P.envcap;
         gcapacity = P.envcap;
     }
-    if (threadIdx.x == 0) { s_gbase = 0; s_tbase = 0; }
-    __syncthreads();
     // unified grid bound = min over functions of the last abscissa (egdst_solver.c:1266-1271); the union is
     // sorted, so the active positions are the prefix with x<=grb
     double grb = EGDST_INF;
@@ -375,10 +379,13 @@ __global__ void __launch_bounds__(EGDST_ENVW) egdst_k_envBC(EgdstDev P, int it) 
     const int Ptot = E.pstart(E.F - 1) + E.npts(E.F - 1);
     int nact;
     { int lo = 0, hi = Ptot; while (lo < hi) { int mid = (lo + hi) >> 1; if (mgX[mid] <= grb) lo = mid + 1; else hi = mid; } nact = lo; }
-    int err = 0;
-    const int CH = blockDim.x * EGDST_ENV_IPT;
-    for (int base = 0; base < nact; base += CH) {
-        const int r0 = base + threadIdx.x * EGDST_ENV_IPT;
+    const int nch = (nact + EGDST_ENV_CHUNK - 1) / EGDST_ENV_CHUNK;
+    if (threadIdx.x == 0) s_chunk = atomicAdd(P.tickE + 2 * slot, 1);
+    __syncthreads();
+    const int chunk = s_chunk;
+    int err = 0, serr = 0;
+    if (chunk < nch) {
+        const int r0 = chunk * EGDST_ENV_CHUNK + threadIdx.x * EGDST_ENV_IPT;
         int ngj[EGDST_ENV_IPT], ntj[EGDST_ENV_IPT], ngs = 0, nts = 0;
 #pragma unroll
         for (int j = 0; j < EGDST_ENV_IPT; j++) {
@@ -387,7 +394,12 @@ __global__ void __launch_bounds__(EGDST_ENVW) egdst_k_envBC(EgdstDev P, int it) 
         }
         long long tot;
         const long long off = egdst_block_excl_scan64(((long long)nts << 32) | (long long)ngs, sh, &tot);
-        int gpos = s_gbase + (int)(off & 0xffffffffLL), tpos = s_tbase + (int)(off >> 32);
+        if (threadIdx.x < 32) {
+            const unsigned long long e = egdst_lookback<0>(st, chunk, egdst_scan_pack((int)(tot & 0xffffffffLL), (int)(tot >> 32)), &serr);
+            if (threadIdx.x == 0) s_excl = e;
+        }
+        __syncthreads();
+        int gpos = egdst_scan_lo(s_excl) + (int)(off & 0xffffffffLL), tpos = egdst_scan_hi(s_excl) + (int)(off >> 32);
 #pragma unroll
         for (int j = 0; j < EGDST_ENV_IPT; j++) {
             int g2, t2;
@@ -396,12 +408,18 @@ __global__ void __launch_bounds__(EGDST_ENVW) egdst_k_envBC(EgdstDev P, int it) 
                 egdst_env_item<MODE, true>(&cx, E, it, ist, mgX, mgF, mgK, mgA, r0 + j < nact, r0 + j, grb, ox, ov, oc, gcapacity, oth, odd, tcapacity, gpos, tpos, g2, t2, &err);
             gpos += ngj[j]; tpos += ntj[j];
         }
-        __syncthreads();
-        if (threadIdx.x == 0) { s_gbase += (int)(tot & 0xffffffffLL); s_tbase += (int)(tot >> 32); }
-        __syncthreads();
     }
     if (err) egdst_fail(P, ivec, err, it, ist, id);
-    const int nout = s_gbase, nth = s_tbase;
+    if (serr) egdst_fail(P, ivec, EGDST_ERR_ENV2SPACE, it, ist, id);
+    // last CTA of the job: totals and epilogue
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(P.tickE + 2 * slot + 1, 1) == (int)gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const unsigned long long totals = nch > 0 ? egdst_scan_inclusive(st, nch - 1) : 0ULL;
+    const int nout = egdst_scan_lo(totals), nth = egdst_scan_hi(totals);
     if (MODE == 0) {
         if (threadIdx.x == 0) {
             if (nout >= cx.ngridmax) egdst_fail(P, ivec, EGDST_ERR_GRIDSPACE, it, ist, -1);
@@ -418,14 +436,14 @@ __global__ void __launch_bounds__(EGDST_ENVW) egdst_k_envBC(EgdstDev P, int it) 
         __syncthreads();
         const int n = nout < gcapacity ? nout : gcapacity;
         double *Mc = egdst_colM(P, cell), *Cc = egdst_colC(P, cell), *Ac = egdst_colA(P, cell);
-        for (int i = threadIdx.x; i <= n; i += blockDim.x) Ac[i] = Mc[i] - Cc[i];
+        for (int i = threadIdx.x; i <= n; i += blockDim.x) Ac[i] = EGDST_LDCG(Mc + i) - EGDST_LDCG(Cc + i);
     } else {
         const int sd = slot;
         if (threadIdx.x == 0 && nout >= cx.ngridmax) egdst_fail(P, ivec, EGDST_ERR_ENV2SPACE, it, ist, id);
         const int n = nout < P.gcap ? nout : P.gcap;
         double *X = P.ptX + (size_t)sd * P.gcap, *Cc = P.ptC + (size_t)sd * P.gcap, *V = P.ptV + (size_t)sd * P.gcap;
         __syncthreads();
-        for (int i = threadIdx.x; i < n; i += blockDim.x) { X[i] = ox[i]; Cc[i] = oc[i]; V[i] = ov[i]; }
+        for (int i = threadIdx.x; i < n; i += blockDim.x) { X[i] = EGDST_LDCG(ox + i); Cc[i] = EGDST_LDCG(oc + i); V[i] = EGDST_LDCG(ov + i); }
         if (threadIdx.x == 0) P.ptN[sd] = n;
     }
 }

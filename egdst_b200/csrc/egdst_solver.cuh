@@ -397,11 +397,21 @@ __global__ void egdst_k_egm(EgdstDev P, int it) {
 // (egdst_solver.c:1100); stored points are those with a finite M and no abort (:640-664).
 // Folds (M or V decreasing, :819) split the list into runs for the secondary envelope.
 // ---------------------------------------------------------------------------------------------
-#define EGDST_CMP_IPT 8  /* consecutive items per thread: a 10^4-point list is two passes of a 1024-thread CTA */
-__global__ void __launch_bounds__(EGDST_WIDE) egdst_k_compact(EgdstDev P, int it) {
+#define EGDST_CMP_IPT 8
+#ifdef EGDST_HOSTEMU
+#define EGDST_CMP_THREADS 64
+#else
+#define EGDST_CMP_THREADS 256
+#endif
+#define EGDST_CMP_CHUNK (EGDST_CMP_THREADS * EGDST_CMP_IPT)  /* raw points per CTA */
+// grid (chC, nst*nd, nvec): the CTAs of one (ist,id) list are chained by a decoupled look-back scan whose state
+// carries (points kept so far, "stop rule fired").  Folds inside a CTA's own output are appended to an unordered
+// list; the last CTA to finish adds the folds on chunk boundaries, orders the list and publishes the counts.
+__global__ void __launch_bounds__(EGDST_CMP_THREADS) egdst_k_compact(EgdstDev P, int it) {
     __shared__ int sh[40];
-    __shared__ int s_base, s_fbase, s_late;
-    const int ivec = blockIdx.z, ist = blockIdx.y, id = blockIdx.x;
+    __shared__ int s_chunk, s_last;
+    __shared__ unsigned long long s_excl;
+    const int ivec = blockIdx.z, ist = blockIdx.y / P.cx.nd, id = blockIdx.y % P.cx.nd;
     const int sd = egdst_sd(P, ivec, ist, id);
     if (!P.active[sd]) return;
     const int N = P.N;
@@ -409,83 +419,105 @@ __global__ void __launch_bounds__(EGDST_WIDE) egdst_k_compact(EgdstDev P, int it
     const int *rawFlag = P.rawFlag + (size_t)sd * N;
     double *X = P.ptX + (size_t)sd * P.gcap, *Cc = P.ptC + (size_t)sd * P.gcap, *V = P.ptV + (size_t)sd * P.gcap;
     int *runStart = P.runStart + (size_t)sd * (P.gcap + 1);
-    if (threadIdx.x == 0) { s_base = 0; s_fbase = 0; s_late = N; }
-    if (rawFlag[0] == EGDST_PT_NONE) { if (threadIdx.x == 0) { P.ptN[sd] = 0; P.nfold[sd] = 0; } return; }
-    // first n whose returned M fails "M<mmax" ends the sequence (that point itself is kept)
-    int mystop = N - 1;
-    for (int n = threadIdx.x; n < N; n += blockDim.x)
-        if (!(rawStop[n] < P.cx.mmax)) { mystop = n; break; }
-    const int nstop = egdst_block_min(mystop, sh);  // also orders the s_* initialisation
-    // compaction: every warp owns 32*EGDST_CMP_IPT consecutive points per pass (coalesced, lane-strided);
-    // positions come from ballots within the warp and one block scan of the warp totals per pass
+    int *foldList = P.foldList + (size_t)sd * (P.gcap + 1);
+    volatile unsigned long long *st = P.scanC + (size_t)sd * P.chC;
+    if (rawFlag[0] == EGDST_PT_NONE) { if (blockIdx.x == 0 && threadIdx.x == 0) { P.ptN[sd] = 0; P.nfold[sd] = 0; } return; }
+    const int nch = (N + EGDST_CMP_CHUNK - 1) / EGDST_CMP_CHUNK;  // chunks that hold raw points
+    if (threadIdx.x == 0) s_chunk = atomicAdd(P.tickC + 2 * sd, 1);
+    __syncthreads();
+    const int chunk = s_chunk;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const unsigned ltmask = (1u << lane) - 1u;
-    const int WCH = 32 * EGDST_CMP_IPT, CH = nw * WCH;
-    for (int base = 0; base <= nstop; base += CH) {
-        const int wbase = base + w * WCH;
-        unsigned bal[EGDST_CMP_IPT];
-        int wtotal = 0;
+    int err = 0;
+    if (chunk < nch) {
+        const int wbase = chunk * EGDST_CMP_CHUNK + w * (32 * EGDST_CMP_IPT);
+        // the stop rule inside this chunk: first n whose returned M fails "M<mmax" (that point itself is kept)
+        int flag[EGDST_CMP_IPT], mystop = 0x7fffffff;
 #pragma unroll
         for (int j = 0; j < EGDST_CMP_IPT; j++) {
             const int n = wbase + j * 32 + lane;
-            const int f = (n <= nstop) ? rawFlag[n] : EGDST_PT_NONE;
-            if (n <= nstop && f == EGDST_PT_C1NEG && n > 0) atomicMin(&s_late, n);
-            if (n <= nstop && f == EGDST_PT_CHECKSUM) egdst_fail(P, ivec, EGDST_ERR_CHECKSUM, it, ist, id);
-            bal[j] = __ballot_sync(EGDST_FULL, f == EGDST_PT_OK);
+            flag[j] = EGDST_PT_NONE;
+            if (n < N) {
+                flag[j] = rawFlag[n];
+                if (!(rawStop[n] < P.cx.mmax) && n < mystop) mystop = n;
+            }
+        }
+        const int ls = egdst_block_min(mystop, sh);
+        unsigned bal[EGDST_CMP_IPT];
+        int wtotal = 0, late = 0x7fffffff, badsum = 0;
+#pragma unroll
+        for (int j = 0; j < EGDST_CMP_IPT; j++) {
+            const int n = wbase + j * 32 + lane;
+            const bool in = n < N && n <= ls;
+            if (in && flag[j] == EGDST_PT_C1NEG && n > 0 && n < late) late = n;
+            if (in && flag[j] == EGDST_PT_CHECKSUM) badsum = 1;
+            bal[j] = __ballot_sync(EGDST_FULL, in && flag[j] == EGDST_PT_OK);
             wtotal += __popc(bal[j]);
         }
         int total;
         int woff = egdst_block_excl_scan(lane == 0 ? wtotal : 0, sh, &total);
-        woff = __shfl_sync(EGDST_FULL, woff, 0) + s_base;
-#pragma unroll
-        for (int j = 0; j < EGDST_CMP_IPT; j++) {
-            const int n = wbase + j * 32 + lane;
-            if (bal[j] & (1u << lane)) {
-                const int dst = woff + __popc(bal[j] & ltmask);
-                if (dst < P.gcap) { X[dst] = rawM[n]; Cc[dst] = rawC[n]; V[dst] = rawV[n]; }
-            }
-            woff += __popc(bal[j]);
+        woff = __shfl_sync(EGDST_FULL, woff, 0);
+        if (w == 0) {
+            const unsigned long long e = egdst_lookback<1>(st, chunk, egdst_scan_pack(total, ls != 0x7fffffff ? 1 : 0), &err);
+            if (lane == 0) s_excl = e;
         }
         __syncthreads();
-        if (threadIdx.x == 0) s_base += total;
-        __syncthreads();
+        const unsigned long long excl = s_excl;
+        if (!egdst_scan_hi(excl)) {  // the grid did not stop in an earlier chunk: this chunk's points count
+            if (late != 0x7fffffff) egdst_fail(P, ivec, EGDST_ERR_RESEND_LATE, it, ist, id);
+            if (badsum) egdst_fail(P, ivec, EGDST_ERR_CHECKSUM, it, ist, id);
+            const int first = egdst_scan_lo(excl);
+            int pos = first + woff;
+#pragma unroll
+            for (int j = 0; j < EGDST_CMP_IPT; j++) {
+                const int n = wbase + j * 32 + lane;
+                if (bal[j] & (1u << lane)) {
+                    const int dst = pos + __popc(bal[j] & ltmask);
+                    if (dst < P.gcap) { X[dst] = rawM[n]; Cc[dst] = rawC[n]; V[dst] = rawV[n]; }
+                }
+                pos += __popc(bal[j]);
+            }
+            __syncthreads();
+            // folds between neighbours that this CTA wrote itself (M or V decreasing, egdst_solver.c:819)
+            const int lim = first + total < P.gcap ? first + total : P.gcap;
+            for (int p = first + 1 + threadIdx.x; p < lim; p += blockDim.x)
+                if (X[p - 1] > X[p] || V[p - 1] > V[p]) { const int k = atomicAdd(P.foldCnt + sd, 1); if (k <= P.gcap) foldList[k] = p; }
+        }
     }
-    const int nvd = s_base < P.gcap ? s_base : P.gcap;
-    if (threadIdx.x == 0) {
-        if (s_base >= P.cx.ngridmax) egdst_fail(P, ivec, EGDST_ERR_GRIDSPACE, it, ist, id);
-        if (s_late < N) egdst_fail(P, ivec, EGDST_ERR_RESEND_LATE, it, ist, id);
-        runStart[0] = 0;
+    if (err) egdst_fail(P, ivec, EGDST_ERR_ENV2SPACE, it, ist, id);
+    // last CTA of this (ist,id): boundary folds, ordering, counts
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(P.tickC + 2 * sd + 1, 1) == (int)gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const unsigned long long tot = egdst_scan_inclusive(st, nch - 1);
+    const int kept = egdst_scan_lo(tot);
+    const int nvd = kept < P.gcap ? kept : P.gcap;
+    for (int c = 1 + threadIdx.x; c < nch; c += blockDim.x) {
+        const unsigned long long pe = egdst_scan_inclusive(st, c - 1), pi = egdst_scan_inclusive(st, c);
+        const int p = egdst_scan_lo(pe);
+        if (!egdst_scan_hi(pe) && egdst_scan_lo(pi) > p && p > 0 && p < nvd)
+            if (EGDST_LDCG(X + p - 1) > EGDST_LDCG(X + p) || EGDST_LDCG(V + p - 1) > EGDST_LDCG(V + p)) {
+                const int k = atomicAdd(P.foldCnt + sd, 1); if (k <= P.gcap) foldList[k] = p;
+            }
     }
     __syncthreads();
-    // fold detection over the compacted list (same scheme)
-    for (int base = 0; base < nvd; base += CH) {
-        const int wbase = base + w * WCH;
-        unsigned bal[EGDST_CMP_IPT];
-        int wtotal = 0;
-#pragma unroll
-        for (int j = 0; j < EGDST_CMP_IPT; j++) {
-            const int i = wbase + j * 32 + lane;
-            bool fold = false;
-            if (i > 0 && i < nvd) fold = X[i - 1] > X[i] || V[i - 1] > V[i];
-            bal[j] = __ballot_sync(EGDST_FULL, fold);
-            wtotal += __popc(bal[j]);
-        }
-        int total;
-        int woff = egdst_block_excl_scan(lane == 0 ? wtotal : 0, sh, &total);
-        woff = __shfl_sync(EGDST_FULL, woff, 0) + s_fbase;
-#pragma unroll
-        for (int j = 0; j < EGDST_CMP_IPT; j++) {
-            if (bal[j] & (1u << lane)) runStart[woff + __popc(bal[j] & ltmask) + 1] = wbase + j * 32 + lane;
-            woff += __popc(bal[j]);
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) s_fbase += total;
-        __syncthreads();
+    int nf = *((volatile int *)(P.foldCnt + sd));
+    if (nf > P.gcap - 1) nf = P.gcap - 1;
+    for (int i = threadIdx.x; i < nf; i += blockDim.x) {  // rank sort (folds are rare)
+        const int v = EGDST_LDCG(foldList + i);
+        int r = 0;
+        for (int j = 0; j < nf; j++) r += EGDST_LDCG(foldList + j) < v ? 1 : 0;
+        runStart[r + 1] = v;
     }
     if (threadIdx.x == 0) {
+        if (kept >= P.cx.ngridmax) egdst_fail(P, ivec, EGDST_ERR_GRIDSPACE, it, ist, id);
+        runStart[0] = 0;
+        runStart[nf + 1] = nvd;
         P.ptN[sd] = nvd;
-        P.nfold[sd] = s_fbase;
-        runStart[s_fbase + 1] = nvd;
+        P.nfold[sd] = nf;
         atomicAdd(P.units + ivec, (unsigned long long)nvd);
     }
 }
