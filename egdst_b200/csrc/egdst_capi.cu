@@ -27,8 +27,8 @@ static thread_local std::string g_err;
 static thread_local cudaStream_t g_stream = 0;
 
 // ---- launch counter and optional per-kernel-class event timing (bench.py's roofline leg) --------------
-enum { KC_SETUP = 0, KC_TERMINAL, KC_SEED, KC_EGM, KC_COMPACT, KC_ENV2, KC_ENV, KC_SIM, KC_OTHER, KC_COUNT };
-static const char *const g_kc_names[KC_COUNT] = {"setup", "terminal", "seed", "egm", "compact", "envelope2", "envelope", "simulate", "other"};
+enum { KC_SETUP = 0, KC_TERMINAL, KC_SEED, KC_EGM, KC_COMPACT, KC_ENV2, KC_ENV, KC_TAB, KC_SIM, KC_OTHER, KC_COUNT };
+static const char *const g_kc_names[KC_COUNT] = {"setup", "terminal", "seed", "egm", "compact", "envelope2", "envelope", "tables", "simulate", "other"};
 static long long g_launches = 0;
 static bool g_prof_on = false;
 struct ProfRec { int cls; cudaEvent_t a, b; };
@@ -104,11 +104,7 @@ struct egdst_solution {
     size_t pack_cap;
     int *d_moff, *d_toff;
     int neq;
-    // simulator acceleration structure (egdst_k_simtab), rebuilt lazily after every (re)solve / import
-    EgdstInterval *d_simivl;
-    EgdstLutEntry *d_simlut;
-    int sim_rowcap, sim_lutcap, sim_mbits;
-    bool sim_valid;
+    bool sim_valid;  // (kept for ABI of the struct users) tables are built with every cell now
     size_t bytes;   // device bytes owned (workspace cache policy)
     int dims[12];   // shape signature for re-use
 };
@@ -129,8 +125,6 @@ static void destroy_solution(egdst_solution *s) {
     cudaSetDevice(s->device);
     for (void *p : s->owned) cudaFree(p);
     if (s->d_pack) cudaFree(s->d_pack);
-    if (s->d_simivl) cudaFree(s->d_simivl);
-    if (s->d_simlut) cudaFree(s->d_simlut);
     delete s;
 }
 
@@ -222,7 +216,7 @@ static int create_solution(const egdst_desc *d, int nvec, egdst_solution **out) 
     }
     egdst_solution *s = new egdst_solution();
     s->bytes = 0; memcpy(s->dims, dims, sizeof(dims));
-    s->device = d->device; s->sizes_valid = false; s->d_simivl = 0; s->d_simlut = 0; s->sim_rowcap = 0; s->sim_lutcap = 0; s->sim_mbits = 0; s->sim_valid = false; s->d_pack = 0; s->pack_cap = 0; s->neq = d->neq;
+    s->device = d->device; s->sizes_valid = false; s->sim_valid = false; s->d_pack = 0; s->pack_cap = 0; s->neq = d->neq;
     EgdstDev &P = s->P;
     memset(&P, 0, sizeof(P));
     P.cx = cx;
@@ -242,6 +236,17 @@ static int create_solution(const egdst_desc *d, int nvec, egdst_solution **out) 
     DA(P.ptN, s->nsd); DA(P.nfold, s->nsd); DA(P.runStart, (size_t)s->nsd * (P.gcap + 1));
     DA(P.mgX, (size_t)s->nslot * P.envcap); DA(P.mgF, (size_t)s->nslot * P.envcap); DA(P.mgK, (size_t)s->nslot * P.envcap); DA(P.mgA, (size_t)s->nslot * P.envcap);
     DA(P.outX, (size_t)s->nsd * P.envcap); DA(P.outC, (size_t)s->nsd * P.envcap); DA(P.outV, (size_t)s->nsd * P.envcap);
+    // lookup tables (egdst_tables.cuh): capacity 2*ngridm+64 intervals per cell, about two buckets per grid row
+    P.tabcap = P.rowcap - 1 < 2 * P.N + 64 ? P.rowcap - 1 : 2 * P.N + 64;
+    {
+        const double span = 2.0 * (d->mmax - d->a0) + 2.0;
+        const double octaves = log2(span > 2.0 ? span : 2.0);
+        int mbits = 3;
+        while (mbits < 16 && (double)(1 << mbits) * octaves < 2.0 * (double)(P.N + 1)) mbits++;
+        P.mbits = mbits;
+        P.lutcap = (int)(octaves * (double)(1 << mbits)) + 2;
+    }
+    DA(P.tabIvl, (size_t)s->ncell * P.tabcap); DA(P.tabLut, (size_t)s->ncell * (P.lutcap + 1));
     P.chC = (P.N + EGDST_CMP_CHUNK - 1) / EGDST_CMP_CHUNK + 1;
     P.chE = (P.envcap + EGDST_ENV_CHUNK - 1) / EGDST_ENV_CHUNK + 1;
     DA(P.scanC, (size_t)s->nsd * P.chC); DA(P.tickC, (size_t)2 * s->nsd); DA(P.foldList, (size_t)s->nsd * (P.gcap + 1)); DA(P.foldCnt, s->nsd);
@@ -288,6 +293,8 @@ static int run_solve(egdst_solution *s, const egdst_desc *d, const double *param
     CK(cudaMemsetAsync(P.mlen, 0, sizeof(int) * s->ncell, st));
     CK(cudaMemsetAsync(P.thlen, 0, sizeof(int) * s->ncell, st));
     const int nst = P.cx.nst, nd = P.cx.nd, nvec = P.nvec, N = P.N, B = EGDST_BLOCK;
+    int tabblocks = (P.lutcap + 1 + B - 1) / B;
+    if (nvec * nst * tabblocks > 4096) tabblocks = (4096 + nvec * nst - 1) / (nvec * nst);  // batched sweeps: fewer, looping CTAs per cell
     const int cellthreads = ((nst + 31) / 32) * 32 < 128 ? 128 : ((nst + 31) / 32) * 32;
     for (int it = P.NT - 1; it >= 0; it--) {
         KLAUNCH(KC_SETUP, egdst_k_cells, dim3(nvec), dim3(cellthreads), 0, st, P, it);
@@ -304,6 +311,7 @@ static int run_solve(egdst_solution *s, const egdst_desc *d, const double *param
         }
         KLAUNCH(KC_ENV, egdst_k_envA<0>, dim3((nd * P.gcap + B - 1) / B, nst, nvec), dim3(B), 0, st, P, it);
         KLAUNCH(KC_ENV, egdst_k_envBC<0>, dim3(P.chE, nst, nvec), dim3(EGDST_ENVW), 0, st, P, it);
+        KLAUNCH(KC_TAB, egdst_k_tab, dim3(tabblocks, nst, nvec), dim3(B), 0, st, P, it);
     }
     s->sizes_valid = false;
     s->sim_valid = false;
@@ -510,6 +518,10 @@ int egdst_solution_import(const egdst_desc *d, const int *mlen, const int *thlen
     cudaMemcpyAsync(s->d_decisions, d->decisions, sizeof(double) * d->nd * d->nnd, cudaMemcpyHostToDevice, st);
     cudaMemsetAsync(s->P.status, 0, sizeof(int) * 4, st);
     KLAUNCH(KC_OTHER, egdst_k_unpack, dim3(s->ncell), dim3(EGDST_BLOCK), 0, st, s->P, s->d_moff, s->d_toff, s->d_pack, s->d_pack + nm, s->ncell);
+    {
+        int tb = (s->P.lutcap + 1 + EGDST_BLOCK - 1) / EGDST_BLOCK;
+        for (int it = 0; it < s->P.NT; it++) KLAUNCH(KC_TAB, egdst_k_tab, dim3(tb, d->nst, 1), dim3(EGDST_BLOCK), 0, st, s->P, it);
+    }
     if (cudaStreamSynchronize(st) != cudaSuccess) { egdst_free_solution(s); return fail(2, "import failed"); }
     memcpy(s->h_mlen.data(), mlen, sizeof(int) * s->ncell);
     memcpy(s->h_thlen.data(), thlen, sizeof(int) * s->ncell);

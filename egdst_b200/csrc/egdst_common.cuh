@@ -34,6 +34,9 @@
 // raw-point flags written by the seed/EGM kernels
 enum { EGDST_PT_OK = 0, EGDST_PT_C1NEG = 1, EGDST_PT_EVFINF = 2, EGDST_PT_CHECKSUM = 3, EGDST_PT_NONFINITE = 4, EGDST_PT_NONE = 5 };
 
+struct EgdstLutEntry { int l, cnt; double m; };
+struct EgdstInterval { double g0, g1, c0, c1, v0, v1; };
+
 // Everything a kernel needs.  Leading dimension of every array is the parameter-vector index `ivec`
 // (batched solves; nvec=1 for a single model).
 struct EgdstDev {
@@ -67,6 +70,10 @@ struct EgdstDev {
     int *tickC, *tickE;                 // [nsd*2], [nslot*2]
     int chC, chE;                       // chunks per job
     int *foldList, *foldCnt;            // [nsd*(gcap+1)] unordered fold positions, [nsd]
+    // per-cell lookup tables (egdst_tables.cuh)
+    EgdstInterval *tabIvl;              // [ncell*tabcap]
+    EgdstLutEntry *tabLut;              // [ncell*(lutcap+1)]
+    int tabcap, lutcap, mbits;
 };
 
 EGDST_DEV int egdst_cell(const EgdstDev &P, int ivec, int it, int ist) { return (ivec * P.NT + it) * P.cx.nst + ist; }

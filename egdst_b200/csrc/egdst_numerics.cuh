@@ -71,6 +71,18 @@ EGDST_DEV double egdst_linter_extrap_at(const egdst_ctx *cx, const PeriodVars *p
     return egdst_lerp(x, g0, g1, f0, f1);
 }
 
+// the same on an interval given by value (gfirst, glast = first and last abscissa of the table)
+EGDST_DEV double egdst_linter_extrap_iv(const egdst_ctx *cx, const PeriodVars *prd, double x, double g0, double g1, double f0, double f1,
+                                         double gfirst, double glast) {
+    if (!isfinite(f0)) return f0;
+    if (!isfinite(f1)) return f1;
+    if (x > cx->a0 && (x > glast || x < gfirst)) {
+        double tx = tr(cx, prd, x - cx->a0), t0 = tr(cx, prd, g0 - cx->a0), t1 = tr(cx, prd, g1 - cx->a0);
+        return f1 * (tx - t0) / (t1 - t0) + f0 * (t1 - tx) / (t1 - t0);
+    }
+    return egdst_lerp(x, g0, g1, f0, f1);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Acklam's rational approximation of the standard normal quantile (egdst_lib.c:435-519).
 // Parity at 1e-9 needs this polynomial, not normcdfinv.

@@ -13,7 +13,7 @@
 // Continuous states (egdst_simulator.c:310-373) are outside the hot-path scope.
 #pragma once
 
-#include "egdst_common.cuh"
+#include "egdst_tables.cuh"
 
 #define EGDST_NSIMOUT_MAX (11 + EGDST_NNST + EGDST_NND + EGDST_NREQ)
 #ifdef EGDST_HOSTEMU
@@ -47,36 +47,6 @@ EGDST_DEV void egdst_philox4x32(unsigned c0, unsigned c1, unsigned c2, unsigned 
 }
 EGDST_DEV double egdst_u01(unsigned x) { return ((double)x + 0.5) * (1.0 / 4294967296.0); }
 
-// Per-solution acceleration structure of the simulator (built once per solve by egdst_k_simtab).  The kernel
-// is bound by the L1 data pipe -- every per-agent table access is a fully divergent gather, 32 wavefronts per
-// instruction -- so the policy lookup is laid out to cost four 16-byte gathers per agent-period:
-//   lut [ncell][lutcap+1] EgdstLutEntry  direct index by the leading bits of the IEEE representation of
-//        (x - a0 + 1): key = exponent and the top `mbits` mantissa bits, a piecewise-linear log2 -- the endogenous
-//        grids are (sym-)log spaced (egdst_solver.c:1104-1136), so buckets are evenly filled.  Entry b holds
-//        l = #rows with key < b, the number of rows in the bucket and the abscissa of its first row: with about
-//        half a row per bucket, #rows <= x is l + (m <= x) without touching the grid (crowded buckets bisect).
-//   ivl [ncell][rowcap-1] EgdstInterval  (M_i, M_i+1, C_i, C_i+1, V_i, V_i+1): everything both interpolations of
-//        policy() need (egdst_simulator.c:178-197) in 48 contiguous bytes.
-// This replaces the two 14-step bisections of bxsearch per agent-period (egdst_lib.c:138-165).
-struct EgdstLutEntry { int l, cnt; double m; };
-struct EgdstInterval { double g0, g1, c0, c1, v0, v1; };
-struct EgdstSimTab {
-    const EgdstInterval *ivl;
-    const EgdstLutEntry *lut;
-    int rowcap, lutcap, mbits;
-};
-
-EGDST_DEV int egdst_lut_key(double x, double a0, int mbits) {
-    const double y = x - a0 + 1.0;
-#ifdef EGDST_HOSTEMU
-    long long bits; memcpy(&bits, &y, 8);
-    const int hi = (int)(bits >> 32);
-#else
-    const int hi = __double2hiint(y);
-#endif
-    return (hi >> (20 - mbits)) - (0x3FF00000 >> (20 - mbits));
-}
-
 struct EgdstSimArgs {
     const double *init;        // [nsim] 1-based ist0 of the agents of this launch
     const double *init_m0;     // [nsim] m0 (the second column of the reference's init matrix)
@@ -90,57 +60,7 @@ struct EgdstSimArgs {
     double *moments;           // [3, nsimout, nt] or null
     int nsimout;
     int mom_smem;              // 1: per-CTA moment accumulators for all periods live in shared memory
-    EgdstSimTab tab;
 };
-
-// one CTA per cell: interval table and direct-index table
-__global__ void egdst_k_simtab(EgdstDev P, EgdstInterval *ivl, EgdstLutEntry *lut, int rowcap, int lutcap, int mbits) {
-    const int cell = blockIdx.x;
-    int n = P.mlen[cell];
-    if (n > rowcap) n = rowcap;
-    const double a0 = P.cx.a0;
-    const double *M = egdst_colM(P, cell), *C = egdst_colC(P, cell), *V = egdst_colV(P, cell);
-    EgdstInterval *r = ivl + (size_t)cell * (rowcap - 1);
-    for (int i = threadIdx.x; i + 1 < n; i += blockDim.x) {
-        EgdstInterval v; v.g0 = M[i]; v.g1 = M[i + 1]; v.c0 = C[i]; v.c1 = C[i + 1]; v.v0 = V[i]; v.v1 = V[i + 1];
-        r[i] = v;
-    }
-    EgdstLutEntry *L = lut + (size_t)cell * (lutcap + 1);
-    for (int b = threadIdx.x; b <= lutcap; b += blockDim.x) {
-        // first row whose key is >= b, and >= b+1 (keys are non-decreasing along the grid)
-        int lo = 0, hi = n, lo2 = 0, hi2 = n;
-        if (b == lutcap) { lo = n; lo2 = n; }
-        else {
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if (egdst_lut_key(M[mid], a0, mbits) < b) lo = mid + 1; else hi = mid; }
-            if (b + 1 == lutcap) lo2 = n;
-            else while (lo2 < hi2) { const int mid = (lo2 + hi2) >> 1; if (egdst_lut_key(M[mid], a0, mbits) < b + 1) lo2 = mid + 1; else hi2 = mid; }
-        }
-        EgdstLutEntry e; e.l = lo; e.cnt = lo2 - lo; e.m = lo < n ? M[lo] : EGDST_INF;
-        L[b] = e;
-    }
-}
-
-// Bracket through the direct-index table.  Same result as egdst_bracket(x, M, n, 0) on a strictly increasing
-// grid: (#rows <= x) - 1 clamped to [0, n-2].
-EGDST_DEV int egdst_bracket_tab(double x, const double *__restrict__ M, int n, const EgdstLutEntry *__restrict__ lut, int lutcap, int mbits, double a0) {
-    int b = egdst_lut_key(x, a0, mbits);
-    b = b < 0 ? 0 : (b > lutcap - 1 ? lutcap - 1 : b);
-#ifdef EGDST_HOSTEMU
-    const EgdstLutEntry e = lut[b];
-#else
-    const int4 raw = *reinterpret_cast<const int4 *>(lut + b);  // one 16-byte gather
-    EgdstLutEntry e; e.l = raw.x; e.cnt = raw.y; e.m = __hiloint2double(raw.w, raw.z);
-#endif
-    int cnt = e.l + ((e.cnt > 0 && e.m <= x) ? 1 : 0);
-    if (e.cnt > 1 && e.m <= x) {  // crowded bucket (double points, coarse tables): bisect its remaining rows
-        int l = e.l + 1, h = e.l + e.cnt;
-        while (l < h) { const int mid = (l + h) >> 1; if (M[mid] <= x) l = mid + 1; else h = mid; }
-        cnt = l;
-    }
-    int i = cnt - 1;
-    if (i > n - 2) i = n - 2;
-    return i < 0 ? 0 : i;
-}
 
 // Dynamic shared memory layout of egdst_k_simulate:
 //   tile[warps][32*TS]                one staged record per agent of the warp's tile (TS = nso|1, odd)
@@ -239,15 +159,18 @@ __global__ void __launch_bounds__(EGDST_SIM_BLOCK, EGDST_SIM_MINBLOCKS) egdst_k_
                 const int nm = P.mlen[cell];
                 if (nm < 2) { state = 1; }
                 else {
-                    const EgdstInterval *ivl = S.tab.ivl + (size_t)cell * (S.tab.rowcap - 1);
-                    const int i = egdst_bracket_tab(cur.cash, egdst_colM(P, cell), nm, S.tab.lut + (size_t)cell * (S.tab.lutcap + 1), S.tab.lutcap, S.tab.mbits, cx.a0);
-#ifdef EGDST_HOSTEMU
-                    const EgdstInterval iv = ivl[i];
-#else
-                    const double2 *q = reinterpret_cast<const double2 *>(ivl + i);  // three 16-byte gathers
-                    const double2 q0 = q[0], q1 = q[1], q2 = q[2];
-                    EgdstInterval iv; iv.g0 = q0.x; iv.g1 = q0.y; iv.c0 = q1.x; iv.c1 = q1.y; iv.v0 = q2.x; iv.v1 = q2.y;
-#endif
+                    const int i = egdst_bracket_tab(P, cell, cur.cash, nm);
+                    EgdstInterval iv;
+                    double M1;
+                    if (egdst_cell_has_tab(P, nm)) {
+                        const EgdstInterval *ivl = egdst_cell_ivl(P, cell);
+                        iv = egdst_load_interval(ivl + i);
+                        M1 = ivl[0].g1;
+                    } else {  // oversized cell: plain columns
+                        const double *Mg = egdst_colM(P, cell), *Cg = egdst_colC(P, cell), *Vg = egdst_colV(P, cell);
+                        iv.g0 = Mg[i]; iv.g1 = Mg[i + 1]; iv.c0 = Cg[i]; iv.c1 = Cg[i + 1]; iv.v0 = Vg[i]; iv.v1 = Vg[i + 1];
+                        M1 = Mg[1];
+                    }
                     c = egdst_lerp(cur.cash, iv.g0, iv.g1, iv.c0, iv.c1);
                     cur.savings = cur.cash - c;
                     const int nth = P.thlen[cell];
@@ -257,7 +180,7 @@ __global__ void __launch_bounds__(EGDST_SIM_BLOCK, EGDST_SIM_MINBLOCKS) egdst_k_
                     cur.id = (int)dd[ith > 0 ? ith - 1 : 0];
                     egdst_fill_decision(&cx, &cur);
                     const double evf = P.evf[cell];  // == V(row 0)
-                    if (cur.cash < ivl[0].g1 && evf > -EGDST_INF) vf = utility(&cx, &cur, c) + discount(&cx, &cur) * evf;
+                    if (cur.cash < M1 && evf > -EGDST_INF) vf = utility(&cx, &cur, c) + discount(&cx, &cur) * evf;
                     else vf = egdst_lerp(cur.cash, iv.g0, iv.g1, iv.v0, iv.v1);
                 }
             }

@@ -14,7 +14,7 @@
 // and (iii) the stop rule, which is applied after all N-1 closed-form grid points were evaluated.
 #pragma once
 
-#include "egdst_common.cuh"
+#include "egdst_tables.cuh"
 
 // next-period tables of one state ist1
 struct EgdstNext {
@@ -22,6 +22,9 @@ struct EgdstNext {
     const double *th, *dd;
     int n1, nth;              // n1 = egdims (rows excluding the a0 row)
     double evf;
+    int cell;
+    const EgdstInterval *ivl; // lookup tables of the cell (egdst_tables.cuh)
+    double M1, Mlast, Clast;  // M[1], M[n1], C[n1]
 };
 
 EGDST_DEV EgdstNext egdst_next_tables(const EgdstDev &P, int ivec, int it1, int ist1) {
@@ -35,6 +38,9 @@ EGDST_DEV EgdstNext egdst_next_tables(const EgdstDev &P, int ivec, int it1, int 
     t.dd = P.thD + (size_t)cell * P.cx.nthrhmax;
     t.nth = P.thlen[cell];
     t.evf = P.evf[cell];
+    t.cell = cell;
+    t.ivl = egdst_cell_ivl(P, cell);
+    t.M1 = t.M[1]; t.Mlast = t.M[t.n1]; t.Clast = t.C[t.n1];
     return t;
 }
 
@@ -84,27 +90,34 @@ EGDST_DEV void egdst_eval_nodes(const egdst_ctx *cx, const EgdstDev &P, int ivec
             if (q > acc.badq) break;  // the reference would have stopped before this node
             acc.checksum += pr1;
             next.cash = cashinhand(cx, curr, &next);
-            // one bracket search serves consumption (rows 0..n1) and value (rows 1..n1): the second
-            // bracket of the reference is max(i,1) of the first (same strictly increasing grid).
-            const int i = egdst_bracket(next.cash, t.M, t.n1 + 1, 0);
-            double c1 = egdst_lerp(next.cash, t.M[i], t.M[i + 1], t.C[i], t.C[i + 1]);
-            if (next.cash > t.M[t.n1]) c1 = MAX(c1, t.C[t.n1]);  // constant extrapolation guard (egdst_solver.c:554)
+            // one bracket lookup serves consumption (rows 0..n1) and value (rows 1..n1): the second bracket of the
+            // reference is max(i,1) of the first (same strictly increasing grid); rows i, i+1 come as one record
+            const int i = egdst_bracket_tab(P, t.cell, next.cash, t.n1 + 1);
+            const bool tab = egdst_cell_has_tab(P, t.n1 + 1);
+            EgdstInterval iv;
+            if (tab) iv = egdst_load_interval(t.ivl + i);
+            else { iv.g0 = t.M[i]; iv.g1 = t.M[i + 1]; iv.c0 = t.C[i]; iv.c1 = t.C[i + 1]; iv.v0 = t.V[i]; iv.v1 = t.V[i + 1]; }
+            double c1 = egdst_lerp(next.cash, iv.g0, iv.g1, iv.c0, iv.c1);
+            if (next.cash > t.Mlast) c1 = MAX(c1, t.Clast);  // constant extrapolation guard (egdst_solver.c:554)
             if (c1 <= 0) {
                 acc.badq = q; acc.badtype = EGDST_PT_C1NEG; acc.badcash = next.cash; acc.badshock = next.shock;
                 break;
             }
-            if (cx->optim_MUnoD != 1 || (cx->optim_UnoD != 1 && keep == 1 && next.cash < t.M[1]))
+            if (cx->optim_MUnoD != 1 || (cx->optim_UnoD != 1 && keep == 1 && next.cash < t.M1))
                 next.id = egdst_optimd(next.cash, t.th, t.dd, t.nth);
             else
                 next.id = 0;
             acc.rhs += pr1 * utility_marginal(cx, &next, c1) * cashinhand_marginal(cx, curr, &next);
             if (keep == 1) {
                 double v1;
-                if (next.cash < t.M[1] && t.evf > -EGDST_INF) {
+                if (next.cash < t.M1 && t.evf > -EGDST_INF) {
                     v1 = utility(cx, &next, next.cash - cx->a0) + discount(cx, &next) * t.evf;  // egdst_solver.c:763
                 } else {
-                    const int j = i < 1 ? 1 : i;
-                    v1 = egdst_linter_extrap_at(cx, &next, next.cash, j - 1, t.n1, t.M + 1, t.V + 1);
+                    if (i < 1) {  // value table starts at row 1 (row 0 of V is evf(a0), not a value)
+                        if (tab) iv = egdst_load_interval(t.ivl + 1);
+                        else { iv.g0 = t.M[1]; iv.g1 = t.M[2]; iv.v0 = t.V[1]; iv.v1 = t.V[2]; }
+                    }
+                    v1 = egdst_linter_extrap_iv(cx, &next, next.cash, iv.g0, iv.g1, iv.v0, iv.v1, t.M1, t.Mlast);
                 }
                 const double term = pr1 * v1;
                 acc.evf += term;
