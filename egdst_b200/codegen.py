@@ -279,6 +279,36 @@ def _ctxify(model, s: str) -> str:
     return s
 
 
+def shock_independent_of_savings(model) -> bool:
+    """True when neither the shock parameters nor the transition probabilities can depend on end-of-period
+    savings (the strings, after equation references are expanded one level, mention neither ``savings`` nor ``cash``
+    nor ``shock``).  Then the quadrature shocks and their probabilities are the same for every point of the savings
+    grid and the EGM kernel computes them once per CTA instead of once per node."""
+    import re as _re
+    eqrefs = {e["ref"]: (e["expression"] if isinstance(e["expression"], str) else " ".join(e["expression"])) for e in model.eq}
+
+    def text(x):
+        return x if isinstance(x, str) else " ".join(str(v) for v in x)
+
+    def depends(expr, depth=0):
+        expr = text(expr)
+        if _re.search(r"\b(savings|cash|shock)\b", expr):
+            return True
+        if depth < 4:
+            for ref, body in eqrefs.items():
+                if _re.search(r"\b" + _re.escape(ref) + r"\b", expr) and depends(body, depth + 1):
+                    return True
+        return False
+
+    if depends(model.shock["mu"]) or depends(model.shock["sigma"]):
+        return False
+    for t in model.trpr:
+        for c in t["cases"]:
+            if depends(c["condition"]) or any(depends(x) for row in c["prob"] for x in row):
+                return False
+    return True
+
+
 def emit_devspec(model) -> str:
     """One header with every model function of the reference's modelspec (compile.m:254-655),
     ctx-explicit.  ``EGDST_FN`` / ``EGDST_CONST`` / ``egdst_ctx`` come from ``egdst_modelctx.h``."""
@@ -293,6 +323,7 @@ def emit_devspec(model) -> str:
           "#define EGDST_NNST %d" % ns, "#define EGDST_NND %d" % ndv,
           "#define EGDST_NREQ %d" % len(model.eq), "#define EGDST_NPARAM %d" % len(model.param),
           "#define EGDST_DISTRIB %d" % (1 if model.shock["type"] == "lognormal" else 2),
+          "#define EGDST_SHOCK_INDEP_A %d" % (1 if shock_independent_of_savings(model) else 0),
           '#include "egdst_modelctx.h"', ""]
     for cf in model.coef:
         arr = cf["array"]

@@ -144,9 +144,11 @@ __global__ void egdst_k_cells(EgdstDev P, int it) {
     for (int i = threadIdx.x; i < nsdv; i += blockDim.x) P.foldCnt[sd0 + i] = 0;
     for (int i = threadIdx.x; i < nsdv * P.chE; i += blockDim.x) P.scanE[(size_t)sd0 * P.chE + i] = 0ULL;          // secondary slots
     for (int i = threadIdx.x; i < nsdv * 2; i += blockDim.x) P.tickE[2 * sd0 + i] = 0;
+    for (int i = threadIdx.x; i < nsdv; i += blockDim.x) P.envNact[sd0 + i] = 0;
     const int ps0 = P.nvec * nsdv + ivec * P.cx.nst;                                                                // primary slots
     for (int i = threadIdx.x; i < P.cx.nst * P.chE; i += blockDim.x) P.scanE[(size_t)ps0 * P.chE + i] = 0ULL;
     for (int i = threadIdx.x; i < P.cx.nst * 2; i += blockDim.x) P.tickE[2 * ps0 + i] = 0;
+    for (int i = threadIdx.x; i < P.cx.nst; i += blockDim.x) P.envNact[ps0 + i] = 0;
     const int ist = threadIdx.x;
     if (ist >= P.cx.nst) return;
     egdst_ctx cx; egdst_load_ctx(P, ivec, cx);
@@ -250,7 +252,7 @@ static int create_solution(const egdst_desc *d, int nvec, egdst_solution **out) 
     P.chC = (P.N + EGDST_CMP_CHUNK - 1) / EGDST_CMP_CHUNK + 1;
     P.chE = (P.envcap + EGDST_ENV_CHUNK - 1) / EGDST_ENV_CHUNK + 1;
     DA(P.scanC, (size_t)s->nsd * P.chC); DA(P.tickC, (size_t)2 * s->nsd); DA(P.foldList, (size_t)s->nsd * (P.gcap + 1)); DA(P.foldCnt, s->nsd);
-    DA(P.scanE, (size_t)s->nslot * P.chE); DA(P.tickE, (size_t)2 * s->nslot);
+    DA(P.scanE, (size_t)s->nslot * P.chE); DA(P.tickE, (size_t)2 * s->nslot); DA(P.envNact, s->nslot);
     DA(P.status, 4 * nvec); DA(P.units, nvec); DA(s->d_moff, s->ncell + 1); DA(s->d_toff, s->ncell + 1);
 #undef DA
     cudaMemset(P.units, 0, sizeof(unsigned long long) * nvec);
@@ -293,6 +295,10 @@ static int run_solve(egdst_solution *s, const egdst_desc *d, const double *param
     CK(cudaMemsetAsync(P.mlen, 0, sizeof(int) * s->ncell, st));
     CK(cudaMemsetAsync(P.thlen, 0, sizeof(int) * s->ncell, st));
     const int nst = P.cx.nst, nd = P.cx.nd, nvec = P.nvec, N = P.N, B = EGDST_BLOCK;
+    // per-CTA table of quadrature shocks and node probabilities (models whose shocks cannot depend on savings)
+    const size_t shbytes = (size_t)2 * nst * P.cx.ny * sizeof(double);
+    const int useTab = (EGDST_SHOCK_INDEP_A && shbytes <= 40 * 1024) ? 1 : 0;
+    const size_t shsmem = useTab ? shbytes : 0;
     int tabblocks = (P.lutcap + 1 + B - 1) / B;
     if (nvec * nst * tabblocks > 4096) tabblocks = (4096 + nvec * nst - 1) / (nvec * nst);  // batched sweeps: fewer, looping CTAs per cell
     const int cellthreads = ((nst + 31) / 32) * 32 < 128 ? 128 : ((nst + 31) / 32) * 32;
@@ -301,8 +307,8 @@ static int run_solve(egdst_solution *s, const egdst_desc *d, const double *param
         if (it == P.NT - 1) {
             KLAUNCH(KC_TERMINAL, egdst_k_terminal, dim3((N + B - 1) / B, nst * nd, nvec), dim3(B), 0, st, P, it);
         } else {
-            KLAUNCH(KC_SEED, egdst_k_seed, dim3(nd, nst, nvec), dim3(B), 0, st, P, it);
-            KLAUNCH(KC_EGM, egdst_k_egm, dim3((N - 1 + 31) / 32, nst * nd, nvec), dim3(32, EGDST_EGM_SPLIT), 0, st, P, it);
+            KLAUNCH(KC_SEED, egdst_k_seed, dim3(nd, nst, nvec), dim3(B), shsmem, st, P, it, useTab);
+            KLAUNCH(KC_EGM, egdst_k_egm, dim3((N - 1 + 31) / 32, nst * nd, nvec), dim3(32, EGDST_EGM_SPLIT), shsmem, st, P, it, useTab);
             KLAUNCH(KC_COMPACT, egdst_k_compact, dim3(P.chC, nst * nd, nvec), dim3(EGDST_CMP_THREADS), 0, st, P, it);
             // secondary envelope (no-op for (ist,id) without folds)
             KLAUNCH(KC_ENV2, egdst_k_envA<1>, dim3((2 * P.gcap + B - 1) / B, nst * nd, nvec), dim3(B), 0, st, P, it);

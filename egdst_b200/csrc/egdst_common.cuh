@@ -70,6 +70,7 @@ struct EgdstDev {
     int *tickC, *tickE;                 // [nsd*2], [nslot*2]
     int chC, chE;                       // chunks per job
     int *foldList, *foldCnt;            // [nsd*(gcap+1)] unordered fold positions, [nsd]
+    int *envNact;                       // [nslot] active prefix length of the merged union (egdst_k_envA)
     // per-cell lookup tables (egdst_tables.cuh)
     EgdstInterval *tabIvl;              // [ncell*tabcap]
     EgdstLutEntry *tabLut;              // [ncell*(lutcap+1)]

@@ -170,7 +170,8 @@ __global__ void egdst_k_envA(EgdstDev P, int it) {
     }
     size_t o = (size_t)slot * P.envcap + rank;
     P.mgX[o] = x; P.mgF[o] = f; P.mgK[o] = k; P.mgA[o] = best;
-    (void)grb;
+    // the active positions of the union are the prefix with x <= grb: its length for the merge kernel
+    if (x <= grb) atomicMax(P.envNact + slot, rank + 1);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -197,7 +198,7 @@ EGDST_DEV double egdst_env_brsolve(const egdst_ctx *cx, const View &E, int it, i
 
 template <class View>
 EGDST_DEV void egdst_env_chain(const egdst_ctx *cx, const View &E, int it, int ist, double xr, double vr, int fr, int kr,
-                               int pri0, int nwi0, bool write, double *gx, double *gv, double *gc, int gleft,
+                               int pri0, int nwi0, bool write, double *gx, double *gv, double *gc, double *ga, int gleft,
                                double *tth, double *tdd, int tleft, int &ng, int &nt, int *err) {
     unsigned marks[EGDST_ENV_MARKW];
     for (int w = 0; w < EGDST_ENV_MARKW; w++) marks[w] = 0u;
@@ -270,9 +271,17 @@ EGDST_DEV void egdst_env_chain(const egdst_ctx *cx, const View &E, int it, int i
         const double c_left = egdst_env_value2(cx, E, p, cp, newpoint), c_right = egdst_env_value2(cx, E, q, cq, newpoint);
         const bool single = (E.evf(q) == -EGDST_INF && cq == -1);  // egdst_solver.c:1892-1896
         if (write && (threadIdx.x & 31) == 0) {
-            if (ng < gleft) { gx[ng] = single ? newpoint - cx->tolerance : newpoint; gv[ng] = cmax; gc[ng] = c_left; }
+            if (ng < gleft) {
+                const double xs = single ? newpoint - cx->tolerance : newpoint;
+                gx[ng] = xs; gv[ng] = cmax; gc[ng] = c_left;
+                if (ga) ga[ng] = xs - c_left;
+            }
             if (nt < tleft) { tth[nt] = newpoint; tdd[nt] = (double)q; }
-            if (!single && ng + 1 < gleft) { gx[ng + 1] = newpoint + cx->doublepoint_delta; gv[ng + 1] = cmax; gc[ng + 1] = c_right; }
+            if (!single && ng + 1 < gleft) {
+                const double xd = newpoint + cx->doublepoint_delta;
+                gx[ng + 1] = xd; gv[ng + 1] = cmax; gc[ng + 1] = c_right;
+                if (ga) ga[ng + 1] = xd - c_right;
+            }
         }
         ng += single ? 1 : 2;
         nt += 1;
@@ -293,7 +302,7 @@ EGDST_DEV void egdst_env_chain(const egdst_ctx *cx, const View &E, int it, int i
 // are run one after the other by the whole warp.
 template <int MODE, bool WRITE>
 EGDST_DEV void egdst_env_item(const egdst_ctx *cx, const EgdstEnvView<MODE> &E, int it, int ist, const double *mgX, const int *mgF,
-                              const int *mgK, const int *mgA, bool valid, int r, double grb, double *ox, double *ov, double *oc, int gcapacity,
+                              const int *mgK, const int *mgA, bool valid, int r, double grb, double *ox, double *ov, double *oc, double *oa, int gcapacity,
                               double *oth, double *odd, int tcapacity, int gpos, int tpos, int &ng, int &nt, int *err) {
     double x = 0, v = 0, c = 0;
     int f = 0, k = 0, a = 0, aprev = 0;
@@ -319,10 +328,10 @@ EGDST_DEV void egdst_env_item(const egdst_ctx *cx, const EgdstEnvView<MODE> &E, 
         const int bg = __shfl_sync(EGDST_FULL, gpos, src), bt = __shfl_sync(EGDST_FULL, tpos, src);
         int cg, ct;
         if (WRITE)
-            egdst_env_chain(cx, E, it, ist, bx, bv, bf, bk, bp, ba, true, ox + bg, ov + bg, oc + bg, gcapacity - bg,
+            egdst_env_chain(cx, E, it, ist, bx, bv, bf, bk, bp, ba, true, ox + bg, ov + bg, oc + bg, oa ? oa + bg : (double *)0, gcapacity - bg,
                             MODE == 0 ? oth + bt : (double *)0, MODE == 0 ? odd + bt : (double *)0, MODE == 0 ? tcapacity - bt : 0, cg, ct, err);
         else
-            egdst_env_chain(cx, E, it, ist, bx, bv, bf, bk, bp, ba, false, (double *)0, (double *)0, (double *)0, 0, (double *)0, (double *)0, 0, cg, ct, err);
+            egdst_env_chain(cx, E, it, ist, bx, bv, bf, bk, bp, ba, false, (double *)0, (double *)0, (double *)0, (double *)0, 0, (double *)0, (double *)0, 0, cg, ct, err);
         if (lane == src) { ng += cg; nt += ct; gpos += cg; }
     }
     if (valid && newx) {
@@ -338,7 +347,7 @@ EGDST_DEV void egdst_env_item(const egdst_ctx *cx, const EgdstEnvView<MODE> &E, 
             }
         }
         if (emit) {
-            if (WRITE && gpos < gcapacity) { ox[gpos] = x; ov[gpos] = v; oc[gpos] = c; }
+            if (WRITE && gpos < gcapacity) { ox[gpos] = x; ov[gpos] = v; oc[gpos] = c; if (oa) oa[gpos] = x - c; }
             ng += 1;
         }
     }
@@ -361,11 +370,11 @@ __global__ void __launch_bounds__(EGDST_ENVW) egdst_k_envBC(EgdstDev P, int it) 
     const double *mgX = P.mgX + (size_t)slot * P.envcap;
     const int *mgF = P.mgF + (size_t)slot * P.envcap, *mgK = P.mgK + (size_t)slot * P.envcap, *mgA = P.mgA + (size_t)slot * P.envcap;
     volatile unsigned long long *st = P.scanE + (size_t)slot * P.chE;
-    double *ox, *oc, *ov, *oth = 0, *odd = 0;
+    double *ox, *oc, *ov, *oa = 0, *oth = 0, *odd = 0;
     int gcapacity, tcapacity = 0, cell = 0;
     if (MODE == 0) {
         cell = egdst_cell(P, ivec, it, ist);
-        ox = egdst_colM(P, cell) + 1; oc = egdst_colC(P, cell) + 1; ov = egdst_colV(P, cell) + 1;
+        ox = egdst_colM(P, cell) + 1; oc = egdst_colC(P, cell) + 1; ov = egdst_colV(P, cell) + 1; oa = egdst_colA(P, cell) + 1;
         oth = P.thTH + (size_t)cell * cx.nthrhmax; odd = P.thD + (size_t)cell * cx.nthrhmax;
         gcapacity = P.rowcap - 1; tcapacity = cx.nthrhmax;
     } else {
@@ -373,12 +382,10 @@ __global__ void __launch_bounds__(EGDST_ENVW) egdst_k_envBC(EgdstDev P, int it) 
         gcapacity = P.envcap;
     }
     // unified grid bound = min over functions of the last abscissa (egdst_solver.c:1266-1271); the union is
-    // sorted, so the active positions are the prefix with x<=grb
+    // sorted, so the active positions are the prefix with x<=grb, whose length egdst_k_envA recorded
     double grb = EGDST_INF;
     for (int g = 0; g < E.F; g++) { const int ng_ = E.npts(g); if (ng_ > 0) { const double xl = E.x(g, ng_ - 1); if (xl < grb) grb = xl; } }
-    const int Ptot = E.pstart(E.F - 1) + E.npts(E.F - 1);
-    int nact;
-    { int lo = 0, hi = Ptot; while (lo < hi) { int mid = (lo + hi) >> 1; if (mgX[mid] <= grb) lo = mid + 1; else hi = mid; } nact = lo; }
+    const int nact = P.envNact[slot];
     const int nch = (nact + EGDST_ENV_CHUNK - 1) / EGDST_ENV_CHUNK;
     if (threadIdx.x == 0) s_chunk = atomicAdd(P.tickE + 2 * slot, 1);
     __syncthreads();
@@ -389,7 +396,7 @@ __global__ void __launch_bounds__(EGDST_ENVW) egdst_k_envBC(EgdstDev P, int it) 
         int ngj[EGDST_ENV_IPT], ntj[EGDST_ENV_IPT], ngs = 0, nts = 0;
 #pragma unroll
         for (int j = 0; j < EGDST_ENV_IPT; j++) {
-            egdst_env_item<MODE, false>(&cx, E, it, ist, mgX, mgF, mgK, mgA, r0 + j < nact, r0 + j, grb, ox, ov, oc, gcapacity, oth, odd, tcapacity, 0, 0, ngj[j], ntj[j], &err);
+            egdst_env_item<MODE, false>(&cx, E, it, ist, mgX, mgF, mgK, mgA, r0 + j < nact, r0 + j, grb, ox, ov, oc, oa, gcapacity, oth, odd, tcapacity, 0, 0, ngj[j], ntj[j], &err);
             ngs += ngj[j]; nts += ntj[j];
         }
         long long tot;
@@ -405,7 +412,7 @@ __global__ void __launch_bounds__(EGDST_ENVW) egdst_k_envBC(EgdstDev P, int it) 
             int g2, t2;
             // warp-uniform skip: nothing to write for this j anywhere in the warp
             if (__ballot_sync(EGDST_FULL, (ngj[j] | ntj[j]) != 0))
-                egdst_env_item<MODE, true>(&cx, E, it, ist, mgX, mgF, mgK, mgA, r0 + j < nact, r0 + j, grb, ox, ov, oc, gcapacity, oth, odd, tcapacity, gpos, tpos, g2, t2, &err);
+                egdst_env_item<MODE, true>(&cx, E, it, ist, mgX, mgF, mgK, mgA, r0 + j < nact, r0 + j, grb, ox, ov, oc, oa, gcapacity, oth, odd, tcapacity, gpos, tpos, g2, t2, &err);
             gpos += ngj[j]; tpos += ntj[j];
         }
     }
@@ -432,11 +439,8 @@ __global__ void __launch_bounds__(EGDST_ENVW) egdst_k_envBC(EgdstDev P, int it) 
             P.mlen[cell] = n + 1;
             P.thlen[cell] = nth < tcapacity ? nth : tcapacity;
             egdst_colM(P, cell)[0] = cx.a0; egdst_colC(P, cell)[0] = 0.0; egdst_colV(P, cell)[0] = e;  // saveoutput :931-941
+            egdst_colA(P, cell)[0] = cx.a0 - 0.0;
         }
-        __syncthreads();
-        const int n = nout < gcapacity ? nout : gcapacity;
-        double *Mc = egdst_colM(P, cell), *Cc = egdst_colC(P, cell), *Ac = egdst_colA(P, cell);
-        for (int i = threadIdx.x; i <= n; i += blockDim.x) Ac[i] = EGDST_LDCG(Mc + i) - EGDST_LDCG(Cc + i);
     } else {
         const int sd = slot;
         if (threadIdx.x == 0 && nout >= cx.ngridmax) egdst_fail(P, ivec, EGDST_ERR_ENV2SPACE, it, ist, id);

@@ -55,8 +55,32 @@ struct EgdstAcc {
 
 // Evaluate nodes q = part, part+nparts, ... of the expectation at end-of-period savings A
 // (egdst_solver.c:494-574).  keep==0 skips the value function (adraw seed phase).
+// Quadrature shocks and node probabilities of one (it, ist, id) for every (ist1, iy): shk/shp [nst*ny].
+// Valid when the model image says they cannot depend on savings (EGDST_SHOCK_INDEP_A, codegen): computed once
+// per CTA instead of once per node (one exp per node saved).  shp == 0 marks nodes the reference skips
+// (infeasible ist1, zero transition probability, iy >= niy).
+EGDST_DEV void egdst_fill_shocktab(const egdst_ctx *cx, const EgdstDev &P, const PeriodVars *curr, double *shk, double *shp, int tid, int nthreads) {
+    const int ny = cx->ny, nst = cx->nst;
+    for (int q = tid; q < nst * ny; q += nthreads) {
+        const int ist1 = q / ny, iy = q - ist1 * ny;
+        PeriodVars next;
+        next.it = curr->it + 1; next.savings = 0.0; next.id = 0; next.cash = 0.0; next.shock = 0.0; next.ist = ist1;
+        double p = 0.0, sh = 0.0;
+        if (feasible(cx, &next) == 1) {
+            const int niy = (sigma_param(cx, curr, &next) <= 0 || ny == 1) ? 1 : ny;
+            if (iy < niy) {
+                sh = (niy == 1) ? egdst_expectation(cx, curr, &next) : egdst_rescale(cx, curr, &next, P.qz[iy]);
+                next.shock = sh;
+                p = trpr(cx, curr, &next, 1);
+                if (niy > 1) p *= P.qw[iy];
+            }
+        }
+        shk[q] = sh; shp[q] = p;
+    }
+}
+
 EGDST_DEV void egdst_eval_nodes(const egdst_ctx *cx, const EgdstDev &P, int ivec, const PeriodVars *curr, double A, int keep,
-                                int part, int nparts, EgdstAcc &acc) {
+                                int part, int nparts, EgdstAcc &acc, const double *shk = 0, const double *shp = 0) {
     const int ny = cx->ny, nst = cx->nst;
     acc.rhs = 0.0; acc.evf = 0.0; acc.checksum = 0.0; acc.badq = EGDST_NOBAD; acc.badtype = 0; acc.badcash = 0.0; acc.badshock = 0.0;
     PeriodVars next;
@@ -69,15 +93,21 @@ EGDST_DEV void egdst_eval_nodes(const egdst_ctx *cx, const EgdstDev &P, int ivec
         next.ist = ist1;
         if (feasible(cx, &next) != 1) continue;
         double pr1pre = 0.0;
-        if (cx->optim_TRPRnoSH == 1) {
-            pr1pre = trpr(cx, curr, &next, 1);
-            if (pr1pre == 0.0) continue;
+        int niy = ny;
+        if (!shk) {
+            if (cx->optim_TRPRnoSH == 1) {
+                pr1pre = trpr(cx, curr, &next, 1);
+                if (pr1pre == 0.0) continue;
+            }
+            niy = (sigma_param(cx, curr, &next) <= 0 || ny == 1) ? 1 : ny;
         }
-        const int niy = (sigma_param(cx, curr, &next) <= 0 || ny == 1) ? 1 : ny;
         const EgdstNext t = egdst_next_tables(P, ivec, next.it, ist1);
         for (int iy = part; iy < niy; iy += nparts) {
             double pr1;
-            if (niy == 1) {
+            if (shk) {
+                pr1 = shp[ist1 * ny + iy];
+                next.shock = shk[ist1 * ny + iy];
+            } else if (niy == 1) {
                 next.shock = egdst_expectation(cx, curr, &next);
                 pr1 = (cx->optim_TRPRnoSH != 1) ? trpr(cx, curr, &next, 1) : pr1pre;
             } else {
@@ -97,6 +127,8 @@ EGDST_DEV void egdst_eval_nodes(const egdst_ctx *cx, const EgdstDev &P, int ivec
             EgdstInterval iv;
             if (tab) iv = egdst_load_interval(t.ivl + i);
             else { iv.g0 = t.M[i]; iv.g1 = t.M[i + 1]; iv.c0 = t.C[i]; iv.c1 = t.C[i + 1]; iv.v0 = t.V[i]; iv.v1 = t.V[i + 1]; }
+            // the reference's operation order is kept (two divisions per interpolation, egdst_lib.c:175): next to its
+            // instability boundary a reciprocal-multiply variant drifted 1e-2 away in C
             double c1 = egdst_lerp(next.cash, iv.g0, iv.g1, iv.c0, iv.c1);
             if (next.cash > t.Mlast) c1 = MAX(c1, t.Clast);  // constant extrapolation guard (egdst_solver.c:554)
             if (c1 <= 0) {
@@ -187,9 +219,9 @@ struct EgdstSeedShared {
 };
 
 EGDST_DEV void egdst_block_eval(const egdst_ctx *cx, const EgdstDev &P, int ivec, const PeriodVars *curr, double A, int keep,
-                                EgdstSeedShared &S) {
+                                EgdstSeedShared &S, const double *shk, const double *shp) {
     EgdstAcc a;
-    egdst_eval_nodes(cx, P, ivec, curr, A, keep, threadIdx.x, blockDim.x, a);
+    egdst_eval_nodes(cx, P, ivec, curr, A, keep, threadIdx.x, blockDim.x, a, shk, shp);
     egdst_warp_combine(a);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
     if (lane == 0) { S.wr[w] = a.rhs; S.we[w] = a.evf; S.wc[w] = a.checksum; S.wq[w] = a.badq; S.wt[w] = a.badtype; S.wcash[w] = a.badcash; S.wshock[w] = a.badshock; }
@@ -202,8 +234,9 @@ EGDST_DEV void egdst_block_eval(const egdst_ctx *cx, const EgdstDev &P, int ivec
     __syncthreads();
 }
 
-__global__ void egdst_k_seed(EgdstDev P, int it) {
+__global__ void egdst_k_seed(EgdstDev P, int it, int useTab) {
     __shared__ EgdstSeedShared S;
+    EGDST_DYN_SMEM(double, shsm);
     const int ivec = blockIdx.z, ist = blockIdx.y, id = blockIdx.x;
     egdst_ctx cx; egdst_load_ctx(P, ivec, cx);
     const int sd = egdst_sd(P, ivec, ist, id);
@@ -229,6 +262,12 @@ __global__ void egdst_k_seed(EgdstDev P, int it) {
     if (!act) return;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const double beta = discount(&cx, &curr);
+    const double *shk = 0, *shp = 0;
+    if (useTab) {  // shocks and node probabilities of this (it, ist, id), once per CTA
+        egdst_fill_shocktab(&cx, P, &curr, shsm, shsm + cx.nst * cx.ny, threadIdx.x, blockDim.x);
+        shk = shsm; shp = shsm + cx.nst * cx.ny;
+        __syncthreads();
+    }
     // stage 0 in waves of one candidate per warp: the base point is almost always among the first few
     // candidates (mmax, (mmax+a0)/2, ...), so later waves rarely run
     double baseA = 0, baseM = 0;
@@ -238,7 +277,7 @@ __global__ void egdst_k_seed(EgdstDev P, int it) {
         const int kk = k0 + w;
         if (kk < S.ncand) {
             EgdstAcc a;
-            egdst_eval_nodes(&cx, P, ivec, &curr, S.candA[kk], 0, lane, 32, a);
+            egdst_eval_nodes(&cx, P, ivec, &curr, S.candA[kk], 0, lane, 32, a, shk, shp);
             egdst_warp_combine(a);
             if (lane == 0) {
                 int bad = 0;
@@ -273,7 +312,7 @@ __global__ void egdst_k_seed(EgdstDev P, int it) {
     double lim1 = 0, lim2 = 0, lim3 = 0, lim2p = 0, lim3p = 0, k3 = 0, lastA = cx.a0, aM = 0, evfa0 = 0.0;
     int stored = 0;
     while (true) {
-        egdst_block_eval(&cx, P, ivec, &curr, S.A, 1, S);
+        egdst_block_eval(&cx, P, ivec, &curr, S.A, 1, S, shk, shp);
         if (threadIdx.x == 0) {
             lastA = S.A;
             int resend = 0, fatal = 0;
@@ -361,7 +400,8 @@ EGDST_DEV double egdst_agrid(const egdst_ctx *cx, const PeriodVars *curr, const 
 #endif
 #endif
 
-__global__ void egdst_k_egm(EgdstDev P, int it) {
+__global__ void egdst_k_egm(EgdstDev P, int it, int useTab) {
+    EGDST_DYN_SMEM(double, shsm);
     __shared__ double s_rhs[EGDST_EGM_SPLIT][32], s_evf[EGDST_EGM_SPLIT][32], s_chk[EGDST_EGM_SPLIT][32], s_cash[EGDST_EGM_SPLIT][32];
     __shared__ int s_q[EGDST_EGM_SPLIT][32], s_t[EGDST_EGM_SPLIT][32];
     const int ivec = blockIdx.z, ist = blockIdx.y / P.cx.nd, id = blockIdx.y % P.cx.nd;
@@ -375,9 +415,15 @@ __global__ void egdst_k_egm(EgdstDev P, int it) {
     const double *seed = P.seed + (size_t)sd * 8;
     double A = 0.0;
     EgdstAcc a; a.rhs = 0; a.evf = 0; a.checksum = 0; a.badq = EGDST_NOBAD; a.badtype = 0; a.badcash = 0; a.badshock = 0;
+    const double *shk = 0, *shp = 0;
+    if (useTab) {  // shocks and node probabilities of this (it, ist, id), once per CTA
+        egdst_fill_shocktab(&cx, P, &curr, shsm, shsm + cx.nst * cx.ny, threadIdx.y * 32 + threadIdx.x, 32 * EGDST_EGM_SPLIT);
+        shk = shsm; shp = shsm + cx.nst * cx.ny;
+        __syncthreads();
+    }
     if (n < N) {
         A = egdst_agrid(&cx, &curr, seed, n, N);
-        egdst_eval_nodes(&cx, P, ivec, &curr, A, 1, part, EGDST_EGM_SPLIT, a);
+        egdst_eval_nodes(&cx, P, ivec, &curr, A, 1, part, EGDST_EGM_SPLIT, a, shk, shp);
     }
     s_rhs[part][lane] = a.rhs; s_evf[part][lane] = a.evf; s_chk[part][lane] = a.checksum;
     s_q[part][lane] = a.badq; s_t[part][lane] = a.badtype; s_cash[part][lane] = a.badcash;

@@ -56,18 +56,44 @@ __global__ void egdst_k_tab(EgdstDev P, int it) {
         EgdstInterval v; v.g0 = M[i]; v.g1 = M[i + 1]; v.c0 = C[i]; v.c1 = C[i + 1]; v.v0 = V[i]; v.v1 = V[i + 1];
         r[i] = v;
     }
+    // direct index, row-centric (no searches): row r is the first row with key >= b for every bucket b in
+    // (key(r-1), key(r)]; the bucket key(r) also gets the number of rows that share the key
     EgdstLutEntry *L = P.tabLut + (size_t)cell * (P.lutcap + 1);
-    for (int b = t0; b <= P.lutcap; b += stride) {
-        // first row whose key is >= b, and >= b+1 (keys are non-decreasing along the grid)
-        int lo = 0, hi = n, lo2 = 0, hi2 = n;
-        if (b == P.lutcap) { lo = n; lo2 = n; }
-        else {
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if (egdst_lut_key(M[mid], a0, P.mbits) < b) lo = mid + 1; else hi = mid; }
-            if (b + 1 == P.lutcap) lo2 = n;
-            else { lo2 = lo; while (lo2 < hi2) { const int mid = (lo2 + hi2) >> 1; if (egdst_lut_key(M[mid], a0, P.mbits) < b + 1) lo2 = mid + 1; else hi2 = mid; } }
+    const int kmax = P.lutcap - 1;
+    const int lane = threadIdx.x & 31;
+    for (int base = blockIdx.x * blockDim.x; base < n; base += stride) {  // warp-uniform trip count
+        const int r = base + threadIdx.x;
+        int gap0 = 0, gap1 = 0;
+        EgdstLutEntry e; e.l = r; e.cnt = 0; e.m = 0.0;
+        if (r < n) {
+            const double m = M[r];
+            int kr = egdst_lut_key(m, a0, P.mbits); kr = kr < 0 ? 0 : (kr > kmax ? kmax : kr);
+            int kp = -1;
+            if (r > 0) { kp = egdst_lut_key(M[r - 1], a0, P.mbits); kp = kp < 0 ? 0 : (kp > kmax ? kmax : kp); }
+            if (kr > kp) {
+                int cnt = 1;
+                while (r + cnt < n) { int kn = egdst_lut_key(M[r + cnt], a0, P.mbits); kn = kn < 0 ? 0 : (kn > kmax ? kmax : kn); if (kn != kr) break; cnt++; }
+                e.m = m; e.cnt = cnt;
+                L[kr] = e;
+                e.cnt = 0;
+                gap0 = kp + 1; gap1 = kr;  // empty buckets [gap0, gap1) point at row r too
+            }
         }
-        EgdstLutEntry e; e.l = lo; e.cnt = lo2 - lo; e.m = lo < n ? M[lo] : EGDST_INF;
-        L[b] = e;
+        if (gap1 - gap0 <= 8) { for (int bb = gap0; bb < gap1; bb++) L[bb] = e; gap1 = gap0; }
+        // long runs of empty buckets (coarse stretches of a sym-log grid) are filled by the whole warp
+        unsigned longm = __ballot_sync(EGDST_FULL, gap1 > gap0);
+        while (longm) {
+            const int src = __ffs(longm) - 1;
+            longm &= longm - 1;
+            const int b0 = __shfl_sync(EGDST_FULL, gap0, src), b1 = __shfl_sync(EGDST_FULL, gap1, src);
+            EgdstLutEntry f; f.l = __shfl_sync(EGDST_FULL, e.l, src); f.cnt = 0; f.m = __shfl_sync(EGDST_FULL, e.m, src);
+            for (int bb = b0 + lane; bb < b1; bb += 32) L[bb] = f;
+        }
+    }
+    {   // buckets above the last row's key
+        int kl = egdst_lut_key(M[n - 1], a0, P.mbits); kl = kl < 0 ? 0 : (kl > kmax ? kmax : kl);
+        EgdstLutEntry e; e.l = n; e.cnt = 0; e.m = EGDST_INF;
+        for (int bb = kl + 1 + t0; bb <= P.lutcap; bb += stride) L[bb] = e;
     }
 }
 

@@ -102,6 +102,12 @@ inline int atomicAdd(int *p, int v) { return std::atomic_ref<int>(*p).fetch_add(
 inline double atomicAdd(double *p, double v) { return std::atomic_ref<double>(*p).fetch_add(v); }
 inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return std::atomic_ref<unsigned long long>(*p).fetch_add(v); }
 inline int atomicCAS(int *p, int cmp, int val) { std::atomic_ref<int>(*p).compare_exchange_strong(cmp, val); return cmp; }
+inline int atomicMax(int *p, int v) {
+    std::atomic_ref<int> a(*p);
+    int old = a.load();
+    while (v > old && !a.compare_exchange_weak(old, v)) {}
+    return old;
+}
 inline int atomicMin(int *p, int v) {
     std::atomic_ref<int> a(*p);
     int old = a.load();
