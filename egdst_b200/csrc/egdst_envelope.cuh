@@ -138,8 +138,25 @@ EGDST_DEV bool egdst_env_job(const EgdstDev &P, int ivec, int jy, int &ist, int 
     }
 }
 
+// unified grid bound = min over functions of the last abscissa (egdst_solver.c:1266-1271), computed once per CTA
+// (the secondary envelope can have ~10^2 functions).  sh: 33 doubles.  Contains two __syncthreads().
+template <class View>
+EGDST_DEV double egdst_env_grb_block(const View &E, double *sh) {
+    double g = EGDST_INF;
+    for (int f = threadIdx.x; f < E.F; f += blockDim.x) { const int n = E.npts(f); if (n > 0) { const double xl = E.x(f, n - 1); if (xl < g) g = xl; } }
+    for (int o = 16; o > 0; o >>= 1) { const double w = __shfl_xor_sync(EGDST_FULL, g, o); if (w < g) g = w; }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    if (lane == 0) sh[w] = g;
+    __syncthreads();
+    double r = sh[0];
+    for (int k = 1; k < nw; k++) if (sh[k] < r) r = sh[k];
+    __syncthreads();
+    return r;
+}
+
 template <int MODE>
 __global__ void egdst_k_envA(EgdstDev P, int it) {
+    __shared__ double shg[33];
     const int ivec = blockIdx.z;
     int ist, id, slot;
     EgdstEnvView<MODE> E;
@@ -147,9 +164,7 @@ __global__ void egdst_k_envA(EgdstDev P, int it) {
     egdst_ctx cx; egdst_load_ctx(P, ivec, cx);
     const int Ptot = E.pstart(E.F - 1) + E.npts(E.F - 1);
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    // grid bound: min over functions of the last abscissa (egdst_solver.c:1266-1271)
-    double grb = EGDST_INF;
-    for (int g = 0; g < E.F; g++) { const int ng = E.npts(g); if (ng > 0) { const double xl = E.x(g, ng - 1); if (xl < grb) grb = xl; } }
+    const double grb = egdst_env_grb_block(E, shg);
     if (p >= Ptot) return;
     // flattened index -> (f,k)
     int f = 0;
@@ -297,71 +312,32 @@ EGDST_DEV void egdst_env_chain(const egdst_ctx *cx, const View &E, int it, int i
 // ---------------------------------------------------------------------------------------------
 #define EGDST_ENV_IPT 8
 
-// one position r of the union per lane: what it contributes (ng grid points, nt thresholds) and, when WRITE, the
-// output.  Called by all lanes of a warp (valid=false for lanes without a position): the rare crossing chains
-// are run one after the other by the whole warp.
-template <int MODE, bool WRITE>
-EGDST_DEV void egdst_env_item(const egdst_ctx *cx, const EgdstEnvView<MODE> &E, int it, int ist, const double *mgX, const int *mgF,
-                              const int *mgK, const int *mgA, bool valid, int r, double grb, double *ox, double *ov, double *oc, double *oa, int gcapacity,
-                              double *oth, double *odd, int tcapacity, int gpos, int tpos, int &ng, int &nt, int *err) {
-    double x = 0, v = 0, c = 0;
-    int f = 0, k = 0, a = 0, aprev = 0;
-    bool newx = false, chain = false;
-    ng = 0; nt = 0;
-    if (valid) {
-        x = mgX[r]; f = mgF[r]; k = mgK[r]; a = mgA[r];
-        v = E.v(f, k);
-        newx = (r == 0) || (mgX[r - 1] < x);
-        if (r == 0) {
-            nt = 1;  // (a0, argmax at the first point)  egdst_solver.c:1321-1325
-            if (WRITE) { if (MODE == 0 && tpos < tcapacity) { oth[tpos] = cx->a0; odd[tpos] = (double)a; } tpos += 1; }
-        } else if (newx) { aprev = mgA[r - 1]; chain = aprev != a; }
-    }
-    unsigned need = __ballot_sync(EGDST_FULL, chain);
-    const int lane = threadIdx.x & 31;
-    while (need) {
-        const int src = __ffs(need) - 1;
-        need &= need - 1;
-        const double bx = __shfl_sync(EGDST_FULL, x, src), bv = __shfl_sync(EGDST_FULL, v, src);
-        const int bf = __shfl_sync(EGDST_FULL, f, src), bk = __shfl_sync(EGDST_FULL, k, src);
-        const int bp = __shfl_sync(EGDST_FULL, aprev, src), ba = __shfl_sync(EGDST_FULL, a, src);
-        const int bg = __shfl_sync(EGDST_FULL, gpos, src), bt = __shfl_sync(EGDST_FULL, tpos, src);
-        int cg, ct;
-        if (WRITE)
-            egdst_env_chain(cx, E, it, ist, bx, bv, bf, bk, bp, ba, true, ox + bg, ov + bg, oc + bg, oa ? oa + bg : (double *)0, gcapacity - bg,
-                            MODE == 0 ? oth + bt : (double *)0, MODE == 0 ? odd + bt : (double *)0, MODE == 0 ? tcapacity - bt : 0, cg, ct, err);
-        else
-            egdst_env_chain(cx, E, it, ist, bx, bv, bf, bk, bp, ba, false, (double *)0, (double *)0, (double *)0, (double *)0, 0, (double *)0, (double *)0, 0, cg, ct, err);
-        if (lane == src) { ng += cg; nt += ct; gpos += cg; }
-    }
-    if (valid && newx) {
-        bool emit = false;
-        if (a == f) { emit = true; if (WRITE) c = E.c(f, k); }
-        else if (x == grb) {  // last abscissa of the unified grid: keep the interpolated maximum
-            emit = true;
-            if (WRITE) {
-                const int na = E.npts(a);
-                const int ca = egdst_env_cur(egdst_env_count_before(E, a, x, v, f, k), na);
-                v = egdst_env_value(cx, E, it, ist, a, ca, x);
-                c = egdst_env_value2(cx, E, a, ca, x);
-            }
-        }
-        if (emit) {
-            if (WRITE && gpos < gcapacity) { ox[gpos] = x; ov[gpos] = v; oc[gpos] = c; if (oa) oa[gpos] = x - c; }
-            ng += 1;
-        }
-    }
+// one position r of the union: its own contribution (kept point, first threshold) and whether a crossing chain
+// sits on the boundary before it.  The chains themselves are queued and run one per warp (egdst_k_envBC).
+struct EgdstEnvPos { double x, v; int f, k, a, aprev; bool newx, chain; };
+template <int MODE>
+EGDST_DEV EgdstEnvPos egdst_env_pos(const EgdstEnvView<MODE> &E, const double *mgX, const int *mgF, const int *mgK, const int *mgA, int r) {
+    EgdstEnvPos q;
+    q.x = mgX[r]; q.f = mgF[r]; q.k = mgK[r]; q.a = mgA[r];
+    q.v = E.v(q.f, q.k);
+    q.newx = (r == 0) || (mgX[r - 1] < q.x);
+    q.aprev = 0; q.chain = false;
+    if (r > 0 && q.newx) { q.aprev = mgA[r - 1]; q.chain = q.aprev != q.a; }
+    return q;
 }
 
 #define EGDST_ENV_CHUNK (EGDST_ENVW * EGDST_ENV_IPT)  /* union positions per CTA */
+#define EGDST_ENV_QCAP 512                             /* crossing chains queued per CTA */
 // grid (chE, njobs_y, nvec): the CTAs of one job are chained by a decoupled look-back scan over
 // (grid points, thresholds) emitted so far; the last CTA to finish writes the cell header (MODE 0) or copies the
 // staged result back over the decision's point list (MODE 1).
 template <int MODE>
 __global__ void __launch_bounds__(EGDST_ENVW) egdst_k_envBC(EgdstDev P, int it) {
     __shared__ long long sh[40];
-    __shared__ int s_chunk, s_last;
+    __shared__ double s_grb[33];
+    __shared__ int s_chunk, s_last, s_qn;
     __shared__ unsigned long long s_excl;
+    __shared__ int s_qr[EGDST_ENV_QCAP], s_qg[EGDST_ENV_QCAP], s_qt[EGDST_ENV_QCAP], s_qgpos[EGDST_ENV_QCAP], s_qtpos[EGDST_ENV_QCAP];
     const int ivec = blockIdx.z;
     int ist, id, slot;
     EgdstEnvView<MODE> E;
@@ -381,22 +357,46 @@ __global__ void __launch_bounds__(EGDST_ENVW) egdst_k_envBC(EgdstDev P, int it) 
         ox = P.outX + (size_t)slot * P.envcap; oc = P.outC + (size_t)slot * P.envcap; ov = P.outV + (size_t)slot * P.envcap;
         gcapacity = P.envcap;
     }
-    // unified grid bound = min over functions of the last abscissa (egdst_solver.c:1266-1271); the union is
-    // sorted, so the active positions are the prefix with x<=grb, whose length egdst_k_envA recorded
-    double grb = EGDST_INF;
-    for (int g = 0; g < E.F; g++) { const int ng_ = E.npts(g); if (ng_ > 0) { const double xl = E.x(g, ng_ - 1); if (xl < grb) grb = xl; } }
+    // the active positions of the union are the prefix with x<=grb (length recorded by egdst_k_envA)
+    const double grb = egdst_env_grb_block(E, s_grb);
     const int nact = P.envNact[slot];
     const int nch = (nact + EGDST_ENV_CHUNK - 1) / EGDST_ENV_CHUNK;
-    if (threadIdx.x == 0) s_chunk = atomicAdd(P.tickE + 2 * slot, 1);
+    if (threadIdx.x == 0) { s_chunk = atomicAdd(P.tickE + 2 * slot, 1); s_qn = 0; }
     __syncthreads();
     const int chunk = s_chunk;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     int err = 0, serr = 0;
     if (chunk < nch) {
         const int r0 = chunk * EGDST_ENV_CHUNK + threadIdx.x * EGDST_ENV_IPT;
-        int ngj[EGDST_ENV_IPT], ntj[EGDST_ENV_IPT], ngs = 0, nts = 0;
+        // pass 1: own contribution of every position; crossing chains go to the CTA's queue
+        int ngj[EGDST_ENV_IPT], ntj[EGDST_ENV_IPT], qj[EGDST_ENV_IPT];
 #pragma unroll
         for (int j = 0; j < EGDST_ENV_IPT; j++) {
-            egdst_env_item<MODE, false>(&cx, E, it, ist, mgX, mgF, mgK, mgA, r0 + j < nact, r0 + j, grb, ox, ov, oc, oa, gcapacity, oth, odd, tcapacity, 0, 0, ngj[j], ntj[j], &err);
+            ngj[j] = 0; ntj[j] = 0; qj[j] = -1;
+            const int r = r0 + j;
+            if (r < nact) {
+                const EgdstEnvPos q = egdst_env_pos<MODE>(E, mgX, mgF, mgK, mgA, r);
+                if (r == 0) ntj[j] = 1;  // (a0, argmax at the first point)  egdst_solver.c:1321-1325
+                if (q.newx && (q.a == q.f || q.x == grb)) ngj[j] = 1;
+                if (q.chain) { const int c = atomicAdd(&s_qn, 1); if (c < EGDST_ENV_QCAP) { s_qr[c] = r; qj[j] = c; } else qj[j] = -2; }
+            }
+        }
+        __syncthreads();
+        const int qn = s_qn < EGDST_ENV_QCAP ? s_qn : EGDST_ENV_QCAP;
+        if (s_qn > EGDST_ENV_QCAP) serr = 2;  // more crossings in one chunk than the queue holds
+        // pass 2: one chain per warp, counting
+        for (int c = warp; c < qn; c += nwarps) {
+            const int r = s_qr[c];
+            const EgdstEnvPos q = egdst_env_pos<MODE>(E, mgX, mgF, mgK, mgA, r);
+            int cg, ct;
+            egdst_env_chain(&cx, E, it, ist, q.x, q.v, q.f, q.k, q.aprev, q.a, false, (double *)0, (double *)0, (double *)0, (double *)0, 0, (double *)0, (double *)0, 0, cg, ct, &err);
+            if (lane == 0) { s_qg[c] = cg; s_qt[c] = ct; }
+        }
+        __syncthreads();
+        int ngs = 0, nts = 0;
+#pragma unroll
+        for (int j = 0; j < EGDST_ENV_IPT; j++) {
+            if (qj[j] >= 0) { ngj[j] += s_qg[qj[j]]; ntj[j] += s_qt[qj[j]]; }
             ngs += ngj[j]; nts += ntj[j];
         }
         long long tot;
@@ -407,17 +407,42 @@ __global__ void __launch_bounds__(EGDST_ENVW) egdst_k_envBC(EgdstDev P, int it) 
         }
         __syncthreads();
         int gpos = egdst_scan_lo(s_excl) + (int)(off & 0xffffffffLL), tpos = egdst_scan_hi(s_excl) + (int)(off >> 32);
+        // pass 3: write the kept points; chains get their output offsets
 #pragma unroll
         for (int j = 0; j < EGDST_ENV_IPT; j++) {
-            int g2, t2;
-            // warp-uniform skip: nothing to write for this j anywhere in the warp
-            if (__ballot_sync(EGDST_FULL, (ngj[j] | ntj[j]) != 0))
-                egdst_env_item<MODE, true>(&cx, E, it, ist, mgX, mgF, mgK, mgA, r0 + j < nact, r0 + j, grb, ox, ov, oc, oa, gcapacity, oth, odd, tcapacity, gpos, tpos, g2, t2, &err);
+            const int r = r0 + j;
+            if (r < nact && (ngj[j] | ntj[j])) {
+                const EgdstEnvPos q = egdst_env_pos<MODE>(E, mgX, mgF, mgK, mgA, r);
+                int g = gpos, t = tpos;
+                if (r == 0) { if (MODE == 0 && t < tcapacity) { oth[t] = cx.a0; odd[t] = (double)q.a; } t += 1; }
+                if (qj[j] >= 0) { s_qgpos[qj[j]] = g; s_qtpos[qj[j]] = t; g += s_qg[qj[j]]; }
+                if (q.newx && (q.a == q.f || q.x == grb)) {
+                    double v = q.v, c;
+                    if (q.a == q.f) c = E.c(q.f, q.k);
+                    else {  // last abscissa of the unified grid: keep the interpolated maximum
+                        const int na = E.npts(q.a);
+                        const int ca = egdst_env_cur(egdst_env_count_before(E, q.a, q.x, q.v, q.f, q.k), na);
+                        v = egdst_env_value(&cx, E, it, ist, q.a, ca, q.x);
+                        c = egdst_env_value2(&cx, E, q.a, ca, q.x);
+                    }
+                    if (g < gcapacity) { ox[g] = q.x; ov[g] = v; oc[g] = c; if (oa) oa[g] = q.x - c; }
+                }
+            }
             gpos += ngj[j]; tpos += ntj[j];
+        }
+        __syncthreads();
+        // pass 4: one chain per warp, writing
+        for (int c = warp; c < qn; c += nwarps) {
+            const int r = s_qr[c];
+            const EgdstEnvPos q = egdst_env_pos<MODE>(E, mgX, mgF, mgK, mgA, r);
+            const int bg = s_qgpos[c], bt = s_qtpos[c];
+            int cg, ct;
+            egdst_env_chain(&cx, E, it, ist, q.x, q.v, q.f, q.k, q.aprev, q.a, true, ox + bg, ov + bg, oc + bg, oa ? oa + bg : (double *)0, gcapacity - bg,
+                            MODE == 0 ? oth + bt : (double *)0, MODE == 0 ? odd + bt : (double *)0, MODE == 0 ? tcapacity - bt : 0, cg, ct, &err);
         }
     }
     if (err) egdst_fail(P, ivec, err, it, ist, id);
-    if (serr) egdst_fail(P, ivec, EGDST_ERR_ENV2SPACE, it, ist, id);
+    if (serr) egdst_fail(P, ivec, serr == 2 ? EGDST_ERR_THRSPACE : EGDST_ERR_ENV2SPACE, it, ist, id);
     // last CTA of the job: totals and epilogue
     __threadfence();
     __syncthreads();

@@ -400,7 +400,10 @@ EGDST_DEV double egdst_agrid(const egdst_ctx *cx, const PeriodVars *curr, const 
 #endif
 #endif
 
-__global__ void egdst_k_egm(EgdstDev P, int it, int useTab) {
+#ifndef EGDST_EGM_MINB
+#define EGDST_EGM_MINB 3
+#endif
+__global__ void __launch_bounds__(32 * EGDST_EGM_SPLIT, EGDST_EGM_MINB) egdst_k_egm(EgdstDev P, int it, int useTab) {
     EGDST_DYN_SMEM(double, shsm);
     __shared__ double s_rhs[EGDST_EGM_SPLIT][32], s_evf[EGDST_EGM_SPLIT][32], s_chk[EGDST_EGM_SPLIT][32], s_cash[EGDST_EGM_SPLIT][32];
     __shared__ int s_q[EGDST_EGM_SPLIT][32], s_t[EGDST_EGM_SPLIT][32];
