@@ -142,7 +142,8 @@ def own_arm(a):
     m.device = local
     m.compile()
     lib = m._capi()
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()  # a capturable (non-legacy) stream: the solve replays as a CUDA graph
+    torch.cuda.set_stream(stream)
     lib.set_stream(stream.cuda_stream)
     desc = capi.Desc(m)
     nt, nso = m.nt, m.nsimout()

@@ -105,6 +105,12 @@ struct egdst_solution {
     int *d_moff, *d_toff;
     int neq;
     bool sim_valid;  // (kept for ABI of the struct users) tables are built with every cell now
+    // CUDA graph of the period chain (run_solve)
+    cudaGraphExec_t g_exec;
+    EgdstDev g_P;
+    cudaStream_t g_stream;
+    bool g_seen;
+    long long g_nlaunch;
     size_t bytes;   // device bytes owned (workspace cache policy)
     int dims[12];   // shape signature for re-use
 };
@@ -123,6 +129,9 @@ static egdst_solution *g_cached = 0;
 static const size_t EGDST_CACHE_MAX_BYTES = (size_t)2 << 30;
 static void destroy_solution(egdst_solution *s) {
     cudaSetDevice(s->device);
+#ifndef EGDST_HOSTEMU
+    if (s->g_exec) cudaGraphExecDestroy(s->g_exec);
+#endif
     for (void *p : s->owned) cudaFree(p);
     if (s->d_pack) cudaFree(s->d_pack);
     delete s;
@@ -218,6 +227,7 @@ static int create_solution(const egdst_desc *d, int nvec, egdst_solution **out) 
     }
     egdst_solution *s = new egdst_solution();
     s->bytes = 0; memcpy(s->dims, dims, sizeof(dims));
+    s->g_exec = 0; s->g_seen = false; s->g_stream = 0; s->g_nlaunch = 0;
     s->device = d->device; s->sizes_valid = false; s->sim_valid = false; s->d_pack = 0; s->pack_cap = 0; s->neq = d->neq;
     EgdstDev &P = s->P;
     memset(&P, 0, sizeof(P));
@@ -263,33 +273,9 @@ static int create_solution(const egdst_desc *d, int nvec, egdst_solution **out) 
     return 0;
 }
 
-// one backward-induction pass; asynchronous
-static int run_solve(egdst_solution *s, const egdst_desc *d, const double *params) {
+// one backward-induction pass as a chain of launches on `st` (also what the CUDA graph captures)
+static int launch_periods(egdst_solution *s, cudaStream_t st) {
     EgdstDev &P = s->P;
-    egdst_ctx cx;
-    int rc = fill_ctx(d, &cx);
-    if (rc) return rc;
-    if (d->ny > 1 && !d->quadrature) return fail(2, "quadrature missing");
-    if (d->ngridm != P.N || d->ngridmax != P.gcap || d->T - d->t0 + 1 != P.NT || d->nst != P.cx.nst || d->nd != P.cx.nd ||
-        d->ny != P.cx.ny || d->nthrhmax != P.cx.nthrhmax)
-        return fail(2, "egdst_resolve: dimensions differ from the solution object");
-    CK(cudaSetDevice(s->device));
-    cx.stm = s->d_stm; cx.states = s->d_states; cx.decisions = s->d_decisions;
-    P.cx = cx;
-    cudaStream_t st = g_stream;
-    CK(cudaMemcpyAsync(s->d_stm, d->stm, sizeof(double) * 2 * d->nnst, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(s->d_states, d->states, sizeof(double) * d->nst * d->nnst, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(s->d_decisions, d->decisions, sizeof(double) * d->nd * d->nnd, cudaMemcpyHostToDevice, st));
-    if (params) {
-        CK(cudaMemcpyAsync(s->d_bparams, params, sizeof(double) * (size_t)P.nvec * EGDST_NPARAM, cudaMemcpyHostToDevice, st));
-        P.bparams = s->d_bparams;
-    } else {
-        P.bparams = 0;
-    }
-    if (d->ny > 1) {
-        CK(cudaMemcpyAsync(s->d_qraw, d->quadrature, sizeof(double) * 2 * d->ny, cudaMemcpyHostToDevice, st));
-        KLAUNCH(KC_SETUP, egdst_k_quadrature, dim3((d->ny + 127) / 128), dim3(128), 0, st, s->d_qraw, s->d_q, d->ny);
-    }
     CK(cudaMemsetAsync(P.status, 0, sizeof(int) * 4 * P.nvec, st));
     CK(cudaMemsetAsync(P.units, 0, sizeof(unsigned long long) * P.nvec, st));
     CK(cudaMemsetAsync(P.mlen, 0, sizeof(int) * s->ncell, st));
@@ -319,6 +305,70 @@ static int run_solve(egdst_solution *s, const egdst_desc *d, const double *param
         KLAUNCH(KC_ENV, egdst_k_envBC<0>, dim3(P.chE, nst, nvec), dim3(EGDST_ENVW), 0, st, P, it);
         KLAUNCH(KC_TAB, egdst_k_tab, dim3(tabblocks, nst, nvec), dim3(B), 0, st, P, it);
     }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// one backward-induction pass; asynchronous
+static int run_solve(egdst_solution *s, const egdst_desc *d, const double *params) {
+    EgdstDev &P = s->P;
+    egdst_ctx cx;
+    int rc = fill_ctx(d, &cx);
+    if (rc) return rc;
+    if (d->ny > 1 && !d->quadrature) return fail(2, "quadrature missing");
+    if (d->ngridm != P.N || d->ngridmax != P.gcap || d->T - d->t0 + 1 != P.NT || d->nst != P.cx.nst || d->nd != P.cx.nd ||
+        d->ny != P.cx.ny || d->nthrhmax != P.cx.nthrhmax)
+        return fail(2, "egdst_resolve: dimensions differ from the solution object");
+    CK(cudaSetDevice(s->device));
+    cx.stm = s->d_stm; cx.states = s->d_states; cx.decisions = s->d_decisions;
+    P.cx = cx;
+    cudaStream_t st = g_stream;
+    CK(cudaMemcpyAsync(s->d_stm, d->stm, sizeof(double) * 2 * d->nnst, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(s->d_states, d->states, sizeof(double) * d->nst * d->nnst, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(s->d_decisions, d->decisions, sizeof(double) * d->nd * d->nnd, cudaMemcpyHostToDevice, st));
+    // parameter values always travel through the device array (one row per vector), never through the kernel
+    // arguments: the argument block then depends on the shape only
+    if (!params && P.nvec != 1) return fail(2, "egdst_resolve: a batched solution needs the parameter matrix");
+    if (EGDST_NPARAM > 0) CK(cudaMemcpyAsync(s->d_bparams, params ? params : d->params, sizeof(double) * (size_t)P.nvec * EGDST_NPARAM, cudaMemcpyHostToDevice, st));
+    P.bparams = s->d_bparams;
+    for (int i = 0; i < EGDST_NPARAM_; i++) P.cx.param[i] = 0.0;
+    if (d->ny > 1) {
+        CK(cudaMemcpyAsync(s->d_qraw, d->quadrature, sizeof(double) * 2 * d->ny, cudaMemcpyHostToDevice, st));
+        KLAUNCH(KC_SETUP, egdst_k_quadrature, dim3((d->ny + 127) / 128), dim3(128), 0, st, s->d_qraw, s->d_q, d->ny);
+    }
+    // The period chain (~10 launches per period) is replayed as a CUDA graph from the third solve of an unchanged
+    // shape on: the first runs eagerly, the second is captured while it runs.  Everything that varies between
+    // solves of one shape (parameters, quadrature, state tables) lives in device memory, so the kernel arguments
+    // -- the EgdstDev block -- are identical and the instantiated graph stays valid.
+#ifndef EGDST_HOSTEMU
+    static const bool graphs_env_off = getenv("EGDST_NO_GRAPH") != 0;
+    const bool graphs_off = graphs_env_off || st == 0;  // the legacy default stream cannot be captured
+    const bool same = s->g_seen && s->g_stream == st && memcmp(&s->g_P, &P, sizeof(P)) == 0;
+    if (!g_prof_on && !graphs_off && same && s->g_exec) {
+        CK(cudaGraphLaunch(s->g_exec, st));
+        g_launches += s->g_nlaunch;
+    } else if (!g_prof_on && !graphs_off && same) {
+        cudaGraph_t graph = 0;
+        const long long l0 = g_launches;
+        CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        rc = launch_periods(s, st);
+        cudaError_t e = cudaStreamEndCapture(st, &graph);
+        if (rc || e != cudaSuccess || !graph) { if (graph) cudaGraphDestroy(graph); return rc ? rc : fail(2, std::string("graph capture failed: ") + cudaGetErrorString(e)); }
+        s->g_nlaunch = g_launches - l0;
+        e = cudaGraphInstantiate(&s->g_exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) { s->g_exec = 0; return fail(2, std::string("graph instantiation failed: ") + cudaGetErrorString(e)); }
+        CK(cudaGraphLaunch(s->g_exec, st));
+    } else {
+        if (s->g_exec && !same) { cudaGraphExecDestroy(s->g_exec); s->g_exec = 0; }
+        rc = launch_periods(s, st);
+        if (rc) return rc;
+        s->g_P = P; s->g_stream = st; s->g_seen = true;
+    }
+#else
+    rc = launch_periods(s, st);
+    if (rc) return rc;
+#endif
     s->sizes_valid = false;
     s->sim_valid = false;
     CK(cudaGetLastError());

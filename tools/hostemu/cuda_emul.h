@@ -171,6 +171,7 @@ inline cudaError_t cudaSetDevice(int) { return 0; }
 inline cudaError_t cudaGetDevice(int *d) { *d = 0; return 0; }
 inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return 0; }
 typedef int cudaEvent_t;
+typedef void *cudaGraphExec_t;
 inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = 0; return 0; }
 inline cudaError_t cudaEventDestroy(cudaEvent_t) { return 0; }
 inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return 0; }

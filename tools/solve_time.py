@@ -10,6 +10,7 @@ for a in sys.argv[1:]:
     k, v = a.split("="); kw[k] = float(v) if "." in v else int(v)
 m = examples.retirement2_scaled(**kw); m.compile()
 lib = m._capi()
+stream = torch.cuda.Stream(); torch.cuda.set_stream(stream); lib.set_stream(stream.cuda_stream)
 sol = lib.solve(m, strict=True)
 for _ in range(3):
     lib.resolve(sol, m)
