@@ -28,7 +28,7 @@ class _Port:
         self.p = port.Port(model)
 
     def solve(self):
-        return self.p.solve()
+        return self.p.solve()  # raises: the solver's checker is the compiled reference only
 
     def simulate(self, M, D, init, rs, rndtype=0):
         return self.p.simulate(M, D, init, rs, rndtype)
