@@ -294,6 +294,30 @@ def own_arm(a):
            "d2h_bytes_per_step": int(8 * nso * nt * ne), "agents_per_gpu": ne, "ms": e2e_s * 1e3,
            "api": "egdst_simulate_philox (host init in, host sims out; pinned buffers)"}
 
+    # the moments-only entry point (no path array crosses PCIe): what an estimation loop calls
+    h_mom = torch.zeros(3 * nso * nt, dtype=torch.float64).pin_memory()
+    nm_agents = min(nsim, 10_000_000)
+    h_init_m = torch.empty(2 * nm_agents, dtype=torch.float64).pin_memory()
+    h_init_m[:nm_agents] = 1.0
+    h_init_m[nm_agents:] = m.a0 + 0.5 * (m.mmax - m.a0) * torch.rand(nm_agents, dtype=torch.float64)
+
+    def e2e_mom_step():
+        rc = lib.L.egdst_simulate_philox(C.byref(desc.c), sol.handle, 0, C.cast(h_init_m.data_ptr(), dp), nm_agents, agent0, SEED_SHOCKS,
+                                         None, C.cast(h_mom.data_ptr(), dp))
+        if rc:
+            raise SystemExit("bench.py: e2e moments failed: " + lib.last_error())
+
+    e2e_mom_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.e2e_steps):
+        e2e_mom_step()
+    torch.cuda.synchronize()
+    e2e_mom_s = max_over_ranks((time.perf_counter() - t0) / a.e2e_steps)
+    e2e["moments_only"] = {"value": world * nm_agents * nt / e2e_mom_s, "unit": "agent-periods/s", "agents_per_gpu": nm_agents, "ms": e2e_mom_s * 1e3,
+                           "h2d_bytes_per_step": int(16 * nm_agents), "d2h_bytes_per_step": int(8 * 3 * nso * nt),
+                           "api": "egdst_simulate_philox(sims=NULL, moments): host init in, [3,nsimout,nt] moments out"}
+
     # cpu baseline: the unmodified reference C on one host core (it is single-threaded), rank 0 at N=1 only
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu:

@@ -112,6 +112,7 @@ struct egdst_solution {
     bool g_seen;
     long long g_nlaunch;
     size_t bytes;   // device bytes owned (workspace cache policy)
+    void *tab_base; size_t tab_bytes;  // lookup tables (one allocation)
     int dims[12];   // shape signature for re-use
 };
 
@@ -258,7 +259,14 @@ static int create_solution(const egdst_desc *d, int nvec, egdst_solution **out) 
         P.mbits = mbits;
         P.lutcap = (int)(octaves * (double)(1 << mbits)) + 2;
     }
-    DA(P.tabIvl, (size_t)s->ncell * P.tabcap); DA(P.tabLut, (size_t)s->ncell * (P.lutcap + 1));
+    {   // one allocation for both tables: a single L2 access-policy window can then keep them resident (sim_launch)
+        const size_t lutbytes = ((sizeof(EgdstLutEntry) * (size_t)s->ncell * (P.lutcap + 1) + 255) / 256) * 256;
+        const size_t ivlbytes = sizeof(EgdstInterval) * (size_t)s->ncell * P.tabcap;
+        unsigned char *base = 0;
+        DA(base, lutbytes + ivlbytes);
+        P.tabLut = (EgdstLutEntry *)base; P.tabIvl = (EgdstInterval *)(base + lutbytes);
+        s->tab_base = base; s->tab_bytes = lutbytes + ivlbytes;
+    }
     P.chC = (P.N + EGDST_CMP_CHUNK - 1) / EGDST_CMP_CHUNK + 1;
     P.chE = (P.envcap + EGDST_ENV_CHUNK - 1) / EGDST_ENV_CHUNK + 1;
     DA(P.scanC, (size_t)s->nsd * P.chC); DA(P.tickC, (size_t)2 * s->nsd); DA(P.foldList, (size_t)s->nsd * (P.gcap + 1)); DA(P.foldCnt, s->nsd);

@@ -30,7 +30,11 @@
 #ifdef EGDST_HOSTEMU
 #define EGDST_STREAM_STORE2(ptr, v) (*reinterpret_cast<double2 *>(ptr) = (v))
 #else
+#ifdef EGDST_SIM_EXP_PLAINST
+#define EGDST_STREAM_STORE2(ptr, v) (*reinterpret_cast<double2 *>(ptr) = (v))
+#else
 #define EGDST_STREAM_STORE2(ptr, v) __stcs(reinterpret_cast<double2 *>(ptr), (v))
+#endif
 #endif
 
 // Philox4x32-10 (Salmon et al. 2011); counter = (c0,c1,c2,c3), key = (k0,k1)
@@ -65,10 +69,11 @@ struct EgdstSimArgs {
 // Dynamic shared memory layout of egdst_k_simulate:
 //   tile[warps][32*TS]                one staged record per agent of the warp's tile (TS = nso|1, odd)
 //   mom[nt][nso][3]   (mom_smem)      per-CTA moment accumulators, flushed once at the end
-__global__ void __launch_bounds__(EGDST_SIM_BLOCK, EGDST_SIM_MINBLOCKS) egdst_k_simulate(EgdstDev P, EgdstSimArgs S) {
+template <int PB>
+__global__ void __launch_bounds__(EGDST_SIM_BLOCK, PB == 2 ? EGDST_SIM_MINBLOCKS - 1 : EGDST_SIM_MINBLOCKS) egdst_k_simulate(EgdstDev P, EgdstSimArgs S) {
     EGDST_DYN_SMEM(double, egdst_sim_smem);
     constexpr int NSO = EGDST_NSIMOUT_MAX;   // the model image fixes nsimout (checked on the host)
-    constexpr int TS = NSO | 1;              // odd record stride: conflict-free staging and column walks
+    constexpr int TS = (PB * NSO) | 1;       // odd record stride: conflict-free staging and column walks
     constexpr int WPB = EGDST_SIM_BLOCK / 32;
     // blockIdx.y walks the parameter vectors of a batched sweep: same agents and shocks under every vector,
     // per-vector output blocks (sims [nvec][nsimout,nt,nsim], moments [nvec][3,nsimout,nt])
@@ -81,10 +86,12 @@ __global__ void __launch_bounds__(EGDST_SIM_BLOCK, EGDST_SIM_MINBLOCKS) egdst_k_
     if (S.moments) S.moments += (size_t)blockIdx.y * EGDST_NSIMOUT_MAX * nt * 3;
     double *tile = egdst_sim_smem + (size_t)w * 32 * TS;
     double *mom = egdst_sim_smem + (size_t)WPB * 32 * TS;
+    int *clean_s = reinterpret_cast<int *>(mom + (size_t)nt * NSO * 3);  // [nt] clean tiles per period (mom_smem only)
     const double NaN = EGDST_NAN;
     const int ntiles = (S.nsim + 31) / 32;
     if (S.moments && S.mom_smem) {
         for (int i = threadIdx.x; i < nt * NSO * 3; i += blockDim.x) mom[i] = 0.0;
+        for (int i = threadIdx.x; i < nt; i += blockDim.x) clean_s[i] = 0;
         __syncthreads();
     }
     // persistent: every warp strides over tiles of 32 agents and walks each tile through all periods
@@ -105,7 +112,16 @@ __global__ void __launch_bounds__(EGDST_SIM_BLOCK, EGDST_SIM_MINBLOCKS) egdst_k_
             if (ist0 < 0 || ist0 >= cx.nst || m0 < cx.a0 || m0 > cx.mmax) state = 1;  // egdst_simulator.c:215-216
             else { cur.ist = ist0; cur.cash = m0; egdst_fill_state(&cx, &cur); if (!feasible(&cx, &cur)) state = 1; }
         }
+        // the uniforms of period it+1 are drawn during period it: the Philox rounds are independent of the agent's
+        // state, so their integer pipeline work overlaps the table-gather latency of the current period
+        unsigned pr0 = 0, pr1 = 0, pr2 = 0, pr3 = 0;
+        const unsigned long long gid = (unsigned long long)(S.agent0 + isim);
+        if (!S.randstream && nt > 1)
+            egdst_philox4x32((unsigned)gid, (unsigned)(gid >> 32), 1u, 0u, (unsigned)S.seed, (unsigned)(S.seed >> 32), pr0, pr1, pr2, pr3);
         for (int it = 0; it < nt; it++) {
+            const unsigned cr0 = pr0, cr1 = pr1, cr2 = pr2;
+            if (!S.randstream && it > 0 && it + 1 < nt)
+                egdst_philox4x32((unsigned)gid, (unsigned)(gid >> 32), (unsigned)(it + 1), 0u, (unsigned)S.seed, (unsigned)(S.seed >> 32), pr0, pr1, pr2, pr3);
             if (state == 0 && it > 0) {
                 PeriodVars nx = cur;
                 nx.it = it;
@@ -115,10 +131,7 @@ __global__ void __launch_bounds__(EGDST_SIM_BLOCK, EGDST_SIM_MINBLOCKS) egdst_k_
                     const double *rs = S.randstream + (S.rndtype == 1 ? 0 : (size_t)4 * nt * isim) + (size_t)3 * (it - 1);
                     rrr = rs[0]; rrr1 = rs[1]; rrr2 = rs[2];
                 } else {
-                    const unsigned long long g = (unsigned long long)(S.agent0 + isim);
-                    unsigned r0, r1, r2, r3;
-                    egdst_philox4x32((unsigned)g, (unsigned)(g >> 32), (unsigned)it, 0u, (unsigned)S.seed, (unsigned)(S.seed >> 32), r0, r1, r2, r3);
-                    rrr = egdst_u01(r0); rrr1 = egdst_u01(r1); rrr2 = egdst_u01(r2);
+                    rrr = egdst_u01(cr0); rrr1 = egdst_u01(cr1); rrr2 = egdst_u01(cr2);
                 }
                 if (rrr2 > survival(&cx, &cur)) {
                     state = 1;  // death: the rest of the record stays NaN
@@ -171,7 +184,10 @@ __global__ void __launch_bounds__(EGDST_SIM_BLOCK, EGDST_SIM_MINBLOCKS) egdst_k_
                         iv.g0 = Mg[i]; iv.g1 = Mg[i + 1]; iv.c0 = Cg[i]; iv.c1 = Cg[i + 1]; iv.v0 = Vg[i]; iv.v1 = Vg[i + 1];
                         M1 = Mg[1];
                     }
-                    c = egdst_lerp(cur.cash, iv.g0, iv.g1, iv.c0, iv.c1);
+                    // one division for the weights of both interpolations (the reference divides four times, egdst_lib.c:175;
+                    // the difference is in the last bit and the simulator has no discrete branch that depends on it)
+                    const double rw = 1.0 / (iv.g1 - iv.g0), wl = (cur.cash - iv.g0) * rw, wr = (iv.g1 - cur.cash) * rw;
+                    c = iv.c1 * wl + iv.c0 * wr;
                     cur.savings = cur.cash - c;
                     const int nth = P.thlen[cell];
                     const double *th = P.thTH + (size_t)cell * cx.nthrhmax, *dd = P.thD + (size_t)cell * cx.nthrhmax;
@@ -181,11 +197,16 @@ __global__ void __launch_bounds__(EGDST_SIM_BLOCK, EGDST_SIM_MINBLOCKS) egdst_k_
                     egdst_fill_decision(&cx, &cur);
                     const double evf = P.evf[cell];  // == V(row 0)
                     if (cur.cash < M1 && evf > -EGDST_INF) vf = utility(&cx, &cur, c) + discount(&cx, &cur) * evf;
-                    else vf = egdst_lerp(cur.cash, iv.g0, iv.g1, iv.v0, iv.v1);
+                    else vf = iv.v1 * wl + iv.v0 * wr;
                 }
             }
             // stage the record of this period
-            double *rec = tile + lane * TS;
+            // two consecutive periods of an agent are staged side by side (PB = 2 when nt is even): their 2*NSO doubles
+            // are written together, so every 32-byte DRAM sector of the sims array is written whole -- one period alone
+            // (112 B at S2) ends in a half sector, and half-sector write-backs halve the achieved write bandwidth
+            // (tools/micro/wpat.cu: 2.5 TB/s for 112-byte chunks, 4.2 TB/s for 224-byte chunks)
+            const int half = (PB == 2) ? (it & 1) : 0;
+            double *rec = tile + lane * TS + half * NSO;
             if (state == 0) {
                 rec[0] = cur.cash; rec[1] = c; rec[2] = cur.savings; rec[3] = vf; rec[4] = (double)cur.id; rec[5] = (double)cur.ist;
                 rec[6] = mu; rec[7] = sigma; rec[8] = cur.shock; rec[9] = utility(&cx, &cur, c); rec[10] = discount(&cx, &cur);
@@ -201,29 +222,36 @@ __global__ void __launch_bounds__(EGDST_SIM_BLOCK, EGDST_SIM_MINBLOCKS) egdst_k_
             }
             const bool clean = __all_sync(EGDST_FULL, state == 0) && it > 0;  // no NaN record in the tile
             __syncwarp();
-            if (S.sims) {
-                // cooperative write of the tile: the 32 records of this period, NSO contiguous doubles each
+            if (S.sims && (PB == 1 || half == 1)) {
+                // cooperative write of the tile: PB records per agent, PB*NSO contiguous doubles each
                 const int na = S.nsim - tileidx * 32 < 32 ? S.nsim - tileidx * 32 : 32;
-                double *dst = S.sims + ((size_t)tileidx * 32 * nt + it) * NSO;
-                if ((NSO & 1) == 0 && NSO <= 16 && (((size_t)S.sims & 15) == 0)) {
-                    // 16-byte pieces, 8 slots per agent (NSO/2 used): agent = 4*t + lane/8, piece = lane%8
-                    const int k = lane & 7, a0 = lane >> 3;
-                    if (k < NSO / 2) {
+                const int it0 = it - (PB - 1);
+#ifdef EGDST_SIM_EXP_WRAP
+                double *dst = S.sims + (((size_t)tileidx * 32 * nt + it0) * NSO) % ((size_t)4 << 20);  // experiment: stay inside 32 MB
+#else
+                double *dst = S.sims + ((size_t)tileidx * 32 * nt + it0) * NSO;
+#endif
+                constexpr int W = PB * NSO;  // doubles per agent per write
+                if ((W & 1) == 0 && W <= 32 && (((size_t)S.sims & 15) == 0)) {
+                    // 16-byte pieces, SL slots per agent (W/2 used): agent = (32/SL)*t + lane/SL, piece = lane%SL
+                    constexpr int SL = W / 2 <= 8 ? 8 : 16, APT = 32 / SL;
+                    const int k = lane % SL, a0 = lane / SL;
+                    if (k < W / 2) {
                         const double *src = tile + a0 * TS + 2 * k;
                         double *d = dst + (size_t)a0 * nt * NSO + 2 * k;
-                        const size_t dstride = (size_t)4 * nt * NSO;
+                        const size_t dstride = (size_t)APT * nt * NSO;
                         if (na == 32) {
 #pragma unroll
-                            for (int t = 0; t < 8; t++)
-                                EGDST_STREAM_STORE2(d + t * dstride, make_double2(src[t * 4 * TS], src[t * 4 * TS + 1]));
+                            for (int t = 0; t < 32 / APT; t++)
+                                EGDST_STREAM_STORE2(d + t * dstride, make_double2(src[t * APT * TS], src[t * APT * TS + 1]));
                         } else {
-                            for (int t = 0; 4 * t + a0 < na; t++)
-                                EGDST_STREAM_STORE2(d + t * dstride, make_double2(src[t * 4 * TS], src[t * 4 * TS + 1]));
+                            for (int t = 0; APT * t + a0 < na; t++)
+                                EGDST_STREAM_STORE2(d + t * dstride, make_double2(src[t * APT * TS], src[t * APT * TS + 1]));
                         }
                     }
                 } else {
-                    for (int e = lane; e < na * NSO; e += 32) {
-                        const int a = e / NSO, j = e - a * NSO;
+                    for (int e = lane; e < na * W; e += 32) {
+                        const int a = e / W, j = e - a * W;
                         dst[(size_t)a * nt * NSO + j] = tile[a * TS + j];
                     }
                 }
@@ -234,7 +262,7 @@ __global__ void __launch_bounds__(EGDST_SIM_BLOCK, EGDST_SIM_MINBLOCKS) egdst_k_
                 double s1 = 0, s2 = 0, n = 0;
                 if (lane < HV * NSO) {
                     const int j = lane % NSO, h = lane / NSO;
-                    const double *col = tile + h * (32 / HV) * TS + j;
+                    const double *col = tile + h * (32 / HV) * TS + half * NSO + j;
                     if (clean) {
                         // every agent of the tile is alive: sum without NaN tests (warp-uniform branch); a column that
                         // holds a NaN after all (user equations) shows up as a NaN sum and is redone below
@@ -252,9 +280,14 @@ __global__ void __launch_bounds__(EGDST_SIM_BLOCK, EGDST_SIM_MINBLOCKS) egdst_k_
                     s2 += __shfl_down_sync(EGDST_FULL, s2, NSO);
                     n += __shfl_down_sync(EGDST_FULL, n, NSO);
                 }
+                // a clean tile adds 32 to the count of every column: one integer atomic per tile instead of NSO
+                // floating-point ones (clean_s[it], folded into the counts at the final flush)
+                const bool cntint = S.mom_smem && clean && __all_sync(EGDST_FULL, lane >= NSO || n == 32.0);
+                if (cntint && lane == 0) atomicAdd(clean_s + it, 1);
                 if (lane < NSO && n > 0) {
                     double *dstm = S.mom_smem ? mom + ((size_t)it * NSO + lane) * 3 : S.moments + ((size_t)it * NSO + lane) * 3;
-                    atomicAdd(dstm + 0, s1); atomicAdd(dstm + 1, s2); atomicAdd(dstm + 2, n);
+                    atomicAdd(dstm + 0, s1); atomicAdd(dstm + 1, s2);
+                    if (!cntint) atomicAdd(dstm + 2, n);
                 }
             }
             __syncwarp();
@@ -263,7 +296,8 @@ __global__ void __launch_bounds__(EGDST_SIM_BLOCK, EGDST_SIM_MINBLOCKS) egdst_k_
     if (S.moments && S.mom_smem) {
         __syncthreads();
         for (int i = threadIdx.x; i < nt * NSO * 3; i += blockDim.x) {
-            const double v = mom[i];
+            double v = mom[i];
+            if (i % 3 == 2) v += 32.0 * clean_s[i / (3 * NSO)];
             if (v != 0.0) atomicAdd(S.moments + i, v);
         }
     }

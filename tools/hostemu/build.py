@@ -23,11 +23,14 @@ def build(model, opt="-O1"):
     os.makedirs(out, exist_ok=True)
     with open(os.path.join(out, "modelspec_dev.h"), "w") as f:
         f.write(codegen.emit_devspec(model))
-    lib = os.path.join(out, "libemu.so")
+    asan = os.environ.get("EGDST_EMU_ASAN") == "1"  # AddressSanitizer build: out-of-bounds accesses of the kernels' logic
+    lib = os.path.join(out, "libemu_asan.so" if asan else "libemu.so")
     csrc = os.path.join(ROOT, "egdst_b200", "csrc")
     cmd = ["g++", "-std=c++20", opt, "-g", "-DEGDST_HOSTEMU", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-w",
            "-I" + out, "-I" + HERE, "-I" + os.path.join(ROOT, "include"), "-I" + csrc,
            '-DEGDST_MODEL_KEY="%s"' % key, "-x", "c++", os.path.join(csrc, "egdst_capi.cu"), "-o", lib]
+    if asan:
+        cmd[3:3] = ["-fsanitize=address", "-fno-omit-frame-pointer"]
     subprocess.run(cmd, check=True)
     return lib
 
