@@ -144,41 +144,9 @@ __global__ void egdst_k_quadrature(const double *qraw, double *q, int ny) {
     if (i < ny) { q[i] = qraw[i]; q[ny + i] = egdst_cdfni(qraw[ny + i]); }
 }
 
-// mark infeasible (it,ist) cells as empty and detect empty choice sets (egdst_solver.c:294-300, 694-702)
-__global__ void egdst_k_cells(EgdstDev P, int it) {
-    const int ivec = blockIdx.x;
-    // reset the chained-scan state of this parameter vector's jobs for the coming period
-    const int nsdv = P.cx.nst * P.cx.nd, sd0 = ivec * nsdv;
-    for (int i = threadIdx.x; i < nsdv * P.chC; i += blockDim.x) P.scanC[(size_t)sd0 * P.chC + i] = 0ULL;
-    for (int i = threadIdx.x; i < nsdv * 2; i += blockDim.x) P.tickC[2 * sd0 + i] = 0;
-    for (int i = threadIdx.x; i < nsdv; i += blockDim.x) P.foldCnt[sd0 + i] = 0;
-    for (int i = threadIdx.x; i < nsdv * P.chE; i += blockDim.x) P.scanE[(size_t)sd0 * P.chE + i] = 0ULL;          // secondary slots
-    for (int i = threadIdx.x; i < nsdv * 2; i += blockDim.x) P.tickE[2 * sd0 + i] = 0;
-    for (int i = threadIdx.x; i < nsdv; i += blockDim.x) P.envNact[sd0 + i] = 0;
-    const int ps0 = P.nvec * nsdv + ivec * P.cx.nst;                                                                // primary slots
-    for (int i = threadIdx.x; i < P.cx.nst * P.chE; i += blockDim.x) P.scanE[(size_t)ps0 * P.chE + i] = 0ULL;
-    for (int i = threadIdx.x; i < P.cx.nst * 2; i += blockDim.x) P.tickE[2 * ps0 + i] = 0;
-    for (int i = threadIdx.x; i < P.cx.nst; i += blockDim.x) P.envNact[ps0 + i] = 0;
-    const int ist = threadIdx.x;
-    if (ist >= P.cx.nst) return;
-    egdst_ctx cx; egdst_load_ctx(P, ivec, cx);
-    PeriodVars curr; curr.it = it; curr.ist = ist; curr.id = 0; curr.cash = 0; curr.savings = 0; curr.shock = 0;
-    const int cell = egdst_cell(P, ivec, it, ist);
-    if (feasible(&cx, &curr) != 1) { P.mlen[cell] = 0; P.thlen[cell] = 0; return; }
-    int any = 0;
-    for (curr.id = 0; curr.id < cx.nd; curr.id++) any |= (inchoiceset(&cx, &curr) == 1);
-    if (!any) { P.mlen[cell] = 0; P.thlen[cell] = 0; egdst_fail(P, ivec, EGDST_ERR_EMPTYCHOICE, it, ist, -1); }
-}
-
-// after the per-id EGM: "all choices produced empty grids" (egdst_solver.c:704-710)
-__global__ void egdst_k_checkempty(EgdstDev P, int it) {
-    const int ivec = blockIdx.x, ist = threadIdx.x;
-    if (ist >= P.cx.nst) return;
-    const int sd0 = egdst_sd(P, ivec, ist, 0);
-    int any = 0, tot = 0;
-    for (int id = 0; id < P.cx.nd; id++) { any |= P.active[sd0 + id]; tot += P.ptN[sd0 + id]; }
-    if (any && tot == 0) egdst_fail(P, ivec, EGDST_ERR_ALLINF, it, ist, -1);
-}
+// mark infeasible (it,ist) cells as empty, detect empty choice sets and reset the chained-scan state: the first
+// period's call; later periods get this from egdst_k_tab of the period before (egdst_tables.cuh)
+__global__ void egdst_k_cells(EgdstDev P, int it) { egdst_cells_body(P, blockIdx.x, it); }
 
 static int fill_ctx(const egdst_desc *d, egdst_ctx *cx) {
     if (!d) return fail(2, "null descriptor");
@@ -297,8 +265,8 @@ static int launch_periods(egdst_solution *s, cudaStream_t st) {
     if (nvec * nst * tabblocks > 4096) tabblocks = (4096 + nvec * nst - 1) / (nvec * nst);  // batched sweeps: fewer, looping CTAs per cell
     const int cellthreads = ((nst + 31) / 32) * 32 < 128 ? 128 : ((nst + 31) / 32) * 32;
     for (int it = P.NT - 1; it >= 0; it--) {
-        KLAUNCH(KC_SETUP, egdst_k_cells, dim3(nvec), dim3(cellthreads), 0, st, P, it);
         if (it == P.NT - 1) {
+            KLAUNCH(KC_SETUP, egdst_k_cells, dim3(nvec), dim3(cellthreads), 0, st, P, it);
             KLAUNCH(KC_TERMINAL, egdst_k_terminal, dim3((N + B - 1) / B, nst * nd, nvec), dim3(B), 0, st, P, it);
         } else {
             KLAUNCH(KC_SEED, egdst_k_seed, dim3(nd, nst, nvec), dim3(B), shsmem, st, P, it, useTab);
@@ -307,7 +275,6 @@ static int launch_periods(egdst_solution *s, cudaStream_t st) {
             // secondary envelope (no-op for (ist,id) without folds)
             KLAUNCH(KC_ENV2, egdst_k_envA<1>, dim3((2 * P.gcap + B - 1) / B, nst * nd, nvec), dim3(B), 0, st, P, it);
             KLAUNCH(KC_ENV2, egdst_k_envBC<1>, dim3(P.chE, nst * nd, nvec), dim3(EGDST_ENVW), 0, st, P, it);
-            KLAUNCH(KC_SETUP, egdst_k_checkempty, dim3(nvec), dim3(cellthreads), 0, st, P, it);
         }
         KLAUNCH(KC_ENV, egdst_k_envA<0>, dim3((nd * P.gcap + B - 1) / B, nst, nvec), dim3(B), 0, st, P, it);
         KLAUNCH(KC_ENV, egdst_k_envBC<0>, dim3(P.chE, nst, nvec), dim3(EGDST_ENVW), 0, st, P, it);

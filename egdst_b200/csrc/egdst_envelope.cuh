@@ -160,6 +160,13 @@ __global__ void egdst_k_envA(EgdstDev P, int it) {
     const int ivec = blockIdx.z;
     int ist, id, slot;
     EgdstEnvView<MODE> E;
+    if (MODE == 0 && blockIdx.x == 0 && threadIdx.x == 0) {
+        // "all choices produced empty grids" (egdst_solver.c:704-710), checked where the per-decision lists are final
+        const int sd0 = egdst_sd(P, ivec, blockIdx.y, 0);
+        int any = 0, tot = 0;
+        for (int d_ = 0; d_ < P.cx.nd; d_++) { any |= P.active[sd0 + d_]; tot += P.ptN[sd0 + d_]; }
+        if (any && tot == 0) egdst_fail(P, ivec, EGDST_ERR_ALLINF, it, blockIdx.y, -1);
+    }
     if (!egdst_env_job<MODE>(P, ivec, blockIdx.y, ist, id, slot, E)) return;
     egdst_ctx cx; egdst_load_ctx(P, ivec, cx);
     const int Ptot = E.pstart(E.F - 1) + E.npts(E.F - 1);

@@ -42,9 +42,36 @@ EGDST_DEV EgdstInterval egdst_load_interval(const EgdstInterval *p) {
 #endif
 }
 
+// Start-of-period housekeeping for parameter vector ivec (all threads of one CTA): reset the chained-scan state of
+// its jobs, mark infeasible (it,ist) cells as empty and detect empty choice sets (egdst_solver.c:294-300, 694-702).
+EGDST_DEV void egdst_cells_body(const EgdstDev &P, int ivec, int it) {
+    const int nsdv = P.cx.nst * P.cx.nd, sd0 = ivec * nsdv;
+    for (int i = threadIdx.x; i < nsdv * P.chC; i += blockDim.x) P.scanC[(size_t)sd0 * P.chC + i] = 0ULL;
+    for (int i = threadIdx.x; i < nsdv * 2; i += blockDim.x) P.tickC[2 * sd0 + i] = 0;
+    for (int i = threadIdx.x; i < nsdv; i += blockDim.x) P.foldCnt[sd0 + i] = 0;
+    for (int i = threadIdx.x; i < nsdv * P.chE; i += blockDim.x) P.scanE[(size_t)sd0 * P.chE + i] = 0ULL;          // secondary slots
+    for (int i = threadIdx.x; i < nsdv * 2; i += blockDim.x) P.tickE[2 * sd0 + i] = 0;
+    for (int i = threadIdx.x; i < nsdv; i += blockDim.x) P.envNact[sd0 + i] = 0;
+    const int ps0 = P.nvec * nsdv + ivec * P.cx.nst;                                                                // primary slots
+    for (int i = threadIdx.x; i < P.cx.nst * P.chE; i += blockDim.x) P.scanE[(size_t)ps0 * P.chE + i] = 0ULL;
+    for (int i = threadIdx.x; i < P.cx.nst * 2; i += blockDim.x) P.tickE[2 * ps0 + i] = 0;
+    for (int i = threadIdx.x; i < P.cx.nst; i += blockDim.x) P.envNact[ps0 + i] = 0;
+    for (int ist = threadIdx.x; ist < P.cx.nst; ist += blockDim.x) {
+        egdst_ctx cx; egdst_load_ctx(P, ivec, cx);
+        PeriodVars curr; curr.it = it; curr.ist = ist; curr.id = 0; curr.cash = 0; curr.savings = 0; curr.shock = 0;
+        const int cell = egdst_cell(P, ivec, it, ist);
+        if (feasible(&cx, &curr) != 1) { P.mlen[cell] = 0; P.thlen[cell] = 0; continue; }
+        int any = 0;
+        for (curr.id = 0; curr.id < cx.nd; curr.id++) any |= (inchoiceset(&cx, &curr) == 1);
+        if (!any) { P.mlen[cell] = 0; P.thlen[cell] = 0; egdst_fail(P, ivec, EGDST_ERR_EMPTYCHOICE, it, ist, -1); }
+    }
+}
+
 // build the tables of the cells (ivec, it, all ist): grid (nblk, nst, nvec)
 __global__ void egdst_k_tab(EgdstDev P, int it) {
     const int ivec = blockIdx.z, ist = blockIdx.y;
+    // the last kernel of period `it` also opens period it-1 (saves a launch per period)
+    if (blockIdx.x == 0 && blockIdx.y == 0 && it > 0) egdst_cells_body(P, ivec, it - 1);
     const int cell = egdst_cell(P, ivec, it, ist);
     const int n = P.mlen[cell];
     if (n < 2 || !egdst_cell_has_tab(P, n)) return;
