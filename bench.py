@@ -351,6 +351,79 @@ def own_arm(a):
         dist.destroy_process_group()
 
 
+# =====================================================================================================
+# optional workload: BASELINE config[4], the batched estimation sweep (S3)
+# =====================================================================================================
+def batch_arm(a):
+    """4096 deaton2 parameter vectors, block-partitioned over the ranks (strong scaling): one batched solve, one
+    batched moments-only simulation of 1024 agents under every vector, one all-reduce that assembles the moment
+    table [nvec, 3, nsimout, nt] on every rank.  A step = the whole sweep."""
+    import torch
+    import torch.distributed as dist
+    from egdst_b200 import capi, examples
+    from egdst_b200.distributed import shard_range
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
+        dist.init_process_group("nccl", device_id=dev)
+    m = examples.deaton2(); m.device = local; m.compile()
+    lib = m._capi()
+    stream = torch.cuda.Stream(); torch.cuda.set_stream(stream); lib.set_stream(stream.cuda_stream)
+    nvec, nsim = a.batch_nvec, a.batch_nsim
+    rng = np.random.default_rng(4096)
+    params = np.column_stack([rng.uniform(0.0, 0.05, nvec), rng.uniform(0.75, 1.75, nvec)])
+    lo, hi = shard_range(nvec, rank, world)
+    mine = np.ascontiguousarray(params[lo:hi])
+    sol = lib.solve_batch(m, mine)
+    nso, nt = m.nsimout(), m.nt
+    nmom = 3 * nso * nt
+    d_init = torch.empty(2 * nsim, dtype=torch.float64, device=dev); d_init[:nsim] = 1.0; d_init[nsim:] = 0.25
+    table = torch.zeros(nvec * nmom, dtype=torch.float64, device=dev)
+    desc = capi.Desc(m)
+
+    def step():
+        lib.resolve(sol, m, mine)
+        table.zero_()
+        lib.sim_moments_device(m, sol, d_init.data_ptr(), nsim, 0, 7, table.data_ptr() + 8 * lo * nmom, desc=desc)
+        if world > 1:
+            dist.all_reduce(table)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(a.warmup):
+        step()
+    barrier()
+    l0 = lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / a.steps
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+    bad = sum(1 for v in range(hi - lo) if sol.status(v)[0])
+    if rank == 0:
+        units = nvec * nominal_units(m)
+        print(json.dumps({
+            "metric": "parameter vectors/s (batched solve + simulated moments)", "value": nvec / (ms / 1e3), "unit": "vectors/s", "n_gpus": world,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "S3: %d deaton2 parameter vectors (interest~U[0,.05], income~U[.75,1.75], default_rng(4096)), %d agents each, moments all-reduced" % (nvec, nsim),
+                       "parallelism": "parameter vectors sharded, dp%d" % world},
+            "gpu_launches": int(lib.launch_count() - l0), "solve_units_per_s": units / (ms / 1e3), "agent_periods_per_s": nvec * nsim * nt / (ms / 1e3),
+            "vectors_with_error_status_on_rank0": bad}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def cpu_baseline(m, sol, a):
     """Reference C (oracle/_ref) on one core: simulate a bounded sample of agents on the exported tables, and one S1 solve."""
     from tests.oracles import oracle_for
@@ -446,12 +519,17 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-nsim", type=int, default=200_000)
     ap.add_argument("--ref-nsim", type=int, default=400_000)
+    ap.add_argument("--workload", default="s1s2", choices=["s1s2", "batch"], help="s1s2: BASELINE config[3] (default); batch: config[4] sweep")
+    ap.add_argument("--batch-nvec", type=int, default=4096)
+    ap.add_argument("--batch-nsim", type=int, default=1024)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-cpu-solve", action="store_true")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "own" else a.warmup
     if a.impl == "reference":
         reference_arm(a)
+    elif a.workload == "batch":
+        batch_arm(a)
     else:
         own_arm(a)
 

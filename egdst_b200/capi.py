@@ -331,7 +331,8 @@ class ModelLibrary:
         rc = self.L.egdst_sim_moments(C.byref(d.c), sol.handle, ivec0, nvec, _ptr(initf), nsim, agent0, seed, _ptr(mom))
         if rc:
             self._raise(rc)
-        return np.stack([mom[i * 3 * nso * nt:(i + 1) * 3 * nso * nt].reshape((3, nso, nt), order="F") for i in range(nvec)])
+        # per vector [3, nsimout, nt] column-major == C-order (nt, nsimout, 3): one reshape + transpose, no copies
+        return mom.reshape(nvec, nt, nso, 3).transpose(0, 3, 2, 1)
 
     def sim_moments_device(self, model, sol: Solution, d_init: int, nsim: int, agent0: int, seed: int, d_moments: int,
                            ivec0: int = 0, nvec: Optional[int] = None, desc: "Desc" = None):

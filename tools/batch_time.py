@@ -34,6 +34,8 @@ t = time.perf_counter()
 for _ in range(3):
     mom = lib.sim_moments(m, sol, init, 7)
 ms2 = (time.perf_counter() - t) / 3 * 1e3
+lib.profile_enable(True); lib.sim_moments(m, sol, init, 7); prof = lib.profile_read(); lib.profile_enable(False)
+print("   sim kernel device time:", {k: round(v[0], 2) for k, v in prof.items() if v[1]})
 print("batched sim moments (host API): %.2f ms for %d x %d agents x %d periods = %.3e agent-periods/s" % (ms2, nvec, nsim, m.nt, nvec * nsim * m.nt / ms2 * 1e3))
 # CPU reference for a few vectors
 secs = []
