@@ -153,3 +153,39 @@ def test_batched_solve_matches_individual_solves_and_reference():
     # higher income => higher mean consumption in the first period, all else equal is not guaranteed across interest,
     # so just check the moments are finite and differ across vectors
     assert np.all(np.isfinite(table[:, 0, 1, :])) and np.ptp(table[:, 0, 1, 5]) > 0
+
+
+def test_resolve_and_graph_replay_track_parameter_changes():
+    """egdst_resolve re-runs the period chain into the same object; from the third call on it is replayed as a CUDA
+    graph with the parameters read from device memory -- results must equal fresh solves for every parameter set."""
+    import torch
+    m = examples.deaton2()
+    m.compile()
+    lib = m._capi()
+    stream = torch.cuda.Stream()
+    lib.set_stream(stream.cuda_stream)
+    try:
+        sol = lib.solve(m, strict=True)
+        for k, (interest, income) in enumerate([(0.01, 1.25), (0.03, 1.0), (0.045, 1.6), (0.02, 0.8), (0.01, 1.25)]):
+            m.setparam("interest", interest, "income", income)
+            lib.resolve(sol, m)                       # k=0 eager, k=1 captured, k>=2 replayed
+            stream.synchronize()
+            assert sol.status()[0] == 0
+            fresh = examples.deaton2(interest=interest, income=income)
+            fresh.compile(); fresh.solve()
+            Mr, Dr = sol.cells(0)
+            for it in range(m.nt):
+                assert np.array_equal(Mr[0][it], fresh.M[0][it]) and np.array_equal(Dr[0][it], fresh.D[0][it]), (k, it)
+        # batched resolve with a new parameter matrix
+        rng = np.random.default_rng(1)
+        p1 = np.column_stack([rng.uniform(0, 0.05, 8), rng.uniform(0.75, 1.75, 8)])
+        bs = lib.solve_batch(m, p1)
+        for rep in range(3):
+            p2 = np.column_stack([rng.uniform(0, 0.05, 8), rng.uniform(0.75, 1.75, 8)])
+            lib.resolve(bs, m, p2)
+            stream.synchronize()
+            one = examples.deaton2(interest=p2[5, 0], income=p2[5, 1]); one.compile(); one.solve()
+            Mb, Db = bs.cells(5)
+            assert all(np.array_equal(Mb[0][it], one.M[0][it]) for it in range(m.nt)), rep
+    finally:
+        lib.set_stream(0)
