@@ -104,7 +104,6 @@ struct egdst_solution {
     size_t pack_cap;
     int *d_moff, *d_toff;
     int neq;
-    bool sim_valid;  // (kept for ABI of the struct users) tables are built with every cell now
     // CUDA graph of the period chain (run_solve)
     cudaGraphExec_t g_exec;
     EgdstDev g_P;
@@ -185,7 +184,7 @@ static int create_solution(const egdst_desc *d, int nvec, egdst_solution **out) 
         if (g_cached && memcmp(g_cached->dims, dims, sizeof(dims)) == 0) {
             egdst_solution *s = g_cached;
             g_cached = 0;
-            s->sizes_valid = false; s->sim_valid = false; s->neq = d->neq;
+            s->sizes_valid = false; s->neq = d->neq;
             const double *stm = s->d_stm, *states = s->d_states, *decisions = s->d_decisions;
             s->P.cx = cx; s->P.cx.stm = stm; s->P.cx.states = states; s->P.cx.decisions = decisions;
             s->P.bparams = 0;
@@ -197,7 +196,7 @@ static int create_solution(const egdst_desc *d, int nvec, egdst_solution **out) 
     egdst_solution *s = new egdst_solution();
     s->bytes = 0; memcpy(s->dims, dims, sizeof(dims));
     s->g_exec = 0; s->g_seen = false; s->g_stream = 0; s->g_nlaunch = 0;
-    s->device = d->device; s->sizes_valid = false; s->sim_valid = false; s->d_pack = 0; s->pack_cap = 0; s->neq = d->neq;
+    s->device = d->device; s->sizes_valid = false; s->d_pack = 0; s->pack_cap = 0; s->neq = d->neq;
     EgdstDev &P = s->P;
     memset(&P, 0, sizeof(P));
     P.cx = cx;
@@ -345,7 +344,6 @@ static int run_solve(egdst_solution *s, const egdst_desc *d, const double *param
     if (rc) return rc;
 #endif
     s->sizes_valid = false;
-    s->sim_valid = false;
     CK(cudaGetLastError());
     return 0;
 }

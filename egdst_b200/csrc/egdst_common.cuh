@@ -8,12 +8,10 @@
 // their logic can be debugged without a GPU.  Development aid only -- never loaded by the product.
 #include "cuda_emul.h"
 #define EGDST_BLOCK 64
-#define EGDST_WIDE 64
 #define EGDST_ENVW 64
 #else
 #include <cuda_runtime.h>
 #define EGDST_BLOCK 256
-#define EGDST_WIDE 1024  /* single-CTA scan/compaction kernels: one CTA owns a whole (state, decision) list */
 #define EGDST_ENVW 256   /* envelope merge kernels: 8 positions per thread, chained across CTAs */
 #define EGDST_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #define EGDST_DYN_SMEM(type, name) extern __shared__ __align__(16) type name[]
