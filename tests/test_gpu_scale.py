@@ -189,3 +189,38 @@ def test_resolve_and_graph_replay_track_parameter_changes():
             assert all(np.array_equal(Mb[0][it], one.M[0][it]) for it in range(m.nt)), rep
     finally:
         lib.set_stream(0)
+
+
+def test_lecture_model2_at_the_authors_largest_configuration():
+    """lecture_code/start.m:73 runs model2('T',6,'ngridm',5000,'nquad',100): two labour-market states (absorbing
+    retirement), two decisions, lognormal returns -- the largest configuration the reference's author exercises."""
+    m = _solve(examples.model2(T=6, ngridm=5000, nquad=100, sigma=0.25, duw=float(np.log(5.0)), r=0.02, df=0.98))
+    orc = oracle_for(m)
+    Mr, Dr = orc.solve()
+    e = solution_errors(m.M, m.D, Mr, Dr)
+    assert e["cells"] == 12
+    assert e["C"] < TOL and e["V"] < TOL and e["evf"] < TOL and e["TH"] < TOL and e["Dseq"], e
+    rng = np.random.default_rng(11)
+    nsim = 2000
+    init = np.column_stack([np.full(nsim, 2.0), rng.uniform(1.0, 60.0, nsim)])  # everybody starts working
+    rs = rng.random(4 * nsim * m.nt)
+    m.sim(init, "own_shocks", randstream=rs)
+    sr = orc.simulate(Mr, Dr, init, rs, 0)
+    assert np.array_equal(np.isnan(m.sims), np.isnan(sr))
+    both = ~np.isnan(sr)
+    diff = ((m.sims[:, :, 4] != sr[:, :, 4]) | (m.sims[:, :, 5] != sr[:, :, 5])) & both[:, :, 4]
+    assert diff.sum() == 0
+    fin = both & np.isfinite(sr)
+    assert np.max(np.abs(m.sims[fin] - sr[fin]) / np.maximum(1, np.abs(sr[fin]))) < TOL
+    # retirement is absorbing: once ist == 0 (retired) it stays 0
+    ist = m.sims[:, :, 5]
+    assert np.all(np.diff(ist, axis=1) <= 0)
+
+
+def test_occ3_three_choices_on_a_fine_grid():
+    # (the reference itself segfaults on occ3 at ngridm=1000; 400 points is the finest grid it survives here)
+    m = _solve(examples.occ3(ngridm=400, ngridmax=1000, ny=20))
+    Mr, Dr = oracle_for(m).solve()
+    e = solution_errors(m.M, m.D, Mr, Dr)
+    assert e["C"] < TOL and e["V"] < TOL and e["TH"] < 1e-8 and e["Dseq"], e
+    assert max(Dr[0][it].shape[0] for it in range(m.nt)) >= 3  # several thresholds per period
