@@ -112,6 +112,7 @@ struct egdst_solution {
     long long g_nlaunch;
     size_t bytes;   // device bytes owned (workspace cache policy)
     void *tab_base; size_t tab_bytes;  // lookup tables (one allocation)
+    double *d_momscratch; size_t momscratch_cap;  // per-CTA moment slices of the wide simulator variant
     int dims[12];   // shape signature for re-use
 };
 
@@ -134,6 +135,7 @@ static void destroy_solution(egdst_solution *s) {
 #endif
     for (void *p : s->owned) cudaFree(p);
     if (s->d_pack) cudaFree(s->d_pack);
+    if (s->d_momscratch) cudaFree(s->d_momscratch);
     delete s;
 }
 
@@ -195,6 +197,7 @@ static int create_solution(const egdst_desc *d, int nvec, egdst_solution **out) 
     }
     egdst_solution *s = new egdst_solution();
     s->bytes = 0; memcpy(s->dims, dims, sizeof(dims));
+    s->d_momscratch = 0; s->momscratch_cap = 0;
     s->g_exec = 0; s->g_seen = false; s->g_stream = 0; s->g_nlaunch = 0;
     s->device = d->device; s->sizes_valid = false; s->d_pack = 0; s->pack_cap = 0; s->neq = d->neq;
     EgdstDev &P = s->P;

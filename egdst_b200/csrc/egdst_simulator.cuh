@@ -24,6 +24,11 @@
 #ifndef EGDST_SIM_MINBLOCKS
 #define EGDST_SIM_MINBLOCKS 4
 #endif
+#ifdef EGDST_HOSTEMU
+#define EGDST_SIM_WIDE 128
+#else
+#define EGDST_SIM_WIDE 512
+#endif
 
 // the sims array is written once and never re-read by the kernel: evict-first (st.global.cs) keeps the policy
 // tables resident in L2 instead of the output stream
@@ -64,17 +69,25 @@ struct EgdstSimArgs {
     double *moments;           // [3, nsimout, nt] or null
     int nsimout;
     int mom_smem;              // 1: per-CTA moment accumulators for all periods live in shared memory
+    double *momscratch;        // or: per-CTA slices [nt*nsimout*3 doubles + nt ints] of a zeroed global scratch
 };
 
 // Dynamic shared memory layout of egdst_k_simulate:
 //   tile[warps][32*TS]                one staged record per agent of the warp's tile (TS = nso|1, odd)
 //   mom[nt][nso][3]   (mom_smem)      per-CTA moment accumulators, flushed once at the end
-template <int PB>
-__global__ void __launch_bounds__(EGDST_SIM_BLOCK, PB == 2 ? EGDST_SIM_MINBLOCKS - 1 : EGDST_SIM_MINBLOCKS) egdst_k_simulate(EgdstDev P, EgdstSimArgs S) {
+// Kernel variants (chosen on the host, sim_launch):
+//   <1, 256, 4, false>  one period per write, padded (odd-stride) tile, 4 CTAs/SM, moments in shared memory
+//   <2, 512, 2, true>   two periods per write (whole 32-byte sectors in DRAM), 16 warps per CTA, 2 CTAs/SM: the
+//                       unpadded 2*NSO-double rows of 16 warps fill the CTA's shared memory exactly, so rows are
+//                       column-rotated by (lane/4)%4 instead of padded and moments accumulate in a per-CTA global
+//                       scratch with fire-and-forget reductions (summed by egdst_k_momreduce)
+template <int PB, int BLOCK, int MINB, bool SWZ>
+__global__ void __launch_bounds__(BLOCK, MINB) egdst_k_simulate(EgdstDev P, EgdstSimArgs S) {
     EGDST_DYN_SMEM(double, egdst_sim_smem);
     constexpr int NSO = EGDST_NSIMOUT_MAX;   // the model image fixes nsimout (checked on the host)
-    constexpr int TS = (PB * NSO) | 1;       // odd record stride: conflict-free staging and column walks
-    constexpr int WPB = EGDST_SIM_BLOCK / 32;
+    constexpr int W = PB * NSO;              // doubles per staged row (one agent)
+    constexpr int TS = SWZ ? W : (W | 1);    // padded rows have an odd stride: conflict-free staging and column walks
+    constexpr int WPB = BLOCK / 32;
     // blockIdx.y walks the parameter vectors of a batched sweep: same agents and shocks under every vector,
     // per-vector output blocks (sims [nvec][nsimout,nt,nsim], moments [nvec][3,nsimout,nt])
     const int ivec = S.ivec + blockIdx.y;
@@ -82,14 +95,18 @@ __global__ void __launch_bounds__(EGDST_SIM_BLOCK, PB == 2 ? EGDST_SIM_MINBLOCKS
     cx.status = 0;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int nt = P.NT;
+    // position of column j in the row of the agent staged by lane l: rotated rows spread a column over the banks
+#define EGDST_TILE_POS(l, j) ((l) * TS + (SWZ ? (((j) + (((l) >> 2) & 3) >= W) ? (j) + (((l) >> 2) & 3) - W : (j) + (((l) >> 2) & 3)) : (j)))
     if (S.sims) S.sims += (size_t)blockIdx.y * EGDST_NSIMOUT_MAX * nt * S.nsim;
     if (S.moments) S.moments += (size_t)blockIdx.y * EGDST_NSIMOUT_MAX * nt * 3;
     double *tile = egdst_sim_smem + (size_t)w * 32 * TS;
-    double *mom = egdst_sim_smem + (size_t)WPB * 32 * TS;
-    int *clean_s = reinterpret_cast<int *>(mom + (size_t)nt * NSO * 3);  // [nt] clean tiles per period (mom_smem only)
+    // moment accumulators of this CTA: shared memory (mom_smem) or its slice of the global scratch (momscratch)
+    double *mom = S.momscratch ? S.momscratch + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * ((size_t)nt * NSO * 3 + nt)
+                               : egdst_sim_smem + (size_t)WPB * 32 * TS;
+    int *clean_s = reinterpret_cast<int *>(mom + (size_t)nt * NSO * 3);  // [nt] clean tiles per period
     const double NaN = EGDST_NAN;
     const int ntiles = (S.nsim + 31) / 32;
-    if (S.moments && S.mom_smem) {
+    if (S.moments && S.mom_smem && !S.momscratch) {
         for (int i = threadIdx.x; i < nt * NSO * 3; i += blockDim.x) mom[i] = 0.0;
         for (int i = threadIdx.x; i < nt; i += blockDim.x) clean_s[i] = 0;
         __syncthreads();
@@ -206,20 +223,22 @@ __global__ void __launch_bounds__(EGDST_SIM_BLOCK, PB == 2 ? EGDST_SIM_MINBLOCKS
             // (112 B at S2) ends in a half sector, and half-sector write-backs halve the achieved write bandwidth
             // (tools/micro/wpat.cu: 2.5 TB/s for 112-byte chunks, 4.2 TB/s for 224-byte chunks)
             const int half = (PB == 2) ? (it & 1) : 0;
-            double *rec = tile + lane * TS + half * NSO;
+            const int hoff = half * NSO;
+#define EGDST_REC(j) tile[EGDST_TILE_POS(lane, hoff + (j))]
             if (state == 0) {
-                rec[0] = cur.cash; rec[1] = c; rec[2] = cur.savings; rec[3] = vf; rec[4] = (double)cur.id; rec[5] = (double)cur.ist;
-                rec[6] = mu; rec[7] = sigma; rec[8] = cur.shock; rec[9] = utility(&cx, &cur, c); rec[10] = discount(&cx, &cur);
+                EGDST_REC(0) = cur.cash; EGDST_REC(1) = c; EGDST_REC(2) = cur.savings; EGDST_REC(3) = vf; EGDST_REC(4) = (double)cur.id; EGDST_REC(5) = (double)cur.ist;
+                EGDST_REC(6) = mu; EGDST_REC(7) = sigma; EGDST_REC(8) = cur.shock; EGDST_REC(9) = utility(&cx, &cur, c); EGDST_REC(10) = discount(&cx, &cur);
 #pragma unroll
-                for (int i = 0; i < EGDST_NNST; i++) rec[11 + i] = cur.st[i];
+                for (int i = 0; i < EGDST_NNST; i++) EGDST_REC(11 + i) = cur.st[i];
 #pragma unroll
-                for (int i = 0; i < EGDST_NND; i++) rec[11 + EGDST_NNST + i] = cur.dc[i];
+                for (int i = 0; i < EGDST_NND; i++) EGDST_REC(11 + EGDST_NNST + i) = cur.dc[i];
 #pragma unroll
-                for (int i = 0; i < EGDST_NREQ; i++) rec[11 + EGDST_NNST + EGDST_NND + i] = eqs[i];
+                for (int i = 0; i < EGDST_NREQ; i++) EGDST_REC(11 + EGDST_NNST + EGDST_NND + i) = eqs[i];
             } else {
 #pragma unroll
-                for (int j = 0; j < NSO; j++) rec[j] = NaN;
+                for (int j = 0; j < NSO; j++) EGDST_REC(j) = NaN;
             }
+#undef EGDST_REC
             const bool clean = __all_sync(EGDST_FULL, state == 0) && it > 0;  // no NaN record in the tile
             __syncwarp();
             if (S.sims && (PB == 1 || half == 1)) {
@@ -237,22 +256,25 @@ __global__ void __launch_bounds__(EGDST_SIM_BLOCK, PB == 2 ? EGDST_SIM_MINBLOCKS
                     constexpr int SL = W / 2 <= 8 ? 8 : 16, APT = 32 / SL;
                     const int k = lane % SL, a0 = lane / SL;
                     if (k < W / 2) {
-                        const double *src = tile + a0 * TS + 2 * k;
                         double *d = dst + (size_t)a0 * nt * NSO + 2 * k;
                         const size_t dstride = (size_t)APT * nt * NSO;
                         if (na == 32) {
 #pragma unroll
-                            for (int t = 0; t < 32 / APT; t++)
-                                EGDST_STREAM_STORE2(d + t * dstride, make_double2(src[t * APT * TS], src[t * APT * TS + 1]));
+                            for (int t = 0; t < 32 / APT; t++) {
+                                const int a = APT * t + a0;
+                                EGDST_STREAM_STORE2(d + t * dstride, make_double2(tile[EGDST_TILE_POS(a, 2 * k)], tile[EGDST_TILE_POS(a, 2 * k + 1)]));
+                            }
                         } else {
-                            for (int t = 0; APT * t + a0 < na; t++)
-                                EGDST_STREAM_STORE2(d + t * dstride, make_double2(src[t * APT * TS], src[t * APT * TS + 1]));
+                            for (int t = 0; APT * t + a0 < na; t++) {
+                                const int a = APT * t + a0;
+                                EGDST_STREAM_STORE2(d + t * dstride, make_double2(tile[EGDST_TILE_POS(a, 2 * k)], tile[EGDST_TILE_POS(a, 2 * k + 1)]));
+                            }
                         }
                     }
                 } else {
                     for (int e = lane; e < na * W; e += 32) {
                         const int a = e / W, j = e - a * W;
-                        dst[(size_t)a * nt * NSO + j] = tile[a * TS + j];
+                        dst[(size_t)a * nt * NSO + j] = tile[EGDST_TILE_POS(a, j)];
                     }
                 }
             }
@@ -262,17 +284,17 @@ __global__ void __launch_bounds__(EGDST_SIM_BLOCK, PB == 2 ? EGDST_SIM_MINBLOCKS
                 double s1 = 0, s2 = 0, n = 0;
                 if (lane < HV * NSO) {
                     const int j = lane % NSO, h = lane / NSO;
-                    const double *col = tile + h * (32 / HV) * TS + half * NSO + j;
+                    const int a_lo = h * (32 / HV), cj = half * NSO + j;
                     if (clean) {
                         // every agent of the tile is alive: sum without NaN tests (warp-uniform branch); a column that
                         // holds a NaN after all (user equations) shows up as a NaN sum and is redone below
 #pragma unroll 8
-                        for (int a = 0; a < 32 / HV; a++) { const double x = col[a * TS]; s1 += x; s2 = fma(x, x, s2); }
+                        for (int a = 0; a < 32 / HV; a++) { const double x = tile[EGDST_TILE_POS(a_lo + a, cj)]; s1 += x; s2 = fma(x, x, s2); }
                         n = 32 / HV;
                     }
                     if (!clean || s1 != s1 || s2 != s2) {
                         s1 = 0; s2 = 0; n = 0;
-                        for (int a = 0; a < 32 / HV; a++) { const double x = col[a * TS]; if (x == x) { s1 += x; s2 = fma(x, x, s2); n += 1; } }
+                        for (int a = 0; a < 32 / HV; a++) { const double x = tile[EGDST_TILE_POS(a_lo + a, cj)]; if (x == x) { s1 += x; s2 = fma(x, x, s2); n += 1; } }
                     }
                 }
                 if (HV == 2) {
@@ -282,10 +304,10 @@ __global__ void __launch_bounds__(EGDST_SIM_BLOCK, PB == 2 ? EGDST_SIM_MINBLOCKS
                 }
                 // a clean tile adds 32 to the count of every column: one integer atomic per tile instead of NSO
                 // floating-point ones (clean_s[it], folded into the counts at the final flush)
-                const bool cntint = S.mom_smem && clean && __all_sync(EGDST_FULL, lane >= NSO || n == 32.0);
+                const bool cntint = (S.mom_smem || S.momscratch) && clean && __all_sync(EGDST_FULL, lane >= NSO || n == 32.0);
                 if (cntint && lane == 0) atomicAdd(clean_s + it, 1);
                 if (lane < NSO && n > 0) {
-                    double *dstm = S.mom_smem ? mom + ((size_t)it * NSO + lane) * 3 : S.moments + ((size_t)it * NSO + lane) * 3;
+                    double *dstm = (S.mom_smem || S.momscratch) ? mom + ((size_t)it * NSO + lane) * 3 : S.moments + ((size_t)it * NSO + lane) * 3;
                     atomicAdd(dstm + 0, s1); atomicAdd(dstm + 1, s2);
                     if (!cntint) atomicAdd(dstm + 2, n);
                 }
@@ -293,7 +315,7 @@ __global__ void __launch_bounds__(EGDST_SIM_BLOCK, PB == 2 ? EGDST_SIM_MINBLOCKS
             __syncwarp();
         }
     }
-    if (S.moments && S.mom_smem) {
+    if (S.moments && S.mom_smem && !S.momscratch) {
         __syncthreads();
         for (int i = threadIdx.x; i < nt * NSO * 3; i += blockDim.x) {
             double v = mom[i];
@@ -301,4 +323,21 @@ __global__ void __launch_bounds__(EGDST_SIM_BLOCK, PB == 2 ? EGDST_SIM_MINBLOCKS
             if (v != 0.0) atomicAdd(S.moments + i, v);
         }
     }
+}
+#undef EGDST_TILE_POS
+
+// sums the per-CTA moment slices of the global scratch into the caller's moment buffer (adds, like the kernel's own
+// flush); the integer clean-tile counters become 32 agents per tile in every column's count
+__global__ void egdst_k_momreduce(const double *scratch, int nslices, int nt, int nso, double *moments) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = nt * nso * 3;
+    if (i >= n) return;
+    const size_t stride = (size_t)n + nt;
+    double acc = 0.0;
+    for (int c = 0; c < nslices; c++) {
+        const double *sl = scratch + (size_t)c * stride;
+        acc += sl[i];
+        if (i % 3 == 2) acc += 32.0 * reinterpret_cast<const int *>(sl + n)[i / (3 * nso)];
+    }
+    if (acc != 0.0) atomicAdd(moments + i, acc);
 }
