@@ -112,6 +112,8 @@ struct egdst_solution {
     long long g_nlaunch;
     size_t bytes;   // device bytes owned (workspace cache policy)
     void *tab_base; size_t tab_bytes;  // lookup tables (one allocation)
+    std::vector<double> h_params;  // host copy of the parameter matrix of the last solve (simulator kernel arguments)
+    EgdstCellHdr *d_hdr; std::vector<EgdstCellHdr> h_hdr; int hdr_ivec;  // simulator cell headers (kernel argument), -1 = stale
     double *d_momscratch; size_t momscratch_cap;  // per-CTA moment slices of the wide simulator variant
     int dims[12];   // shape signature for re-use
 };
@@ -136,6 +138,7 @@ static void destroy_solution(egdst_solution *s) {
     for (void *p : s->owned) cudaFree(p);
     if (s->d_pack) cudaFree(s->d_pack);
     if (s->d_momscratch) cudaFree(s->d_momscratch);
+    if (s->d_hdr) cudaFree(s->d_hdr);
     delete s;
 }
 
@@ -186,7 +189,7 @@ static int create_solution(const egdst_desc *d, int nvec, egdst_solution **out) 
         if (g_cached && memcmp(g_cached->dims, dims, sizeof(dims)) == 0) {
             egdst_solution *s = g_cached;
             g_cached = 0;
-            s->sizes_valid = false; s->neq = d->neq;
+            s->sizes_valid = false; s->hdr_ivec = -1; s->neq = d->neq;
             const double *stm = s->d_stm, *states = s->d_states, *decisions = s->d_decisions;
             s->P.cx = cx; s->P.cx.stm = stm; s->P.cx.states = states; s->P.cx.decisions = decisions;
             s->P.bparams = 0;
@@ -197,7 +200,7 @@ static int create_solution(const egdst_desc *d, int nvec, egdst_solution **out) 
     }
     egdst_solution *s = new egdst_solution();
     s->bytes = 0; memcpy(s->dims, dims, sizeof(dims));
-    s->d_momscratch = 0; s->momscratch_cap = 0;
+    s->d_momscratch = 0; s->momscratch_cap = 0; s->d_hdr = 0; s->hdr_ivec = -1;
     s->g_exec = 0; s->g_seen = false; s->g_stream = 0; s->g_nlaunch = 0;
     s->device = d->device; s->sizes_valid = false; s->d_pack = 0; s->pack_cap = 0; s->neq = d->neq;
     EgdstDev &P = s->P;
@@ -306,6 +309,7 @@ static int run_solve(egdst_solution *s, const egdst_desc *d, const double *param
     // parameter values always travel through the device array (one row per vector), never through the kernel
     // arguments: the argument block then depends on the shape only
     if (!params && P.nvec != 1) return fail(2, "egdst_resolve: a batched solution needs the parameter matrix");
+    s->h_params.assign(params ? params : d->params, (params ? params : d->params) + (size_t)P.nvec * EGDST_NPARAM);
     if (EGDST_NPARAM > 0) CK(cudaMemcpyAsync(s->d_bparams, params ? params : d->params, sizeof(double) * (size_t)P.nvec * EGDST_NPARAM, cudaMemcpyHostToDevice, st));
     P.bparams = s->d_bparams;
     for (int i = 0; i < EGDST_NPARAM_; i++) P.cx.param[i] = 0.0;
@@ -347,6 +351,7 @@ static int run_solve(egdst_solution *s, const egdst_desc *d, const double *param
     if (rc) return rc;
 #endif
     s->sizes_valid = false;
+    s->hdr_ivec = -1;
     CK(cudaGetLastError());
     return 0;
 }

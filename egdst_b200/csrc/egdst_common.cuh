@@ -16,6 +16,7 @@
 #define EGDST_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #define EGDST_DYN_SMEM(type, name) extern __shared__ __align__(16) type name[]
 #define EGDST_LDCG(p) __ldcg(p)
+#define EGDST_GRID_CONSTANT __grid_constant__
 #endif
 
 #ifdef __CUDACC__

@@ -56,6 +56,29 @@ EGDST_DEV void egdst_philox4x32(unsigned c0, unsigned c1, unsigned c2, unsigned 
 }
 EGDST_DEV double egdst_u01(unsigned x) { return ((double)x + 0.5) * (1.0 / 4294967296.0); }
 
+// Per-cell scalars the policy lookup needs every period (rows, thresholds, evf(a0), M[1]).  With ~190 KB of the SM's
+// SRAM carved out as shared memory the L1 is a few tens of KB and these 'uniform' global loads would go to L2 every
+// agent-period; they travel instead as a by-value kernel argument (constant bank, up to EGDST_SIM_MAXHDR cells).
+#define EGDST_SIM_TH8 4
+#define EGDST_SIM_MAXHDR 128
+struct EgdstCellHdr { int n, nth; double evf, M1; double th[EGDST_SIM_TH8], dd[EGDST_SIM_TH8]; };
+struct EgdstSimHdrs { EgdstCellHdr h[EGDST_SIM_MAXHDR]; };
+
+// gathers the headers of parameter vector ivec (host copy -> kernel argument of later simulations)
+__global__ void egdst_k_simhdr(EgdstDev P, int ivec, EgdstCellHdr *out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= P.NT * P.cx.nst) return;
+    const int cell = egdst_cell(P, ivec, c / P.cx.nst, c % P.cx.nst);
+    EgdstCellHdr h;
+    h.n = P.mlen[cell]; h.nth = P.thlen[cell]; h.evf = P.evf[cell];
+    h.M1 = h.n > 1 ? egdst_colM(P, cell)[1] : 0.0;
+    for (int k = 0; k < EGDST_SIM_TH8; k++) {
+        h.th[k] = k < h.nth ? P.thTH[(size_t)cell * P.cx.nthrhmax + k] : EGDST_INF;
+        h.dd[k] = k < h.nth ? P.thD[(size_t)cell * P.cx.nthrhmax + k] : 0.0;
+    }
+    out[c] = h;
+}
+
 struct EgdstSimArgs {
     const double *init;        // [nsim] 1-based ist0 of the agents of this launch
     const double *init_m0;     // [nsim] m0 (the second column of the reference's init matrix)
@@ -70,6 +93,9 @@ struct EgdstSimArgs {
     int nsimout;
     int mom_smem;              // 1: per-CTA moment accumulators for all periods live in shared memory
     double *momscratch;        // or: per-CTA slices [nt*nsimout*3 doubles + nt ints] of a zeroed global scratch
+    int hdr_smem;              // 1: the per-cell headers of the vector are in the kernel argument H
+    int has_param;             // 1: parameter values travel in `param` (constant bank) instead of the device array
+    double param[EGDST_NPARAM_];
 };
 
 // Dynamic shared memory layout of egdst_k_simulate:
@@ -82,7 +108,7 @@ struct EgdstSimArgs {
 //                       column-rotated by (lane/4)%4 instead of padded and moments accumulate in a per-CTA global
 //                       scratch with fire-and-forget reductions (summed by egdst_k_momreduce)
 template <int PB, int BLOCK, int MINB, bool SWZ>
-__global__ void __launch_bounds__(BLOCK, MINB) egdst_k_simulate(EgdstDev P, EgdstSimArgs S) {
+__global__ void __launch_bounds__(BLOCK, MINB) egdst_k_simulate(EgdstDev P, EgdstSimArgs S, const EGDST_GRID_CONSTANT EgdstSimHdrs H) {
     EGDST_DYN_SMEM(double, egdst_sim_smem);
     constexpr int NSO = EGDST_NSIMOUT_MAX;   // the model image fixes nsimout (checked on the host)
     constexpr int W = PB * NSO;              // doubles per staged row (one agent)
@@ -93,6 +119,10 @@ __global__ void __launch_bounds__(BLOCK, MINB) egdst_k_simulate(EgdstDev P, Egds
     const int ivec = S.ivec + blockIdx.y;
     egdst_ctx cx; egdst_load_ctx(P, ivec, cx);
     cx.status = 0;
+    if (S.has_param) {
+#pragma unroll
+        for (int i = 0; i < EGDST_NPARAM; i++) cx.param[i] = S.param[i];
+    }
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int nt = P.NT;
     // position of column j in the row of the agent staged by lane l: rotated rows spread a column over the banks
@@ -106,6 +136,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) egdst_k_simulate(EgdstDev P, Egds
     int *clean_s = reinterpret_cast<int *>(mom + (size_t)nt * NSO * 3);  // [nt] clean tiles per period
     const double NaN = EGDST_NAN;
     const int ntiles = (S.nsim + 31) / 32;
+#ifndef EGDST_HOSTEMU
+    const unsigned long long l2keep = egdst_policy_evict_last();
+#else
+    const unsigned long long l2keep = 0ULL;
+#endif
+    const EgdstCellHdr *hdr = H.h;
     if (S.moments && S.mom_smem && !S.momscratch) {
         for (int i = threadIdx.x; i < nt * NSO * 3; i += blockDim.x) mom[i] = 0.0;
         for (int i = threadIdx.x; i < nt; i += blockDim.x) clean_s[i] = 0;
@@ -186,16 +222,17 @@ __global__ void __launch_bounds__(BLOCK, MINB) egdst_k_simulate(EgdstDev P, Egds
             if (state == 0) {
                 // policy (egdst_simulator.c:145-199)
                 const int cell = egdst_cell(P, ivec, it, cur.ist);
-                const int nm = P.mlen[cell];
+                const EgdstCellHdr *hc = hdr + it * cx.nst + cur.ist;
+                const int nm = S.hdr_smem ? hc->n : P.mlen[cell];
                 if (nm < 2) { state = 1; }
                 else {
-                    const int i = egdst_bracket_tab(P, cell, cur.cash, nm);
+                    const int i = egdst_bracket_tab<true>(P, cell, cur.cash, nm, l2keep);
                     EgdstInterval iv;
                     double M1;
                     if (egdst_cell_has_tab(P, nm)) {
                         const EgdstInterval *ivl = egdst_cell_ivl(P, cell);
-                        iv = egdst_load_interval(ivl + i);
-                        M1 = ivl[0].g1;
+                        iv = egdst_load_interval_keep(ivl + i, l2keep);
+                        M1 = S.hdr_smem ? hc->M1 : ivl[0].g1;
                     } else {  // oversized cell: plain columns
                         const double *Mg = egdst_colM(P, cell), *Cg = egdst_colC(P, cell), *Vg = egdst_colV(P, cell);
                         iv.g0 = Mg[i]; iv.g1 = Mg[i + 1]; iv.c0 = Cg[i]; iv.c1 = Cg[i + 1]; iv.v0 = Vg[i]; iv.v1 = Vg[i + 1];
@@ -206,13 +243,19 @@ __global__ void __launch_bounds__(BLOCK, MINB) egdst_k_simulate(EgdstDev P, Egds
                     const double rw = 1.0 / (iv.g1 - iv.g0), wl = (cur.cash - iv.g0) * rw, wr = (iv.g1 - cur.cash) * rw;
                     c = iv.c1 * wl + iv.c0 * wr;
                     cur.savings = cur.cash - c;
-                    const int nth = P.thlen[cell];
-                    const double *th = P.thTH + (size_t)cell * cx.nthrhmax, *dd = P.thD + (size_t)cell * cx.nthrhmax;
-                    int ith = 0;
-                    while (ith < nth && cur.cash >= th[ith]) ith++;
-                    cur.id = (int)dd[ith > 0 ? ith - 1 : 0];
+                    const int nth = S.hdr_smem ? hc->nth : P.thlen[cell];
+                    if (S.hdr_smem && nth <= EGDST_SIM_TH8) {
+                        int ith = 0;
+                        while (ith < nth && cur.cash >= hc->th[ith]) ith++;
+                        cur.id = (int)hc->dd[ith > 0 ? ith - 1 : 0];
+                    } else {
+                        const double *th = P.thTH + (size_t)cell * cx.nthrhmax, *dd = P.thD + (size_t)cell * cx.nthrhmax;
+                        int ith = 0;
+                        while (ith < nth && cur.cash >= th[ith]) ith++;
+                        cur.id = (int)dd[ith > 0 ? ith - 1 : 0];
+                    }
                     egdst_fill_decision(&cx, &cur);
-                    const double evf = P.evf[cell];  // == V(row 0)
+                    const double evf = S.hdr_smem ? hc->evf : P.evf[cell];  // == V(row 0)
                     if (cur.cash < M1 && evf > -EGDST_INF) vf = utility(&cx, &cur, c) + discount(&cx, &cur) * evf;
                     else vf = iv.v1 * wl + iv.v0 * wr;
                 }

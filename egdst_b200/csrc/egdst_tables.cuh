@@ -31,6 +31,21 @@ EGDST_DEV const EgdstInterval *egdst_cell_ivl(const EgdstDev &P, int cell) { ret
 EGDST_DEV const EgdstLutEntry *egdst_cell_lut(const EgdstDev &P, int cell) { return P.tabLut + (size_t)cell * (P.lutcap + 1); }
 EGDST_DEV bool egdst_cell_has_tab(const EgdstDev &P, int n) { return n - 1 <= P.tabcap; }
 
+// L2 eviction-priority hints (PTX createpolicy / ld.global.L2::cache_hint): the simulator streams tens of GB of
+// output through L2; table lines loaded with evict_last survive that stream, the output is written evict_first.
+#ifndef EGDST_HOSTEMU
+EGDST_DEV unsigned long long egdst_policy_evict_last() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+EGDST_DEV double2 egdst_ld16_hint(const void *p, unsigned long long pol) {
+    double2 v;
+    asm volatile("ld.global.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
+    return v;
+}
+#endif
+
 EGDST_DEV EgdstInterval egdst_load_interval(const EgdstInterval *p) {
 #ifdef EGDST_HOSTEMU
     return *p;
@@ -124,9 +139,21 @@ __global__ void egdst_k_tab(EgdstDev P, int it) {
     }
 }
 
+// the simulator's versions: same lookups with the evict_last hint
+EGDST_DEV EgdstInterval egdst_load_interval_keep(const EgdstInterval *p, unsigned long long pol) {
+#ifdef EGDST_HOSTEMU
+    return *p;
+#else
+    const double2 q0 = egdst_ld16_hint(p, pol), q1 = egdst_ld16_hint((const double2 *)p + 1, pol), q2 = egdst_ld16_hint((const double2 *)p + 2, pol);
+    EgdstInterval iv; iv.g0 = q0.x; iv.g1 = q0.y; iv.c0 = q1.x; iv.c1 = q1.y; iv.v0 = q2.x; iv.v1 = q2.y;
+    return iv;
+#endif
+}
+
 // Bracket of x in the cell's grid.  Same result as egdst_bracket(x, M, n, 0) on a strictly increasing grid:
-// (#rows <= x) - 1 clamped to [0, n-2].
-EGDST_DEV int egdst_bracket_tab(const EgdstDev &P, int cell, double x, int n) {
+// (#rows <= x) - 1 clamped to [0, n-2].  KEEP: load the table entry with the evict_last hint `pol`.
+template <bool KEEP = false>
+EGDST_DEV int egdst_bracket_tab(const EgdstDev &P, int cell, double x, int n, unsigned long long pol = 0ULL) {
     const double *M = egdst_colM(P, cell);
     if (!egdst_cell_has_tab(P, n)) return egdst_bracket(x, M, n, 0);
     int b = egdst_lut_key(x, P.cx.a0, P.mbits);
@@ -135,8 +162,15 @@ EGDST_DEV int egdst_bracket_tab(const EgdstDev &P, int cell, double x, int n) {
 #ifdef EGDST_HOSTEMU
     const EgdstLutEntry e = lut[b];
 #else
-    const int4 raw = *reinterpret_cast<const int4 *>(lut + b);  // one 16-byte load
-    EgdstLutEntry e; e.l = raw.x; e.cnt = raw.y; e.m = __hiloint2double(raw.w, raw.z);
+    EgdstLutEntry e;
+    if (KEEP) {
+        const double2 raw = egdst_ld16_hint(lut + b, pol);  // one 16-byte load
+        const long long lo = __double_as_longlong(raw.x);
+        e.l = (int)(lo & 0xffffffffLL); e.cnt = (int)(lo >> 32); e.m = raw.y;
+    } else {
+        const int4 raw = *reinterpret_cast<const int4 *>(lut + b);  // one 16-byte load
+        e.l = raw.x; e.cnt = raw.y; e.m = __hiloint2double(raw.w, raw.z);
+    }
 #endif
     int cnt = e.l + ((e.cnt > 0 && e.m <= x) ? 1 : 0);
     if (e.cnt > 1 && e.m <= x) {  // crowded bucket (double points, coarse tables): bisect its remaining rows

@@ -34,6 +34,7 @@ inline double2 make_double2(double x, double y) { double2 v; v.x = x; v.y = y; r
 inline void *emu_dyn_smem = nullptr;
 #define EGDST_DYN_SMEM(type, name) type *name = (type *)emu_dyn_smem
 #define EGDST_LDCG(p) (*(p))
+#define EGDST_GRID_CONSTANT
 inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 
 struct dim3 {
