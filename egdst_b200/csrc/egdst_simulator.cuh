@@ -62,7 +62,13 @@ EGDST_DEV double egdst_u01(unsigned x) { return ((double)x + 0.5) * (1.0 / 42949
 #define EGDST_SIM_TH8 4
 #define EGDST_SIM_MAXHDR 128
 struct EgdstCellHdr { int n, nth; double evf, M1; double th[EGDST_SIM_TH8], dd[EGDST_SIM_TH8]; };
-struct EgdstSimHdrs { EgdstCellHdr h[EGDST_SIM_MAXHDR]; };
+#define EGDST_SIM_MAXTAB 96
+struct EgdstSimHdrs {
+    EgdstCellHdr h[EGDST_SIM_MAXHDR];
+    // the model's small tables (stm, states, decisions: egdst_lib.c:241-252), when they fit
+    double stm[16], states[EGDST_SIM_MAXTAB], decisions[EGDST_SIM_MAXTAB];
+    int tabs_ok;
+};
 
 // gathers the headers of parameter vector ivec (host copy -> kernel argument of later simulations)
 __global__ void egdst_k_simhdr(EgdstDev P, int ivec, EgdstCellHdr *out) {
@@ -142,6 +148,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) egdst_k_simulate(EgdstDev P, Egds
     const unsigned long long l2keep = 0ULL;
 #endif
     const EgdstCellHdr *hdr = H.h;
+    if (H.tabs_ok) { cx.stm = H.stm; cx.states = H.states; cx.decisions = H.decisions; }
     if (S.moments && S.mom_smem && !S.momscratch) {
         for (int i = threadIdx.x; i < nt * NSO * 3; i += blockDim.x) mom[i] = 0.0;
         for (int i = threadIdx.x; i < nt; i += blockDim.x) clean_s[i] = 0;
