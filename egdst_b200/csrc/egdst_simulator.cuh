@@ -245,8 +245,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) egdst_k_simulate(EgdstDev P, Egds
                         iv.g0 = Mg[i]; iv.g1 = Mg[i + 1]; iv.c0 = Cg[i]; iv.c1 = Cg[i + 1]; iv.v0 = Vg[i]; iv.v1 = Vg[i + 1];
                         M1 = Mg[1];
                     }
-                    // one division for the weights of both interpolations (the reference divides four times, egdst_lib.c:175;
-                    // the difference is in the last bit and the simulator has no discrete branch that depends on it)
+                    // one division for the weights of both interpolations (the reference divides four times, egdst_lib.c:175).
+                    // The exactly rounded shared-reciprocal form of the solver (egdst_div_by) costs 7 % of this kernel; here the
+                    // difference is in the last bit and no discrete branch of the simulator depends on it.
                     const double rw = 1.0 / (iv.g1 - iv.g0), wl = (cur.cash - iv.g0) * rw, wr = (iv.g1 - cur.cash) * rw;
                     c = iv.c1 * wl + iv.c0 * wr;
                     cur.savings = cur.cash - c;

@@ -127,9 +127,12 @@ EGDST_DEV void egdst_eval_nodes(const egdst_ctx *cx, const EgdstDev &P, int ivec
             EgdstInterval iv;
             if (tab) iv = egdst_load_interval(t.ivl + i);
             else { iv.g0 = t.M[i]; iv.g1 = t.M[i + 1]; iv.c0 = t.C[i]; iv.c1 = t.C[i + 1]; iv.v0 = t.V[i]; iv.v1 = t.V[i + 1]; }
-            // the reference's operation order is kept (two divisions per interpolation, egdst_lib.c:175): next to its
-            // instability boundary a reciprocal-multiply variant drifted 1e-2 away in C
-            double c1 = egdst_lerp(next.cash, iv.g0, iv.g1, iv.c0, iv.c1);
+            // the reference's quotients are kept bit for bit (two divisions per interpolation, egdst_lib.c:175): next to its
+            // instability boundary a plain reciprocal-multiply variant drifted 1e-2 away in C, so the
+            // shared-reciprocal form below is the exactly rounded one (egdst_div_by)
+            double w = iv.g1 - iv.g0;
+            double y = egdst_div_safe(w) ? 1.0 / w : 0.0;  // shared correctly rounded reciprocal (0: degenerate interval)
+            double c1 = y != 0.0 ? egdst_lerp_y(next.cash, iv.g0, iv.g1, iv.c0, iv.c1, w, y) : egdst_lerp(next.cash, iv.g0, iv.g1, iv.c0, iv.c1);
             if (next.cash > t.Mlast) c1 = MAX(c1, t.Clast);  // constant extrapolation guard (egdst_solver.c:554)
             if (c1 <= 0) {
                 acc.badq = q; acc.badtype = EGDST_PT_C1NEG; acc.badcash = next.cash; acc.badshock = next.shock;
@@ -148,8 +151,10 @@ EGDST_DEV void egdst_eval_nodes(const egdst_ctx *cx, const EgdstDev &P, int ivec
                     if (i < 1) {  // value table starts at row 1 (row 0 of V is evf(a0), not a value)
                         if (tab) iv = egdst_load_interval(t.ivl + 1);
                         else { iv.g0 = t.M[1]; iv.g1 = t.M[2]; iv.v0 = t.V[1]; iv.v1 = t.V[2]; }
+                        w = iv.g1 - iv.g0;
+                        y = egdst_div_safe(w) ? 1.0 / w : 0.0;
                     }
-                    v1 = egdst_linter_extrap_iv(cx, &next, next.cash, iv.g0, iv.g1, iv.v0, iv.v1, t.M1, t.Mlast);
+                    v1 = egdst_linter_extrap_iv(cx, &next, next.cash, iv.g0, iv.g1, iv.v0, iv.v1, t.M1, t.Mlast, w, y);
                 }
                 const double term = pr1 * v1;
                 acc.evf += term;
