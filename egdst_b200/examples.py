@@ -34,7 +34,7 @@ def _log_utility(m: EgdstModel, util="log(consumption)"):
 
 
 def deaton(label="deaton1", a0=0.0, sigma="0", mu="0", mmax=50, ny=2, T=25, ngridm=100, ngridmax=1000,
-           interest=0.01, income=1.25) -> EgdstModel:
+           interest=0.01, income=1.25, shocktype="lognormal") -> EgdstModel:
     """egdst_examples/model_deaton1.m:6-46 (and model_deaton2.m with a0=-25, sigma=0.75, mmax=100, ny=10)."""
     m = EgdstModel(label)
     _common(m, T, mmax, ngridmax, ngridm, 10, ny)
@@ -49,7 +49,7 @@ def deaton(label="deaton1", a0=0.0, sigma="0", mu="0", mmax=50, ny=2, T=25, ngri
     m.eq = ("income_level", "Realized income", "income*shock", "next")
     m.param = ("income", "income (times multiplicator shock)", income)
     m.a0 = a0
-    m.shock = "lognormal"
+    m.shock = shocktype
     m.shock = ("sigma", sigma)
     m.shock = ("mu", mu)
     return m

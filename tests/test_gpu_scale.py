@@ -224,3 +224,29 @@ def test_occ3_three_choices_on_a_fine_grid():
     e = solution_errors(m.M, m.D, Mr, Dr)
     assert e["C"] < TOL and e["V"] < TOL and e["TH"] < 1e-8 and e["Dseq"], e
     assert max(Dr[0][it].shape[0] for it in range(m.nt)) >= 3  # several thresholds per period
+
+
+def test_normal_shock_distribution_matches_reference():
+    """DISTRIB=2 (egdst_lib.c:66-101): none of the shipped examples uses normal shocks with sigma>0; this variant of the
+    Deaton model does (income multiplier ~ N(1, 0.15))."""
+    m = _solve(examples.deaton("deaton_normal", a0=0.0, sigma="0.15", mu="1.0", mmax=60, ny=12, T=15, ngridm=300, ngridmax=1000,
+                               shocktype="normal"))
+    orc = oracle_for(m)
+    Mr, Dr = orc.solve()
+    e = solution_errors(m.M, m.D, Mr, Dr)
+    assert e["C"] < TOL and e["V"] < TOL and e["Dseq"], e
+    rng = np.random.default_rng(2)
+    nsim = 500
+    init = np.column_stack([np.ones(nsim), rng.uniform(0.5, 20.0, nsim)])
+    rs = rng.random(4 * nsim * m.nt)
+    m.sim(init, "own_shocks", randstream=rs)
+    sr = orc.simulate(Mr, Dr, init, rs, 0)
+    from tests.goldens import sims_errors
+    se = sims_errors(m.sims, sr)
+    assert se["nan_mismatch"] == 0 and se["discrete_mismatch"] == 0 and se["max"] < TOL, se
+    # same_shocks mode: every agent sees the same shock sequence (egdst_simulator.c:109-114)
+    m.sim(init, "same_shocks", randstream=rs)
+    sr1 = orc.simulate(Mr, Dr, init, rs, 1)
+    se1 = sims_errors(m.sims, sr1)
+    assert se1["nan_mismatch"] == 0 and se1["max"] < TOL
+    assert np.all(np.nanstd(m.sims[:, 1:, 8], axis=0) < 1e-12)
