@@ -59,6 +59,15 @@ def deaton1(**kw) -> EgdstModel:
     return deaton("deaton1", **kw)
 
 
+def deaton_normal(**kw) -> EgdstModel:
+    """Deaton model with normally distributed income multiplier (DISTRIB=2): not shipped by the reference, used to
+    cover the normal-shock code path (egdst_lib.c:66-101)."""
+    args = dict(label="deaton_normal", a0=0.0, sigma="0.15", mu="1.0", mmax=60, ny=12, T=15, ngridm=300, ngridmax=1000, shocktype="normal")
+    args.update(kw)
+    label = args.pop("label")
+    return deaton(label, **args)
+
+
 def deaton2(**kw) -> EgdstModel:
     args = dict(a0=-25.0, sigma="0.75", mu="-0.5*sigma*sigma", mmax=100, ny=10)
     args.update(kw)
@@ -211,6 +220,8 @@ def model2(T=3, ngridm=100, nquad=10, mmax=100, cc=0.0, df=1.0, rho=0.0, r=0.0, 
     m.param = ("sig", "sigma parameter in lognormal return", sigma)
     return m
 
+
+EXTRA = {"deaton_normal": deaton_normal}
 
 ALL = {
     "deaton1": deaton1, "deaton2": deaton2, "retirement1": retirement1, "retirement2": retirement2,

@@ -229,8 +229,7 @@ def test_occ3_three_choices_on_a_fine_grid():
 def test_normal_shock_distribution_matches_reference():
     """DISTRIB=2 (egdst_lib.c:66-101): none of the shipped examples uses normal shocks with sigma>0; this variant of the
     Deaton model does (income multiplier ~ N(1, 0.15))."""
-    m = _solve(examples.deaton("deaton_normal", a0=0.0, sigma="0.15", mu="1.0", mmax=60, ny=12, T=15, ngridm=300, ngridmax=1000,
-                               shocktype="normal"))
+    m = _solve(examples.deaton_normal())
     orc = oracle_for(m)
     Mr, Dr = orc.solve()
     e = solution_errors(m.M, m.D, Mr, Dr)
