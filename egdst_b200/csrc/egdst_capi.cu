@@ -15,6 +15,10 @@
 #include <vector>
 
 #include "egdst_b200.h"
+#ifndef EGDST_HOSTEMU
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#endif
 #include "egdst_envelope.cuh"
 #include "egdst_simulator.cuh"
 #include "egdst_solver.cuh"

@@ -14,7 +14,7 @@
 #define EGDST_BLOCK 256
 #define EGDST_ENVW 256   /* envelope merge kernels: 8 positions per thread, chained across CTAs */
 #define EGDST_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
-#define EGDST_DYN_SMEM(type, name) extern __shared__ __align__(16) type name[]
+#define EGDST_DYN_SMEM(type, name) extern __shared__ __align__(128) type name[]
 #define EGDST_LDCG(p) __ldcg(p)
 #define EGDST_GRID_CONSTANT __grid_constant__
 #endif

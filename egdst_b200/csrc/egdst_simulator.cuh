@@ -85,6 +85,15 @@ __global__ void egdst_k_simhdr(EgdstDev P, int ivec, EgdstCellHdr *out) {
     out[c] = h;
 }
 
+// TMA descriptor of the caller's sims array viewed as a 2-D tensor [nsim rows][nt*nsimout doubles], row pitch
+// nt*nsimout*8 bytes; box = 32 agents x nsimout doubles (one tile-period)
+#ifdef EGDST_HOSTEMU
+struct EgdstTensorMap { unsigned long long opaque[16]; };
+#else
+#include <cuda.h>
+typedef CUtensorMap EgdstTensorMap;
+#endif
+
 struct EgdstSimArgs {
     const double *init;        // [nsim] 1-based ist0 of the agents of this launch
     const double *init_m0;     // [nsim] m0 (the second column of the reference's init matrix)
@@ -108,17 +117,20 @@ struct EgdstSimArgs {
 //   tile[warps][32*TS]                one staged record per agent of the warp's tile (TS = nso|1, odd)
 //   mom[nt][nso][3]   (mom_smem)      per-CTA moment accumulators, flushed once at the end
 // Kernel variants (chosen on the host, sim_launch):
-//   <1, 256, 4, false>  one period per write, padded (odd-stride) tile, 4 CTAs/SM, moments in shared memory
+//   <1, 256, 4, false, false>  one period per write, padded (odd-stride) tile, 4 CTAs/SM, moments in shared memory
+//   <1, 256, 4, false, true>  same, but lane 0 hands the whole tile to the TMA engine as one 2-D tensor store
+//                       (cp.async.bulk.tensor shared -> global, evict-first): no read-back of the tile, no per-piece stores
 //   <2, 512, 2, true>   two periods per write (whole 32-byte sectors in DRAM), 16 warps per CTA, 2 CTAs/SM: the
 //                       unpadded 2*NSO-double rows of 16 warps fill the CTA's shared memory exactly, so rows are
 //                       column-rotated by (lane/4)%4 instead of padded and moments accumulate in a per-CTA global
 //                       scratch with fire-and-forget reductions (summed by egdst_k_momreduce)
-template <int PB, int BLOCK, int MINB, bool SWZ>
-__global__ void __launch_bounds__(BLOCK, MINB) egdst_k_simulate(EgdstDev P, EgdstSimArgs S, const EGDST_GRID_CONSTANT EgdstSimHdrs H) {
+template <int PB, int BLOCK, int MINB, bool SWZ, bool TMAST>
+__global__ void __launch_bounds__(BLOCK, MINB) egdst_k_simulate(EgdstDev P, EgdstSimArgs S, const EGDST_GRID_CONSTANT EgdstSimHdrs H, const EGDST_GRID_CONSTANT EgdstTensorMap TM) {
     EGDST_DYN_SMEM(double, egdst_sim_smem);
     constexpr int NSO = EGDST_NSIMOUT_MAX;   // the model image fixes nsimout (checked on the host)
     constexpr int W = PB * NSO;              // doubles per staged row (one agent)
-    constexpr int TS = SWZ ? W : (W | 1);    // padded rows have an odd stride: conflict-free staging and column walks
+    constexpr int TS = (SWZ || TMAST) ? W : (W | 1);  // padded rows have an odd stride: conflict-free staging and column walks;
+                                                      // TMAST: plain contiguous 16-byte aligned rows, the source of a TMA bulk store
     constexpr int WPB = BLOCK / 32;
     // blockIdx.y walks the parameter vectors of a batched sweep: same agents and shocks under every vector,
     // per-vector output blocks (sims [nvec][nsimout,nt,nsim], moments [nvec][3,nsimout,nt])
@@ -144,6 +156,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) egdst_k_simulate(EgdstDev P, Egds
     const int ntiles = (S.nsim + 31) / 32;
 #ifndef EGDST_HOSTEMU
     const unsigned long long l2keep = egdst_policy_evict_last();
+    unsigned long long l2first = 0ULL;
+    if (TMAST) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(l2first));
 #else
     const unsigned long long l2keep = 0ULL;
 #endif
@@ -275,6 +289,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) egdst_k_simulate(EgdstDev P, Egds
             // (tools/micro/wpat.cu: 2.5 TB/s for 112-byte chunks, 4.2 TB/s for 224-byte chunks)
             const int half = (PB == 2) ? (it & 1) : 0;
             const int hoff = half * NSO;
+#ifndef EGDST_HOSTEMU
+            if (TMAST && half == 0) {  // the TMA engine must be done reading the tile before it is overwritten
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncwarp();
+            }
+#endif
 #define EGDST_REC(j) tile[EGDST_TILE_POS(lane, hoff + (j))]
             if (state == 0) {
                 EGDST_REC(0) = cur.cash; EGDST_REC(1) = c; EGDST_REC(2) = cur.savings; EGDST_REC(3) = vf; EGDST_REC(4) = (double)cur.id; EGDST_REC(5) = (double)cur.ist;
@@ -301,8 +321,22 @@ __global__ void __launch_bounds__(BLOCK, MINB) egdst_k_simulate(EgdstDev P, Egds
 #else
                 double *dst = S.sims + ((size_t)tileidx * 32 * nt + it0) * NSO;
 #endif
-                constexpr int W = PB * NSO;  // doubles per agent per write
-                if ((W & 1) == 0 && W <= 32 && (((size_t)S.sims & 15) == 0)) {
+                if (TMAST) {
+#ifndef EGDST_HOSTEMU
+                    // ONE tensor store per tile: the TMA engine scatters the 32 staged rows (W doubles each) to their
+                    // slots of the sims array (row pitch nt*NSO doubles), clipping rows beyond nsim; evict-first
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // rows were written through the generic proxy
+                    __syncwarp();
+                    if (lane == 0) {
+                        const unsigned saddr = (unsigned)__cvta_generic_to_shared(tile);
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%1, %2}], [%3], %4;"
+                                     :: "l"(reinterpret_cast<unsigned long long>(&TM)), "r"(it0 * NSO), "r"(tileidx * 32), "r"(saddr), "l"(l2first) : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+#else
+                    for (int e = lane; e < na * W; e += 32) { const int a = e / W, j = e - a * W; dst[(size_t)a * nt * NSO + j] = tile[a * TS + j]; }
+#endif
+                } else if ((W & 1) == 0 && W <= 32 && (((size_t)S.sims & 15) == 0)) {
                     // 16-byte pieces, SL slots per agent (W/2 used): agent = (32/SL)*t + lane/SL, piece = lane%SL
                     constexpr int SL = W / 2 <= 8 ? 8 : 16, APT = 32 / SL;
                     const int k = lane % SL, a0 = lane / SL;
@@ -366,6 +400,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) egdst_k_simulate(EgdstDev P, Egds
             __syncwarp();
         }
     }
+#ifndef EGDST_HOSTEMU
+    if (TMAST && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+#endif
     if (S.moments && S.mom_smem && !S.momscratch) {
         __syncthreads();
         for (int i = threadIdx.x; i < nt * NSO * 3; i += blockDim.x) {
