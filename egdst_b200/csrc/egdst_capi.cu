@@ -232,7 +232,8 @@ static int create_solution(const egdst_desc *d, int nvec, egdst_solution **out) 
         const double span = 2.0 * (d->mmax - d->a0) + 2.0;
         const double octaves = log2(span > 2.0 ? span : 2.0);
         int mbits = 3;
-        while (mbits < 16 && (double)(1 << mbits) * octaves < 2.0 * (double)(P.N + 1)) mbits++;
+        static const double density = getenv("EGDST_LUT_DENSITY") ? atof(getenv("EGDST_LUT_DENSITY")) : 2.0;  // buckets per grid row
+        while (mbits < 16 && (double)(1 << mbits) * octaves < density * (double)(P.N + 1)) mbits++;
         P.mbits = mbits;
         P.lutcap = (int)(octaves * (double)(1 << mbits)) + 2;
     }
