@@ -61,6 +61,27 @@ static void prof_collect() {
     }
     g_prof_pending.clear();
 }
+#ifndef EGDST_HOSTEMU
+// launch with programmatic stream serialization allowed (see EGDST_PDL_PROLOGUE).  Measured on the S1 solve: eager chain
+// 7.9 -> 6.9 ms with it; the graph replay is 6.6 ms without and 6.8 ms with programmatic edges, so captures switch it off.
+static thread_local bool g_pdl = true;
+template <typename... KArgs, typename... Args>
+static void egdst_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    static const bool off = getenv("EGDST_NO_PDL") != 0;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = (off || !g_pdl) ? 0 : 1;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#define PLAUNCH(cls, kernel, grid, block, smem, stream, ...) \
+    do { prof_begin(cls, stream); egdst_launch_pdl(kernel, grid, block, smem, stream, __VA_ARGS__); prof_end(stream); } while (0)
+#else
+#define PLAUNCH KLAUNCH
+#endif
 #define KLAUNCH(cls, kernel, grid, block, smem, stream, ...) \
     do { prof_begin(cls, stream); EGDST_LAUNCH(kernel, grid, block, smem, stream, __VA_ARGS__); prof_end(stream); } while (0)
 
@@ -277,18 +298,18 @@ static int launch_periods(egdst_solution *s, cudaStream_t st) {
     for (int it = P.NT - 1; it >= 0; it--) {
         if (it == P.NT - 1) {
             KLAUNCH(KC_SETUP, egdst_k_cells, dim3(nvec), dim3(cellthreads), 0, st, P, it);
-            KLAUNCH(KC_TERMINAL, egdst_k_terminal, dim3((N + B - 1) / B, nst * nd, nvec), dim3(B), 0, st, P, it);
+            PLAUNCH(KC_TERMINAL, egdst_k_terminal, dim3((N + B - 1) / B, nst * nd, nvec), dim3(B), 0, st, P, it);
         } else {
-            KLAUNCH(KC_SEED, egdst_k_seed, dim3(nd, nst, nvec), dim3(B), shsmem, st, P, it, useTab);
-            KLAUNCH(KC_EGM, egdst_k_egm, dim3((N - 1 + 31) / 32, nst * nd, nvec), dim3(32, EGDST_EGM_SPLIT), shsmem, st, P, it, useTab);
-            KLAUNCH(KC_COMPACT, egdst_k_compact, dim3(P.chC, nst * nd, nvec), dim3(EGDST_CMP_THREADS), 0, st, P, it);
+            PLAUNCH(KC_SEED, egdst_k_seed, dim3(nd, nst, nvec), dim3(B), shsmem, st, P, it, useTab);
+            PLAUNCH(KC_EGM, egdst_k_egm, dim3((N - 1 + 31) / 32, nst * nd, nvec), dim3(32, EGDST_EGM_SPLIT), shsmem, st, P, it, useTab);
+            PLAUNCH(KC_COMPACT, egdst_k_compact, dim3(P.chC, nst * nd, nvec), dim3(EGDST_CMP_THREADS), 0, st, P, it);
             // secondary envelope (no-op for (ist,id) without folds)
-            KLAUNCH(KC_ENV2, egdst_k_envA<1>, dim3((2 * P.gcap + B - 1) / B, nst * nd, nvec), dim3(B), 0, st, P, it);
-            KLAUNCH(KC_ENV2, egdst_k_envBC<1>, dim3(P.chE, nst * nd, nvec), dim3(EGDST_ENVW), 0, st, P, it);
+            PLAUNCH(KC_ENV2, egdst_k_envA<1>, dim3((2 * P.gcap + B - 1) / B, nst * nd, nvec), dim3(B), 0, st, P, it);
+            PLAUNCH(KC_ENV2, egdst_k_envBC<1>, dim3(P.chE, nst * nd, nvec), dim3(EGDST_ENVW), 0, st, P, it);
         }
-        KLAUNCH(KC_ENV, egdst_k_envA<0>, dim3((nd * P.gcap + B - 1) / B, nst, nvec), dim3(B), 0, st, P, it);
-        KLAUNCH(KC_ENV, egdst_k_envBC<0>, dim3(P.chE, nst, nvec), dim3(EGDST_ENVW), 0, st, P, it);
-        KLAUNCH(KC_TAB, egdst_k_tab, dim3(tabblocks, nst, nvec), dim3(B), 0, st, P, it);
+        PLAUNCH(KC_ENV, egdst_k_envA<0>, dim3((nd * P.gcap + B - 1) / B, nst, nvec), dim3(B), 0, st, P, it);
+        PLAUNCH(KC_ENV, egdst_k_envBC<0>, dim3(P.chE, nst, nvec), dim3(EGDST_ENVW), 0, st, P, it);
+        PLAUNCH(KC_TAB, egdst_k_tab, dim3(tabblocks, nst, nvec), dim3(B), 0, st, P, it);
     }
     CK(cudaGetLastError());
     return 0;
@@ -337,7 +358,9 @@ static int run_solve(egdst_solution *s, const egdst_desc *d, const double *param
         cudaGraph_t graph = 0;
         const long long l0 = g_launches;
         CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        g_pdl = false;
         rc = launch_periods(s, st);
+        g_pdl = true;
         cudaError_t e = cudaStreamEndCapture(st, &graph);
         if (rc || e != cudaSuccess || !graph) { if (graph) cudaGraphDestroy(graph); return rc ? rc : fail(2, std::string("graph capture failed: ") + cudaGetErrorString(e)); }
         s->g_nlaunch = g_launches - l0;

@@ -156,6 +156,7 @@ EGDST_DEV double egdst_env_grb_block(const View &E, double *sh) {
 
 template <int MODE>
 __global__ void egdst_k_envA(EgdstDev P, int it) {
+    EGDST_PDL_PROLOGUE();
     __shared__ double shg[33];
     const int ivec = blockIdx.z;
     int ist, id, slot;
@@ -340,6 +341,7 @@ EGDST_DEV EgdstEnvPos egdst_env_pos(const EgdstEnvView<MODE> &E, const double *m
 // staged result back over the decision's point list (MODE 1).
 template <int MODE>
 __global__ void __launch_bounds__(EGDST_ENVW) egdst_k_envBC(EgdstDev P, int it) {
+    EGDST_PDL_PROLOGUE();
     __shared__ long long sh[40];
     __shared__ double s_grb[33];
     __shared__ int s_chunk, s_last, s_qn;

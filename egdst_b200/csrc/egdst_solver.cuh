@@ -188,6 +188,7 @@ EGDST_DEV void egdst_warp_combine(EgdstAcc &a) {
 // grid (ceil(N/B), nst*nd, nvec)
 // ---------------------------------------------------------------------------------------------
 __global__ void egdst_k_terminal(EgdstDev P, int it) {
+    EGDST_PDL_PROLOGUE();
     const int ivec = blockIdx.z, ist = blockIdx.y / P.cx.nd, id = blockIdx.y % P.cx.nd;
     egdst_ctx cx; egdst_load_ctx(P, ivec, cx);
     const int sd = egdst_sd(P, ivec, ist, id);
@@ -240,6 +241,7 @@ EGDST_DEV void egdst_block_eval(const egdst_ctx *cx, const EgdstDev &P, int ivec
 }
 
 __global__ void egdst_k_seed(EgdstDev P, int it, int useTab) {
+    EGDST_PDL_PROLOGUE();
     __shared__ EgdstSeedShared S;
     EGDST_DYN_SMEM(double, shsm);
     const int ivec = blockIdx.z, ist = blockIdx.y, id = blockIdx.x;
@@ -409,6 +411,7 @@ EGDST_DEV double egdst_agrid(const egdst_ctx *cx, const PeriodVars *curr, const 
 #define EGDST_EGM_MINB 3
 #endif
 __global__ void __launch_bounds__(32 * EGDST_EGM_SPLIT, EGDST_EGM_MINB) egdst_k_egm(EgdstDev P, int it, int useTab) {
+    EGDST_PDL_PROLOGUE();
     EGDST_DYN_SMEM(double, shsm);
     __shared__ double s_rhs[EGDST_EGM_SPLIT][32], s_evf[EGDST_EGM_SPLIT][32], s_chk[EGDST_EGM_SPLIT][32], s_cash[EGDST_EGM_SPLIT][32];
     __shared__ int s_q[EGDST_EGM_SPLIT][32], s_t[EGDST_EGM_SPLIT][32];
@@ -475,6 +478,7 @@ __global__ void __launch_bounds__(32 * EGDST_EGM_SPLIT, EGDST_EGM_MINB) egdst_k_
 // carries (points kept so far, "stop rule fired").  Folds inside a CTA's own output are appended to an unordered
 // list; the last CTA to finish adds the folds on chunk boundaries, orders the list and publishes the counts.
 __global__ void __launch_bounds__(EGDST_CMP_THREADS) egdst_k_compact(EgdstDev P, int it) {
+    EGDST_PDL_PROLOGUE();
     __shared__ int sh[40];
     __shared__ int s_chunk, s_last;
     __shared__ unsigned long long s_excl;

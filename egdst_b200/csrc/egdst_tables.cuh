@@ -84,6 +84,7 @@ EGDST_DEV void egdst_cells_body(const EgdstDev &P, int ivec, int it) {
 
 // build the tables of the cells (ivec, it, all ist): grid (nblk, nst, nvec)
 __global__ void egdst_k_tab(EgdstDev P, int it) {
+    EGDST_PDL_PROLOGUE();
     const int ivec = blockIdx.z, ist = blockIdx.y;
     // the last kernel of period `it` also opens period it-1 (saves a launch per period)
     if (blockIdx.x == 0 && blockIdx.y == 0 && it > 0) egdst_cells_body(P, ivec, it - 1);
