@@ -165,9 +165,9 @@ class Reference:
             L.shim_setfield(sv, i, b"grid", self._dbl(np.zeros(0)))
         sf("s", sv)
         sf("eq", L.shim_struct(len(m.eq)))
-        if quadrature and m.ny > 1:
-            q = model_quadrature(m.ny)  # fresh copy each call: the gateway overwrites the abscissas (egdst_solver.c:164)
-            sf("quadrature", self._dbl(q.reshape(2, m.ny).T, (m.ny, 2)))
+        if quadrature:  # (ny == 1 included: the gateway reads the property unconditionally, egdst_solver.c:162)
+            q = model_quadrature(max(m.ny, 1))  # fresh copy each call: the gateway overwrites the abscissas (egdst_solver.c:164)
+            sf("quadrature", self._dbl(q.reshape(2, max(m.ny, 1)).T, (max(m.ny, 1), 2)))
         if init is not None:
             sf("init", self._dbl(init, init.shape))
         if randstream is not None:

@@ -249,3 +249,31 @@ def test_normal_shock_distribution_matches_reference():
     se1 = sims_errors(m.sims, sr1)
     assert se1["nan_mismatch"] == 0 and se1["max"] < TOL
     assert np.all(np.nanstd(m.sims[:, 1:, 8], axis=0) < 1e-12)
+
+
+@pytest.mark.parametrize("name,kw", [
+    ("retirement2", dict(ngridm=7, ngridmax=100, T=3, ny=3)),
+    ("retirement2", dict(ngridm=33, ngridmax=100, T=2, ny=1)),
+    ("retirement2", dict(ngridm=101, ngridmax=300, T=9, ny=7)),
+    ("retirement2", dict(ngridm=2049, ngridmax=5000, T=6, ny=5, nthrhmax=2049)),
+    ("retirement2", dict(ngridm=50000, ngridmax=100000, T=5, ny=20, nthrhmax=50000, interest=0.02)),
+    ("deaton2", dict(ngridm=5, ngridmax=100, T=4)),
+    ("model2", dict(T=2, ngridm=11, nquad=2, sigma=0.2)),
+    ("occ3", dict(ngridm=17, ngridmax=100, ny=3, T=6)),
+])
+def test_odd_shapes_match_reference(name, kw):
+    """Tiny and ragged grids, one quadrature node, two periods, 25 compaction chunks: the chained scans, lookup tables
+    and batching logic at their edges."""
+    m = _solve(examples.ALL[name](**kw))
+    orc = oracle_for(m)
+    Mr, Dr = orc.solve()
+    e = solution_errors(m.M, m.D, Mr, Dr)
+    assert e["C"] < TOL and e["V"] < TOL and e["TH"] < 1e-8 and e["Dseq"] and e["rowdiff"] == 0, e
+    rng = np.random.default_rng(1)
+    nsim = 200
+    init = np.column_stack([np.full(nsim, float(m.nst)), m.a0 + (m.mmax - m.a0) * rng.random(nsim) * 0.9])
+    rs = rng.random(4 * nsim * m.nt)
+    m.sim(init, "own_shocks", randstream=rs)
+    from tests.goldens import sims_errors
+    se = sims_errors(m.sims, orc.simulate(Mr, Dr, init, rs, 0))
+    assert se["nan_mismatch"] == 0 and se["discrete_mismatch"] == 0 and se["max"] < TOL, se
