@@ -59,6 +59,16 @@ def committed_traffic(kernel: str, key: str):
         return None
 
 
+def micro_peaks():
+    """Committed on-box ceilings and instruction counts (profiles/micro_peaks.json: tools/micro/peaks.cu + ncu SASS page)."""
+    p = os.path.join(ROOT, "profiles", "micro_peaks.json")
+    try:
+        with open(p) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
 class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -106,6 +116,17 @@ class ClockSampler:
         if sm:
             out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
         return out
+
+
+def fp64_side(flop_per_launch, launch_ms):
+    """The FP64 side of the roofline: flop per launch (2*DFMA+DADD+DMUL thread instructions, counted once with ncu on the
+    committed profile) over the live launch duration, against the FP64 FMA rate measured on this pool (tools/micro/peaks.cu)."""
+    mp = micro_peaks()
+    if not flop_per_launch or not mp.get("fp64_fma_tflops"):
+        return None
+    ach = flop_per_launch / (launch_ms / 1e3) / 1e12
+    return {"achieved_tflops": ach, "peak_tflops_measured": mp["fp64_fma_tflops"], "frac": ach / mp["fp64_fma_tflops"],
+            "gather16_l2_Gps_measured": mp.get("gather16_l2_Gps")}
 
 
 def nominal_units(m) -> int:
@@ -218,6 +239,7 @@ def own_arm(a):
                      "traffic": committed_traffic("egdst_k_egm", "S1"),
                      "algorithmic_bytes_per_launch": egm_bytes, "launch_ms": egm_launch_ms,
                      "whole_solve_GBs": solve_alg_bytes / (solve_ms / 1e3) / 1e9,
+                     "fp64": fp64_side(micro_peaks().get("egm_fp64_flop_per_launch_S1"), egm_launch_ms),
                      "note": "FP64-issue/latency-bound, not HBM-bound: ~200 flop per algorithmic byte (SURVEY 8d)"},
         "kernel_share": {k: round(v[0] / ksum, 4) for k, v in prof.items() if v[1]},
         "kernel_ms_per_solve": {k: round(v[0] / 2, 4) for k, v in prof.items() if v[1]},
@@ -342,7 +364,8 @@ def own_arm(a):
             "roofline": {"bound": "hbm", "kernel": "egdst_k_simulate", "achieved": sim_bytes / (kern_ms / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                          "frac": sim_bytes / (kern_ms / 1e3) / 1e9 / hbm_peak, "peak_source": peak_src,
                          "traffic": committed_traffic("egdst_k_simulate", "nsim=%d" % nsim),
-                         "algorithmic_bytes_per_launch": sim_bytes, "launch_ms": kern_ms},
+                         "algorithmic_bytes_per_launch": sim_bytes, "launch_ms": kern_ms,
+                         "fp64": fp64_side((micro_peaks().get("sim_fp64_flop_per_launch_nsim10M") or 0) * nsim / 1e7 or None, kern_ms)},
             "cpu_baseline": cpu,
             "solve": solve_obj,
         }
