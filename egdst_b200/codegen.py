@@ -140,9 +140,6 @@ def emit_refspec(model):
     H: List[str] = []
     cv = lambda s: std_convert(model, s)  # noqa: E731
     ns, ndv = len(model.s), len(model.d)
-    for sv in model.s:
-        if sv["continuous"]:
-            raise NotImplementedError("continuous state variables are outside the hot-path scope (SURVEY 8(f).3)")
     C += ["/*Model specific code for the model '%s'*/" % model.label, '#include "egdst_lib.h"', ""]
     H += ["/*Model specific h for the model '%s'*/" % model.label, "#ifndef MODELSPECguard", "#define  MODELSPECguard", ""]
     H += ["typedef struct curr_variables {int it; int ist; double st[%d]; int id; double dc[%d]; double cash; "
@@ -156,9 +153,20 @@ def emit_refspec(model):
     for p in model.param:
         H.append("extern double %s; /*Parameter:%s*/" % (p["ref"], p["description"]))
         C.append("double %s; /*Parameter:%s*/" % (p["ref"], p["description"]))
+    for i, sv in enumerate(model.s):  # grids of the continuous states (compile.m:229-252)
+        if sv["continuous"]:
+            H.append("extern double *st%dgrid;" % (i + 1))
+            C.append("double *st%dgrid;" % (i + 1))
     H.append("extern double *stgrids[%d]; /*pointers to grids of continous states*/" % ns)
     C += ["double *stgrids[%d];" % ns, ""]
-    C += ["void loadcontinuousgrid() {"] + ["/* stgrids[%d] is never used */" % i for i in range(ns)] + ["}", ""]
+    C += ["void loadcontinuousgrid() {"]
+    for i, sv in enumerate(model.s):
+        if sv["continuous"]:
+            C.append('st%dgrid = (double *) mxGetPr(mxGetField(mxGetProperty(Model,0,"s"),%d,"grid"));' % (i + 1, i))
+            C.append("stgrids[%d] = (double *) st%dgrid;" % (i, i + 1))
+        else:
+            C.append("/* stgrids[%d] is never used */" % i)
+    C += ["}", ""]
     H += ["", "void loadcontinuousgrid();"]
 
     def fn(proto, body_lines):
@@ -219,6 +227,19 @@ def emit_refspec(model):
         for case in tr["cases"]:
             body.append(("if (%s) {" if first else "else if (%s) {") % cv(case["condition"]))
             first = False
+            if model.s[v]["continuous"]:
+                # deterministic motion rule: linear interpolation weights onto the two adjacent grid points
+                # (compile.m:527-537)
+                g = "st%dgrid" % (v + 1)
+                body.append("if (all==1) {")
+                body.append("    nval=%s;" % cv(prohibit(case["prob"], "ist1", "motion rules")))
+                body.append("    varindex = bxsearch(nval,(double*)%s,(int)stm[%d]);" % (g, v))
+                body.append("    if (varindex==varindex1) res*=(%s[varindex+1]-nval)/(%s[varindex+1]-%s[varindex]);" % (g, g, g))
+                body.append("    else if (varindex+1==varindex1) res*=(nval-%s[varindex])/(%s[varindex+1]-%s[varindex]);" % (g, g, g))
+                body.append("    else return 0.0;")
+                body.append("}")
+                body.append("}")
+                continue
             body.append("  switch (varindex) {")
             for ii in range(nv):
                 body.append("  case %d:" % ii)
@@ -242,7 +263,15 @@ def emit_refspec(model):
         body.append("}")
         body.append("if (res==0.0) return 0.0;")
     fn("double trpr(PeriodVars *curr,PeriodVars *next,int all)", body + ["return res;}"])
-    fn("void trpr_cont(PeriodVars *curr,PeriodVars *next)", ["int varindex;", "}"])
+    body = ["int varindex;"]
+    for tr in model.trpr:  # compile.m:556-575
+        v = tr["varindex"] - 1
+        if model.s[v]["continuous"]:
+            for k, case in enumerate(tr["cases"]):
+                body.append(("if (%s) {" if k == 0 else "else if (%s) {") % cv(case["condition"]))
+                body.append(" next->st[%d]=%s;" % (v, cv(case["prob"])))
+                body.append("}")
+    fn("void trpr_cont(PeriodVars *curr,PeriodVars *next)", body + ["}"])
     body = ["int i=0;"]
     for eq in model.eq:
         if eq["type"] == "next":
@@ -304,7 +333,12 @@ def shock_independent_of_savings(model) -> bool:
         return False
     for t in model.trpr:
         for c in t["cases"]:
-            if depends(c["condition"]) or any(depends(x) for row in c["prob"] for x in row):
+            if depends(c["condition"]):
+                return False
+            if isinstance(c["prob"], str):  # motion rule of a continuous state
+                if depends(c["prob"]):
+                    return False
+            elif any(depends(x) for row in c["prob"] for x in row):
                 return False
     return True
 
@@ -312,11 +346,9 @@ def shock_independent_of_savings(model) -> bool:
 def emit_devspec(model) -> str:
     """One header with every model function of the reference's modelspec (compile.m:254-655),
     ctx-explicit.  ``EGDST_FN`` / ``EGDST_CONST`` / ``egdst_ctx`` come from ``egdst_modelctx.h``."""
-    for sv in model.s:
-        if sv["continuous"]:
-            raise NotImplementedError("continuous state variables are outside the hot-path scope (SURVEY 8(f).3)")
     cv = lambda s: _ctxify(model, std_convert(model, s))  # noqa: E731
     ns, ndv = max(len(model.s), 1), max(len(model.d), 1)
+    cont = [i for i, sv in enumerate(model.s) if sv["continuous"]]
     L: List[str] = []
     L += ["/* generated by egdst_b200.codegen for model '%s' -- do not edit */" % model.label,
           "#ifndef EGDST_MODELSPEC_DEV_H", "#define EGDST_MODELSPEC_DEV_H",
@@ -324,7 +356,24 @@ def emit_devspec(model) -> str:
           "#define EGDST_NREQ %d" % len(model.eq), "#define EGDST_NPARAM %d" % len(model.param),
           "#define EGDST_DISTRIB %d" % (1 if model.shock["type"] == "lognormal" else 2),
           "#define EGDST_SHOCK_INDEP_A %d" % (1 if shock_independent_of_savings(model) else 0),
+          "#define EGDST_NCONT %d" % len(cont),
           '#include "egdst_modelctx.h"', ""]
+    if cont:
+        # grids of the continuous states (the reference loads them from model.s(i).grid at run time, compile.m:239-247;
+        # here they are part of the compiled image: re-defining the state variable re-generates it)
+        for i in cont:
+            g = model.s[i]["grid"]
+            L.append("EGDST_CONST double st%dgrid[%d] = {%s};" % (i + 1, len(g), ",".join("%.17g" % x for x in g)))
+        L.append("EGDST_CONST int egdst_contvar[EGDST_NCONT] = {%s};  /* position in st[] of each continuous state */"
+                 % ",".join(str(i) for i in cont))
+        L.append("EGDST_FN const double *egdst_contgrid(int k) {")
+        L.append("  switch (k) {")
+        for k, i in enumerate(cont[:-1]):
+            L.append("  case %d: return st%dgrid;" % (k, i + 1))
+        L.append("  default: return st%dgrid;" % (cont[-1] + 1))
+        L.append("  }")
+        L.append("}")
+        L.append("")
     for cf in model.coef:
         arr = cf["array"]
         L.append("EGDST_CONST double %s[%d][%d] = {" % (cf["ref"], len(arr) + 1, len(arr[0]) + 1))
@@ -343,6 +392,7 @@ def emit_devspec(model) -> str:
     for eq in model.eq:
         protos.append(("double", eq["ref"], P1 if eq["type"] == "current" else P2))
     protos.append(("double", "trpr", P2 + ",int all"))
+    protos.append(("void", "trpr_cont", P1 + ",PeriodVars *next"))
     protos.append(("void", "eqs_sim", P2 + ",double *out"))
     for rt, nm, ar in protos:
         L.append("EGDST_FN %s %s(%s);" % (rt, nm, ar))
@@ -384,7 +434,7 @@ def emit_devspec(model) -> str:
         ex = eq["expression"]
         fn("double", eq["ref"], P1 if eq["type"] == "current" else P2,
            ["return " + cv(ex) + ";}"] if isinstance(ex, str) else [cv(ln) for ln in ex] + ["}"])
-    body = ["double res=1.0;", "int varindex, varindex1;", "(void)all;"]
+    body = ["double nval,res=1.0;", "int varindex, varindex1;", "(void)all; (void)nval;"]
     for tr in model.trpr:
         v = tr["varindex"] - 1
         nv = len(model.s[v]["values"])
@@ -394,6 +444,17 @@ def emit_devspec(model) -> str:
         for case in tr["cases"]:
             body.append(("if (%s) {" if first else "else if (%s) {") % cv(case["condition"]))
             first = False
+            if model.s[v]["continuous"]:  # compile.m:527-537
+                g = "st%dgrid" % (v + 1)
+                body.append("  if (all==1) {")
+                body.append("    nval=%s;" % cv(prohibit(case["prob"], "ist1", "motion rules")))
+                body.append("    varindex = egdst_gridcell(nval,%s,(int)cx->stm[%d]);" % (g, v))
+                body.append("    if (varindex==varindex1) res*=(%s[varindex+1]-nval)/(%s[varindex+1]-%s[varindex]);" % (g, g, g))
+                body.append("    else if (varindex+1==varindex1) res*=(nval-%s[varindex])/(%s[varindex+1]-%s[varindex]);" % (g, g, g))
+                body.append("    else return 0.0;")
+                body.append("  }")
+                body.append("}")
+                continue
             body.append("  switch (varindex) {")
             for ii in range(nv):
                 body.append("  case %d:" % ii)
@@ -409,6 +470,15 @@ def emit_devspec(model) -> str:
         body.append("else { EGDST_MODEL_FAIL(cx,EGDST_ERR_TRPR_CASES); }")
         body.append("if (res==0.0) return 0.0;")
     fn("double", "trpr", P2 + ",int all", body + ["return res;}"])
+    body = ["(void)cx; (void)curr; (void)next;"]
+    for tr in model.trpr:  # compile.m:556-575: the exact next-period values of the continuous states (simulator)
+        v = tr["varindex"] - 1
+        if model.s[v]["continuous"]:
+            for k, case in enumerate(tr["cases"]):
+                body.append(("if (%s) {" if k == 0 else "else if (%s) {") % cv(case["condition"]))
+                body.append("  next->st[%d]=%s;" % (v, cv(case["prob"])))
+                body.append("}")
+    fn("void", "trpr_cont", P1 + ",PeriodVars *next", body + ["}"])
     body = ["int i=0;", "(void)i;"]
     for eq in model.eq:
         if eq["type"] == "next":

@@ -113,6 +113,41 @@ struct EgdstSimArgs {
     double param[EGDST_NPARAM_];
 };
 
+#if EGDST_NCONT > 0
+// Policy of ONE cell of the solution at `cash` (egdst_simulator.c:145-199): consumption, discrete decision and value.
+// Used by the continuous-state branch, which mixes the policies of the 2^NCONT grid cells around the agent's exact
+// continuous state; the all-discrete path below keeps its own inlined copy with the kernel-argument headers.
+EGDST_DEV bool egdst_sim_policy_cell(const EgdstDev &P, const egdst_ctx &cx, int cell, PeriodVars &pv, unsigned long long l2keep,
+                                     double &c, double &vf) {
+    const int nm = P.mlen[cell];
+    if (nm < 2) return false;
+    const int i = egdst_bracket_tab<true>(P, cell, pv.cash, nm, l2keep);
+    EgdstInterval iv;
+    double M1;
+    if (egdst_cell_has_tab(P, nm)) {
+        const EgdstInterval *ivl = egdst_cell_ivl(P, cell);
+        iv = egdst_load_interval_keep(ivl + i, l2keep);
+        M1 = ivl[0].g1;
+    } else {
+        const double *Mg = egdst_colM(P, cell), *Cg = egdst_colC(P, cell), *Vg = egdst_colV(P, cell);
+        iv.g0 = Mg[i]; iv.g1 = Mg[i + 1]; iv.c0 = Cg[i]; iv.c1 = Cg[i + 1]; iv.v0 = Vg[i]; iv.v1 = Vg[i + 1];
+        M1 = Mg[1];
+    }
+    const double rw = 1.0 / (iv.g1 - iv.g0), wl = (pv.cash - iv.g0) * rw, wr = (iv.g1 - pv.cash) * rw;
+    c = iv.c1 * wl + iv.c0 * wr;
+    const int nth = P.thlen[cell];
+    const double *th = P.thTH + (size_t)cell * cx.nthrhmax, *dd = P.thD + (size_t)cell * cx.nthrhmax;
+    int ith = 0;
+    while (ith < nth && pv.cash >= th[ith]) ith++;
+    pv.id = (int)dd[ith > 0 ? ith - 1 : 0];
+    egdst_fill_decision(&cx, &pv);
+    const double evf = P.evf[cell];
+    if (pv.cash < M1 && evf > -EGDST_INF) vf = utility(&cx, &pv, c) + discount(&cx, &pv) * evf;
+    else vf = iv.v1 * wl + iv.v0 * wr;
+    return true;
+}
+#endif
+
 // Dynamic shared memory layout of egdst_k_simulate:
 //   tile[warps][32*TS]                one staged record per agent of the warp's tile (TS = nso|1, odd)
 //   mom[nt][nso][3]   (mom_smem)      per-CTA moment accumulators, flushed once at the end
@@ -137,6 +172,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) egdst_k_simulate(EgdstDev P, Egds
     const int ivec = S.ivec + blockIdx.y;
     egdst_ctx cx; egdst_load_ctx(P, ivec, cx);
     cx.status = 0;
+#if EGDST_NCONT > 0
+    cx.byval = 1;  // model functions read the exact continuous state from curr->st (egdst_simulator.c:91-92)
+#endif
     if (S.has_param) {
 #pragma unroll
         for (int i = 0; i < EGDST_NPARAM; i++) cx.param[i] = S.param[i];
@@ -212,8 +250,23 @@ __global__ void __launch_bounds__(BLOCK, MINB) egdst_k_simulate(EgdstDev P, Egds
                 } else {
                     int chosen = -1, lastfeas = -1;
                     for (int ist1 = 0; ist1 < cx.nst; ist1++) {
+#if EGDST_NCONT > 0
+                        {   // continuous states are carried by value: only the cells at their first grid point stand
+                            // for the discrete part of the state (egdst_simulator.c:268-271)
+                            bool first = true;
+#pragma unroll
+                            for (int k = 0; k < EGDST_NCONT; k++) {
+                                const int j0 = egdst_contvar[k];
+                                if ((ist1 / (int)cx.stm[cx.nnst + j0]) % (int)cx.stm[j0] != 0) first = false;
+                            }
+                            if (!first) continue;
+                        }
+#endif
                         nx.ist = ist1;
                         egdst_fill_state(&cx, &nx);
+#if EGDST_NCONT > 0
+                        trpr_cont(&cx, &cur, &nx);  // exact next-period values of the continuous states
+#endif
                         if (!feasible(&cx, &nx)) continue;
                         lastfeas = ist1;
                         double pr;
@@ -229,6 +282,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) egdst_k_simulate(EgdstDev P, Egds
                     if (chosen < 0) chosen = lastfeas < 0 ? 0 : lastfeas;  // the reference runs off the end here
                     nx.ist = chosen;
                     egdst_fill_state(&cx, &nx);
+#if EGDST_NCONT > 0
+                    trpr_cont(&cx, &cur, &nx);
+#endif
                     if (cx.optim_TRPRnoSH == 1) {  // shocks for the shock-independent case (egdst_simulator.c:292-298)
                         mu = mu_param(&cx, &cur, &nx); sigma = sigma_param(&cx, &cur, &nx);
                         nx.shock = (sigma <= 0) ? egdst_expectation(&cx, &cur, &nx) : egdst_cdfinv(rrr1, mu, sigma);
@@ -240,6 +296,65 @@ __global__ void __launch_bounds__(BLOCK, MINB) egdst_k_simulate(EgdstDev P, Egds
             } else if (state == 0) {
                 eqs_sim(&cx, &cur, (const PeriodVars *)0, eqs);
             }
+#if EGDST_NCONT > 0
+            if (state == 0) {
+                // Continuous states (egdst_simulator.c:309-365): consumption and value are the multilinear mix of the
+                // policies of the 2^NCONT surrounding grid cells (weights <= 0 are skipped, as there); the recorded
+                // cell and discrete decision are those of the corner at which the cumulated weight passes one half.
+                // The reference never assigns the value column on this branch (policy(...,0) skips it); here it is
+                // the same mix of the corner values.  At it == 0 the cell index of `init` may point at any grid point
+                // of a continuous state: its grid part is removed before the corners are addressed (the reference
+                // adds the corner offset on top of it and leaves the table, egdst_simulator.c:313).
+                int j1[EGDST_NCONT], stride[EGDST_NCONT];
+                double wlo[EGDST_NCONT], whi[EGDST_NCONT];
+                int base = cur.ist;
+#pragma unroll
+                for (int k = 0; k < EGDST_NCONT; k++) {
+                    const int j0 = egdst_contvar[k], n = (int)cx.stm[j0];
+                    const double *g = egdst_contgrid(k);
+                    const double x = cur.st[j0];
+                    stride[k] = (int)cx.stm[cx.nnst + j0];
+                    base -= ((cur.ist / stride[k]) % n) * stride[k];
+                    j1[k] = egdst_gridcell(x, g, n);
+                    wlo[k] = (g[j1[k] + 1] - x) / (g[j1[k] + 1] - g[j1[k]]);
+                    whi[k] = (x - g[j1[k]]) / (g[j1[k] + 1] - g[j1[k]]);
+                }
+                double wc = 0, wvf = 0, rr = .5;
+                int ist1 = -1, id1 = 0, istlast = -1, idlast = 0;
+                bool ok = true;
+                for (int ii = 0; ii < (1 << EGDST_NCONT) && ok; ii++) {
+                    double wt = 1;
+                    int ist = base;
+#pragma unroll
+                    for (int k = 0; k < EGDST_NCONT; k++) {
+                        const int up = (ii >> k) & 1;
+                        wt *= up ? whi[k] : wlo[k];
+                        ist += stride[k] * (j1[k] + up);
+                    }
+                    if (!(wt > 0)) continue;
+                    PeriodVars pv = cur;
+                    pv.ist = ist;
+                    double cc, vv;
+                    ok = egdst_sim_policy_cell(P, cx, egdst_cell(P, ivec, it, ist), pv, l2keep, cc, vv);
+                    if (!ok) break;
+                    wc += cc * wt;
+                    wvf += vv * wt;
+                    rr -= wt;
+                    istlast = ist; idlast = pv.id;
+                    if (rr < 0 && ist1 == -1) { ist1 = ist; id1 = pv.id; }
+                }
+                if (!ok || istlast < 0) state = 1;
+                else {
+                    if (ist1 < 0) { ist1 = istlast; id1 = idlast; }
+                    c = MIN(wc, cur.cash - cx.a0);
+                    cur.savings = cur.cash - c;
+                    vf = wvf;
+                    cur.ist = ist1;
+                    cur.id = id1;
+                    egdst_fill_decision(&cx, &cur);
+                }
+            }
+#else
             if (state == 0) {
                 // policy (egdst_simulator.c:145-199)
                 const int cell = egdst_cell(P, ivec, it, cur.ist);
@@ -282,6 +397,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) egdst_k_simulate(EgdstDev P, Egds
                     else vf = iv.v1 * wl + iv.v0 * wr;
                 }
             }
+#endif
             // stage the record of this period
             // two consecutive periods of an agent are staged side by side (PB = 2 when nt is even): their 2*NSO doubles
             // are written together, so every 32-byte DRAM sector of the sims array is written whole -- one period alone

@@ -221,7 +221,49 @@ def model2(T=3, ngridm=100, nquad=10, mmax=100, cc=0.0, df=1.0, rho=0.0, r=0.0, 
     return m
 
 
-EXTRA = {"deaton_normal": deaton_normal}
+def humancapital(T=12, ngridm=100, ngridmax=1000, ny=8, nz=5, nthrhmax=20, sigma="0.2", interest=0.03, duw=0.4, wage=1.0,
+                 depr=0.9, gain=0.15, zlim=(0.4, 1.6), mmax=20.0, a0=0.0, health=False, nh=3) -> EgdstModel:
+    """Work/retire model whose wage scales with a CONTINUOUS human-capital state z: z' = depr*z + gain*work, on a
+    uniform grid of ``nz`` points.  Not shipped by the reference (none of its examples has a continuous state); it
+    exercises the motion-rule code path (egdstmodel.m:629-648 and :1000-1004, compile.m:527-537 and :556-575,
+    egdst_simulator.c:309-365).  ``health=True`` adds a second continuous state (worn down by work, valued in utility),
+    so that the simulator mixes four grid cells."""
+    m = EgdstModel("humancap2" if health else "humancap")
+    _common(m, T, mmax, ngridmax, ngridm, nthrhmax, ny)
+    m.s = ("Human capital", list(zlim), nz)
+    m.trpr = (1, "true", "depr*st1+gain*dc1")
+    if health:
+        m.s = ("Health", [0.5, 1.0], nh)
+        m.trpr = (2, "dc1==1", "0.93*st2+0.05")
+        m.trpr = (2, "dc1==0", "0.93*st2+0.07")
+    m.feasible = ("defaultfeasible", True)
+    m.d = ("Labour supply", [0, "retire", 1, "work"])
+    m.choiceset = ("defaultallow", True)
+    m.u = ("utility", "log(consumption)+duw*(dc1==0)" + ("+0.3*log(st2)" if health else ""))
+    m.param = ("duw", "disutility of work", duw)
+    m.u = ("marginal", "1/consumption")
+    m.u = ("marginalinverse", "1/mutility")
+    m.u = ("extrap", "log(x)")
+    m.budget = ("cashinhand", "savings*(1+interest)+wage_income*dc1")
+    m.budget = ("marginal", "1+interest")
+    m.discount = "1/(1+interest)"
+    m.param = ("interest", "return on savings", interest)
+    m.eq = ("wage_income", "Realized wage income", "wage*st1*shock", "next")
+    m.param = ("wage", "wage per unit of human capital", wage)
+    m.param = ("depr", "human capital carried over", depr)
+    m.param = ("gain", "human capital gained by working", gain)
+    m.a0 = a0
+    m.shock = "lognormal"
+    m.shock = ("sigma", sigma)
+    m.shock = ("mu", "-0.5*sigma*sigma")
+    return m
+
+
+def humancapital2(**kw) -> EgdstModel:
+    return humancapital(health=True, **kw)
+
+
+EXTRA = {"deaton_normal": deaton_normal, "humancapital": humancapital, "humancapital2": humancapital2}
 
 ALL = {
     "deaton1": deaton1, "deaton2": deaton2, "retirement1": retirement1, "retirement2": retirement2,

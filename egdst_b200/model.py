@@ -137,7 +137,15 @@ class EgdstModel:
     def _variable(self, value, kind: str) -> Dict[str, Any]:
         name, spec = value[0], value[1]
         if len(value) == 3:
-            raise NotImplementedError("continuous %s variables are outside the hot-path scope (SURVEY 8(f).3)" % kind)
+            # name + grid limits + number of grid points: a continuous variable on a uniform grid whose points double
+            # as the enumerated "values" (egdstmodel.m:629-648)
+            lim, npts = [float(x) for x in value[1]], int(value[2])
+            if kind != "state" or len(lim) != 2 or npts < 2:
+                raise ValueError("Unrecognized structure for %s variable!" % kind)
+            grid = np.linspace(lim[0], lim[1], npts)
+            return {"name": name, "type": "continuous", "discrete": False, "continuous": True,
+                    "values": [{"value": float(g), "description": "grid point"} for g in grid],
+                    "gridlimits": lim, "gridpoints": npts, "grid": [float(g) for g in grid]}
         vals = []
         if len(spec) and not any(isinstance(v, str) for v in spec):
             # numeric vector of values (egdstmodel.m:618-634)
@@ -288,14 +296,18 @@ class EgdstModel:
         if not (1 <= vi <= self.nnst):
             raise ValueError("Unrecognized structure for trpr definition!")
         n = self.stm[vi - 1]
+        while len(self.trpr) < vi:
+            self.trpr.append({"varindex": None, "cases": []})
         if isinstance(mat, str):
-            raise NotImplementedError("motion rules for continuous states are outside the hot-path scope")
+            # varindex + condition + executable string: the deterministic motion rule of a continuous state
+            # (egdstmodel.m:1000-1004)
+            self.trpr[vi - 1]["varindex"] = vi
+            self.trpr[vi - 1]["cases"].append({"condition": cond, "prob": mat})
+            return
         rows = [list(r) for r in mat]
         if len(rows) != n or any(len(r) != n for r in rows):
             raise ValueError("Unrecognized structure for trpr definition!")
         prob = [[(x if x else "0.0") if isinstance(x, str) else ("%10.10f" % float(x)) for x in r] for r in rows]
-        while len(self.trpr) < vi:
-            self.trpr.append({"varindex": None, "cases": []})
         self.trpr[vi - 1]["varindex"] = vi
         self.trpr[vi - 1]["cases"].append({"condition": cond, "prob": prob})
 
@@ -455,7 +467,9 @@ class EgdstModel:
     def to_dict(self) -> Dict[str, Any]:
         """The public properties as plain data, in the shape ``jsonencode(struct(model))`` gives in MATLAB."""
         d: Dict[str, Any] = {k: getattr(self, k) for k in self._SCALARS}
-        d["s"] = [{"name": v["name"], "values": [dict(x) for x in v["values"]]} for v in self.s]
+        d["s"] = [dict({"name": v["name"], "values": [dict(x) for x in v["values"]]},
+                       **({"gridlimits": list(v["gridlimits"]), "gridpoints": v["gridpoints"]} if v["continuous"] else {}))
+                  for v in self.s]
         d["d"] = [{"name": v["name"], "values": [dict(x) for x in v["values"]]} for v in self.d]
         d["u"] = dict(self.u)
         d["transform"] = dict(self.transform)
@@ -481,6 +495,9 @@ class EgdstModel:
         m.nthrhmax, m.ny, m.a0 = d.get("nthrhmax", 100), d.get("ny", 1), d.get("a0", 0.0)
         for kind in ("s", "d"):
             for v in lst(d.get(kind)):
+                if v.get("gridpoints"):
+                    setattr(m, kind, (v["name"], list(v["gridlimits"]), int(v["gridpoints"])))
+                    continue
                 spec = []
                 for x in lst(v["values"]):
                     spec += [x["value"], x["description"]]

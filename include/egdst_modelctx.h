@@ -91,6 +91,14 @@ typedef struct egdst_ctx {
     double param[EGDST_NPARAM_];
 } egdst_ctx;
 
+/* left grid point of the interval a value of a continuous state falls into, end intervals extended outwards
+ * (what bxsearch, egdst_lib.c:123-165, returns on an increasing grid). */
+EGDST_FN int egdst_gridcell(double x, const double *g, int n) {
+    int i = 0;
+    while (i < n - 2 && x >= g[i + 1]) i++;
+    return i;
+}
+
 #ifdef __CUDACC__
 #define EGDST_MODEL_FAIL(cx, code) do { if ((cx)->status) *((cx)->status) = (code); } while (0)
 #else

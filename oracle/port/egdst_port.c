@@ -139,7 +139,8 @@ static void port_policy(const egdst_ctx *cx, const port_cell *cell, PeriodVars *
 }
 
 /* sims: [nsimout, nt, nsim] column-major, NaN where the agent is dead or was skipped.  Returns the number of
- * skipped agents (bad initial state / cash).  Only discrete state variables (the hot-path scope). */
+ * skipped agents (bad initial state / cash).  With continuous state variables (EGDST_NCONT > 0) the exact values are
+ * carried in st[] and the policy is the multilinear mix of the surrounding grid cells (egdst_simulator.c:309-365). */
 int port_simulate(const egdst_desc *d, const int *mlen, const int *thlen, const double *Mbuf, const double *Dbuf,
                   const double *init, int nsim, const double *rs, int rndtype, double *sims) {
     egdst_ctx cx;
@@ -149,7 +150,7 @@ int port_simulate(const egdst_desc *d, const int *mlen, const int *thlen, const 
     int skipped = 0;
     double eqs[EGDST_NREQ > 0 ? EGDST_NREQ : 1];
     port_ctx(d, &cx);
-    cx.byval = 0;   /* all state variables discrete: model functions read states/decisions by index (egdst_simulator.c:91) */
+    cx.byval = EGDST_NCONT > 0 ? 1 : 0;   /* by index when all state variables are discrete, else by value (egdst_simulator.c:91-92) */
     for (int c = 0; c < nt * nst; c++) {
         port_cell *pc = cells + c;
         pc->n = mlen[c]; pc->nth = thlen[c];
@@ -181,8 +182,19 @@ int port_simulate(const egdst_desc *d, const int *mlen, const int *thlen, const 
                 if (r_alive > survival(&cx, &cur)) break;                 /* death: the remaining rows stay NaN */
                 for (ist1 = 0; ist1 < nst; ist1++) {                       /* inverse-CDF sampling of the next state */
                     double pr;
+#if EGDST_NCONT > 0
+                    {   /* only cells at the first grid point of every continuous state (egdst_simulator.c:268-271) */
+                        int off = 0;
+                        for (int q = 0; q < EGDST_NCONT; q++) {
+                            const int j0 = egdst_contvar[q];
+                            if ((ist1 / (int)cx.stm[cx.nnst + j0]) % (int)cx.stm[j0] != 0) off = 1;
+                        }
+                        if (off) continue;
+                    }
+#endif
                     nx.ist = ist1;
                     for (int i = 0; i < cx.nnst; i++) nx.st[i] = cx.states[i * nst + ist1];
+                    trpr_cont(&cx, &cur, &nx);                              /* continuous states move exactly */
                     if (!feasible(&cx, &nx)) continue;
                     last = ist1;
                     if (cx.optim_TRPRnoSH != 1) {                          /* probabilities may depend on the shock */
@@ -196,6 +208,7 @@ int port_simulate(const egdst_desc *d, const int *mlen, const int *thlen, const 
                 if (ist1 >= nst) {                                          /* ran off the end: keep the last feasible state */
                     nx.ist = last;
                     for (int i = 0; i < cx.nnst; i++) nx.st[i] = cx.states[i * nst + last];
+                    trpr_cont(&cx, &cur, &nx);
                 }
                 if (cx.optim_TRPRnoSH == 1) {
                     mu = mu_param(&cx, &cur, &nx); sigma = sigma_param(&cx, &cur, &nx);
@@ -206,11 +219,54 @@ int port_simulate(const egdst_desc *d, const int *mlen, const int *thlen, const 
                 cur = nx;
             }
             {
-                const port_cell *pc = cells + (size_t)it * nst + cur.ist;
                 double *out = sims + ((size_t)isim * nt + it) * nso;
                 int j = 11;
+#if EGDST_NCONT > 0
+                /* egdst_simulator.c:309-365.  Corner q of the 2^NCONT cells around the exact state takes grid point
+                 * j1 (bit clear) or j1+1 (bit set) of each continuous state; non-positive weights are skipped; the
+                 * recorded cell/decision is the corner where the running weight passes one half.  Column 3 (value)
+                 * is left unassigned by the reference on this branch; the mix of the corner values is written here.
+                 * The grid part of an initial cell index is removed first (the reference adds the corner offset on
+                 * top of it, :313, which only works for initial cells at the first grid point). */
+                {
+                    int j1[EGDST_NCONT], stride[EGDST_NCONT], base = cur.ist, ist_pick = -1, id_pick = 0, bad = 0;
+                    double wlo[EGDST_NCONT], whi[EGDST_NCONT], wc = 0, wvf = 0, half = .5;
+                    for (int q = 0; q < EGDST_NCONT; q++) {
+                        const int j0 = egdst_contvar[q], n = (int)cx.stm[j0];
+                        const double *g = egdst_contgrid(q), x = cur.st[j0];
+                        stride[q] = (int)cx.stm[cx.nnst + j0];
+                        base -= ((cur.ist / stride[q]) % n) * stride[q];
+                        j1[q] = port_bracket(x, g, n, 0);
+                        wlo[q] = (g[j1[q] + 1] - x) / (g[j1[q] + 1] - g[j1[q]]);
+                        whi[q] = (x - g[j1[q]]) / (g[j1[q] + 1] - g[j1[q]]);
+                    }
+                    for (int q = 0; q < (1 << EGDST_NCONT); q++) {
+                        double wt = 1, cc, vv;
+                        PeriodVars pv = cur;
+                        pv.ist = base;
+                        for (int b = 0; b < EGDST_NCONT; b++) {
+                            wt *= ((q >> b) & 1) ? whi[b] : wlo[b];
+                            pv.ist += stride[b] * (j1[b] + ((q >> b) & 1));
+                        }
+                        if (!(wt > 0)) continue;
+                        if (cells[(size_t)it * nst + pv.ist].n < 2) { bad = 1; break; }
+                        port_policy(&cx, cells + (size_t)it * nst + pv.ist, &pv, &cc, &vv);
+                        wc += cc * wt; wvf += vv * wt;
+                        half -= wt;
+                        if (ist_pick < 0 && half < 0) { ist_pick = pv.ist; id_pick = pv.id; }
+                    }
+                    if (bad || ist_pick < 0) break;
+                    c = MIN(wc, cur.cash - cx.a0);
+                    cur.savings = cur.cash - c;
+                    vf = wvf;
+                    cur.ist = ist_pick; cur.id = id_pick;
+                    for (int i = 0; i < cx.nnd; i++) cur.dc[i] = cx.decisions[i * cx.nd + cur.id];
+                }
+#else
+                const port_cell *pc = cells + (size_t)it * nst + cur.ist;
                 if (pc->n < 2) break;
                 port_policy(&cx, pc, &cur, &c, &vf);
+#endif
                 out[0] = cur.cash; out[1] = c; out[2] = cur.savings; out[3] = vf; out[4] = cur.id; out[5] = cur.ist;
                 out[6] = mu; out[7] = sigma; out[8] = cur.shock; out[9] = utility(&cx, &cur, c); out[10] = discount(&cx, &cur);
                 for (int i = 0; i < cx.nnst; i++) out[j++] = cur.st[i];

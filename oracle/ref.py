@@ -162,7 +162,7 @@ class Reference:
         sv = L.shim_struct(len(m.s))
         for i, s in enumerate(m.s):
             L.shim_setfield(sv, i, b"discrete", L.shim_logical(1 if s["discrete"] else 0))
-            L.shim_setfield(sv, i, b"grid", self._dbl(np.zeros(0)))
+            L.shim_setfield(sv, i, b"grid", self._dbl(np.asarray(s.get("grid", []), dtype=np.float64)))
         sf("s", sv)
         sf("eq", L.shim_struct(len(m.eq)))
         if quadrature:  # (ny == 1 included: the gateway reads the property unconditionally, egdst_solver.c:162)

@@ -76,7 +76,7 @@ def test_setparam_getparam():
         m.setparam([1.0])
 
 
-@pytest.mark.parametrize("name", ["cake1", "cake2", "deaton2", "retirement2", "model2"])
+@pytest.mark.parametrize("name", ["cake1", "cake2", "deaton2", "retirement2", "model2", "humancapital"])
 def test_oracle_reproduces_golden_vectors(name):
     """Pins the checker: the compiled reference (prebuilt oracle/_ref or built from /root/reference) against the
     committed outputs of the reference on its own example models."""
@@ -90,7 +90,7 @@ def test_oracle_reproduces_golden_vectors(name):
     e = solution_errors(Mr, Dr, g["M"], g["D"])
     assert e["C"] < 1e-12 and e["V"] < 1e-12 and e["TH"] < 1e-12 and e["Dseq"] and e["rowdiff"] == 0, e
     sims = orc.simulate(Mr, Dr, g["init"], g["randstream"], 0)
-    se = goldens.sims_errors(sims, g["sims"])
+    se = goldens.sims_errors(sims, g["sims"], g["skipcols"])
     assert se["nan_mismatch"] == 0 and se["discrete_mismatch"] == 0 and se["max"] < 1e-12
 
 
@@ -105,3 +105,36 @@ def test_cake_closed_forms_in_golden_vectors():
         ok = M[:, 0] > 1e-6
         b = 0.75
         assert np.allclose(M[ok, 1], M[ok, 0] * (1 - b) / (1 - b ** (25 - it)), rtol=1e-10)
+
+
+def test_continuous_state_spec_motion_rule_and_generated_code():
+    # egdstmodel.m:629-648 (name, limits, points -> uniform grid doubling as the values) and :1000-1004 (motion rule)
+    m = EgdstModel("c")
+    m.s = ("regime", [0, "low", 1, "high"])
+    m.s = ("z", [0.5, 1.5], 5)
+    assert m.nst == 10 and m.stm == [2, 5, 5, 1]
+    z = m.s[1]
+    assert z["continuous"] and not z["discrete"] and z["gridpoints"] == 5 and z["grid"] == [0.5, 0.75, 1.0, 1.25, 1.5]
+    assert [v["value"] for v in z["values"]] == z["grid"] and m.states[:, 1].tolist() == z["grid"] * 2
+    m.trpr = (1, "true", [[0.9, 0.1], [0.2, 0.8]])
+    m.trpr = (2, "true", "0.9*st2+0.1")
+    assert m.trpr[1]["cases"][0]["prob"] == "0.9*st2+0.1"
+    with pytest.raises(ValueError):
+        m.d = ("x", [0.0, 1.0], 3)  # only states can be continuous
+    hc = examples.humancapital()
+    src = codegen.emit_devspec(hc)
+    assert "#define EGDST_NCONT 1" in src and "st1grid[5]" in src and "egdst_gridcell(nval,st1grid" in src
+    assert "next->st[0]=" in src  # trpr_cont: the exact value for the simulator (compile.m:556-575)
+    c, h = codegen.emit_refspec(hc)
+    assert 'st1grid = (double *) mxGetPr(mxGetField(mxGetProperty(Model,0,"s"),0,"grid"));' in c
+    assert "bxsearch(nval,(double*)st1grid,(int)stm[0])" in c and "extern double *st1grid;" in h
+    # a motion rule may not address the next period's cell (compile.m:531)
+    bad = examples.humancapital()
+    bad.trpr = (1, "false", "st1+ist1")
+    with pytest.raises(ValueError):
+        codegen.emit_devspec(bad)
+    # the discrete models carry no continuous-state code
+    assert "#define EGDST_NCONT 0" in codegen.emit_devspec(examples.retirement2())
+    # round trip through plain data
+    again = EgdstModel.from_dict(json.loads(json.dumps(hc.to_dict())))
+    assert codegen.emit_devspec(again) == src and again.s[0]["grid"] == hc.s[0]["grid"]

@@ -20,7 +20,7 @@ def run(name, solve=True):
     else:
         sol = lib.import_solution(m, g["M"], g["D"])
     sims = lib.simulate(m, sol, g["init"], g["randstream"], 0)
-    out["sim"] = goldens.sims_errors(sims, g["sims"])
+    out["sim"] = goldens.sims_errors(sims, g["sims"], g["skipcols"])
     s2, mom = lib.simulate_philox(m, sol, g["init"], 7, want_sims=True, want_moments=True)
     import numpy as np
     ref1 = np.nansum(s2, axis=0).T  # [nso, nt]
