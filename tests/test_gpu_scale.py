@@ -280,8 +280,10 @@ def test_odd_shapes_match_reference(name, kw):
 
 
 @pytest.mark.parametrize("variant,kw", [
-    ("humancapital", dict(T=20, ngridm=400, ny=16, nz=7)),
-    ("humancapital2", dict(T=10, ngridm=150, ny=8, nz=4, nh=3)),
+    # grid sizes of the continuous states stay at their defaults: the grids are part of the compiled image, and the
+    # reference-built checker (oracle/_ref) for an image only exists where /root/reference does
+    ("humancapital", dict(T=20, ngridm=400, ny=16)),
+    ("humancapital2", dict(T=10, ngridm=150, ny=8)),
 ])
 def test_continuous_states_match_reference(variant, kw):
     """Continuous state variables: the solver spreads the deterministic motion rule over the two
@@ -306,7 +308,7 @@ def test_continuous_states_match_reference(variant, kw):
     z = m.sims[:, :, 11]
     work = m.sims[:, :, 11 + m.nnst]
     assert np.allclose(z[:, 1:], 0.9 * z[:, :-1] + 0.15 * work[:, :-1], rtol=0, atol=1e-14)
-    assert len(np.unique(np.round(z[:, -1], 12))) > len(m.s[0]["grid"])
+    assert np.all(np.min(np.abs(z[:, 3, None] - np.asarray(m.s[0]["grid"])[None, :]), axis=1) > 1e-3)  # off the grid
     # the value column is the same multilinear mix as consumption: between the smallest and largest corner values
     assert np.all(np.isfinite(m.sims[:, :, 3]))
 
