@@ -61,27 +61,11 @@ static void prof_collect() {
     }
     g_prof_pending.clear();
 }
-#ifndef EGDST_HOSTEMU
-// launch with programmatic stream serialization allowed (see EGDST_PDL_PROLOGUE).  Measured on the S1 solve: eager chain
-// 7.9 -> 6.9 ms with it; the graph replay is 6.6 ms without and 6.8 ms with programmatic edges, so captures switch it off.
-static thread_local bool g_pdl = true;
-template <typename... KArgs, typename... Args>
-static void egdst_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
-    static const bool off = getenv("EGDST_NO_PDL") != 0;
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = (off || !g_pdl) ? 0 : 1;
-    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
-}
-#define PLAUNCH(cls, kernel, grid, block, smem, stream, ...) \
-    do { prof_begin(cls, stream); egdst_launch_pdl(kernel, grid, block, smem, stream, __VA_ARGS__); prof_end(stream); } while (0)
-#else
+// Period-chain launches.  Programmatic dependent launch (griddepcontrol) was used here for the eager chain and removed:
+// with the successor's CTAs resident while the predecessor still runs, the successor read stale first lines of arrays
+// the predecessor rewrites every period (rawFlag) in 6 of 8 runs of the S1b case -- the eager chain costs 0.5 ms more
+// without it, the graph replay (third solve of a shape onwards) never used it.
 #define PLAUNCH KLAUNCH
-#endif
 #define KLAUNCH(cls, kernel, grid, block, smem, stream, ...) \
     do { prof_begin(cls, stream); EGDST_LAUNCH(kernel, grid, block, smem, stream, __VA_ARGS__); prof_end(stream); } while (0)
 
@@ -267,7 +251,10 @@ static int create_solution(const egdst_desc *d, int nvec, egdst_solution **out) 
         s->tab_base = base; s->tab_bytes = lutbytes + ivlbytes;
     }
     P.chC = (P.N + EGDST_CMP_CHUNK - 1) / EGDST_CMP_CHUNK + 1;
-    P.chE = (P.envcap + EGDST_ENV_CHUNK - 1) / EGDST_ENV_CHUNK + 1;
+    // envelope merge: narrow CTAs when the usual union (nd lists of about N points) fits one narrow chunk -- small
+    // models of a batched sweep then keep four times as many jobs resident per SM
+    P.envW = (nd * (P.N + 64) <= 64 * EGDST_ENV_IPT) ? 64 : EGDST_ENVW;
+    P.chE = (P.envcap + P.envW * EGDST_ENV_IPT - 1) / (P.envW * EGDST_ENV_IPT) + 1;
     DA(P.scanC, (size_t)s->nsd * P.chC); DA(P.tickC, (size_t)2 * s->nsd); DA(P.foldList, (size_t)s->nsd * (P.gcap + 1)); DA(P.foldCnt, s->nsd);
     DA(P.scanE, (size_t)s->nslot * P.chE); DA(P.tickE, (size_t)2 * s->nslot); DA(P.envNact, s->nslot);
     DA(P.status, 4 * nvec); DA(P.units, nvec); DA(s->d_moff, s->ncell + 1); DA(s->d_toff, s->ncell + 1);
@@ -279,6 +266,8 @@ static int create_solution(const egdst_desc *d, int nvec, egdst_solution **out) 
     *out = s;
     return 0;
 }
+
+static inline int imin(int a, int b) { return a < b ? a : b; }
 
 // one backward-induction pass as a chain of launches on `st` (also what the CUDA graph captures)
 static int launch_periods(egdst_solution *s, cudaStream_t st) {
@@ -295,20 +284,46 @@ static int launch_periods(egdst_solution *s, cudaStream_t st) {
     int tabblocks = (P.lutcap + 1 + B - 1) / B;
     if (nvec * nst * tabblocks > 4096) tabblocks = (4096 + nvec * nst - 1) / (nvec * nst);  // batched sweeps: fewer, looping CTAs per cell
     const int cellthreads = ((nst + 31) / 32) * 32 < 128 ? 128 : ((nst + 31) / 32) * 32;
+    // warps per CTA that share the quadrature nodes of 32 grid points in the EGM step: with few nodes, the count
+    // that leaves no warp idle in the last round (10 nodes: 5 warps of 2 nodes)
+    int egmparts = EGDST_EGM_SPLIT;
+    if (P.cx.ny < 2 * EGDST_EGM_SPLIT) {
+        int bestwaste = 1 << 30;
+        for (int p = 1; p <= EGDST_EGM_SPLIT; p++) {
+            const int waste = (P.cx.ny + p - 1) / p * p - P.cx.ny;
+            if (waste <= bestwaste) { bestwaste = waste; egmparts = p; }
+        }
+    }
+    // envelope kernels: grids sized for the usual list lengths (a decision keeps at most N points plus the few the
+    // secondary envelope inserts); longer lists, up to the capacity ngridmax, are covered by the kernels' own loops
+    const int envchunk = P.envW * EGDST_ENV_IPT;
+    const int envA1 = imin((2 * P.gcap + B - 1) / B, (N + 64 + B - 1) / B + 1);
+    const int envA0 = imin((nd * P.gcap + B - 1) / B, (nd * (N + 64) + B - 1) / B + 1);
+    const int envBC1 = imin(P.chE, (N + 64 + envchunk - 1) / envchunk + 1);
+    const int envBC0 = imin(P.chE, (nd * (N + 64) + envchunk - 1) / envchunk);
+    static const bool env_one_cta = getenv("EGDST_ENV_ONECTA") != 0;  // test hook: every job strides with a single CTA
+    if (getenv("EGDST_EGM_PARTS")) { const int p = atoi(getenv("EGDST_EGM_PARTS")); if (p >= 1 && p <= EGDST_EGM_SPLIT) egmparts = p; }
+    // the seed's CTA splits the nst*ny nodes of one savings point over its threads: small models in a batched sweep
+    // get small CTAs (more of the nvec*nst*nd independent seeds resident per SM)
+    int seedthreads = B;
+    if (nvec * nst * nd >= 4 * 148) {
+        seedthreads = ((nst * P.cx.ny + 31) / 32) * 32;
+        seedthreads = seedthreads < 32 ? 32 : (seedthreads > B ? B : seedthreads);
+    }
     for (int it = P.NT - 1; it >= 0; it--) {
         if (it == P.NT - 1) {
             KLAUNCH(KC_SETUP, egdst_k_cells, dim3(nvec), dim3(cellthreads), 0, st, P, it);
             PLAUNCH(KC_TERMINAL, egdst_k_terminal, dim3((N + B - 1) / B, nst * nd, nvec), dim3(B), 0, st, P, it);
         } else {
-            PLAUNCH(KC_SEED, egdst_k_seed, dim3(nd, nst, nvec), dim3(B), shsmem, st, P, it, useTab);
-            PLAUNCH(KC_EGM, egdst_k_egm, dim3((N - 1 + 31) / 32, nst * nd, nvec), dim3(32, EGDST_EGM_SPLIT), shsmem, st, P, it, useTab);
+            PLAUNCH(KC_SEED, egdst_k_seed, dim3(nd, nst, nvec), dim3(seedthreads), shsmem, st, P, it, useTab);
+            PLAUNCH(KC_EGM, egdst_k_egm, dim3((N - 1 + 31) / 32, nst * nd, nvec), dim3(32, egmparts), shsmem, st, P, it, useTab);
             PLAUNCH(KC_COMPACT, egdst_k_compact, dim3(P.chC, nst * nd, nvec), dim3(EGDST_CMP_THREADS), 0, st, P, it);
             // secondary envelope (no-op for (ist,id) without folds)
-            PLAUNCH(KC_ENV2, egdst_k_envA<1>, dim3((2 * P.gcap + B - 1) / B, nst * nd, nvec), dim3(B), 0, st, P, it);
-            PLAUNCH(KC_ENV2, egdst_k_envBC<1>, dim3(P.chE, nst * nd, nvec), dim3(EGDST_ENVW), 0, st, P, it);
+            PLAUNCH(KC_ENV2, egdst_k_envA<1>, dim3(env_one_cta ? 1 : envA1, nst * nd, nvec), dim3(B), 0, st, P, it);
+            PLAUNCH(KC_ENV2, egdst_k_envBC<1>, dim3(env_one_cta ? 1 : envBC1, nst * nd, nvec), dim3(P.envW), 0, st, P, it);
         }
-        PLAUNCH(KC_ENV, egdst_k_envA<0>, dim3((nd * P.gcap + B - 1) / B, nst, nvec), dim3(B), 0, st, P, it);
-        PLAUNCH(KC_ENV, egdst_k_envBC<0>, dim3(P.chE, nst, nvec), dim3(EGDST_ENVW), 0, st, P, it);
+        PLAUNCH(KC_ENV, egdst_k_envA<0>, dim3(env_one_cta ? 1 : envA0, nst, nvec), dim3(B), 0, st, P, it);
+        PLAUNCH(KC_ENV, egdst_k_envBC<0>, dim3(env_one_cta ? 1 : envBC0, nst, nvec), dim3(P.envW), 0, st, P, it);
         PLAUNCH(KC_TAB, egdst_k_tab, dim3(tabblocks, nst, nvec), dim3(B), 0, st, P, it);
     }
     CK(cudaGetLastError());
@@ -358,9 +373,7 @@ static int run_solve(egdst_solution *s, const egdst_desc *d, const double *param
         cudaGraph_t graph = 0;
         const long long l0 = g_launches;
         CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-        g_pdl = false;
         rc = launch_periods(s, st);
-        g_pdl = true;
         cudaError_t e = cudaStreamEndCapture(st, &graph);
         if (rc || e != cudaSuccess || !graph) { if (graph) cudaGraphDestroy(graph); return rc ? rc : fail(2, std::string("graph capture failed: ") + cudaGetErrorString(e)); }
         s->g_nlaunch = g_launches - l0;

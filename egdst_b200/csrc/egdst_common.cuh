@@ -17,10 +17,6 @@
 #define EGDST_DYN_SMEM(type, name) extern __shared__ __align__(128) type name[]
 #define EGDST_LDCG(p) __ldcg(p)
 #define EGDST_GRID_CONSTANT __grid_constant__
-// Programmatic dependent launch: every kernel of the period chain first lets its successor be scheduled (its CTAs become
-// resident and park), then waits until its predecessor has completed and flushed -- the launch latency of kernel N+1
-// hides behind the execution of kernel N.  Correctness only needs the wait.
-#define EGDST_PDL_PROLOGUE() do { asm volatile("griddepcontrol.launch_dependents;"); asm volatile("griddepcontrol.wait;" ::: "memory"); } while (0)
 #endif
 
 #ifdef __CUDACC__
@@ -72,6 +68,7 @@ struct EgdstDev {
     unsigned long long *scanC, *scanE;  // [nsd*chC] compaction, [nslot*chE] envelope merge
     int *tickC, *tickE;                 // [nsd*2], [nslot*2]
     int chC, chE;                       // chunks per job
+    int envW;                           // threads per CTA of the envelope merge (chunk = envW * EGDST_ENV_IPT positions)
     int *foldList, *foldCnt;            // [nsd*(gcap+1)] unordered fold positions, [nsd]
     int *envNact;                       // [nslot] active prefix length of the merged union (egdst_k_envA)
     // per-cell lookup tables (egdst_tables.cuh)

@@ -156,7 +156,6 @@ EGDST_DEV double egdst_env_grb_block(const View &E, double *sh) {
 
 template <int MODE>
 __global__ void egdst_k_envA(EgdstDev P, int it) {
-    EGDST_PDL_PROLOGUE();
     __shared__ double shg[33];
     const int ivec = blockIdx.z;
     int ist, id, slot;
@@ -171,30 +170,32 @@ __global__ void egdst_k_envA(EgdstDev P, int it) {
     if (!egdst_env_job<MODE>(P, ivec, blockIdx.y, ist, id, slot, E)) return;
     egdst_ctx cx; egdst_load_ctx(P, ivec, cx);
     const int Ptot = E.pstart(E.F - 1) + E.npts(E.F - 1);
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (blockIdx.x * blockDim.x >= Ptot) return;  // CTA-uniform
     const double grb = egdst_env_grb_block(E, shg);
-    if (p >= Ptot) return;
-    // flattened index -> (f,k)
-    int f = 0;
-    if (MODE == 0) { int s = 0; while (f < E.F - 1 && p >= s + E.npts(f)) { s += E.npts(f); f++; } }
-    else { int lo = 0, hi = E.F - 1; while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (E.pstart(mid) <= p) lo = mid; else hi = mid - 1; } f = lo; }
-    const int k = p - E.pstart(f);
-    const double x = E.x(f, k), v = E.v(f, k);
-    int rank = 0, best = f;
-    double bestv = v;
-    for (int g = 0; g < E.F; g++) {
-        const int ng = E.npts(g);
-        if (ng <= 0) continue;
-        const int cnt = egdst_env_count_before(E, g, x, v, f, k);
-        rank += cnt;
-        if (g == f) continue;
-        const double val = egdst_env_value(&cx, E, it, ist, g, egdst_env_cur(cnt, ng), x);
-        if (val > bestv || (val == bestv && g < best)) { bestv = val; best = g; }
+    // the grid is sized for the usual number of points (host: launch_periods) and strides over longer lists
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < Ptot; p += gridDim.x * blockDim.x) {
+        // flattened index -> (f,k)
+        int f = 0;
+        if (MODE == 0) { int s = 0; while (f < E.F - 1 && p >= s + E.npts(f)) { s += E.npts(f); f++; } }
+        else { int lo = 0, hi = E.F - 1; while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (E.pstart(mid) <= p) lo = mid; else hi = mid - 1; } f = lo; }
+        const int k = p - E.pstart(f);
+        const double x = E.x(f, k), v = E.v(f, k);
+        int rank = 0, best = f;
+        double bestv = v;
+        for (int g = 0; g < E.F; g++) {
+            const int ng = E.npts(g);
+            if (ng <= 0) continue;
+            const int cnt = egdst_env_count_before(E, g, x, v, f, k);
+            rank += cnt;
+            if (g == f) continue;
+            const double val = egdst_env_value(&cx, E, it, ist, g, egdst_env_cur(cnt, ng), x);
+            if (val > bestv || (val == bestv && g < best)) { bestv = val; best = g; }
+        }
+        size_t o = (size_t)slot * P.envcap + rank;
+        P.mgX[o] = x; P.mgF[o] = f; P.mgK[o] = k; P.mgA[o] = best;
+        // the active positions of the union are the prefix with x <= grb: its length for the merge kernel
+        if (x <= grb) atomicMax(P.envNact + slot, rank + 1);
     }
-    size_t o = (size_t)slot * P.envcap + rank;
-    P.mgX[o] = x; P.mgF[o] = f; P.mgK[o] = k; P.mgA[o] = best;
-    // the active positions of the union are the prefix with x <= grb: its length for the merge kernel
-    if (x <= grb) atomicMax(P.envNact + slot, rank + 1);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -334,14 +335,14 @@ EGDST_DEV EgdstEnvPos egdst_env_pos(const EgdstEnvView<MODE> &E, const double *m
     return q;
 }
 
-#define EGDST_ENV_CHUNK (EGDST_ENVW * EGDST_ENV_IPT)  /* union positions per CTA */
+#define EGDST_ENV_CHUNK (EGDST_ENVW * EGDST_ENV_IPT)  /* union positions per chunk at the widest CTA */
 #define EGDST_ENV_QCAP 512                             /* crossing chains queued per CTA */
-// grid (chE, njobs_y, nvec): the CTAs of one job are chained by a decoupled look-back scan over
-// (grid points, thresholds) emitted so far; the last CTA to finish writes the cell header (MODE 0) or copies the
-// staged result back over the decision's point list (MODE 1).
+// grid (<= chE, njobs_y, nvec), blockDim.x = P.envW: the CTAs of one job take chunks of blockDim.x*IPT union positions
+// by ticket until none is left and are chained by a decoupled look-back scan over (grid points, thresholds) emitted
+// so far; the last CTA to finish writes the cell header (MODE 0) or copies the staged result back over the
+// decision's point list (MODE 1).  Small models in batched sweeps run narrow CTAs (P.envW = 64), one per job.
 template <int MODE>
 __global__ void __launch_bounds__(EGDST_ENVW) egdst_k_envBC(EgdstDev P, int it) {
-    EGDST_PDL_PROLOGUE();
     __shared__ long long sh[40];
     __shared__ double s_grb[33];
     __shared__ int s_chunk, s_last, s_qn;
@@ -367,16 +368,19 @@ __global__ void __launch_bounds__(EGDST_ENVW) egdst_k_envBC(EgdstDev P, int it) 
         gcapacity = P.envcap;
     }
     // the active positions of the union are the prefix with x<=grb (length recorded by egdst_k_envA)
-    const double grb = egdst_env_grb_block(E, s_grb);
     const int nact = P.envNact[slot];
-    const int nch = (nact + EGDST_ENV_CHUNK - 1) / EGDST_ENV_CHUNK;
-    if (threadIdx.x == 0) { s_chunk = atomicAdd(P.tickE + 2 * slot, 1); s_qn = 0; }
-    __syncthreads();
-    const int chunk = s_chunk;
+    const int chunkw = blockDim.x * EGDST_ENV_IPT;
+    const int nch = (nact + chunkw - 1) / chunkw;
+    const double grb = nch > 0 ? egdst_env_grb_block(E, s_grb) : 0.0;  // nch is CTA-uniform
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     int err = 0, serr = 0;
-    if (chunk < nch) {
-        const int r0 = chunk * EGDST_ENV_CHUNK + threadIdx.x * EGDST_ENV_IPT;
+    while (true) {
+        __syncthreads();  // the previous chunk's queue and scan scratch are free again
+        if (threadIdx.x == 0) { s_chunk = atomicAdd(P.tickE + 2 * slot, 1); s_qn = 0; }
+        __syncthreads();
+        const int chunk = s_chunk;
+        if (chunk >= nch) break;
+        const int r0 = chunk * chunkw + threadIdx.x * EGDST_ENV_IPT;
         // pass 1: own contribution of every position; crossing chains go to the CTA's queue
         int ngj[EGDST_ENV_IPT], ntj[EGDST_ENV_IPT], qj[EGDST_ENV_IPT];
 #pragma unroll

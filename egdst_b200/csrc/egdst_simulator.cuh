@@ -121,14 +121,14 @@ EGDST_DEV bool egdst_sim_policy_cell(const EgdstDev &P, const egdst_ctx &cx, int
                                      double &c, double &vf) {
     const int nm = P.mlen[cell];
     if (nm < 2) return false;
-    const int i = egdst_bracket_tab<true>(P, cell, pv.cash, nm, l2keep);
     EgdstInterval iv;
     double M1;
     if (egdst_cell_has_tab(P, nm)) {
         const EgdstInterval *ivl = egdst_cell_ivl(P, cell);
-        iv = egdst_load_interval_keep(ivl + i, l2keep);
+        egdst_lookup_tab<true>(P, cell, ivl, pv.cash, nm, iv, l2keep);
         M1 = ivl[0].g1;
     } else {
+        const int i = egdst_bracket(pv.cash, egdst_colM(P, cell), nm, 0);
         const double *Mg = egdst_colM(P, cell), *Cg = egdst_colC(P, cell), *Vg = egdst_colV(P, cell);
         iv.g0 = Mg[i]; iv.g1 = Mg[i + 1]; iv.c0 = Cg[i]; iv.c1 = Cg[i + 1]; iv.v0 = Vg[i]; iv.v1 = Vg[i + 1];
         M1 = Mg[1];
@@ -362,14 +362,14 @@ __global__ void __launch_bounds__(BLOCK, MINB) egdst_k_simulate(EgdstDev P, Egds
                 const int nm = S.hdr_smem ? hc->n : P.mlen[cell];
                 if (nm < 2) { state = 1; }
                 else {
-                    const int i = egdst_bracket_tab<true>(P, cell, cur.cash, nm, l2keep);
                     EgdstInterval iv;
                     double M1;
                     if (egdst_cell_has_tab(P, nm)) {
                         const EgdstInterval *ivl = egdst_cell_ivl(P, cell);
-                        iv = egdst_load_interval_keep(ivl + i, l2keep);
+                        egdst_lookup_tab<true>(P, cell, ivl, cur.cash, nm, iv, l2keep);
                         M1 = S.hdr_smem ? hc->M1 : ivl[0].g1;
                     } else {  // oversized cell: plain columns
+                        const int i = egdst_bracket(cur.cash, egdst_colM(P, cell), nm, 0);
                         const double *Mg = egdst_colM(P, cell), *Cg = egdst_colC(P, cell), *Vg = egdst_colV(P, cell);
                         iv.g0 = Mg[i]; iv.g1 = Mg[i + 1]; iv.c0 = Cg[i]; iv.c1 = Cg[i + 1]; iv.v0 = Vg[i]; iv.v1 = Vg[i + 1];
                         M1 = Mg[1];

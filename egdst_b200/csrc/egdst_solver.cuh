@@ -122,11 +122,11 @@ EGDST_DEV void egdst_eval_nodes(const egdst_ctx *cx, const EgdstDev &P, int ivec
             next.cash = cashinhand(cx, curr, &next);
             // one bracket lookup serves consumption (rows 0..n1) and value (rows 1..n1): the second bracket of the
             // reference is max(i,1) of the first (same strictly increasing grid); rows i, i+1 come as one record
-            const int i = egdst_bracket_tab(P, t.cell, next.cash, t.n1 + 1);
             const bool tab = egdst_cell_has_tab(P, t.n1 + 1);
             EgdstInterval iv;
-            if (tab) iv = egdst_load_interval(t.ivl + i);
-            else { iv.g0 = t.M[i]; iv.g1 = t.M[i + 1]; iv.c0 = t.C[i]; iv.c1 = t.C[i + 1]; iv.v0 = t.V[i]; iv.v1 = t.V[i + 1]; }
+            int i;
+            if (tab) i = egdst_lookup_tab(P, t.cell, t.ivl, next.cash, t.n1 + 1, iv);
+            else { i = egdst_bracket(next.cash, t.M, t.n1 + 1, 0); iv.g0 = t.M[i]; iv.g1 = t.M[i + 1]; iv.c0 = t.C[i]; iv.c1 = t.C[i + 1]; iv.v0 = t.V[i]; iv.v1 = t.V[i + 1]; }
             // the reference's quotients are kept bit for bit (two divisions per interpolation, egdst_lib.c:175): next to its
             // instability boundary a plain reciprocal-multiply variant drifted 1e-2 away in C, so the
             // shared-reciprocal form below is the exactly rounded one (egdst_div_by)
@@ -188,7 +188,6 @@ EGDST_DEV void egdst_warp_combine(EgdstAcc &a) {
 // grid (ceil(N/B), nst*nd, nvec)
 // ---------------------------------------------------------------------------------------------
 __global__ void egdst_k_terminal(EgdstDev P, int it) {
-    EGDST_PDL_PROLOGUE();
     const int ivec = blockIdx.z, ist = blockIdx.y / P.cx.nd, id = blockIdx.y % P.cx.nd;
     egdst_ctx cx; egdst_load_ctx(P, ivec, cx);
     const int sd = egdst_sd(P, ivec, ist, id);
@@ -241,7 +240,6 @@ EGDST_DEV void egdst_block_eval(const egdst_ctx *cx, const EgdstDev &P, int ivec
 }
 
 __global__ void egdst_k_seed(EgdstDev P, int it, int useTab) {
-    EGDST_PDL_PROLOGUE();
     __shared__ EgdstSeedShared S;
     EGDST_DYN_SMEM(double, shsm);
     const int ivec = blockIdx.z, ist = blockIdx.y, id = blockIdx.x;
@@ -394,9 +392,10 @@ EGDST_DEV double egdst_agrid(const egdst_ctx *cx, const PeriodVars *curr, const 
 }
 
 // ---------------------------------------------------------------------------------------------
-// EGM step for grid points n=1..N-1.  blockDim = (32, SPLIT): lanes are 32 consecutive A points (their
-// next-period cash values are neighbours, so the table searches of a warp stay coherent), the SPLIT
+// EGM step for grid points n=1..N-1.  blockDim = (32, parts <= SPLIT): lanes are 32 consecutive A points (their
+// next-period cash values are neighbours, so the table searches of a warp stay coherent), the `parts`
 // warps of a CTA share the quadrature nodes of the same 32 points and combine through shared memory.
+// The host picks `parts` so that the nodes divide evenly (10 nodes: 5 warps of 2, not 8 warps of 2 and 1).
 // grid (ceil((N-1)/32), nst*nd, nvec)
 // ---------------------------------------------------------------------------------------------
 #ifndef EGDST_EGM_SPLIT
@@ -411,13 +410,12 @@ EGDST_DEV double egdst_agrid(const egdst_ctx *cx, const PeriodVars *curr, const 
 #define EGDST_EGM_MINB 3
 #endif
 __global__ void __launch_bounds__(32 * EGDST_EGM_SPLIT, EGDST_EGM_MINB) egdst_k_egm(EgdstDev P, int it, int useTab) {
-    EGDST_PDL_PROLOGUE();
     EGDST_DYN_SMEM(double, shsm);
     __shared__ double s_rhs[EGDST_EGM_SPLIT][32], s_evf[EGDST_EGM_SPLIT][32], s_chk[EGDST_EGM_SPLIT][32], s_cash[EGDST_EGM_SPLIT][32];
     __shared__ int s_q[EGDST_EGM_SPLIT][32], s_t[EGDST_EGM_SPLIT][32];
     const int ivec = blockIdx.z, ist = blockIdx.y / P.cx.nd, id = blockIdx.y % P.cx.nd;
     const int sd = egdst_sd(P, ivec, ist, id);
-    const int lane = threadIdx.x, part = threadIdx.y;
+    const int lane = threadIdx.x, part = threadIdx.y, nparts = blockDim.y;
     const int N = P.N;
     const int n = 1 + blockIdx.x * 32 + lane;
     if (!P.active[sd] || P.rawFlag[(size_t)sd * N] == EGDST_PT_NONE) return;  // uniform per CTA
@@ -428,20 +426,20 @@ __global__ void __launch_bounds__(32 * EGDST_EGM_SPLIT, EGDST_EGM_MINB) egdst_k_
     EgdstAcc a; a.rhs = 0; a.evf = 0; a.checksum = 0; a.badq = EGDST_NOBAD; a.badtype = 0; a.badcash = 0; a.badshock = 0;
     const double *shk = 0, *shp = 0;
     if (useTab) {  // shocks and node probabilities of this (it, ist, id), once per CTA
-        egdst_fill_shocktab(&cx, P, &curr, shsm, shsm + cx.nst * cx.ny, threadIdx.y * 32 + threadIdx.x, 32 * EGDST_EGM_SPLIT);
+        egdst_fill_shocktab(&cx, P, &curr, shsm, shsm + cx.nst * cx.ny, threadIdx.y * 32 + threadIdx.x, 32 * nparts);
         shk = shsm; shp = shsm + cx.nst * cx.ny;
         __syncthreads();
     }
     if (n < N) {
         A = egdst_agrid(&cx, &curr, seed, n, N);
-        egdst_eval_nodes(&cx, P, ivec, &curr, A, 1, part, EGDST_EGM_SPLIT, a, shk, shp);
+        egdst_eval_nodes(&cx, P, ivec, &curr, A, 1, part, nparts, a, shk, shp);
     }
     s_rhs[part][lane] = a.rhs; s_evf[part][lane] = a.evf; s_chk[part][lane] = a.checksum;
     s_q[part][lane] = a.badq; s_t[part][lane] = a.badtype; s_cash[part][lane] = a.badcash;
     __syncthreads();
     if (part != 0 || n >= N) return;
     double rhs = 0, evf = 0, chk = 0, badcash = 0; int bq = EGDST_NOBAD, bt = 0;
-    for (int k = 0; k < EGDST_EGM_SPLIT; k++) {
+    for (int k = 0; k < nparts; k++) {
         rhs += s_rhs[k][lane]; evf += s_evf[k][lane]; chk += s_chk[k][lane];
         if (s_q[k][lane] < bq) { bq = s_q[k][lane]; bt = s_t[k][lane]; badcash = s_cash[k][lane]; }
     }
@@ -478,7 +476,6 @@ __global__ void __launch_bounds__(32 * EGDST_EGM_SPLIT, EGDST_EGM_MINB) egdst_k_
 // carries (points kept so far, "stop rule fired").  Folds inside a CTA's own output are appended to an unordered
 // list; the last CTA to finish adds the folds on chunk boundaries, orders the list and publishes the counts.
 __global__ void __launch_bounds__(EGDST_CMP_THREADS) egdst_k_compact(EgdstDev P, int it) {
-    EGDST_PDL_PROLOGUE();
     __shared__ int sh[40];
     __shared__ int s_chunk, s_last;
     __shared__ unsigned long long s_excl;
@@ -535,6 +532,17 @@ __global__ void __launch_bounds__(EGDST_CMP_THREADS) egdst_k_compact(EgdstDev P,
         __syncthreads();
         const unsigned long long excl = s_excl;
         if (!egdst_scan_hi(excl)) {  // the grid did not stop in an earlier chunk: this chunk's points count
+#ifdef EGDST_DEBUG_LATE
+            if (threadIdx.x == 0 && it <= 3) {
+                const double *sp = P.seed + (size_t)sd * 8;
+                printf("dbg it=%d id=%d ls=%d seed lim1=%.17g lim2=%.17g lim3=%.17g lim3p=%.17g k3=%g lastA=%.17g | flags", it, id, ls, sp[0], sp[1], sp[2], sp[3], sp[4], sp[5]);
+                for (int q = 0; q < 12; q++) printf(" %d", rawFlag[q]);
+                printf(" | stop");
+                for (int q = 0; q < 6; q++) printf(" %.17g", rawStop[q]);
+                printf("\n");
+            }
+            if (late != 0x7fffffff) printf("late resend: it=%d ist=%d id=%d n=%d ls=%d stop[n]=%g flag0=%d M0=%g stop0=%g\n", it, ist, id, late, ls, rawStop[late], rawFlag[0], rawM[0], rawStop[0]);
+#endif
             if (late != 0x7fffffff) egdst_fail(P, ivec, EGDST_ERR_RESEND_LATE, it, ist, id);
             if (badsum) egdst_fail(P, ivec, EGDST_ERR_CHECKSUM, it, ist, id);
             const int first = egdst_scan_lo(excl);

@@ -84,7 +84,6 @@ EGDST_DEV void egdst_cells_body(const EgdstDev &P, int ivec, int it) {
 
 // build the tables of the cells (ivec, it, all ist): grid (nblk, nst, nvec)
 __global__ void egdst_k_tab(EgdstDev P, int it) {
-    EGDST_PDL_PROLOGUE();
     const int ivec = blockIdx.z, ist = blockIdx.y;
     // the last kernel of period `it` also opens period it-1 (saves a launch per period)
     if (blockIdx.x == 0 && blockIdx.y == 0 && it > 0) egdst_cells_body(P, ivec, it - 1);
@@ -151,12 +150,15 @@ EGDST_DEV EgdstInterval egdst_load_interval_keep(const EgdstInterval *p, unsigne
 #endif
 }
 
-// Bracket of x in the cell's grid.  Same result as egdst_bracket(x, M, n, 0) on a strictly increasing grid:
-// (#rows <= x) - 1 clamped to [0, n-2].  KEEP: load the table entry with the evict_last hint `pol`.
+// Bracket AND interval record of x in a cell that has tables (egdst_cell_has_tab).  Same bracket as
+// egdst_bracket(x, M, n, 0) on a strictly increasing grid: (#rows <= x) - 1 clamped to [0, n-2].  KEEP: load with the
+// evict_last hint `pol`.
+// A bucket that holds two rows (about a quarter of the lookups at two buckets per row) is resolved by fetching the
+// records of both rows at once -- two independent gathers -- instead of a dependent read of the grid column followed
+// by the record: the second row's abscissa is g1 of the first row's record.  Three and more rows bisect as before.
 template <bool KEEP = false>
-EGDST_DEV int egdst_bracket_tab(const EgdstDev &P, int cell, double x, int n, unsigned long long pol = 0ULL) {
-    const double *M = egdst_colM(P, cell);
-    if (!egdst_cell_has_tab(P, n)) return egdst_bracket(x, M, n, 0);
+EGDST_DEV int egdst_lookup_tab(const EgdstDev &P, int cell, const EgdstInterval *ivl, double x, int n, EgdstInterval &iv,
+                               unsigned long long pol = 0ULL) {
     int b = egdst_lut_key(x, P.cx.a0, P.mbits);
     b = b < 0 ? 0 : (b > P.lutcap - 1 ? P.lutcap - 1 : b);
     const EgdstLutEntry *lut = egdst_cell_lut(P, cell);
@@ -165,21 +167,29 @@ EGDST_DEV int egdst_bracket_tab(const EgdstDev &P, int cell, double x, int n, un
 #else
     EgdstLutEntry e;
     if (KEEP) {
-        const double2 raw = egdst_ld16_hint(lut + b, pol);  // one 16-byte load
+        const double2 raw = egdst_ld16_hint(lut + b, pol);
         const long long lo = __double_as_longlong(raw.x);
         e.l = (int)(lo & 0xffffffffLL); e.cnt = (int)(lo >> 32); e.m = raw.y;
     } else {
-        const int4 raw = *reinterpret_cast<const int4 *>(lut + b);  // one 16-byte load
+        const int4 raw = *reinterpret_cast<const int4 *>(lut + b);
         e.l = raw.x; e.cnt = raw.y; e.m = __hiloint2double(raw.w, raw.z);
     }
 #endif
-    int cnt = e.l + ((e.cnt > 0 && e.m <= x) ? 1 : 0);
-    if (e.cnt > 1 && e.m <= x) {  // crowded bucket (double points, coarse tables): bisect its remaining rows
+    const bool in = e.cnt > 0 && e.m <= x;
+    int i = e.l - 1 + (in ? 1 : 0);
+    if (in && e.cnt > 2) {
+        const double *M = egdst_colM(P, cell);
         int l = e.l + 1, h = e.l + e.cnt;
         while (l < h) { const int mid = (l + h) >> 1; if (M[mid] <= x) l = mid + 1; else h = mid; }
-        cnt = l;
+        i = l - 1;
     }
-    int i = cnt - 1;
-    if (i > n - 2) i = n - 2;
-    return i < 0 ? 0 : i;
+    i = i > n - 2 ? n - 2 : i;
+    i = i < 0 ? 0 : i;
+    const bool two = in && e.cnt == 2 && i + 1 <= n - 2;
+    const int i2 = two ? i + 1 : i;
+    EgdstInterval iv2;
+    if (KEEP) { iv = egdst_load_interval_keep(ivl + i, pol); iv2 = two ? egdst_load_interval_keep(ivl + i2, pol) : iv; }
+    else { iv = egdst_load_interval(ivl + i); iv2 = two ? egdst_load_interval(ivl + i2) : iv; }
+    if (two && x >= iv.g1) { iv = iv2; i = i2; }
+    return i;
 }

@@ -64,7 +64,7 @@ enum {
     EGDST_ERR_CASHINVERSE = 12, /* egdst_lib.c:293 */
     EGDST_ERR_INTERP2PT = 13,   /* egdst_lib.c:171 */
     EGDST_ERR_ENV2SPACE = 14,   /* egdst_solver.c:824,839,877 */
-    EGDST_ERR_RESEND_LATE = 15  /* c1<=0 signalled after the seed stage: handled by the serial tail */
+    EGDST_ERR_RESEND_LATE = 15  /* c1<=0 signalled after the seed stage: reported, the parallel grid does not re-send there */
 };
 
 typedef struct curr_variables {

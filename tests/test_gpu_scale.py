@@ -77,7 +77,16 @@ def test_s5_retirement1_2000_points(s1):
 def test_s1b_shipped_parameters_under_noise_floor():
     """Shipped interest=0.045 at T=40 sits next to the reference's own instability: parity is
     asserted only in the cells where two differently rounded builds of the reference agree with each other."""
-    m = _solve(examples.retirement(T=40, ngridm=2000, ngridmax=4000, nthrhmax=2000, ny=20))
+    m = examples.retirement(T=40, ngridm=2000, ngridmax=4000, nthrhmax=2000, ny=20)
+    m.compile()
+    m.solve()
+    # In the unstable early periods (the last ones solved) a rounding-level difference decides whether next-period
+    # consumption turns non-positive far up the savings grid; the reference then re-sends grid points one by one, the
+    # parallel grid reports it (EGDST_ERR_RESEND_LATE) and stops.  Either outcome is accepted there; every period the
+    # two reference builds agree on must have been solved before that.
+    st = m._solution.status()
+    assert st[0] in (0, 15), st
+    first_solved = st[1] + 1 if st[0] else 0
     base = ref.Reference(m)
     Mb, Db = base.solve()
     noise = ref.Reference(m, variant="noise")
@@ -86,6 +95,7 @@ def test_s1b_shipped_parameters_under_noise_floor():
     for it in range(m.nt):
         en = cell_errors(Mn[0][it], Dn[0][it], Mb[0][it], Db[0][it])
         if max(en["C"], en["V"]) < 1e-11 and en["nth"][0] == en["nth"][1]:
+            assert it >= first_solved, (it, st)
             eg = cell_errors(m.M[0][it], m.D[0][it], Mb[0][it], Db[0][it])
             assert eg["C"] < TOL and eg["V"] < TOL, (it, eg, en)
             checked += 1

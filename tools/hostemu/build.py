@@ -31,6 +31,7 @@ def build(model, opt="-O1"):
            '-DEGDST_MODEL_KEY="%s"' % key, "-x", "c++", os.path.join(csrc, "egdst_capi.cu"), "-o", lib]
     if asan:
         cmd[3:3] = ["-fsanitize=address", "-fno-omit-frame-pointer"]
+    cmd[3:3] = os.environ.get("EGDST_EMU_DEFS", "").split()  # extra -D switches (debug prints)
     subprocess.run(cmd, check=True)
     return lib
 

@@ -35,7 +35,6 @@ inline void *emu_dyn_smem = nullptr;
 #define EGDST_DYN_SMEM(type, name) type *name = (type *)emu_dyn_smem
 #define EGDST_LDCG(p) (*(p))
 #define EGDST_GRID_CONSTANT
-#define EGDST_PDL_PROLOGUE() do { } while (0)
 inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 
 struct dim3 {
