@@ -250,7 +250,8 @@ static int create_solution(const egdst_desc *d, int nvec, egdst_solution **out) 
         P.tabLut = (EgdstLutEntry *)base; P.tabIvl = (EgdstInterval *)(base + lutbytes);
         s->tab_base = base; s->tab_bytes = lutbytes + ivlbytes;
     }
-    P.chC = (P.N + EGDST_CMP_CHUNK - 1) / EGDST_CMP_CHUNK + 1;
+    P.cmpW = (P.N <= 64 * EGDST_CMP_IPT) ? 64 : EGDST_CMP_THREADS;
+    P.chC = (P.N + P.cmpW * EGDST_CMP_IPT - 1) / (P.cmpW * EGDST_CMP_IPT);
     // envelope merge: narrow CTAs when the usual union (nd lists of about N points) fits one narrow chunk -- small
     // models of a batched sweep then keep four times as many jobs resident per SM
     P.envW = (nd * (P.N + 64) <= 64 * EGDST_ENV_IPT) ? 64 : EGDST_ENVW;
@@ -302,6 +303,11 @@ static int launch_periods(egdst_solution *s, cudaStream_t st) {
     const int envBC1 = imin(P.chE, (N + 64 + envchunk - 1) / envchunk + 1);
     const int envBC0 = imin(P.chE, (nd * (N + 64) + envchunk - 1) / envchunk);
     static const bool env_one_cta = getenv("EGDST_ENV_ONECTA") != 0;  // test hook: every job strides with a single CTA
+    // CTAs per (ist,id) in the EGM step: one per block of 32 grid points, fewer (looping) when a batched sweep already
+    // fills the machine several times over
+    const int egmblocks = (N - 1 + 31) / 32;
+    int egmgx = egmblocks;
+    while (egmgx > 1 && (long long)nvec * nst * nd * egmgx > 8LL * 148 * 5) egmgx = (egmgx + 1) / 2;
     if (getenv("EGDST_EGM_PARTS")) { const int p = atoi(getenv("EGDST_EGM_PARTS")); if (p >= 1 && p <= EGDST_EGM_SPLIT) egmparts = p; }
     // the seed's CTA splits the nst*ny nodes of one savings point over its threads: small models in a batched sweep
     // get small CTAs (more of the nvec*nst*nd independent seeds resident per SM)
@@ -316,8 +322,8 @@ static int launch_periods(egdst_solution *s, cudaStream_t st) {
             PLAUNCH(KC_TERMINAL, egdst_k_terminal, dim3((N + B - 1) / B, nst * nd, nvec), dim3(B), 0, st, P, it);
         } else {
             PLAUNCH(KC_SEED, egdst_k_seed, dim3(nd, nst, nvec), dim3(seedthreads), shsmem, st, P, it, useTab);
-            PLAUNCH(KC_EGM, egdst_k_egm, dim3((N - 1 + 31) / 32, nst * nd, nvec), dim3(32, egmparts), shsmem, st, P, it, useTab);
-            PLAUNCH(KC_COMPACT, egdst_k_compact, dim3(P.chC, nst * nd, nvec), dim3(EGDST_CMP_THREADS), 0, st, P, it);
+            PLAUNCH(KC_EGM, egdst_k_egm, dim3(egmgx, nst * nd, nvec), dim3(32, egmparts), shsmem, st, P, it, useTab);
+            PLAUNCH(KC_COMPACT, egdst_k_compact, dim3(P.chC, nst * nd, nvec), dim3(P.cmpW), 0, st, P, it);
             // secondary envelope (no-op for (ist,id) without folds)
             PLAUNCH(KC_ENV2, egdst_k_envA<1>, dim3(env_one_cta ? 1 : envA1, nst * nd, nvec), dim3(B), 0, st, P, it);
             PLAUNCH(KC_ENV2, egdst_k_envBC<1>, dim3(env_one_cta ? 1 : envBC1, nst * nd, nvec), dim3(P.envW), 0, st, P, it);

@@ -68,6 +68,7 @@ struct EgdstDev {
     unsigned long long *scanC, *scanE;  // [nsd*chC] compaction, [nslot*chE] envelope merge
     int *tickC, *tickE;                 // [nsd*2], [nslot*2]
     int chC, chE;                       // chunks per job
+    int cmpW;                           // threads per CTA of the compaction (chunk = cmpW * EGDST_CMP_IPT raw points)
     int envW;                           // threads per CTA of the envelope merge (chunk = envW * EGDST_ENV_IPT positions)
     int *foldList, *foldCnt;            // [nsd*(gcap+1)] unordered fold positions, [nsd]
     int *envNact;                       // [nslot] active prefix length of the merged union (egdst_k_envA)

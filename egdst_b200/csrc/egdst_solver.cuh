@@ -417,46 +417,55 @@ __global__ void __launch_bounds__(32 * EGDST_EGM_SPLIT, EGDST_EGM_MINB) egdst_k_
     const int sd = egdst_sd(P, ivec, ist, id);
     const int lane = threadIdx.x, part = threadIdx.y, nparts = blockDim.y;
     const int N = P.N;
-    const int n = 1 + blockIdx.x * 32 + lane;
     if (!P.active[sd] || P.rawFlag[(size_t)sd * N] == EGDST_PT_NONE) return;  // uniform per CTA
     egdst_ctx cx; egdst_load_ctx(P, ivec, cx);
     PeriodVars curr; curr.it = it; curr.ist = ist; curr.id = id; curr.cash = 0; curr.savings = 0; curr.shock = 0;
     const double *seed = P.seed + (size_t)sd * 8;
-    double A = 0.0;
-    EgdstAcc a; a.rhs = 0; a.evf = 0; a.checksum = 0; a.badq = EGDST_NOBAD; a.badtype = 0; a.badcash = 0; a.badshock = 0;
     const double *shk = 0, *shp = 0;
     if (useTab) {  // shocks and node probabilities of this (it, ist, id), once per CTA
         egdst_fill_shocktab(&cx, P, &curr, shsm, shsm + cx.nst * cx.ny, threadIdx.y * 32 + threadIdx.x, 32 * nparts);
         shk = shsm; shp = shsm + cx.nst * cx.ny;
         __syncthreads();
     }
-    if (n < N) {
-        A = egdst_agrid(&cx, &curr, seed, n, N);
-        egdst_eval_nodes(&cx, P, ivec, &curr, A, 1, part, nparts, a, shk, shp);
+    // gridDim.x CTAs share the ceil((N-1)/32) blocks of 32 points of this (ist,id): one block each for a single model,
+    // all of them in turn for the short grids of a batched sweep (context and shock table set up once)
+    for (int xb = blockIdx.x; xb * 32 < N - 1; xb += gridDim.x) {
+        const int n = 1 + xb * 32 + lane;
+        double A = 0.0;
+        EgdstAcc a; a.rhs = 0; a.evf = 0; a.checksum = 0; a.badq = EGDST_NOBAD; a.badtype = 0; a.badcash = 0; a.badshock = 0;
+        if (n < N) {
+            A = egdst_agrid(&cx, &curr, seed, n, N);
+            egdst_eval_nodes(&cx, P, ivec, &curr, A, 1, part, nparts, a, shk, shp);
+        }
+        s_rhs[part][lane] = a.rhs; s_evf[part][lane] = a.evf; s_chk[part][lane] = a.checksum;
+        s_q[part][lane] = a.badq; s_t[part][lane] = a.badtype; s_cash[part][lane] = a.badcash;
+        __syncthreads();
+        if (part == 0 && n < N) {
+            double rhs = 0, evf = 0, chk = 0, badcash = 0; int bq = EGDST_NOBAD, bt = 0;
+            for (int k = 0; k < nparts; k++) {
+                rhs += s_rhs[k][lane]; evf += s_evf[k][lane]; chk += s_chk[k][lane];
+                if (s_q[k][lane] < bq) { bq = s_q[k][lane]; bt = s_t[k][lane]; badcash = s_cash[k][lane]; }
+            }
+            const size_t o = (size_t)sd * N + n;
+            if (bq != EGDST_NOBAD) {
+                P.rawFlag[o] = bt;
+                P.rawStop[o] = (bt == EGDST_PT_C1NEG) ? cx.a0 - 1 : badcash;
+            } else if (fabs(chk - 1) > cx.tolerance) {
+                P.rawFlag[o] = EGDST_PT_CHECKSUM; P.rawStop[o] = EGDST_INF;
+            } else {
+                const double beta = discount(&cx, &curr);
+                const double M = A + utility_marginal_inverse(&cx, &curr, beta * rhs);
+                P.rawStop[o] = M;
+                if (!isfinite(M)) P.rawFlag[o] = EGDST_PT_NONFINITE;
+                else {
+                    const double c = M - A;
+                    P.rawM[o] = M; P.rawC[o] = c; P.rawV[o] = utility(&cx, &curr, c) + beta * evf;
+                    P.rawFlag[o] = EGDST_PT_OK;
+                }
+            }
+        }
+        if (xb + (int)gridDim.x < (N - 1 + 31) / 32) __syncthreads();  // the partial sums are reused by the next block
     }
-    s_rhs[part][lane] = a.rhs; s_evf[part][lane] = a.evf; s_chk[part][lane] = a.checksum;
-    s_q[part][lane] = a.badq; s_t[part][lane] = a.badtype; s_cash[part][lane] = a.badcash;
-    __syncthreads();
-    if (part != 0 || n >= N) return;
-    double rhs = 0, evf = 0, chk = 0, badcash = 0; int bq = EGDST_NOBAD, bt = 0;
-    for (int k = 0; k < nparts; k++) {
-        rhs += s_rhs[k][lane]; evf += s_evf[k][lane]; chk += s_chk[k][lane];
-        if (s_q[k][lane] < bq) { bq = s_q[k][lane]; bt = s_t[k][lane]; badcash = s_cash[k][lane]; }
-    }
-    const size_t o = (size_t)sd * N + n;
-    if (bq != EGDST_NOBAD) {
-        P.rawFlag[o] = bt;
-        P.rawStop[o] = (bt == EGDST_PT_C1NEG) ? cx.a0 - 1 : badcash;
-        return;
-    }
-    if (fabs(chk - 1) > cx.tolerance) { P.rawFlag[o] = EGDST_PT_CHECKSUM; P.rawStop[o] = EGDST_INF; return; }
-    const double beta = discount(&cx, &curr);
-    const double M = A + utility_marginal_inverse(&cx, &curr, beta * rhs);
-    P.rawStop[o] = M;
-    if (!isfinite(M)) { P.rawFlag[o] = EGDST_PT_NONFINITE; return; }
-    const double c = M - A;
-    P.rawM[o] = M; P.rawC[o] = c; P.rawV[o] = utility(&cx, &curr, c) + beta * evf;
-    P.rawFlag[o] = EGDST_PT_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -471,8 +480,7 @@ __global__ void __launch_bounds__(32 * EGDST_EGM_SPLIT, EGDST_EGM_MINB) egdst_k_
 #else
 #define EGDST_CMP_THREADS 256
 #endif
-#define EGDST_CMP_CHUNK (EGDST_CMP_THREADS * EGDST_CMP_IPT)  /* raw points per CTA */
-// grid (chC, nst*nd, nvec): the CTAs of one (ist,id) list are chained by a decoupled look-back scan whose state
+// grid (chC, nst*nd, nvec), blockDim.x = P.cmpW <= EGDST_CMP_THREADS: the CTAs of one (ist,id) list are chained by a decoupled look-back scan whose state
 // carries (points kept so far, "stop rule fired").  Folds inside a CTA's own output are appended to an unordered
 // list; the last CTA to finish adds the folds on chunk boundaries, orders the list and publishes the counts.
 __global__ void __launch_bounds__(EGDST_CMP_THREADS) egdst_k_compact(EgdstDev P, int it) {
@@ -490,7 +498,8 @@ __global__ void __launch_bounds__(EGDST_CMP_THREADS) egdst_k_compact(EgdstDev P,
     int *foldList = P.foldList + (size_t)sd * (P.gcap + 1);
     volatile unsigned long long *st = P.scanC + (size_t)sd * P.chC;
     if (rawFlag[0] == EGDST_PT_NONE) { if (blockIdx.x == 0 && threadIdx.x == 0) { P.ptN[sd] = 0; P.nfold[sd] = 0; } return; }
-    const int nch = (N + EGDST_CMP_CHUNK - 1) / EGDST_CMP_CHUNK;  // chunks that hold raw points
+    const int chunkw = blockDim.x * EGDST_CMP_IPT;  // raw points per CTA (P.cmpW threads: narrow CTAs for short grids)
+    const int nch = (N + chunkw - 1) / chunkw;      // chunks that hold raw points == gridDim.x
     if (threadIdx.x == 0) s_chunk = atomicAdd(P.tickC + 2 * sd, 1);
     __syncthreads();
     const int chunk = s_chunk;
@@ -498,7 +507,7 @@ __global__ void __launch_bounds__(EGDST_CMP_THREADS) egdst_k_compact(EgdstDev P,
     const unsigned ltmask = (1u << lane) - 1u;
     int err = 0;
     if (chunk < nch) {
-        const int wbase = chunk * EGDST_CMP_CHUNK + w * (32 * EGDST_CMP_IPT);
+        const int wbase = chunk * chunkw + w * (32 * EGDST_CMP_IPT);
         // the stop rule inside this chunk: first n whose returned M fails "M<mmax" (that point itself is kept)
         int flag[EGDST_CMP_IPT], mystop = 0x7fffffff;
 #pragma unroll
