@@ -182,10 +182,12 @@ __global__ void egdst_k_envA(EgdstDev P, int it) {
         const double x = E.x(f, k), v = E.v(f, k);
         int rank = 0, best = f;
         double bestv = v;
+        // inside its own (increasing) list a point is preceded by exactly k points unless a neighbour shares its abscissa
+        const bool tie = (k > 0 && E.x(f, k - 1) == x) || (k + 1 < E.npts(f) && E.x(f, k + 1) == x);
         for (int g = 0; g < E.F; g++) {
             const int ng = E.npts(g);
             if (ng <= 0) continue;
-            const int cnt = egdst_env_count_before(E, g, x, v, f, k);
+            const int cnt = (g == f && !tie) ? k : egdst_env_count_before(E, g, x, v, f, k);
             rank += cnt;
             if (g == f) continue;
             const double val = egdst_env_value(&cx, E, it, ist, g, egdst_env_cur(cnt, ng), x);

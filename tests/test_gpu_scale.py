@@ -165,6 +165,30 @@ def test_batched_solve_matches_individual_solves_and_reference():
     assert np.all(np.isfinite(table[:, 0, 1, :])) and np.ptp(table[:, 0, 1, 5]) > 0
 
 
+def test_large_sweep_launch_shapes_match_reference():
+    """A sweep that fills the machine switches to narrow seed CTAs and EGM CTAs that loop over the point blocks
+    (launch_periods): the partition of the node sums changes, so batch and single solves agree to rounding, not bit
+    for bit; both are held to the reference."""
+    m = examples.deaton2()
+    m.compile()
+    lib = m._capi()
+    rng = np.random.default_rng(77)
+    nvec = 2048
+    params = np.column_stack([rng.uniform(0.0, 0.05, nvec), rng.uniform(0.75, 1.75, nvec)])
+    sol = lib.solve_batch(m, params)
+    assert sol.warning is None, sol.warning
+    assert all(sol.status(v)[0] == 0 for v in range(nvec))
+    for i in (0, 1023, 2047):
+        mi = examples.deaton2(interest=params[i, 0], income=params[i, 1])
+        mi.compile(); mi.solve()
+        Mb, Db = sol.cells(i)
+        e1 = solution_errors(Mb, Db, mi.M, mi.D)
+        assert e1["C"] < 1e-12 and e1["V"] < 1e-12 and e1["rowdiff"] == 0, (i, e1)
+        Mr, Dr = oracle_for(mi).solve()
+        e = solution_errors(Mb, Db, Mr, Dr)
+        assert e["C"] < TOL and e["V"] < TOL and e["Dseq"] and e["rowdiff"] == 0, (i, e)
+
+
 def test_resolve_and_graph_replay_track_parameter_changes():
     """egdst_resolve re-runs the period chain into the same object; from the third call on it is replayed as a CUDA
     graph with the parameters read from device memory -- results must equal fresh solves for every parameter set."""
