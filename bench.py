@@ -369,7 +369,7 @@ def own_arm(a):
             "cpu_baseline": cpu,
             "solve": solve_obj,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -435,14 +435,14 @@ def batch_arm(a):
     bad = sum(1 for v in range(hi - lo) if sol.status(v)[0])
     if rank == 0:
         units = nvec * nominal_units(m)
-        print(json.dumps({
+        emit({
             "metric": "parameter vectors/s (batched solve + simulated moments)", "value": nvec / (ms / 1e3), "unit": "vectors/s", "n_gpus": world,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": "S3: %d deaton2 parameter vectors (interest~U[0,.05], income~U[.75,1.75], default_rng(4096)), %d agents each, moments all-reduced" % (nvec, nsim),
                        "parallelism": "parameter vectors sharded, dp%d" % world},
             "gpu_launches": int(lib.launch_count() - l0), "solve_units_per_s": units / (ms / 1e3), "agent_periods_per_s": nvec * nsim * nt / (ms / 1e3),
-            "vectors_with_error_status_on_rank0": bad}), flush=True)
+            "vectors_with_error_status_on_rank0": bad})
     if world > 1:
         dist.destroy_process_group()
 
@@ -528,10 +528,32 @@ def reference_arm(a):
         "solve": {"metric": SOLVE_METRIC, "value": units / solve_s, "unit": "grid-point-periods/s", "ms_per_solve": solve_s * 1e3,
                   "cores": 1, "kind": orc.kind, "sample": "one full S1 solve (the reference solver is single-threaded)", "units_per_solve": units},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_JSON_FD = None
+
+
+def _guard_stdout():
+    """Keep the process's stdout for the one JSON line: everything else that writes to file descriptor 1 -- NCCL
+    prints its version banner there whenever NCCL_DEBUG is set, whatever the level -- goes to stderr."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    data = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
+    _guard_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
