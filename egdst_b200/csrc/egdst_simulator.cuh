@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) egdst_k_simulate(EgdstDev P, Egds
         for (int i = 0; i < EGDST_NNST; i++) cur.st[i] = 0;
 #pragma unroll
         for (int i = 0; i < EGDST_NND; i++) cur.dc[i] = 0;
-        double mu = NaN, sigma = NaN, c = 0, vf = 0;
+        double mu = NaN, sigma = NaN, c = 0, vf = 0, uu = 0, bb = 0;  // uu, bb: utility and discount factor of the record
         double eqs[EGDST_NREQ > 0 ? EGDST_NREQ : 1];
         int state = live_lane ? 0 : 2;  // 0 alive, 1 dead/skipped (NaN rows), 2 no agent
         if (live_lane) {
@@ -352,6 +352,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) egdst_k_simulate(EgdstDev P, Egds
                     cur.ist = ist1;
                     cur.id = id1;
                     egdst_fill_decision(&cx, &cur);
+                    uu = utility(&cx, &cur, c); bb = discount(&cx, &cur);
                 }
             }
 #else
@@ -393,7 +394,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) egdst_k_simulate(EgdstDev P, Egds
                     }
                     egdst_fill_decision(&cx, &cur);
                     const double evf = S.hdr_smem ? hc->evf : P.evf[cell];  // == V(row 0)
-                    if (cur.cash < M1 && evf > -EGDST_INF) vf = utility(&cx, &cur, c) + discount(&cx, &cur) * evf;
+                    uu = utility(&cx, &cur, c); bb = discount(&cx, &cur);  // output columns 9, 10; shared with the exact value below
+                    if (cur.cash < M1 && evf > -EGDST_INF) vf = uu + bb * evf;
                     else vf = iv.v1 * wl + iv.v0 * wr;
                 }
             }
@@ -414,7 +416,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) egdst_k_simulate(EgdstDev P, Egds
 #define EGDST_REC(j) tile[EGDST_TILE_POS(lane, hoff + (j))]
             if (state == 0) {
                 EGDST_REC(0) = cur.cash; EGDST_REC(1) = c; EGDST_REC(2) = cur.savings; EGDST_REC(3) = vf; EGDST_REC(4) = (double)cur.id; EGDST_REC(5) = (double)cur.ist;
-                EGDST_REC(6) = mu; EGDST_REC(7) = sigma; EGDST_REC(8) = cur.shock; EGDST_REC(9) = utility(&cx, &cur, c); EGDST_REC(10) = discount(&cx, &cur);
+                EGDST_REC(6) = mu; EGDST_REC(7) = sigma; EGDST_REC(8) = cur.shock; EGDST_REC(9) = uu; EGDST_REC(10) = bb;
 #pragma unroll
                 for (int i = 0; i < EGDST_NNST; i++) EGDST_REC(11 + i) = cur.st[i];
 #pragma unroll

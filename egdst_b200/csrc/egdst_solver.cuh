@@ -541,17 +541,6 @@ __global__ void __launch_bounds__(EGDST_CMP_THREADS) egdst_k_compact(EgdstDev P,
         __syncthreads();
         const unsigned long long excl = s_excl;
         if (!egdst_scan_hi(excl)) {  // the grid did not stop in an earlier chunk: this chunk's points count
-#ifdef EGDST_DEBUG_LATE
-            if (threadIdx.x == 0 && it <= 3) {
-                const double *sp = P.seed + (size_t)sd * 8;
-                printf("dbg it=%d id=%d ls=%d seed lim1=%.17g lim2=%.17g lim3=%.17g lim3p=%.17g k3=%g lastA=%.17g | flags", it, id, ls, sp[0], sp[1], sp[2], sp[3], sp[4], sp[5]);
-                for (int q = 0; q < 12; q++) printf(" %d", rawFlag[q]);
-                printf(" | stop");
-                for (int q = 0; q < 6; q++) printf(" %.17g", rawStop[q]);
-                printf("\n");
-            }
-            if (late != 0x7fffffff) printf("late resend: it=%d ist=%d id=%d n=%d ls=%d stop[n]=%g flag0=%d M0=%g stop0=%g\n", it, ist, id, late, ls, rawStop[late], rawFlag[0], rawM[0], rawStop[0]);
-#endif
             if (late != 0x7fffffff) egdst_fail(P, ivec, EGDST_ERR_RESEND_LATE, it, ist, id);
             if (badsum) egdst_fail(P, ivec, EGDST_ERR_CHECKSUM, it, ist, id);
             const int first = egdst_scan_lo(excl);
