@@ -302,7 +302,7 @@ static int launch_periods(egdst_solution *s, cudaStream_t st) {
     const int envA0 = imin((nd * P.gcap + B - 1) / B, (nd * (N + 64) + B - 1) / B + 1);
     const int envBC1 = imin(P.chE, (N + 64 + envchunk - 1) / envchunk + 1);
     const int envBC0 = imin(P.chE, (nd * (N + 64) + envchunk - 1) / envchunk);
-    static const bool env_one_cta = getenv("EGDST_ENV_ONECTA") != 0;  // test hook: every job strides with a single CTA
+    const bool env_one_cta = getenv("EGDST_ENV_ONECTA") != 0;  // test hook: every job strides with a single CTA
     // CTAs per (ist,id) in the EGM step: one per block of 32 grid points, fewer (looping) when a batched sweep already
     // fills the machine several times over
     const int egmblocks = (N - 1 + 31) / 32;

@@ -1,0 +1,72 @@
+"""The CUDA kernels' logic without a GPU: tools/hostemu compiles the same .cu sources with g++ (one std::thread per
+CUDA thread, CTAs in ticket order) and the C ABI is driven exactly as on the device.  Small models only -- this is a
+logic check (chained scans, ticket loops, envelope chains, lookup tables, continuous-state branch), not the product
+path: the emulator lives under tools/ and is never loaded by egdst_b200."""
+import os
+import shutil
+import sys
+
+import numpy as np
+import pytest
+
+from egdst_b200 import capi, examples
+from tests import goldens
+from tests.oracles import oracle_for, ref_available
+from tests.parity import solution_errors
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(os.path.dirname(HERE), "tools", "hostemu"))
+
+pytestmark = pytest.mark.skipif(shutil.which("g++") is None, reason="g++ not available")
+
+
+def _emulated(model):
+    from build import build  # tools/hostemu/build.py
+    model.prepare()
+    return capi.ModelLibrary(build(model))
+
+
+@pytest.mark.parametrize("make,kw", [
+    (examples.retirement2, dict(T=6, ngridm=40, ngridmax=200, ny=4)),
+    (examples.humancapital, dict(T=5, ngridm=30, ny=3)),
+])
+def test_emulated_kernels_match_reference(make, kw):
+    m = make(**kw)
+    if not ref_available(m):
+        pytest.skip("oracle/_ref not built and /root/reference absent")
+    lib = _emulated(m)
+    sol = lib.solve(m)
+    assert sol.status()[0] == 0, sol.status()
+    orc = oracle_for(m)
+    Mr, Dr = orc.solve()
+    e = solution_errors(sol.M, sol.D, Mr, Dr)
+    assert e["C"] < 1e-9 and e["V"] < 1e-9 and e["TH"] < 1e-8 and e["Dseq"] and e["rowdiff"] == 0, e
+    rng = np.random.default_rng(11)
+    nsim = 96
+    cont = any(v["continuous"] for v in m.s)
+    ist0 = np.ones(nsim) if cont else np.full(nsim, float(m.nst))
+    init = np.column_stack([ist0, m.a0 + (m.mmax - m.a0) * (0.05 + 0.5 * rng.random(nsim))])
+    rs = rng.random(4 * nsim * m.nt)
+    sims = lib.simulate(m, lib.import_solution(m, Mr, Dr), init, rs, 0)
+    se = goldens.sims_errors(sims, orc.simulate(Mr, Dr, init, rs, 0), skipcols=[3] if cont else [])
+    assert se["nan_mismatch"] == 0 and se["discrete_mismatch"] == 0 and se["max"] < 1e-9, se
+    # counter-based draws: moments accumulated in the kernel equal the sums over the returned paths
+    s2, mom = lib.simulate_philox(m, sol, init, 7, want_sims=True, want_moments=True)
+    alive = ~np.isnan(s2)
+    assert np.array_equal(mom[2], alive.sum(axis=0).T.astype(float))
+    assert np.allclose(mom[0], np.where(alive, s2, 0.0).sum(axis=0).T, rtol=1e-12, atol=1e-9)
+
+
+def test_emulated_envelope_with_a_single_striding_cta(monkeypatch):
+    """EGDST_ENV_ONECTA: every envelope job runs with one CTA, so the stride loop of the rank kernel and the ticket
+    loop of the merge kernel take several chunks each."""
+    monkeypatch.setenv("EGDST_ENV_ONECTA", "1")
+    m = examples.retirement2(T=3, ngridm=700, ngridmax=1500, ny=2, nthrhmax=700)
+    if not ref_available(m):
+        pytest.skip("oracle/_ref not built and /root/reference absent")
+    lib = _emulated(m)
+    sol = lib.solve(m)
+    assert sol.status()[0] == 0, sol.status()
+    Mr, Dr = oracle_for(m).solve()
+    e = solution_errors(sol.M, sol.D, Mr, Dr)
+    assert e["C"] < 1e-9 and e["V"] < 1e-9 and e["TH"] < 1e-8 and e["Dseq"] and e["rowdiff"] == 0, e
