@@ -225,6 +225,31 @@ def test_resolve_and_graph_replay_track_parameter_changes():
         lib.set_stream(0)
 
 
+def test_repeated_solves_are_bit_identical(s1):
+    """Run-to-run determinism of the whole chain (eager launches, graph capture, graph replays): no floating-point
+    atomics, ticket-ordered scans -- every export of the same model is the same bytes.  (A programmatic-dependent-
+    launch version of the eager chain failed exactly this kind of check on the S1b case and was removed.)"""
+    import torch
+    lib = s1._capi()
+    stream = torch.cuda.Stream()
+    lib.set_stream(stream.cuda_stream)
+    try:
+        sol = lib.solve(s1, strict=True)
+        first = None
+        for k in range(6):
+            lib.resolve(sol, s1)
+            stream.synchronize()
+            assert sol.status()[0] == 0
+            M, Dd = sol.cells(0)
+            blob = [np.ascontiguousarray(M[0][it]).tobytes() + np.ascontiguousarray(Dd[0][it]).tobytes() for it in range(s1.nt)]
+            if first is None:
+                first = blob
+            else:
+                assert blob == first, k
+    finally:
+        lib.set_stream(0)
+
+
 def test_lecture_model2_at_the_authors_largest_configuration():
     """lecture_code/start.m:73 runs model2('T',6,'ngridm',5000,'nquad',100): two labour-market states (absorbing
     retirement), two decisions, lognormal returns -- the largest configuration the reference's author exercises."""
