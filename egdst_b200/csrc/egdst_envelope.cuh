@@ -77,6 +77,15 @@ EGDST_DEV double egdst_linter2(double x, double g0, double g1, double f0, double
 template <class View>
 EGDST_DEV int egdst_env_count_before(const View &E, int g, double x, double v, int f, int k) {
     const int ng = E.npts(g);
+    // Lists that do not straddle x need no search: three independent probes instead of a chain of dependent ones.
+    // The secondary envelope of a zig-zagging grid has ~10^2 short runs of which two or three contain a given x;
+    // every run but the last ends in the far-away sentinel, so "x between the last two points" is the common case.
+    if (ng > 0) {
+        if (x < E.x(g, 0)) return 0;
+        const double xl = E.x(g, ng - 1);
+        if (x > xl) return ng;
+        if (ng >= 2 && x < xl && x > E.x(g, ng - 2)) return ng - 1;
+    }
     int lo = 0, hi = ng;  // lower bound: first index with x_g >= x
     while (lo < hi) { int mid = (lo + hi) >> 1; if (E.x(g, mid) < x) lo = mid + 1; else hi = mid; }
     int cnt = lo;
