@@ -298,8 +298,13 @@ static int launch_periods(egdst_solution *s, cudaStream_t st) {
     // envelope kernels: grids sized for the usual list lengths (a decision keeps at most N points plus the few the
     // secondary envelope inserts); longer lists, up to the capacity ngridmax, are covered by the kernels' own loops
     const int envchunk = P.envW * EGDST_ENV_IPT;
-    const int envA1 = imin((2 * P.gcap + B - 1) / B, (N + 64 + B - 1) / B + 1);
+    int envA1 = imin((2 * P.gcap + B - 1) / B, (N + 64 + B - 1) / B + 1);
     const int envA0 = imin((nd * P.gcap + B - 1) / B, (nd * (N + 64) + B - 1) / B + 1);
+    // a point of the secondary envelope ranks itself against every run (~10^2 in the zig-zag periods of S1): with few
+    // jobs, 8 threads share the runs of a point
+    const bool envA1split = nvec * nst * nd < 148;
+    const dim3 envA1block = envA1split ? dim3(32, 8) : dim3(B, 1);
+    if (envA1split) envA1 = imin((2 * P.gcap + 31) / 32, (N + 64 + 31) / 32 + 1);
     const int envBC1 = imin(P.chE, (N + 64 + envchunk - 1) / envchunk + 1);
     const int envBC0 = imin(P.chE, (nd * (N + 64) + envchunk - 1) / envchunk);
     const bool env_one_cta = getenv("EGDST_ENV_ONECTA") != 0;  // test hook: every job strides with a single CTA
@@ -325,7 +330,7 @@ static int launch_periods(egdst_solution *s, cudaStream_t st) {
             PLAUNCH(KC_EGM, egdst_k_egm, dim3(egmgx, nst * nd, nvec), dim3(32, egmparts), shsmem, st, P, it, useTab);
             PLAUNCH(KC_COMPACT, egdst_k_compact, dim3(P.chC, nst * nd, nvec), dim3(P.cmpW), 0, st, P, it);
             // secondary envelope (no-op for (ist,id) without folds)
-            PLAUNCH(KC_ENV2, egdst_k_envA<1>, dim3(env_one_cta ? 1 : envA1, nst * nd, nvec), dim3(B), 0, st, P, it);
+            PLAUNCH(KC_ENV2, egdst_k_envA<1>, dim3(env_one_cta ? 1 : envA1, nst * nd, nvec), envA1block, 0, st, P, it);
             PLAUNCH(KC_ENV2, egdst_k_envBC<1>, dim3(env_one_cta ? 1 : envBC1, nst * nd, nvec), dim3(P.envW), 0, st, P, it);
         }
         PLAUNCH(KC_ENV, egdst_k_envA<0>, dim3(env_one_cta ? 1 : envA0, nst, nvec), dim3(B), 0, st, P, it);

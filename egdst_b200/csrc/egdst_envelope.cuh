@@ -165,11 +165,17 @@ EGDST_DEV double egdst_env_grb_block(const View &E, double *sh) {
 
 template <int MODE>
 __global__ void egdst_k_envA(EgdstDev P, int it) {
+    // blockDim = (points, parts): `parts` threads share the functions of one point (g = part, part + parts, ...) and
+    // combine rank and argmax through shared memory -- the secondary envelope of a zig-zagging grid has ~10^2 runs,
+    // and a point that walks them alone is a chain of ~10^2 dependent loads
     __shared__ double shg[33];
+    __shared__ int s_rank[256], s_best[256];
+    __shared__ double s_bv[256];
     const int ivec = blockIdx.z;
+    const int lane = threadIdx.x, part = threadIdx.y, nparts = blockDim.y, npt = blockDim.x;
     int ist, id, slot;
     EgdstEnvView<MODE> E;
-    if (MODE == 0 && blockIdx.x == 0 && threadIdx.x == 0) {
+    if (MODE == 0 && blockIdx.x == 0 && lane == 0 && part == 0) {
         // "all choices produced empty grids" (egdst_solver.c:704-710), checked where the per-decision lists are final
         const int sd0 = egdst_sd(P, ivec, blockIdx.y, 0);
         int any = 0, tot = 0;
@@ -179,33 +185,53 @@ __global__ void egdst_k_envA(EgdstDev P, int it) {
     if (!egdst_env_job<MODE>(P, ivec, blockIdx.y, ist, id, slot, E)) return;
     egdst_ctx cx; egdst_load_ctx(P, ivec, cx);
     const int Ptot = E.pstart(E.F - 1) + E.npts(E.F - 1);
-    if (blockIdx.x * blockDim.x >= Ptot) return;  // CTA-uniform
+    if (blockIdx.x * npt >= Ptot) return;  // CTA-uniform
     const double grb = egdst_env_grb_block(E, shg);
     // the grid is sized for the usual number of points (host: launch_periods) and strides over longer lists
-    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < Ptot; p += gridDim.x * blockDim.x) {
-        // flattened index -> (f,k)
-        int f = 0;
-        if (MODE == 0) { int s = 0; while (f < E.F - 1 && p >= s + E.npts(f)) { s += E.npts(f); f++; } }
-        else { int lo = 0, hi = E.F - 1; while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (E.pstart(mid) <= p) lo = mid; else hi = mid - 1; } f = lo; }
-        const int k = p - E.pstart(f);
-        const double x = E.x(f, k), v = E.v(f, k);
-        int rank = 0, best = f;
-        double bestv = v;
-        // inside its own (increasing) list a point is preceded by exactly k points unless a neighbour shares its abscissa
-        const bool tie = (k > 0 && E.x(f, k - 1) == x) || (k + 1 < E.npts(f) && E.x(f, k + 1) == x);
-        for (int g = 0; g < E.F; g++) {
-            const int ng = E.npts(g);
-            if (ng <= 0) continue;
-            const int cnt = (g == f && !tie) ? k : egdst_env_count_before(E, g, x, v, f, k);
-            rank += cnt;
-            if (g == f) continue;
-            const double val = egdst_env_value(&cx, E, it, ist, g, egdst_env_cur(cnt, ng), x);
-            if (val > bestv || (val == bestv && g < best)) { bestv = val; best = g; }
+    for (int base = blockIdx.x * npt; base < Ptot; base += gridDim.x * npt) {
+        const int p = base + lane;
+        const bool valid = p < Ptot;
+        int f = 0, k = 0, rank = 0, best = 0x7fffffff;
+        double x = 0, v = 0, bestv = -EGDST_INF;
+        if (valid) {
+            // flattened index -> (f,k)
+            if (MODE == 0) { int s = 0; while (f < E.F - 1 && p >= s + E.npts(f)) { s += E.npts(f); f++; } }
+            else { int lo = 0, hi = E.F - 1; while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (E.pstart(mid) <= p) lo = mid; else hi = mid - 1; } f = lo; }
+            k = p - E.pstart(f);
+            x = E.x(f, k); v = E.v(f, k);
+            // inside its own (increasing) list a point is preceded by exactly k points unless a neighbour shares its abscissa
+            const bool tie = (k > 0 && E.x(f, k - 1) == x) || (k + 1 < E.npts(f) && E.x(f, k + 1) == x);
+            // argmax: highest value, lowest function index among equals (the sweep's "first strictly greater wins");
+            // the point's own function takes part with its own value
+            for (int g = part; g < E.F; g += nparts) {
+                const int ng = E.npts(g);
+                if (ng <= 0) continue;
+                const int cnt = (g == f && !tie) ? k : egdst_env_count_before(E, g, x, v, f, k);
+                rank += cnt;
+                const double val = (g == f) ? v : egdst_env_value(&cx, E, it, ist, g, egdst_env_cur(cnt, ng), x);
+                if (val > bestv || (val == bestv && g < best)) { bestv = val; best = g; }
+            }
         }
-        size_t o = (size_t)slot * P.envcap + rank;
-        P.mgX[o] = x; P.mgF[o] = f; P.mgK[o] = k; P.mgA[o] = best;
-        // the active positions of the union are the prefix with x <= grb: its length for the merge kernel
-        if (x <= grb) atomicMax(P.envNact + slot, rank + 1);
+        if (nparts > 1) {
+            const int slotx = part * npt + lane;
+            s_rank[slotx] = rank; s_best[slotx] = best; s_bv[slotx] = bestv;
+            __syncthreads();
+            if (part == 0 && valid) {
+                for (int q = 1; q < nparts; q++) {
+                    const int o = q * npt + lane;
+                    rank += s_rank[o];
+                    if (s_bv[o] > bestv || (s_bv[o] == bestv && s_best[o] < best)) { bestv = s_bv[o]; best = s_best[o]; }
+                }
+            }
+        }
+        if (part == 0 && valid) {
+            if (best == 0x7fffffff) best = f;  // every value -inf (cannot happen: the own value is finite or the maximum)
+            size_t o = (size_t)slot * P.envcap + rank;
+            P.mgX[o] = x; P.mgF[o] = f; P.mgK[o] = k; P.mgA[o] = best;
+            // the active positions of the union are the prefix with x <= grb: its length for the merge kernel
+            if (x <= grb) atomicMax(P.envNact + slot, rank + 1);
+        }
+        if (nparts > 1 && base + (int)(gridDim.x * npt) < Ptot) __syncthreads();  // scratch reused by the next stride
     }
 }
 
