@@ -69,7 +69,8 @@ struct EgdstDev {
     int *tickC, *tickE;                 // [nsd*2], [nslot*2]
     int chC, chE;                       // chunks per job
     int cmpW;                           // threads per CTA of the compaction (chunk = cmpW * EGDST_CMP_IPT raw points)
-    int envW;                           // threads per CTA of the envelope merge (chunk = envW * EGDST_ENV_IPT positions)
+    int envW;                           // threads per CTA of the envelope merge (chunk = envW * IPT positions)
+    int envIPT1;                        // positions per thread in the secondary envelope's merge (8 or 2)
     int *foldList, *foldCnt;            // [nsd*(gcap+1)] unordered fold positions, [nsd]
     int *envNact;                       // [nslot] active prefix length of the merged union (egdst_k_envA)
     // per-cell lookup tables (egdst_tables.cuh)

@@ -374,11 +374,13 @@ EGDST_DEV EgdstEnvPos egdst_env_pos(const EgdstEnvView<MODE> &E, const double *m
 
 #define EGDST_ENV_CHUNK (EGDST_ENVW * EGDST_ENV_IPT)  /* union positions per chunk at the widest CTA */
 #define EGDST_ENV_QCAP 512                             /* crossing chains queued per CTA */
+// IPT positions per thread: 8, or 2 for the secondary envelope of a single large model, whose crossing chains (one
+// per warp at a time) then spread over four times as many warps.
 // grid (<= chE, njobs_y, nvec), blockDim.x = P.envW: the CTAs of one job take chunks of blockDim.x*IPT union positions
 // by ticket until none is left and are chained by a decoupled look-back scan over (grid points, thresholds) emitted
 // so far; the last CTA to finish writes the cell header (MODE 0) or copies the staged result back over the
 // decision's point list (MODE 1).  Small models in batched sweeps run narrow CTAs (P.envW = 64), one per job.
-template <int MODE>
+template <int MODE, int IPT>
 __global__ void __launch_bounds__(EGDST_ENVW) egdst_k_envBC(EgdstDev P, int it) {
     __shared__ long long sh[40];
     __shared__ double s_grb[33];
@@ -406,7 +408,7 @@ __global__ void __launch_bounds__(EGDST_ENVW) egdst_k_envBC(EgdstDev P, int it) 
     }
     // the active positions of the union are the prefix with x<=grb (length recorded by egdst_k_envA)
     const int nact = P.envNact[slot];
-    const int chunkw = blockDim.x * EGDST_ENV_IPT;
+    const int chunkw = blockDim.x * IPT;
     const int nch = (nact + chunkw - 1) / chunkw;
     const double grb = nch > 0 ? egdst_env_grb_block(E, s_grb) : 0.0;  // nch is CTA-uniform
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -417,11 +419,11 @@ __global__ void __launch_bounds__(EGDST_ENVW) egdst_k_envBC(EgdstDev P, int it) 
         __syncthreads();
         const int chunk = s_chunk;
         if (chunk >= nch) break;
-        const int r0 = chunk * chunkw + threadIdx.x * EGDST_ENV_IPT;
+        const int r0 = chunk * chunkw + threadIdx.x * IPT;
         // pass 1: own contribution of every position; crossing chains go to the CTA's queue
-        int ngj[EGDST_ENV_IPT], ntj[EGDST_ENV_IPT], qj[EGDST_ENV_IPT];
+        int ngj[IPT], ntj[IPT], qj[IPT];
 #pragma unroll
-        for (int j = 0; j < EGDST_ENV_IPT; j++) {
+        for (int j = 0; j < IPT; j++) {
             ngj[j] = 0; ntj[j] = 0; qj[j] = -1;
             const int r = r0 + j;
             if (r < nact) {
@@ -445,7 +447,7 @@ __global__ void __launch_bounds__(EGDST_ENVW) egdst_k_envBC(EgdstDev P, int it) 
         __syncthreads();
         int ngs = 0, nts = 0;
 #pragma unroll
-        for (int j = 0; j < EGDST_ENV_IPT; j++) {
+        for (int j = 0; j < IPT; j++) {
             if (qj[j] >= 0) { ngj[j] += s_qg[qj[j]]; ntj[j] += s_qt[qj[j]]; }
             ngs += ngj[j]; nts += ntj[j];
         }
@@ -459,7 +461,7 @@ __global__ void __launch_bounds__(EGDST_ENVW) egdst_k_envBC(EgdstDev P, int it) 
         int gpos = egdst_scan_lo(s_excl) + (int)(off & 0xffffffffLL), tpos = egdst_scan_hi(s_excl) + (int)(off >> 32);
         // pass 3: write the kept points; chains get their output offsets
 #pragma unroll
-        for (int j = 0; j < EGDST_ENV_IPT; j++) {
+        for (int j = 0; j < IPT; j++) {
             const int r = r0 + j;
             if (r < nact && (ngj[j] | ntj[j])) {
                 const EgdstEnvPos q = egdst_env_pos<MODE>(E, mgX, mgF, mgK, mgA, r);
@@ -522,7 +524,20 @@ __global__ void __launch_bounds__(EGDST_ENVW) egdst_k_envBC(EgdstDev P, int it) 
         const int n = nout < P.gcap ? nout : P.gcap;
         double *X = P.ptX + (size_t)sd * P.gcap, *Cc = P.ptC + (size_t)sd * P.gcap, *V = P.ptV + (size_t)sd * P.gcap;
         __syncthreads();
-        for (int i = threadIdx.x; i < n; i += blockDim.x) { X[i] = EGDST_LDCG(ox + i); Cc[i] = EGDST_LDCG(oc + i); V[i] = EGDST_LDCG(ov + i); }
+        // copy-back by one CTA: batches of independent loads (a plain loop is a chain of n/blockDim L2 round trips)
+        for (int i0 = threadIdx.x; i0 < n; i0 += 8 * blockDim.x) {
+            double bx[8], bc[8], bv[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int i = i0 + u * blockDim.x;
+                if (i < n) { bx[u] = EGDST_LDCG(ox + i); bc[u] = EGDST_LDCG(oc + i); bv[u] = EGDST_LDCG(ov + i); }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int i = i0 + u * blockDim.x;
+                if (i < n) { X[i] = bx[u]; Cc[i] = bc[u]; V[i] = bv[u]; }
+            }
+        }
         if (threadIdx.x == 0) P.ptN[sd] = n;
     }
 }
