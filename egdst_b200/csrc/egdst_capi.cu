@@ -251,14 +251,16 @@ static int create_solution(const egdst_desc *d, int nvec, egdst_solution **out) 
         s->tab_base = base; s->tab_bytes = lutbytes + ivlbytes;
     }
     P.cmpW = (P.N <= 64 * EGDST_CMP_IPT) ? 64 : EGDST_CMP_THREADS;
-    P.chC = (P.N + P.cmpW * EGDST_CMP_IPT - 1) / (P.cmpW * EGDST_CMP_IPT);
+    P.cmpIPT = (nvec * d->nst * nd < 148 && P.cmpW == EGDST_CMP_THREADS) ? 2 : EGDST_CMP_IPT;
+    P.chC = (P.N + P.cmpW * P.cmpIPT - 1) / (P.cmpW * P.cmpIPT);
     // envelope merge: narrow CTAs when the usual union (nd lists of about N points) fits one narrow chunk -- small
     // models of a batched sweep then keep four times as many jobs resident per SM
     P.envW = (nd * (P.N + 64) <= 64 * EGDST_ENV_IPT) ? 64 : EGDST_ENVW;
-    // secondary envelope of one large model: 2 positions per thread, so that its crossing chains (~2 per run, ~10^2
-    // runs in the zig-zag periods, one chain per warp at a time) find four times as many warps
-    P.envIPT1 = (nvec * d->nst * nd < 148 && P.envW == EGDST_ENVW) ? 2 : EGDST_ENV_IPT;
-    P.chE = (P.envcap + P.envW * P.envIPT1 - 1) / (P.envW * P.envIPT1) + 1;
+    // envelope merges of one large model: 2 positions per thread instead of 8 -- four times as many CTAs share the
+    // latency of the passes, and the crossing chains of the secondary envelope (~2 per run, ~10^2 runs in the zig-zag
+    // periods, one chain per warp at a time) find four times as many warps
+    P.envIPT = (nvec * d->nst * nd < 148 && P.envW == EGDST_ENVW) ? 2 : EGDST_ENV_IPT;
+    P.chE = (P.envcap + P.envW * P.envIPT - 1) / (P.envW * P.envIPT) + 1;
     DA(P.scanC, (size_t)s->nsd * P.chC); DA(P.tickC, (size_t)2 * s->nsd); DA(P.foldList, (size_t)s->nsd * (P.gcap + 1)); DA(P.foldCnt, s->nsd);
     DA(P.scanE, (size_t)s->nslot * P.chE); DA(P.tickE, (size_t)2 * s->nslot); DA(P.envNact, s->nslot);
     DA(P.status, 4 * nvec); DA(P.units, nvec); DA(s->d_moff, s->ncell + 1); DA(s->d_toff, s->ncell + 1);
@@ -300,7 +302,7 @@ static int launch_periods(egdst_solution *s, cudaStream_t st) {
     }
     // envelope kernels: grids sized for the usual list lengths (a decision keeps at most N points plus the few the
     // secondary envelope inserts); longer lists, up to the capacity ngridmax, are covered by the kernels' own loops
-    const int envchunk = P.envW * EGDST_ENV_IPT;
+    const int envchunk = P.envW * P.envIPT;
     int envA1 = imin((2 * P.gcap + B - 1) / B, (N + 64 + B - 1) / B + 1);
     const int envA0 = imin((nd * P.gcap + B - 1) / B, (nd * (N + 64) + B - 1) / B + 1);
     // a point of the secondary envelope ranks itself against every run (~10^2 in the zig-zag periods of S1): with few
@@ -308,8 +310,7 @@ static int launch_periods(egdst_solution *s, cudaStream_t st) {
     const bool envA1split = nvec * nst * nd < 148;
     const dim3 envA1block = envA1split ? dim3(32, 8) : dim3(B, 1);
     if (envA1split) envA1 = imin((2 * P.gcap + 31) / 32, (N + 64 + 31) / 32 + 1);
-    const int envchunk1 = P.envW * P.envIPT1;
-    const int envBC1 = imin(P.chE, (N + 64 + envchunk1 - 1) / envchunk1 + 1);
+    const int envBC1 = imin(P.chE, (N + 64 + envchunk - 1) / envchunk + 1);
     const int envBC0 = imin(P.chE, (nd * (N + 64) + envchunk - 1) / envchunk);
     const bool env_one_cta = getenv("EGDST_ENV_ONECTA") != 0;  // test hook: every job strides with a single CTA
     // CTAs per (ist,id) in the EGM step: one per block of 32 grid points, fewer (looping) when a batched sweep already
@@ -332,14 +333,16 @@ static int launch_periods(egdst_solution *s, cudaStream_t st) {
         } else {
             PLAUNCH(KC_SEED, egdst_k_seed, dim3(nd, nst, nvec), dim3(seedthreads), shsmem, st, P, it, useTab);
             PLAUNCH(KC_EGM, egdst_k_egm, dim3(egmgx, nst * nd, nvec), dim3(32, egmparts), shsmem, st, P, it, useTab);
-            PLAUNCH(KC_COMPACT, egdst_k_compact, dim3(P.chC, nst * nd, nvec), dim3(P.cmpW), 0, st, P, it);
+            if (P.cmpIPT == 2) PLAUNCH(KC_COMPACT, egdst_k_compact<2>, dim3(P.chC, nst * nd, nvec), dim3(P.cmpW), 0, st, P, it);
+            else PLAUNCH(KC_COMPACT, egdst_k_compact<EGDST_CMP_IPT>, dim3(P.chC, nst * nd, nvec), dim3(P.cmpW), 0, st, P, it);
             // secondary envelope (no-op for (ist,id) without folds)
             PLAUNCH(KC_ENV2, egdst_k_envA<1>, dim3(env_one_cta ? 1 : envA1, nst * nd, nvec), envA1block, 0, st, P, it);
-            if (P.envIPT1 == 2) PLAUNCH(KC_ENV2, (egdst_k_envBC<1, 2>), dim3(env_one_cta ? 1 : envBC1, nst * nd, nvec), dim3(P.envW), 0, st, P, it);
+            if (P.envIPT == 2) PLAUNCH(KC_ENV2, (egdst_k_envBC<1, 2>), dim3(env_one_cta ? 1 : envBC1, nst * nd, nvec), dim3(P.envW), 0, st, P, it);
             else PLAUNCH(KC_ENV2, (egdst_k_envBC<1, EGDST_ENV_IPT>), dim3(env_one_cta ? 1 : envBC1, nst * nd, nvec), dim3(P.envW), 0, st, P, it);
         }
         PLAUNCH(KC_ENV, egdst_k_envA<0>, dim3(env_one_cta ? 1 : envA0, nst, nvec), dim3(B), 0, st, P, it);
-        PLAUNCH(KC_ENV, (egdst_k_envBC<0, EGDST_ENV_IPT>), dim3(env_one_cta ? 1 : envBC0, nst, nvec), dim3(P.envW), 0, st, P, it);
+        if (P.envIPT == 2) PLAUNCH(KC_ENV, (egdst_k_envBC<0, 2>), dim3(env_one_cta ? 1 : envBC0, nst, nvec), dim3(P.envW), 0, st, P, it);
+        else PLAUNCH(KC_ENV, (egdst_k_envBC<0, EGDST_ENV_IPT>), dim3(env_one_cta ? 1 : envBC0, nst, nvec), dim3(P.envW), 0, st, P, it);
         PLAUNCH(KC_TAB, egdst_k_tab, dim3(tabblocks, nst, nvec), dim3(B), 0, st, P, it);
     }
     CK(cudaGetLastError());

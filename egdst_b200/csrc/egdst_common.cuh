@@ -68,9 +68,9 @@ struct EgdstDev {
     unsigned long long *scanC, *scanE;  // [nsd*chC] compaction, [nslot*chE] envelope merge
     int *tickC, *tickE;                 // [nsd*2], [nslot*2]
     int chC, chE;                       // chunks per job
-    int cmpW;                           // threads per CTA of the compaction (chunk = cmpW * EGDST_CMP_IPT raw points)
+    int cmpW, cmpIPT;                   // threads per CTA and raw points per thread of the compaction (chunk = cmpW * cmpIPT)
     int envW;                           // threads per CTA of the envelope merge (chunk = envW * IPT positions)
-    int envIPT1;                        // positions per thread in the secondary envelope's merge (8 or 2)
+    int envIPT;                        // positions per thread in the envelope merges (8, or 2 for a single large model)
     int *foldList, *foldCnt;            // [nsd*(gcap+1)] unordered fold positions, [nsd]
     int *envNact;                       // [nslot] active prefix length of the merged union (egdst_k_envA)
     // per-cell lookup tables (egdst_tables.cuh)

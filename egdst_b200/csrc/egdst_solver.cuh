@@ -480,9 +480,11 @@ __global__ void __launch_bounds__(32 * EGDST_EGM_SPLIT, EGDST_EGM_MINB) egdst_k_
 #else
 #define EGDST_CMP_THREADS 256
 #endif
+// IPT raw points per thread (8; 2 for a single large model: more CTAs share the latency of the passes).
 // grid (chC, nst*nd, nvec), blockDim.x = P.cmpW <= EGDST_CMP_THREADS: the CTAs of one (ist,id) list are chained by a decoupled look-back scan whose state
 // carries (points kept so far, "stop rule fired").  Folds inside a CTA's own output are appended to an unordered
 // list; the last CTA to finish adds the folds on chunk boundaries, orders the list and publishes the counts.
+template <int IPT>
 __global__ void __launch_bounds__(EGDST_CMP_THREADS) egdst_k_compact(EgdstDev P, int it) {
     __shared__ int sh[40];
     __shared__ int s_chunk, s_last;
@@ -498,7 +500,7 @@ __global__ void __launch_bounds__(EGDST_CMP_THREADS) egdst_k_compact(EgdstDev P,
     int *foldList = P.foldList + (size_t)sd * (P.gcap + 1);
     volatile unsigned long long *st = P.scanC + (size_t)sd * P.chC;
     if (rawFlag[0] == EGDST_PT_NONE) { if (blockIdx.x == 0 && threadIdx.x == 0) { P.ptN[sd] = 0; P.nfold[sd] = 0; } return; }
-    const int chunkw = blockDim.x * EGDST_CMP_IPT;  // raw points per CTA (P.cmpW threads: narrow CTAs for short grids)
+    const int chunkw = blockDim.x * IPT;  // raw points per CTA (P.cmpW threads: narrow CTAs for short grids)
     const int nch = (N + chunkw - 1) / chunkw;      // chunks that hold raw points == gridDim.x
     if (threadIdx.x == 0) s_chunk = atomicAdd(P.tickC + 2 * sd, 1);
     __syncthreads();
@@ -507,11 +509,11 @@ __global__ void __launch_bounds__(EGDST_CMP_THREADS) egdst_k_compact(EgdstDev P,
     const unsigned ltmask = (1u << lane) - 1u;
     int err = 0;
     if (chunk < nch) {
-        const int wbase = chunk * chunkw + w * (32 * EGDST_CMP_IPT);
+        const int wbase = chunk * chunkw + w * (32 * IPT);
         // the stop rule inside this chunk: first n whose returned M fails "M<mmax" (that point itself is kept)
-        int flag[EGDST_CMP_IPT], mystop = 0x7fffffff;
+        int flag[IPT], mystop = 0x7fffffff;
 #pragma unroll
-        for (int j = 0; j < EGDST_CMP_IPT; j++) {
+        for (int j = 0; j < IPT; j++) {
             const int n = wbase + j * 32 + lane;
             flag[j] = EGDST_PT_NONE;
             if (n < N) {
@@ -520,10 +522,10 @@ __global__ void __launch_bounds__(EGDST_CMP_THREADS) egdst_k_compact(EgdstDev P,
             }
         }
         const int ls = egdst_block_min(mystop, sh);
-        unsigned bal[EGDST_CMP_IPT];
+        unsigned bal[IPT];
         int wtotal = 0, late = 0x7fffffff, badsum = 0;
 #pragma unroll
-        for (int j = 0; j < EGDST_CMP_IPT; j++) {
+        for (int j = 0; j < IPT; j++) {
             const int n = wbase + j * 32 + lane;
             const bool in = n < N && n <= ls;
             if (in && flag[j] == EGDST_PT_C1NEG && n > 0 && n < late) late = n;
@@ -546,7 +548,7 @@ __global__ void __launch_bounds__(EGDST_CMP_THREADS) egdst_k_compact(EgdstDev P,
             const int first = egdst_scan_lo(excl);
             int pos = first + woff;
 #pragma unroll
-            for (int j = 0; j < EGDST_CMP_IPT; j++) {
+            for (int j = 0; j < IPT; j++) {
                 const int n = wbase + j * 32 + lane;
                 if (bal[j] & (1u << lane)) {
                     const int dst = pos + __popc(bal[j] & ltmask);
