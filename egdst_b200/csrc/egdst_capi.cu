@@ -255,11 +255,13 @@ static int create_solution(const egdst_desc *d, int nvec, egdst_solution **out) 
     P.chC = (P.N + P.cmpW * P.cmpIPT - 1) / (P.cmpW * P.cmpIPT);
     // envelope merge: narrow CTAs when the usual union (nd lists of about N points) fits one narrow chunk -- small
     // models of a batched sweep then keep four times as many jobs resident per SM
-    P.envW = (nd * (P.N + 64) <= 64 * EGDST_ENV_IPT) ? 64 : EGDST_ENVW;
+    const bool smalljob = nd * (P.N + 64) <= 64 * EGDST_ENV_IPT;
+    P.envW = smalljob ? 64 : EGDST_ENVW;
+    P.envFuse = smalljob ? 1 : 0;  // one narrow CTA per job also ranks the points (no launch of its own)
     // envelope merges of one large model: 2 positions per thread instead of 8 -- four times as many CTAs share the
     // latency of the passes, and the crossing chains of the secondary envelope (~2 per run, ~10^2 runs in the zig-zag
     // periods, one chain per warp at a time) find four times as many warps
-    P.envIPT = (nvec * d->nst * nd < 148 && P.envW == EGDST_ENVW) ? 2 : EGDST_ENV_IPT;
+    P.envIPT = (nvec * d->nst * nd < 148 && !smalljob) ? 2 : EGDST_ENV_IPT;
     P.chE = (P.envcap + P.envW * P.envIPT - 1) / (P.envW * P.envIPT) + 1;
     DA(P.scanC, (size_t)s->nsd * P.chC); DA(P.tickC, (size_t)2 * s->nsd); DA(P.foldList, (size_t)s->nsd * (P.gcap + 1)); DA(P.foldCnt, s->nsd);
     DA(P.scanE, (size_t)s->nslot * P.chE); DA(P.tickE, (size_t)2 * s->nslot); DA(P.envNact, s->nslot);
@@ -312,7 +314,7 @@ static int launch_periods(egdst_solution *s, cudaStream_t st) {
     if (envA1split) envA1 = imin((2 * P.gcap + 31) / 32, (N + 64 + 31) / 32 + 1);
     const int envBC1 = imin(P.chE, (N + 64 + envchunk - 1) / envchunk + 1);
     const int envBC0 = imin(P.chE, (nd * (N + 64) + envchunk - 1) / envchunk);
-    const bool env_one_cta = getenv("EGDST_ENV_ONECTA") != 0;  // test hook: every job strides with a single CTA
+    const bool env_one_cta = getenv("EGDST_ENV_ONECTA") != 0 || P.envFuse;  // test hook / fused rank step: a single CTA per job
     // CTAs per (ist,id) in the EGM step: one per block of 32 grid points, fewer (looping) when a batched sweep already
     // fills the machine several times over
     const int egmblocks = (N - 1 + 31) / 32;
@@ -336,11 +338,11 @@ static int launch_periods(egdst_solution *s, cudaStream_t st) {
             if (P.cmpIPT == 2) PLAUNCH(KC_COMPACT, egdst_k_compact<2>, dim3(P.chC, nst * nd, nvec), dim3(P.cmpW), 0, st, P, it);
             else PLAUNCH(KC_COMPACT, egdst_k_compact<EGDST_CMP_IPT>, dim3(P.chC, nst * nd, nvec), dim3(P.cmpW), 0, st, P, it);
             // secondary envelope (no-op for (ist,id) without folds)
-            PLAUNCH(KC_ENV2, egdst_k_envA<1>, dim3(env_one_cta ? 1 : envA1, nst * nd, nvec), envA1block, 0, st, P, it);
+            if (!P.envFuse) PLAUNCH(KC_ENV2, egdst_k_envA<1>, dim3(env_one_cta ? 1 : envA1, nst * nd, nvec), envA1block, 0, st, P, it);
             if (P.envIPT == 2) PLAUNCH(KC_ENV2, (egdst_k_envBC<1, 2>), dim3(env_one_cta ? 1 : envBC1, nst * nd, nvec), dim3(P.envW), 0, st, P, it);
             else PLAUNCH(KC_ENV2, (egdst_k_envBC<1, EGDST_ENV_IPT>), dim3(env_one_cta ? 1 : envBC1, nst * nd, nvec), dim3(P.envW), 0, st, P, it);
         }
-        PLAUNCH(KC_ENV, egdst_k_envA<0>, dim3(env_one_cta ? 1 : envA0, nst, nvec), dim3(B), 0, st, P, it);
+        if (!P.envFuse) PLAUNCH(KC_ENV, egdst_k_envA<0>, dim3(env_one_cta ? 1 : envA0, nst, nvec), dim3(B), 0, st, P, it);
         if (P.envIPT == 2) PLAUNCH(KC_ENV, (egdst_k_envBC<0, 2>), dim3(env_one_cta ? 1 : envBC0, nst, nvec), dim3(P.envW), 0, st, P, it);
         else PLAUNCH(KC_ENV, (egdst_k_envBC<0, EGDST_ENV_IPT>), dim3(env_one_cta ? 1 : envBC0, nst, nvec), dim3(P.envW), 0, st, P, it);
         PLAUNCH(KC_TAB, egdst_k_tab, dim3(tabblocks, nst, nvec), dim3(B), 0, st, P, it);

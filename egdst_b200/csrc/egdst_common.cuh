@@ -70,6 +70,7 @@ struct EgdstDev {
     int chC, chE;                       // chunks per job
     int cmpW, cmpIPT;                   // threads per CTA and raw points per thread of the compaction (chunk = cmpW * cmpIPT)
     int envW;                           // threads per CTA of the envelope merge (chunk = envW * IPT positions)
+    int envFuse;                        // 1: the envelope merge kernels run the rank step themselves (single-CTA jobs)
     int envIPT;                        // positions per thread in the envelope merges (8, or 2 for a single large model)
     int *foldList, *foldCnt;            // [nsd*(gcap+1)] unordered fold positions, [nsd]
     int *envNact;                       // [nslot] active prefix length of the merged union (egdst_k_envA)

@@ -163,11 +163,50 @@ EGDST_DEV double egdst_env_grb_block(const View &E, double *sh) {
     return r;
 }
 
+// One input point p of the flattened lists: its (f,k), abscissa and value, and -- over the functions g = part,
+// part + nparts, ... -- the number of points that precede it in the union and the best function at its abscissa
+// (highest value, lowest index among equals: the sweep's "first strictly greater wins"; the point's own function takes
+// part with its own value).
+template <int MODE>
+EGDST_DEV void egdst_env_point_partial(const egdst_ctx &cx, const EgdstEnvView<MODE> &E, int it, int ist, int p, int part, int nparts,
+                                       int &f, int &k, double &x, double &v, int &rank, int &best, double &bestv) {
+    f = 0;
+    if (MODE == 0) { int s = 0; while (f < E.F - 1 && p >= s + E.npts(f)) { s += E.npts(f); f++; } }
+    else { int lo = 0, hi = E.F - 1; while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (E.pstart(mid) <= p) lo = mid; else hi = mid - 1; } f = lo; }
+    k = p - E.pstart(f);
+    x = E.x(f, k); v = E.v(f, k);
+    rank = 0; best = 0x7fffffff; bestv = -EGDST_INF;
+    // inside its own (increasing) list a point is preceded by exactly k points unless a neighbour shares its abscissa
+    const bool tie = (k > 0 && E.x(f, k - 1) == x) || (k + 1 < E.npts(f) && E.x(f, k + 1) == x);
+    for (int g = part; g < E.F; g += nparts) {
+        const int ng = E.npts(g);
+        if (ng <= 0) continue;
+        const int cnt = (g == f && !tie) ? k : egdst_env_count_before(E, g, x, v, f, k);
+        rank += cnt;
+        const double val = (g == f) ? v : egdst_env_value(&cx, E, it, ist, g, egdst_env_cur(cnt, ng), x);
+        if (val > bestv || (val == bestv && g < best)) { bestv = val; best = g; }
+    }
+}
+// record the point at its position of the union; the active positions are the prefix with x <= grb
+EGDST_DEV void egdst_env_point_commit(const EgdstDev &P, int slot, double grb, int f, int k, double x, int rank, int best) {
+    if (best == 0x7fffffff) best = f;  // every value -inf (cannot happen: the own value is finite or the maximum)
+    const size_t o = (size_t)slot * P.envcap + rank;
+    P.mgX[o] = x; P.mgF[o] = f; P.mgK[o] = k; P.mgA[o] = best;
+    if (x <= grb) atomicMax(P.envNact + slot, rank + 1);
+}
+// "all choices produced empty grids" (egdst_solver.c:704-710), checked where the per-decision lists are final
+EGDST_DEV void egdst_env_check_allinf(const EgdstDev &P, int ivec, int it, int ist) {
+    const int sd0 = egdst_sd(P, ivec, ist, 0);
+    int any = 0, tot = 0;
+    for (int d_ = 0; d_ < P.cx.nd; d_++) { any |= P.active[sd0 + d_]; tot += P.ptN[sd0 + d_]; }
+    if (any && tot == 0) egdst_fail(P, ivec, EGDST_ERR_ALLINF, it, ist, -1);
+}
+
 template <int MODE>
 __global__ void egdst_k_envA(EgdstDev P, int it) {
-    // blockDim = (points, parts): `parts` threads share the functions of one point (g = part, part + parts, ...) and
-    // combine rank and argmax through shared memory -- the secondary envelope of a zig-zagging grid has ~10^2 runs,
-    // and a point that walks them alone is a chain of ~10^2 dependent loads
+    // blockDim = (points, parts): `parts` threads share the functions of one point and combine rank and argmax through
+    // shared memory -- the secondary envelope of a zig-zagging grid has ~10^2 runs, and a point that walks them alone
+    // is a chain of ~10^2 dependent loads
     __shared__ double shg[33];
     __shared__ int s_rank[256], s_best[256];
     __shared__ double s_bv[256];
@@ -175,13 +214,7 @@ __global__ void egdst_k_envA(EgdstDev P, int it) {
     const int lane = threadIdx.x, part = threadIdx.y, nparts = blockDim.y, npt = blockDim.x;
     int ist, id, slot;
     EgdstEnvView<MODE> E;
-    if (MODE == 0 && blockIdx.x == 0 && lane == 0 && part == 0) {
-        // "all choices produced empty grids" (egdst_solver.c:704-710), checked where the per-decision lists are final
-        const int sd0 = egdst_sd(P, ivec, blockIdx.y, 0);
-        int any = 0, tot = 0;
-        for (int d_ = 0; d_ < P.cx.nd; d_++) { any |= P.active[sd0 + d_]; tot += P.ptN[sd0 + d_]; }
-        if (any && tot == 0) egdst_fail(P, ivec, EGDST_ERR_ALLINF, it, blockIdx.y, -1);
-    }
+    if (MODE == 0 && blockIdx.x == 0 && lane == 0 && part == 0) egdst_env_check_allinf(P, ivec, it, blockIdx.y);
     if (!egdst_env_job<MODE>(P, ivec, blockIdx.y, ist, id, slot, E)) return;
     egdst_ctx cx; egdst_load_ctx(P, ivec, cx);
     const int Ptot = E.pstart(E.F - 1) + E.npts(E.F - 1);
@@ -193,25 +226,7 @@ __global__ void egdst_k_envA(EgdstDev P, int it) {
         const bool valid = p < Ptot;
         int f = 0, k = 0, rank = 0, best = 0x7fffffff;
         double x = 0, v = 0, bestv = -EGDST_INF;
-        if (valid) {
-            // flattened index -> (f,k)
-            if (MODE == 0) { int s = 0; while (f < E.F - 1 && p >= s + E.npts(f)) { s += E.npts(f); f++; } }
-            else { int lo = 0, hi = E.F - 1; while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (E.pstart(mid) <= p) lo = mid; else hi = mid - 1; } f = lo; }
-            k = p - E.pstart(f);
-            x = E.x(f, k); v = E.v(f, k);
-            // inside its own (increasing) list a point is preceded by exactly k points unless a neighbour shares its abscissa
-            const bool tie = (k > 0 && E.x(f, k - 1) == x) || (k + 1 < E.npts(f) && E.x(f, k + 1) == x);
-            // argmax: highest value, lowest function index among equals (the sweep's "first strictly greater wins");
-            // the point's own function takes part with its own value
-            for (int g = part; g < E.F; g += nparts) {
-                const int ng = E.npts(g);
-                if (ng <= 0) continue;
-                const int cnt = (g == f && !tie) ? k : egdst_env_count_before(E, g, x, v, f, k);
-                rank += cnt;
-                const double val = (g == f) ? v : egdst_env_value(&cx, E, it, ist, g, egdst_env_cur(cnt, ng), x);
-                if (val > bestv || (val == bestv && g < best)) { bestv = val; best = g; }
-            }
-        }
+        if (valid) egdst_env_point_partial<MODE>(cx, E, it, ist, p, part, nparts, f, k, x, v, rank, best, bestv);
         if (nparts > 1) {
             const int slotx = part * npt + lane;
             s_rank[slotx] = rank; s_best[slotx] = best; s_bv[slotx] = bestv;
@@ -224,13 +239,7 @@ __global__ void egdst_k_envA(EgdstDev P, int it) {
                 }
             }
         }
-        if (part == 0 && valid) {
-            if (best == 0x7fffffff) best = f;  // every value -inf (cannot happen: the own value is finite or the maximum)
-            size_t o = (size_t)slot * P.envcap + rank;
-            P.mgX[o] = x; P.mgF[o] = f; P.mgK[o] = k; P.mgA[o] = best;
-            // the active positions of the union are the prefix with x <= grb: its length for the merge kernel
-            if (x <= grb) atomicMax(P.envNact + slot, rank + 1);
-        }
+        if (part == 0 && valid) egdst_env_point_commit(P, slot, grb, f, k, x, rank, best);
         if (nparts > 1 && base + (int)(gridDim.x * npt) < Ptot) __syncthreads();  // scratch reused by the next stride
     }
 }
@@ -407,7 +416,21 @@ __global__ void __launch_bounds__(EGDST_ENVW) egdst_k_envBC(EgdstDev P, int it) 
         gcapacity = P.envcap;
     }
     // the active positions of the union are the prefix with x<=grb (length recorded by egdst_k_envA)
-    const int nact = P.envNact[slot];
+    if (P.envFuse) {
+        // small jobs (a single CTA per job, host: launch_periods): the rank step runs here instead of as a launch of
+        // its own; __syncthreads() orders this CTA's global writes before its reads below
+        if (MODE == 0 && threadIdx.x == 0) egdst_env_check_allinf(P, ivec, it, ist);
+        const int Ptot = E.pstart(E.F - 1) + E.npts(E.F - 1);
+        const double grbA = egdst_env_grb_block(E, s_grb);
+        for (int p = threadIdx.x; p < Ptot; p += blockDim.x) {
+            int f, k, rank, best; double x, v, bestv;
+            egdst_env_point_partial<MODE>(cx, E, it, ist, p, 0, 1, f, k, x, v, rank, best, bestv);
+            egdst_env_point_commit(P, slot, grbA, f, k, x, rank, best);
+        }
+        __threadfence();
+        __syncthreads();
+    }
+    const int nact = EGDST_LDCG(P.envNact + slot);
     const int chunkw = blockDim.x * IPT;
     const int nch = (nact + chunkw - 1) / chunkw;
     const double grb = nch > 0 ? egdst_env_grb_block(E, s_grb) : 0.0;  // nch is CTA-uniform
