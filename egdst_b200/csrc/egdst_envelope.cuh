@@ -389,11 +389,10 @@ EGDST_DEV EgdstEnvPos egdst_env_pos(const EgdstEnvView<MODE> &E, const double *m
 // by ticket until none is left and are chained by a decoupled look-back scan over (grid points, thresholds) emitted
 // so far; the last CTA to finish writes the cell header (MODE 0) or copies the staged result back over the
 // decision's point list (MODE 1).  Small models in batched sweeps run narrow CTAs (P.envW = 64), one per job.
-#ifndef EGDST_ENV_MINB
-#define EGDST_ENV_MINB 4
-#endif
+// register budget: the 8-positions-per-thread instances serve sweeps of small models, where CTAs per SM count (64
+// registers, 4 x 256 threads); the 2-positions instances serve one large model and keep their registers
 template <int MODE, int IPT>
-__global__ void __launch_bounds__(EGDST_ENVW, EGDST_ENV_MINB) egdst_k_envBC(EgdstDev P, int it) {
+__global__ void __launch_bounds__(EGDST_ENVW, IPT == 8 ? 4 : 1) egdst_k_envBC(EgdstDev P, int it) {
     __shared__ long long sh[40];
     __shared__ double s_grb[33];
     __shared__ int s_chunk, s_last, s_qn;

@@ -142,6 +142,9 @@ class EgdstModel:
             lim, npts = [float(x) for x in value[1]], int(value[2])
             if kind != "state" or len(lim) != 2 or npts < 2:
                 raise ValueError("Unrecognized structure for %s variable!" % kind)
+            if not lim[0] < lim[1]:
+                # the reference accepts any pair; its grid search and the interpolation weights assume an increasing grid
+                raise ValueError("Grid limits of a continuous state variable must be increasing!")
             grid = np.linspace(lim[0], lim[1], npts)
             return {"name": name, "type": "continuous", "discrete": False, "continuous": True,
                     "values": [{"value": float(g), "description": "grid point"} for g in grid],

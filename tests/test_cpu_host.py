@@ -121,6 +121,8 @@ def test_continuous_state_spec_motion_rule_and_generated_code():
     assert m.trpr[1]["cases"][0]["prob"] == "0.9*st2+0.1"
     with pytest.raises(ValueError):
         m.d = ("x", [0.0, 1.0], 3)  # only states can be continuous
+    with pytest.raises(ValueError):
+        m.s = ("w", [2.0, 1.0], 4)  # decreasing grid
     hc = examples.humancapital()
     src = codegen.emit_devspec(hc)
     assert "#define EGDST_NCONT 1" in src and "st1grid[5]" in src and "egdst_gridcell(nval,st1grid" in src
