@@ -390,3 +390,15 @@ def test_continuous_state_initial_cells_off_the_first_grid_point():
     # at it = 0 the agent sits exactly on a grid point: the record names its own cell and that cell's policy
     assert np.array_equal(m.sims[:, 0, 5], init[:, 0] - 1)
     assert np.allclose(m.sims[:, 0, 11], np.asarray(m.s[0]["grid"])[(init[:, 0] - 1).astype(int)])
+
+
+def test_random_small_configurations_match_reference():
+    """Differential sweep (tools/random_probe.py): 48 seeded draws of horizon, grid size (20..600), node count (1..12),
+    borrowing limit, mmax and parameters for the retirement and Deaton images -- solve and a 64-agent simulation of
+    each against the compiled reference.  Covers the launch shapes between the fixtures (fused envelope for tiny grids,
+    wide shapes above 200 points) and the table lookups at arbitrary grid densities."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import random_probe
+    assert random_probe.main(100, 48) == 0
