@@ -42,11 +42,20 @@ def main(seed0, count):
         init = np.column_stack([np.full(nsim, float(m.nst)), m.a0 + (m.mmax - m.a0) * (0.02 + 0.6 * rng.random(nsim))])
         rs = rng.random(4 * nsim * m.nt)
         m.sim(init, "own_shocks", randstream=rs)
-        se = sims_errors(m.sims, r.simulate(Mr, Dr, init, rs, 0))
-        ok = e["C"] < 1e-9 and e["V"] < 1e-9 and e["TH"] < 1e-8 and e["Dseq"] and e["rowdiff"] == 0 and se["nan_mismatch"] == 0 and se["discrete_mismatch"] == 0 and se["max"] < 1e-9
+        sr = r.simulate(Mr, Dr, init, rs, 0)
+        se = sims_errors(m.sims, sr)
+        # noise floor of the configuration: the reference against itself, built with contraction allowed (oracle/ref.py
+        # variant "noise").  Consumption next to the borrowing limit makes log(c) amplify last-bit differences of the
+        # math library; such configurations are held to twice what the reference's own two builds differ by.
+        rn = ref.Reference(m, variant="noise"); Mn, Dn = rn.solve()
+        en = solution_errors(Mn, Dn, Mr, Dr)
+        sn = sims_errors(rn.simulate(Mn, Dn, init, rs, 0), sr)
+        tol = lambda k, base: max(base, 2.0 * en[k])  # noqa: E731
+        ok = (e["C"] < tol("C", 1e-9) and e["V"] < tol("V", 1e-9) and e["TH"] < tol("TH", 1e-8) and e["Dseq"] and e["rowdiff"] <= en["rowdiff"]
+              and se["nan_mismatch"] == 0 and se["discrete_mismatch"] <= sn["discrete_mismatch"] and se["max"] < max(1e-9, 2.0 * sn["max"]))
         if not ok:
             bad += 1
-            print(seed, kind, "MISMATCH", {k: v for k, v in e.items() if k != "where"}, se, kw, flush=True)
+            print(seed, kind, "MISMATCH", {k: v for k, v in e.items() if k != "where"}, se, "noise:", {k: v for k, v in en.items() if k != "where"}, sn, kw, flush=True)
     print("checked", count, "bad", bad)
     return bad
 
