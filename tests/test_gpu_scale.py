@@ -404,3 +404,13 @@ def test_random_small_configurations_match_reference():
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
     import random_probe
     assert random_probe.main(100, 48) == 0
+
+
+def test_random_configurations_of_the_multi_state_images_match_reference():
+    """The same differential sweep over occ3 (three decisions, CRRA, decision-dependent shock variance), the lecture
+    model2 (two labour-market states) and humancapital (continuous state): 48 seeded draws of sizes and parameters."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import random_probe
+    assert random_probe.main(200, 48, ("occ3", "model2", "humancapital")) == 0
