@@ -414,3 +414,14 @@ def test_random_configurations_of_the_multi_state_images_match_reference():
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
     import random_probe
     assert random_probe.main(200, 48, ("occ3", "model2", "humancapital")) == 0
+
+
+def test_random_large_grids_match_reference():
+    """Twelve seeded draws of the retirement image at 600..6000 grid points, 4..40 nodes: the wide launch shapes
+    (several compaction and envelope chunks per job, two positions per thread, eight threads per point in the
+    secondary-envelope rank step)."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import random_probe
+    assert random_probe.main(300, 12, ("retirement_large",)) == 0

@@ -16,6 +16,11 @@ def draw(rng, kinds=("retirement", "deaton")):
         kw = dict(T=T, ngridm=n, ngridmax=2 * n + 50, nthrhmax=max(n, 20), ny=ny, interest=float(rng.uniform(0, 0.03)),
                   duw=float(rng.uniform(0.2, 0.8)), wage=float(rng.uniform(0.8, 1.5)), a0=a0, mmax=mmax)
         return kind, kw, examples.retirement(**kw)
+    if kind == "retirement_large":  # wide launch shapes: several compaction / envelope chunks, long node loops
+        n = int(rng.integers(600, 6001))
+        kw = dict(T=int(rng.integers(3, 9)), ngridm=n, ngridmax=2 * n + 50, nthrhmax=n, ny=int(rng.integers(4, 41)), interest=float(rng.uniform(0, 0.02)),
+                  duw=float(rng.uniform(0.2, 0.8)), wage=float(rng.uniform(0.8, 1.5)), a0=a0, mmax=mmax)
+        return kind, kw, examples.retirement(**kw)
     if kind == "occ3":      # three occupations, CRRA utility, decision-dependent shock variance; parameters set after
         m = examples.occ3(ngridm=int(rng.integers(20, 120)), ngridmax=1000, ny=max(ny, 2), T=int(rng.integers(3, 15)))  # the reference itself crashes on larger occ3 grids
         vals = dict(crra=float(rng.uniform(1.1, 2.0)), coefleisure=float(rng.uniform(0.05, 0.4)), wagegap=float(rng.uniform(1.1, 1.6)),
