@@ -425,3 +425,24 @@ def test_random_large_grids_match_reference():
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
     import random_probe
     assert random_probe.main(300, 12, ("retirement_large",)) == 0
+
+
+@pytest.mark.parametrize("nvec,ngridm", [(100, 100), (200, 100), (700, 100), (1600, 100), (200, 500), (640, 500)])
+def test_sweep_sizes_across_launch_shape_switches(nvec, ngridm):
+    """Sweeps on either side of the thresholds at which launch_periods changes shapes (148 and 592 jobs for the seed and
+    envelope kernels, 5920 CTAs for the looping EGM step, 448/512 grid points for the narrow and fused envelope and
+    compaction CTAs): first, middle and last vector of each sweep against the reference."""
+    m = examples.deaton2(ngridm=ngridm, ngridmax=2 * ngridm + 50)
+    m.compile()
+    lib = m._capi()
+    rng = np.random.default_rng(nvec + ngridm)
+    params = np.column_stack([rng.uniform(0.0, 0.05, nvec), rng.uniform(0.75, 1.75, nvec)])
+    sol = lib.solve_batch(m, params)
+    assert sol.warning is None, sol.warning
+    for i in (0, nvec // 2, nvec - 1):
+        assert sol.status(i)[0] == 0, (i, sol.status(i))
+        mi = examples.deaton2(ngridm=ngridm, ngridmax=2 * ngridm + 50, interest=params[i, 0], income=params[i, 1])
+        Mr, Dr = oracle_for(mi).solve()
+        Mb, Db = sol.cells(i)
+        e = solution_errors(Mb, Db, Mr, Dr)
+        assert e["C"] < TOL and e["V"] < TOL and e["Dseq"] and e["rowdiff"] == 0, (i, e)
