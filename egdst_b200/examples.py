@@ -259,11 +259,21 @@ def humancapital(T=12, ngridm=100, ngridmax=1000, ny=8, nz=5, nthrhmax=20, sigma
     return m
 
 
+def retirement_mortal(**kw) -> EgdstModel:
+    """retirement2 with age-dependent mortality: survival enters only the simulator (egdst_simulator.c:261-265: a
+    death event ends the agent's record, the remaining rows stay NaN).  Not shipped by the reference -- none of its
+    examples sets ``survival`` -- it exercises the death path and the NaN bookkeeping of the moment accumulators."""
+    m = retirement(label="retire_mortal", **kw)
+    m.survival = "0.995-0.002*age"
+    return m
+
+
 def humancapital2(**kw) -> EgdstModel:
     return humancapital(health=True, **kw)
 
 
-EXTRA = {"deaton_normal": deaton_normal, "humancapital": humancapital, "humancapital2": humancapital2}
+EXTRA = {"deaton_normal": deaton_normal, "humancapital": humancapital, "humancapital2": humancapital2,
+         "retirement_mortal": retirement_mortal}
 
 ALL = {
     "deaton1": deaton1, "deaton2": deaton2, "retirement1": retirement1, "retirement2": retirement2,

@@ -446,3 +446,40 @@ def test_sweep_sizes_across_launch_shape_switches(nvec, ngridm):
         Mb, Db = sol.cells(i)
         e = solution_errors(Mb, Db, Mr, Dr)
         assert e["C"] < TOL and e["V"] < TOL and e["Dseq"] and e["rowdiff"] == 0, (i, e)
+
+
+def test_mortality_ends_records_and_keeps_the_moment_counts():
+    """survival < 1 (egdst_simulator.c:261-265): a death event ends the agent's record; rows after it stay NaN and drop
+    out of the moment sums and counts (the kernel's "clean tile" fast path must hand over to the NaN-aware one)."""
+    m = _solve(examples.retirement_mortal(T=30, ngridm=300, ngridmax=700, nthrhmax=300, ny=10))
+    orc = oracle_for(m)
+    assert orc.kind == "reference"
+    Mr, Dr = orc.solve()
+    e = solution_errors(m.M, m.D, Mr, Dr)
+    assert e["C"] < TOL and e["V"] < TOL and e["Dseq"], e
+    rng = np.random.default_rng(8)
+    nsim = 4000
+    init = np.column_stack([np.ones(nsim), rng.uniform(-4.0, 8.0, nsim)])
+    rs = rng.random(4 * nsim * m.nt)
+    from tests.goldens import sims_errors
+    for mode, rnd in (("own_shocks", 0), ("same_shocks", 1)):
+        m.sim(init, mode, randstream=rs)
+        se = sims_errors(m.sims, orc.simulate(Mr, Dr, init, rs, rnd))
+        assert se["nan_mismatch"] == 0 and se["discrete_mismatch"] == 0 and se["max"] < TOL, (mode, se)
+    alive = (~np.isnan(m.sims[:, :, 0])).sum(axis=0)
+    assert alive[0] == nsim and alive[-1] < alive[0] and np.all(np.diff(alive) <= 0)
+    if rnd == 1:  # same survival draw for everybody: all agents die in the same period
+        assert set(np.unique(alive)) <= {0, nsim}
+    # counter-based draws: moments from the kernel = sums over the returned paths, NaN rows excluded
+    lib = m._capi()
+    n2 = 50_000
+    init2 = np.column_stack([np.ones(n2), rng.uniform(-4.0, 8.0, n2)])
+    s2, mom = lib.simulate_philox(m, m._solution, init2, 99, want_sims=True, want_moments=True)
+    ok = ~np.isnan(s2)
+    assert np.array_equal(mom[2], ok.sum(axis=0).T.astype(float))
+    assert np.allclose(mom[0], np.where(ok, s2, 0.0).sum(axis=0).T, rtol=1e-11, atol=1e-8)
+    assert np.allclose(mom[1], np.where(ok, s2 * s2, 0.0).sum(axis=0).T, rtol=1e-11, atol=1e-8)
+    dead_share = 1.0 - ok[:, -1, 0].mean()
+    assert 0.2 < dead_share < 0.9
+    _, mom_only = lib.simulate_philox(m, m._solution, init2, 99, want_sims=False, want_moments=True)
+    assert np.allclose(mom_only, mom, rtol=1e-12, atol=1e-9)
