@@ -268,12 +268,44 @@ def retirement_mortal(**kw) -> EgdstModel:
     return m
 
 
+def retirement_jobloss(T=15, ngridm=100, ngridmax=1000, nthrhmax=50, ny=8, interest=0.02, mmax=12.0, a0=0.0, duw=0.4, wage=1.0,
+                       sigma="0.3") -> EgdstModel:
+    """Work/retire model with an employment state whose transition probabilities depend on the realised shock (a low
+    draw costs the job, a high one finds one).  Not shipped by the reference: it takes the branch none of the shipped
+    examples takes -- optim_TRPRnoSH = 0: trpr evaluated per quadrature node and per simulated draw
+    (egdst_solver.c:507-530, egdst_simulator.c:280-290), no per-CTA shock table.  (optim_MUnoD = 0 cannot be reached:
+    compile.m rejects a marginal utility that depends on the decision as "not yet implemented".)"""
+    m = EgdstModel("jobloss")
+    _common(m, T, mmax, ngridmax, ngridm, nthrhmax, ny)
+    m.s = ("Employment", [0, "unemployed", 1, "employed"])
+    m.trpr = ("true", [["1-0.5*(shock>1.0)", "0.5*(shock>1.0)"], ["0.3*(shock<0.7)", "1-0.3*(shock<0.7)"]])
+    m.feasible = ("defaultfeasible", True)
+    m.d = ("Labour supply", [0, "retire", 1, "work"])
+    m.choiceset = ("defaultallow", True)
+    m.u = ("utility", "log(consumption)+duw*(id==0)")
+    m.param = ("duw", "utility of leisure", duw)
+    m.u = ("marginal", "1/consumption")
+    m.u = ("marginalinverse", "1/mutility")
+    m.u = ("extrap", "log(x)")
+    m.budget = ("cashinhand", "savings*(1+interest)+wage_income*(id!=0)")
+    m.budget = ("marginal", "1+interest")
+    m.discount = "1/(1+interest)"
+    m.param = ("interest", "return on savings", interest)
+    m.eq = ("wage_income", "Realized wage income", "wage*shock*(0.4+0.6*st1)", "next")
+    m.param = ("wage", "wage (times multiplicator shock)", wage)
+    m.a0 = a0
+    m.shock = "lognormal"
+    m.shock = ("sigma", sigma)
+    m.shock = ("mu", "-0.5*sigma*sigma")
+    return m
+
+
 def humancapital2(**kw) -> EgdstModel:
     return humancapital(health=True, **kw)
 
 
 EXTRA = {"deaton_normal": deaton_normal, "humancapital": humancapital, "humancapital2": humancapital2,
-         "retirement_mortal": retirement_mortal}
+         "retirement_mortal": retirement_mortal, "retirement_jobloss": retirement_jobloss}
 
 ALL = {
     "deaton1": deaton1, "deaton2": deaton2, "retirement1": retirement1, "retirement2": retirement2,

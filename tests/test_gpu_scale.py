@@ -483,3 +483,26 @@ def test_mortality_ends_records_and_keeps_the_moment_counts():
     assert 0.2 < dead_share < 0.9
     _, mom_only = lib.simulate_philox(m, m._solution, init2, 99, want_sims=False, want_moments=True)
     assert np.allclose(mom_only, mom, rtol=1e-12, atol=1e-9)
+
+
+def test_shock_dependent_transitions_match_reference():
+    """optim_TRPRnoSH = 0 (no shipped example): the employment state's transition probabilities depend on the realised
+    shock, so trpr is evaluated per quadrature node in the solver (no per-CTA shock table) and per candidate state with
+    the drawn shock in the simulator (egdst_solver.c:507-530, egdst_simulator.c:280-290)."""
+    m = _solve(examples.retirement_jobloss(T=20, ngridm=400, ngridmax=1000, nthrhmax=100, ny=12))
+    assert m.optim["optim_TRPRnoSH"] is False
+    orc = oracle_for(m)
+    assert orc.kind == "reference"
+    Mr, Dr = orc.solve()
+    e = solution_errors(m.M, m.D, Mr, Dr)
+    assert e["C"] < TOL and e["V"] < TOL and e["TH"] < 1e-8 and e["Dseq"] and e["rowdiff"] == 0, e
+    rng = np.random.default_rng(21)
+    nsim = 3000
+    init = np.column_stack([rng.integers(1, 3, nsim).astype(float), rng.uniform(0.2, 8.0, nsim)])
+    rs = rng.random(4 * nsim * m.nt)
+    m.sim(init, "own_shocks", randstream=rs)
+    from tests.goldens import sims_errors
+    se = sims_errors(m.sims, orc.simulate(Mr, Dr, init, rs, 0))
+    assert se["nan_mismatch"] == 0 and se["discrete_mismatch"] == 0 and se["max"] < TOL, se
+    ist = m.sims[:, :, 5]
+    assert set(np.unique(ist)) == {0.0, 1.0} and 0.05 < (ist[:, -1] == 0).mean() < 0.95  # both employment states are visited
