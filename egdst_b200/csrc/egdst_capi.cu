@@ -233,6 +233,7 @@ static int create_solution(const egdst_desc *d, int nvec, egdst_solution **out) 
     DA(P.outX, (size_t)s->nsd * P.envcap); DA(P.outC, (size_t)s->nsd * P.envcap); DA(P.outV, (size_t)s->nsd * P.envcap);
     // lookup tables (egdst_tables.cuh): capacity 2*ngridm+64 intervals per cell, about two buckets per grid row
     P.tabcap = P.rowcap - 1 < 2 * P.N + 64 ? P.rowcap - 1 : 2 * P.N + 64;
+    if (getenv("EGDST_TABCAP")) { const int c = atoi(getenv("EGDST_TABCAP")); if (c >= 1 && c < P.tabcap) P.tabcap = c; }  // test hook: cells with more rows take the table-free path
     {
         const double span = 2.0 * (d->mmax - d->a0) + 2.0;
         const double octaves = log2(span > 2.0 ? span : 2.0);

@@ -70,3 +70,25 @@ def test_emulated_envelope_with_a_single_striding_cta(monkeypatch):
     Mr, Dr = oracle_for(m).solve()
     e = solution_errors(sol.M, sol.D, Mr, Dr)
     assert e["C"] < 1e-9 and e["V"] < 1e-9 and e["TH"] < 1e-8 and e["Dseq"] and e["rowdiff"] == 0, e
+
+
+def test_emulated_table_free_path_for_oversized_cells(monkeypatch):
+    """EGDST_TABCAP: cells with more rows than the table capacity keep the plain columns and the reference's bisection
+    in the EGM step and in the simulator (normally reached only when ngridmax far above 2*ngridm is actually used)."""
+    monkeypatch.setenv("EGDST_TABCAP", "12")
+    m = examples.retirement2(T=5, ngridm=40, ngridmax=200, ny=3)
+    if not ref_available(m):
+        pytest.skip("oracle/_ref not built and /root/reference absent")
+    lib = _emulated(m)
+    sol = lib.solve(m)
+    assert sol.status()[0] == 0, sol.status()
+    orc = oracle_for(m)
+    Mr, Dr = orc.solve()
+    e = solution_errors(sol.M, sol.D, Mr, Dr)
+    assert e["C"] < 1e-9 and e["V"] < 1e-9 and e["TH"] < 1e-8 and e["Dseq"] and e["rowdiff"] == 0, e
+    rng = np.random.default_rng(5)
+    nsim = 64
+    init = np.column_stack([np.ones(nsim), m.a0 + (m.mmax - m.a0) * (0.05 + 0.5 * rng.random(nsim))])
+    rs = rng.random(4 * nsim * m.nt)
+    se = goldens.sims_errors(lib.simulate(m, sol, init, rs, 0), orc.simulate(Mr, Dr, init, rs, 0))
+    assert se["nan_mismatch"] == 0 and se["discrete_mismatch"] == 0 and se["max"] < 1e-9, se

@@ -506,3 +506,22 @@ def test_shock_dependent_transitions_match_reference():
     assert se["nan_mismatch"] == 0 and se["discrete_mismatch"] == 0 and se["max"] < TOL, se
     ist = m.sims[:, :, 5]
     assert set(np.unique(ist)) == {0.0, 1.0} and 0.05 < (ist[:, -1] == 0).mean() < 0.95  # both employment states are visited
+
+
+def test_table_free_path_for_oversized_cells(monkeypatch):
+    """EGDST_TABCAP (test hook): every cell exceeds the lookup-table capacity, so the EGM step, the seed and the simulator
+    bisect the plain columns as the reference does (egdst_lib.c:138-165)."""
+    monkeypatch.setenv("EGDST_TABCAP", "16")
+    m = _solve(examples.retirement2(T=12, ngridm=700, ngridmax=1500, nthrhmax=700, ny=8, interest=0.02))
+    orc = oracle_for(m)
+    Mr, Dr = orc.solve()
+    e = solution_errors(m.M, m.D, Mr, Dr)
+    assert e["C"] < TOL and e["V"] < TOL and e["TH"] < 1e-8 and e["Dseq"] and e["rowdiff"] == 0, e
+    rng = np.random.default_rng(6)
+    nsim = 1000
+    init = np.column_stack([np.ones(nsim), m.a0 + (m.mmax - m.a0) * (0.05 + 0.5 * rng.random(nsim))])
+    rs = rng.random(4 * nsim * m.nt)
+    m.sim(init, "own_shocks", randstream=rs)
+    from tests.goldens import sims_errors
+    se = sims_errors(m.sims, orc.simulate(Mr, Dr, init, rs, 0))
+    assert se["nan_mismatch"] == 0 and se["discrete_mismatch"] == 0 and se["max"] < TOL, se
