@@ -562,7 +562,7 @@ def main():
     ap.add_argument("--nsim", type=int, default=int(os.environ.get("EGDST_BENCH_NSIM", 10_000_000)), help="agents per GPU")
     ap.add_argument("--e2e-nsim", type=int, default=1_000_000)
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--cpu-nsim", type=int, default=200_000)
+    ap.add_argument("--cpu-nsim", type=int, default=700_000, help="agents of the CPU baseline sample (about 11 s of the reference simulator on one core)")
     ap.add_argument("--ref-nsim", type=int, default=400_000)
     ap.add_argument("--workload", default="s1s2", choices=["s1s2", "batch"], help="s1s2: BASELINE config[3] (default); batch: config[4] sweep")
     ap.add_argument("--batch-nvec", type=int, default=4096)
