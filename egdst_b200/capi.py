@@ -156,7 +156,7 @@ class ModelLibrary:
                "egdst_profile_enable", "egdst_profile_read", "egdst_solve", "egdst_solve_batch", "egdst_resolve", "egdst_solution_sizes",
                "egdst_solution_export", "egdst_solution_status", "egdst_solution_nvec", "egdst_solution_units",
                "egdst_free_solution", "egdst_solution_import", "egdst_simulate", "egdst_simulate_philox",
-               "egdst_simulate_device", "egdst_sim_moments", "egdst_sim_moments_device", "egdst_call"]
+               "egdst_simulate_device", "egdst_sim_moments", "egdst_sim_moments_device", "egdst_call", "egdst_shutdown"]
 
     def __init__(self, path: str):
         if not os.path.isfile(path):
@@ -184,6 +184,7 @@ class ModelLibrary:
         L.egdst_solution_units.restype = C.c_longlong
         L.egdst_free_solution.argtypes = [vp]
         L.egdst_free_solution.restype = None
+        L.egdst_shutdown.restype = None
         L.egdst_solution_import.argtypes = [C.POINTER(EgdstDesc), _ip, _ip, _dp, _dp, C.POINTER(vp)]
         L.egdst_simulate.argtypes = [C.POINTER(EgdstDesc), vp, C.c_int, _dp, C.c_int, _dp, C.c_longlong, C.c_int, _dp]
         L.egdst_simulate_philox.argtypes = [C.POINTER(EgdstDesc), vp, C.c_int, _dp, C.c_int, C.c_longlong, C.c_ulonglong, _dp, _dp]
@@ -347,8 +348,15 @@ class ModelLibrary:
         a = np.atleast_2d(np.asarray(args, dtype=np.float64))
         narg, k = a.shape
         af = _arr(a.ravel(order="F"))
-        res = np.empty(narg, dtype=np.float64)
+        res = np.full(narg, np.nan, dtype=np.float64)
         rc = self.L.egdst_call(C.byref(d.c), sol.handle, sw, _ptr(af), narg, k, _ptr(res))
         if rc == 2:
             self._raise(rc)
+        if rc == 1:  # the reference warns ("Wrong number of arguments") and returns the NaN vector
+            import warnings
+            warnings.warn(self.last_error(), EgdstWarning)
         return res
+
+    def shutdown(self):
+        """Release the library's cached solution object and this thread's simulation workspace."""
+        self.L.egdst_shutdown()

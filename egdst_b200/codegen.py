@@ -356,8 +356,13 @@ def emit_devspec(model) -> str:
           "#define EGDST_NREQ %d" % len(model.eq), "#define EGDST_NPARAM %d" % len(model.param),
           "#define EGDST_DISTRIB %d" % (1 if model.shock["type"] == "lognormal" else 2),
           "#define EGDST_SHOCK_INDEP_A %d" % (1 if shock_independent_of_savings(model) else 0),
-          "#define EGDST_NCONT %d" % len(cont),
-          '#include "egdst_modelctx.h"', ""]
+          "#define EGDST_NCONT %d" % len(cont)]
+    # the optim_* switches are functions of the exec strings (compile.m:669-747), hence constants of the image: the
+    # kernels specialise on them at compile time and the host checks the descriptor against them
+    opt = infer_optim(model)
+    L += ["#define EGDST_OPT_%s %d" % (k[len("optim_"):].upper(), 1 if opt[k] else 0)
+          for k in ("optim_UasD", "optim_MUnoD", "optim_UnoD", "optim_TRPRnoSH")]
+    L += ['#include "egdst_modelctx.h"', ""]
     if cont:
         # grids of the continuous states (the reference loads them from model.s(i).grid at run time, compile.m:239-247;
         # here they are part of the compiled image: re-defining the state variable re-generates it)
@@ -438,8 +443,12 @@ def emit_devspec(model) -> str:
     for tr in model.trpr:
         v = tr["varindex"] - 1
         nv = len(model.s[v]["values"])
-        body.append("varindex =(curr->ist/(int)cx->stm[cx->nnst+%d])%%(int)cx->stm[%d];" % (v, v))
-        body.append("varindex1=(next->ist/(int)cx->stm[cx->nnst+%d])%%(int)cx->stm[%d];" % (v, v))
+        if ns == 1:  # a single state variable: its index is the state index (stride 1, size nst)
+            body.append("varindex =curr->ist;")
+            body.append("varindex1=next->ist;")
+        else:
+            body.append("varindex =(curr->ist/(int)cx->stm[cx->nnst+%d])%%(int)cx->stm[%d];" % (v, v))
+            body.append("varindex1=(next->ist/(int)cx->stm[cx->nnst+%d])%%(int)cx->stm[%d];" % (v, v))
         first = True
         for case in tr["cases"]:
             body.append(("if (%s) {" if first else "else if (%s) {") % cv(case["condition"]))

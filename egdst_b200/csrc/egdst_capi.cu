@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -33,8 +34,8 @@ static thread_local cudaStream_t g_stream = 0;
 // ---- launch counter and optional per-kernel-class event timing (bench.py's roofline leg) --------------
 enum { KC_SETUP = 0, KC_TERMINAL, KC_SEED, KC_EGM, KC_COMPACT, KC_ENV2, KC_ENV, KC_TAB, KC_SIM, KC_OTHER, KC_COUNT };
 static const char *const g_kc_names[KC_COUNT] = {"setup", "terminal", "seed", "egm", "compact", "envelope2", "envelope", "tables", "simulate", "other"};
-static long long g_launches = 0;
-static bool g_prof_on = false;
+static std::atomic<long long> g_launches{0};
+static bool g_prof_on = false;  // profiling is a single-threaded measurement aid (egdst_profile_enable)
 struct ProfRec { int cls; cudaEvent_t a, b; };
 static std::vector<ProfRec> g_prof_pending;
 static double g_prof_ms[KC_COUNT];
@@ -125,6 +126,7 @@ struct egdst_solution {
     EgdstCellHdr *d_hdr; std::vector<EgdstCellHdr> h_hdr; int hdr_ivec;  // simulator cell headers (kernel argument), -1 = stale
     double *d_momscratch; size_t momscratch_cap;  // per-CTA moment slices of the wide simulator variant
     int dims[12];   // shape signature for re-use
+    double dkey[2]; // mmax, a0: the geometry of the lookup tables (mbits, lutcap) is derived from them at creation
 };
 
 template <class T>
@@ -161,11 +163,23 @@ __global__ void egdst_k_quadrature(const double *qraw, double *q, int ny) {
 // period's call; later periods get this from egdst_k_tab of the period before (egdst_tables.cuh)
 __global__ void egdst_k_cells(EgdstDev P, int it) { egdst_cells_body(P, blockIdx.x, it); }
 
-static int fill_ctx(const egdst_desc *d, egdst_ctx *cx) {
+// the descriptor must describe the model this image was generated from: sizes of the generated structures and the
+// optim_* switches, which are functions of the exec strings (compile.m:669-747) and compiled into the kernels
+static int check_image(const egdst_desc *d) {
     if (!d) return fail(2, "null descriptor");
     if (d->abi_version != EGDST_ABI_VERSION) return fail(2, "egdst_desc.abi_version mismatch");
     if (d->nparam != EGDST_NPARAM) return fail(2, "number of parameters does not match the compiled model image");
     if (d->nnst > EGDST_NNST || d->nnd > EGDST_NND) return fail(2, "state/decision vector size does not match the compiled model image");
+    if ((d->optim_UasD != 0) != (EGDST_OPT_UASD != 0) || (d->optim_MUnoD != 0) != (EGDST_OPT_MUNOD != 0) ||
+        (d->optim_UnoD != 0) != (EGDST_OPT_UNOD != 0) || (d->optim_TRPRnoSH != 0) != (EGDST_OPT_TRPRNOSH != 0))
+        return fail(2, "optim_* switches of the descriptor do not match the compiled model image");
+    if (EGDST_NPARAM > 0 && !d->params) return fail(2, "parameter values missing");
+    return 0;
+}
+
+static int fill_ctx(const egdst_desc *d, egdst_ctx *cx) {
+    const int rci = check_image(d);
+    if (rci) return rci;
     if (d->ngridm < 2 || d->ngridmax <= d->ngridm || d->T < d->t0 || d->nst < 1 || d->nd < 1 || d->ny < 1 || d->nthrhmax < 2)
         return fail(2, "invalid model dimensions");
     memset(cx, 0, sizeof(*cx));
@@ -195,10 +209,15 @@ static int create_solution(const egdst_desc *d, int nvec, egdst_solution **out) 
     const int dims[12] = {d->device, nvec, d->T - d->t0 + 1, d->nst, d->nd, d->ngridm, d->ngridmax, d->nthrhmax, d->ny, d->nnst, d->nnd, 0};
     {
         std::lock_guard<std::mutex> lk(g_cache_mu);
-        if (g_cached && memcmp(g_cached->dims, dims, sizeof(dims)) == 0) {
+        if (g_cached && memcmp(g_cached->dims, dims, sizeof(dims)) == 0 && g_cached->dkey[0] == d->mmax && g_cached->dkey[1] == d->a0) {
             egdst_solution *s = g_cached;
             g_cached = 0;
+            // nothing of the previous owner survives: sizes, status, parameter values, simulator headers
             s->sizes_valid = false; s->hdr_ivec = -1; s->neq = d->neq;
+            s->h_params.clear();
+            std::fill(s->h_status.begin(), s->h_status.end(), 0);
+            std::fill(s->h_mlen.begin(), s->h_mlen.end(), 0);
+            std::fill(s->h_thlen.begin(), s->h_thlen.end(), 0);
             const double *stm = s->d_stm, *states = s->d_states, *decisions = s->d_decisions;
             s->P.cx = cx; s->P.cx.stm = stm; s->P.cx.states = states; s->P.cx.decisions = decisions;
             s->P.bparams = 0;
@@ -208,7 +227,7 @@ static int create_solution(const egdst_desc *d, int nvec, egdst_solution **out) 
         }
     }
     egdst_solution *s = new egdst_solution();
-    s->bytes = 0; memcpy(s->dims, dims, sizeof(dims));
+    s->bytes = 0; memcpy(s->dims, dims, sizeof(dims)); s->dkey[0] = d->mmax; s->dkey[1] = d->a0;
     s->d_momscratch = 0; s->momscratch_cap = 0; s->d_hdr = 0; s->hdr_ivec = -1;
     s->g_exec = 0; s->g_seen = false; s->g_stream = 0; s->g_nlaunch = 0;
     s->device = d->device; s->sizes_valid = false; s->d_pack = 0; s->pack_cap = 0; s->neq = d->neq;
@@ -238,17 +257,19 @@ static int create_solution(const egdst_desc *d, int nvec, egdst_solution **out) 
         const double span = 2.0 * (d->mmax - d->a0) + 2.0;
         const double octaves = log2(span > 2.0 ? span : 2.0);
         int mbits = 3;
-        static const double density = getenv("EGDST_LUT_DENSITY") ? atof(getenv("EGDST_LUT_DENSITY")) : 2.0;  // buckets per grid row
+        // buckets per grid row: an index entry resolves up to three rows of a bucket by itself, so about one bucket
+        // per row keeps the index small (the simulator wants every period's tables L2-resident next to its output stream)
+        static const double density = getenv("EGDST_LUT_DENSITY") ? atof(getenv("EGDST_LUT_DENSITY")) : 1.0;
         while (mbits < 16 && (double)(1 << mbits) * octaves < density * (double)(P.N + 1)) mbits++;
         P.mbits = mbits;
         P.lutcap = (int)(octaves * (double)(1 << mbits)) + 2;
     }
     {   // one allocation for both tables: a single L2 access-policy window can then keep them resident (sim_launch)
         const size_t lutbytes = ((sizeof(EgdstLutEntry) * (size_t)s->ncell * (P.lutcap + 1) + 255) / 256) * 256;
-        const size_t ivlbytes = sizeof(EgdstInterval) * (size_t)s->ncell * P.tabcap;
+        const size_t ivlbytes = sizeof(EgdstRow) * (size_t)s->ncell * (P.tabcap + 1);
         unsigned char *base = 0;
         DA(base, lutbytes + ivlbytes);
-        P.tabLut = (EgdstLutEntry *)base; P.tabIvl = (EgdstInterval *)(base + lutbytes);
+        P.tabLut = (EgdstLutEntry *)base; P.tabRow = (EgdstRow *)(base + lutbytes);
         s->tab_base = base; s->tab_bytes = lutbytes + ivlbytes;
     }
     P.cmpW = (P.N <= 64 * EGDST_CMP_IPT) ? 64 : EGDST_CMP_THREADS;
@@ -483,7 +504,7 @@ int egdst_model_nparam(void) { return EGDST_NPARAM; }
 int egdst_model_neq(void) { return EGDST_NREQ; }
 const char *egdst_last_error(void) { return g_err.c_str(); }
 void egdst_set_stream(void *cuda_stream) { g_stream = (cudaStream_t)cuda_stream; }
-long long egdst_launch_count(void) { return g_launches; }
+long long egdst_launch_count(void) { return g_launches.load(); }
 int egdst_profile_classes(void) { return KC_COUNT; }
 const char *egdst_profile_class_name(int cls) { return (cls >= 0 && cls < KC_COUNT) ? g_kc_names[cls] : ""; }
 void egdst_profile_enable(int on) {
@@ -588,6 +609,9 @@ void egdst_free_solution(egdst_solution *s) {
 }
 
 
+// tables of imported cells: the table part of egdst_k_tab only (no period housekeeping)
+__global__ void egdst_k_tabonly(EgdstDev P, int it) { egdst_tab_cell(P, egdst_cell(P, blockIdx.z, it, blockIdx.y), blockIdx.x, gridDim.x); }
+
 int egdst_solution_import(const egdst_desc *d, const int *mlen, const int *thlen, const double *Mbuf, const double *Dbuf, egdst_solution **out) {
     if (!out || !mlen || !thlen || !Mbuf || !Dbuf) return fail(2, "invalid arguments");
     *out = 0;
@@ -597,6 +621,7 @@ int egdst_solution_import(const egdst_desc *d, const int *mlen, const int *thlen
     std::vector<int> moff(s->ncell + 1, 0), toff(s->ncell + 1, 0);
     for (int c = 0; c < s->ncell; c++) {
         if (mlen[c] > s->P.rowcap || thlen[c] > d->nthrhmax) { egdst_free_solution(s); return fail(2, "imported cell exceeds ngridmax/nthrhmax"); }
+        if (mlen[c] < 0 || mlen[c] == 1 || thlen[c] < 0 || (mlen[c] == 0) != (thlen[c] == 0)) { egdst_free_solution(s); return fail(2, "imported cell has an invalid number of rows"); }
         moff[c + 1] = moff[c] + mlen[c]; toff[c + 1] = toff[c] + thlen[c];
     }
     const size_t nm = (size_t)4 * moff[s->ncell], nd2 = (size_t)2 * toff[s->ncell];
@@ -607,29 +632,37 @@ int egdst_solution_import(const egdst_desc *d, const int *mlen, const int *thlen
         if (cudaMalloc((void **)&s->d_pack, sizeof(double) * (nm + nd2 + 1)) != cudaSuccess) { egdst_free_solution(s); return fail(2, "cudaMalloc failed"); }
         s->pack_cap = nm + nd2;
     }
-    cudaMemcpyAsync(s->d_pack, Mbuf, sizeof(double) * nm, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(s->d_pack + nm, Dbuf, sizeof(double) * nd2, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(s->P.mlen, mlen, sizeof(int) * s->ncell, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(s->P.thlen, thlen, sizeof(int) * s->ncell, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(s->d_moff, moff.data(), sizeof(int) * (s->ncell + 1), cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(s->d_toff, toff.data(), sizeof(int) * (s->ncell + 1), cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(s->d_stm, d->stm, sizeof(double) * 2 * d->nnst, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(s->d_states, d->states, sizeof(double) * d->nst * d->nnst, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(s->d_decisions, d->decisions, sizeof(double) * d->nd * d->nnd, cudaMemcpyHostToDevice, st);
-    cudaMemsetAsync(s->P.status, 0, sizeof(int) * 4, st);
-    KLAUNCH(KC_OTHER, egdst_k_unpack, dim3(s->ncell), dim3(EGDST_BLOCK), 0, st, s->P, s->d_moff, s->d_toff, s->d_pack, s->d_pack + nm, s->ncell);
-    {
-        int tb = (s->P.lutcap + 1 + EGDST_BLOCK - 1) / EGDST_BLOCK;
-        for (int it = 0; it < s->P.NT; it++) KLAUNCH(KC_TAB, egdst_k_tab, dim3(tb, d->nst, 1), dim3(EGDST_BLOCK), 0, st, s->P, it);
+    cudaError_t ce = cudaSuccess;
+#define EGDST_TRY(call) do { if (ce == cudaSuccess) ce = (call); } while (0)
+    EGDST_TRY(cudaMemcpyAsync(s->d_pack, Mbuf, sizeof(double) * nm, cudaMemcpyHostToDevice, st));
+    EGDST_TRY(cudaMemcpyAsync(s->d_pack + nm, Dbuf, sizeof(double) * nd2, cudaMemcpyHostToDevice, st));
+    EGDST_TRY(cudaMemcpyAsync(s->P.mlen, mlen, sizeof(int) * s->ncell, cudaMemcpyHostToDevice, st));
+    EGDST_TRY(cudaMemcpyAsync(s->P.thlen, thlen, sizeof(int) * s->ncell, cudaMemcpyHostToDevice, st));
+    EGDST_TRY(cudaMemcpyAsync(s->d_moff, moff.data(), sizeof(int) * (s->ncell + 1), cudaMemcpyHostToDevice, st));
+    EGDST_TRY(cudaMemcpyAsync(s->d_toff, toff.data(), sizeof(int) * (s->ncell + 1), cudaMemcpyHostToDevice, st));
+    EGDST_TRY(cudaMemcpyAsync(s->d_stm, d->stm, sizeof(double) * 2 * d->nnst, cudaMemcpyHostToDevice, st));
+    EGDST_TRY(cudaMemcpyAsync(s->d_states, d->states, sizeof(double) * d->nst * d->nnst, cudaMemcpyHostToDevice, st));
+    EGDST_TRY(cudaMemcpyAsync(s->d_decisions, d->decisions, sizeof(double) * d->nd * d->nnd, cudaMemcpyHostToDevice, st));
+    EGDST_TRY(cudaMemsetAsync(s->P.status, 0, sizeof(int) * 4, st));
+    if (ce == cudaSuccess) {
+        KLAUNCH(KC_OTHER, egdst_k_unpack, dim3(s->ncell), dim3(EGDST_BLOCK), 0, st, s->P, s->d_moff, s->d_toff, s->d_pack, s->d_pack + nm, s->ncell);
+        const int tb = (s->P.lutcap + 1 + EGDST_BLOCK - 1) / EGDST_BLOCK;
+        for (int it = 0; it < s->P.NT; it++) KLAUNCH(KC_TAB, egdst_k_tabonly, dim3(tb, d->nst, 1), dim3(EGDST_BLOCK), 0, st, s->P, it);
+        EGDST_TRY(cudaGetLastError());
     }
-    if (cudaStreamSynchronize(st) != cudaSuccess) { egdst_free_solution(s); return fail(2, "import failed"); }
+    EGDST_TRY(cudaStreamSynchronize(st));
+#undef EGDST_TRY
+    if (ce != cudaSuccess) { egdst_free_solution(s); return fail(2, std::string("CUDA error in import: ") + cudaGetErrorString(ce)); }
     memcpy(s->h_mlen.data(), mlen, sizeof(int) * s->ncell);
     memcpy(s->h_thlen.data(), thlen, sizeof(int) * s->ncell);
+    std::fill(s->h_status.begin(), s->h_status.end(), 0);
+    s->h_params.assign(d->params, d->params + EGDST_NPARAM);  // the imported model's own parameter values
+    s->P.bparams = 0;
     s->sizes_valid = true;
     *out = s;
     return 0;
 }
 
-#include "egdst_capi_sim.inc"
-
 }  // extern "C"
+
+#include "egdst_capi_sim.inc"

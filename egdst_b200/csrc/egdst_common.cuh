@@ -33,8 +33,10 @@
 // raw-point flags written by the seed/EGM kernels
 enum { EGDST_PT_OK = 0, EGDST_PT_C1NEG = 1, EGDST_PT_EVFINF = 2, EGDST_PT_CHECKSUM = 3, EGDST_PT_NONFINITE = 4, EGDST_PT_NONE = 5 };
 
-struct EgdstLutEntry { int l, cnt; double m; };
-struct EgdstInterval { double g0, g1, c0, c1, v0, v1; };
+// lookup tables of a solution cell (egdst_tables.cuh): 32-byte index entries, 64-byte interval records
+struct EgdstLutEntry { int l, cnt; double m0, m1, m2; };                 // first row of the bucket, rows in it, their abscissas (+inf: none)
+struct EgdstRow { double m, c, v, y; };                                   // row i of (M, C, V); y = RN(1/(M[i+1]-M[i])), 0 when not safely invertible / last row
+struct EgdstInterval { double g0, g1, c0, c1, v0, v1, y, pad; };        // rows i, i+1 as the interpolations use them (two consecutive EgdstRow)
 
 // Everything a kernel needs.  Leading dimension of every array is the parameter-vector index `ivec`
 // (batched solves; nvec=1 for a single model).
@@ -75,7 +77,7 @@ struct EgdstDev {
     int *foldList, *foldCnt;            // [nsd*(gcap+1)] unordered fold positions, [nsd]
     int *envNact;                       // [nslot] active prefix length of the merged union (egdst_k_envA)
     // per-cell lookup tables (egdst_tables.cuh)
-    EgdstInterval *tabIvl;              // [ncell*tabcap]
+    EgdstRow *tabRow;                   // [ncell*(tabcap+1)]
     EgdstLutEntry *tabLut;              // [ncell*(lutcap+1)]
     int tabcap, lutcap, mbits;
 };

@@ -133,12 +133,35 @@ EGDST_DEV double egdst_cdfni(double p) {
            (((((K[6] * r + K[7]) * r + K[8]) * r + K[9]) * r + K[10]) * r + 1);
 }
 
+// The simulator's quantile: the same rational functions with fused Horner steps.  The solver transforms its ny
+// quadrature abscissas with the separately rounded form above (bit-compatible with the reference build); the
+// simulator evaluates one quantile per agent-period, where the contraction changes the shock in its last bits
+// (far inside the 1e-9 of the parity protocol) and no discrete branch depends on those bits except at exact ties.
+EGDST_DEV double egdst_cdfni_fused(double p) {
+    const double *K = EGDST_CDFNI_K;
+    if (p < 0 || p > 1) return 0.0;
+    if (p == 0) return -EGDST_INF;
+    if (p == 1) return EGDST_INF;
+    if (p < 0.02425 || p > 0.97575) {
+        const bool upper = p > 0.97575;
+        const double q = sqrt(-2 * log(upper ? 1 - p : p));
+        const double num = fma(fma(fma(fma(fma(K[11], q, K[12]), q, K[13]), q, K[14]), q, K[15]), q, K[16]);
+        const double den = fma(fma(fma(fma(K[17], q, K[18]), q, K[19]), q, K[20]), q, 1.0);
+        const double v = num / den;
+        return upper ? -v : v;
+    }
+    const double q = p - 0.5, r = q * q;
+    const double num = fma(fma(fma(fma(fma(K[0], r, K[1]), r, K[2]), r, K[3]), r, K[4]), r, K[5]) * q;
+    const double den = fma(fma(fma(fma(fma(K[6], r, K[7]), r, K[8]), r, K[9]), r, K[10]), r, 1.0);
+    return num / den;
+}
+
 // shock distribution helpers (egdst_lib.c:66-101); DISTRIB 1 = lognormal, 2 = normal
 EGDST_DEV double egdst_cdfinv(double p, double mu, double sigma) {
 #if EGDST_DISTRIB == 1
-    return exp(sigma * egdst_cdfni(p) + mu);
+    return exp(sigma * egdst_cdfni_fused(p) + mu);
 #else
-    return sigma * egdst_cdfni(p) + mu;
+    return sigma * egdst_cdfni_fused(p) + mu;
 #endif
 }
 EGDST_DEV double egdst_expectation(const egdst_ctx *cx, const PeriodVars *curr, const PeriodVars *next) {

@@ -5,12 +5,17 @@
 //                            sampling over trpr, shock = cdfinv(u) or expectation, budget, equations)
 //   policy()      :145-199   c = linter(cash; M,C), id by threshold scan, vf exact below M(a0) else linter
 //   simsoutput()  :122-143   the nsimout output columns
-// One thread per agent, all agents of a CTA in the same period (the period's policy table is shared
-// through L1/L2).  The [nsimout, nt, nsim] output is written through a per-warp shared-memory tile so
-// that each store instruction covers contiguous runs of an agent's record (the per-thread pattern of
-// the reference has stride nsimout*nt).  Uniforms come either from the reference's randstream layout
-// (parity mode) or from counter-based Philox4x32-10 keyed by (seed; global agent id, period).
-// Continuous states (egdst_simulator.c:310-373) are outside the hot-path scope.
+//   continuous states :310-373 (multilinear mix over the 2^k surrounding grid cells; compiled in when EGDST_NCONT > 0)
+// A warp walks a tile of 32 agents through all periods (persistent grid of one resident wave).  The
+// [nsimout, nt, nsim] output is written through a per-warp shared-memory tile so that each store instruction
+// covers contiguous runs of an agent's record (the per-thread pattern of the reference has stride nsimout*nt).
+// Uniforms come either from the reference's randstream layout (parity mode) or from counter-based
+// Philox4x32-10 keyed by (seed; global agent id, period).
+//
+// The kernel is bound by instruction issue and gather latency before it is bound by the output stream, so
+// everything the launch knows in advance is a template parameter (source of uniforms, which outputs exist, where
+// the moment accumulators and the per-cell headers live) and everything the model image knows in advance is a
+// macro of the generated header (EGDST_OPT_TRPRNOSH ...): the period loop carries no run-time mode switches.
 #pragma once
 
 #include "egdst_tables.cuh"
@@ -24,6 +29,7 @@
 #ifndef EGDST_SIM_MINBLOCKS
 #define EGDST_SIM_MINBLOCKS 4
 #endif
+// CTA width of the two-periods-per-write variant: the unpadded 2*NSO-double rows of 16 warps fill two CTAs per SM
 #ifdef EGDST_HOSTEMU
 #define EGDST_SIM_WIDE 128
 #else
@@ -35,11 +41,7 @@
 #ifdef EGDST_HOSTEMU
 #define EGDST_STREAM_STORE2(ptr, v) (*reinterpret_cast<double2 *>(ptr) = (v))
 #else
-#ifdef EGDST_SIM_EXP_PLAINST
-#define EGDST_STREAM_STORE2(ptr, v) (*reinterpret_cast<double2 *>(ptr) = (v))
-#else
 #define EGDST_STREAM_STORE2(ptr, v) __stcs(reinterpret_cast<double2 *>(ptr), (v))
-#endif
 #endif
 
 // Philox4x32-10 (Salmon et al. 2011); counter = (c0,c1,c2,c3), key = (k0,k1)
@@ -85,55 +87,54 @@ __global__ void egdst_k_simhdr(EgdstDev P, int ivec, EgdstCellHdr *out) {
     out[c] = h;
 }
 
-// TMA descriptor of the caller's sims array viewed as a 2-D tensor [nsim rows][nt*nsimout doubles], row pitch
-// nt*nsimout*8 bytes; box = 32 agents x nsimout doubles (one tile-period)
-#ifdef EGDST_HOSTEMU
-struct EgdstTensorMap { unsigned long long opaque[16]; };
-#else
-#include <cuda.h>
-typedef CUtensorMap EgdstTensorMap;
-#endif
-
 struct EgdstSimArgs {
     const double *init;        // [nsim] 1-based ist0 of the agents of this launch
     const double *init_m0;     // [nsim] m0 (the second column of the reference's init matrix)
     int nsim;
     int ivec;
-    const double *randstream;  // reference layout, or null => Philox
+    const double *randstream;  // reference layout (template PHILOX = false)
     int rndtype;               // 1 = same shocks for all agents
     long long agent0;
     unsigned long long seed;
-    double *sims;              // [nsimout, nt, nsim] or null
-    double *moments;           // [3, nsimout, nt] or null
+    double *sims;              // [nsimout, nt, nsim]   (template OUT & 1)
+    double *moments;           // [3, nsimout, nt]      (template OUT & 2)
     int nsimout;
-    int mom_smem;              // 1: per-CTA moment accumulators for all periods live in shared memory
-    double *momscratch;        // or: per-CTA slices [nt*nsimout*3 doubles + nt ints] of a zeroed global scratch
-    int hdr_smem;              // 1: the per-cell headers of the vector are in the kernel argument H
-    int has_param;             // 1: parameter values travel in `param` (constant bank) instead of the device array
-    double param[EGDST_NPARAM_];
+    int mom_smem;              // 1: per-CTA moment accumulators for all periods live in shared memory (flushed at the end)
+    double *momscratch;        // or: per-CTA slices [nt*nsimout*3 doubles + nt ints] of a zeroed global scratch (egdst_k_momreduce)
+    double param[EGDST_NPARAM_];  // parameter values of the vector (template HDR: single-vector launches)
 };
 
+// One cell's policy at `cash` (egdst_simulator.c:145-199): interval record and M[1]; false if the cell holds no solution.
+EGDST_DEV bool egdst_sim_interval(const EgdstDev &P, int cell, int nm, double cash, unsigned long long l2keep, EgdstInterval &iv) {
+    if (nm < 2) return false;
+    if (egdst_cell_has_tab(P, nm)) {
+        egdst_lookup_tab<true>(P, cell, egdst_cell_rows(P, cell), cash, nm, iv, l2keep);
+    } else {  // oversized cell: plain columns
+        const double *Mg = egdst_colM(P, cell), *Cg = egdst_colC(P, cell), *Vg = egdst_colV(P, cell);
+        const int i = egdst_bracket(cash, Mg, nm, 0);
+        iv.g0 = Mg[i]; iv.g1 = Mg[i + 1]; iv.c0 = Cg[i]; iv.c1 = Cg[i + 1]; iv.v0 = Vg[i]; iv.v1 = Vg[i + 1]; iv.y = 0.0;
+    }
+    return true;
+}
+// One division for the weights of both interpolations (the reference divides four times, egdst_lib.c:175): the
+// reciprocal comes with the record.  The exactly rounded quotients of the solver (egdst_div_by) are not needed here:
+// the difference is in the last bit and no discrete branch of the simulator depends on it.
+EGDST_DEV void egdst_sim_weights(const EgdstInterval &iv, double cash, double &wl, double &wr) {
+    const double rw = iv.y != 0.0 ? iv.y : 1.0 / (iv.g1 - iv.g0);
+    wl = (cash - iv.g0) * rw; wr = (iv.g1 - cash) * rw;
+}
+
 #if EGDST_NCONT > 0
-// Policy of ONE cell of the solution at `cash` (egdst_simulator.c:145-199): consumption, discrete decision and value.
-// Used by the continuous-state branch, which mixes the policies of the 2^NCONT grid cells around the agent's exact
-// continuous state; the all-discrete path below keeps its own inlined copy with the kernel-argument headers.
+// Policy of ONE cell of the solution at `cash`: consumption, discrete decision and value.  Used by the
+// continuous-state branch, which mixes the policies of the 2^NCONT grid cells around the agent's exact state.
 EGDST_DEV bool egdst_sim_policy_cell(const EgdstDev &P, const egdst_ctx &cx, int cell, PeriodVars &pv, unsigned long long l2keep,
                                      double &c, double &vf) {
     const int nm = P.mlen[cell];
-    if (nm < 2) return false;
     EgdstInterval iv;
-    double M1;
-    if (egdst_cell_has_tab(P, nm)) {
-        const EgdstInterval *ivl = egdst_cell_ivl(P, cell);
-        egdst_lookup_tab<true>(P, cell, ivl, pv.cash, nm, iv, l2keep);
-        M1 = ivl[0].g1;
-    } else {
-        const int i = egdst_bracket(pv.cash, egdst_colM(P, cell), nm, 0);
-        const double *Mg = egdst_colM(P, cell), *Cg = egdst_colC(P, cell), *Vg = egdst_colV(P, cell);
-        iv.g0 = Mg[i]; iv.g1 = Mg[i + 1]; iv.c0 = Cg[i]; iv.c1 = Cg[i + 1]; iv.v0 = Vg[i]; iv.v1 = Vg[i + 1];
-        M1 = Mg[1];
-    }
-    const double rw = 1.0 / (iv.g1 - iv.g0), wl = (pv.cash - iv.g0) * rw, wr = (iv.g1 - pv.cash) * rw;
+    if (!egdst_sim_interval(P, cell, nm, pv.cash, l2keep, iv)) return false;
+    const double M1 = egdst_colM(P, cell)[1];
+    double wl, wr;
+    egdst_sim_weights(iv, pv.cash, wl, wr);
     c = iv.c1 * wl + iv.c0 * wr;
     const int nth = P.thlen[cell];
     const double *th = P.thTH + (size_t)cell * cx.nthrhmax, *dd = P.thD + (size_t)cell * cx.nthrhmax;
@@ -149,24 +150,32 @@ EGDST_DEV bool egdst_sim_policy_cell(const EgdstDev &P, const egdst_ctx &cx, int
 #endif
 
 // Dynamic shared memory layout of egdst_k_simulate:
-//   tile[warps][32*TS]                one staged record per agent of the warp's tile (TS = nso|1, odd)
-//   mom[nt][nso][3]   (mom_smem)      per-CTA moment accumulators, flushed once at the end
-// Kernel variants (chosen on the host, sim_launch):
-//   <1, 256, 4, false, false>  one period per write, padded (odd-stride) tile, 4 CTAs/SM, moments in shared memory
-//   <1, 256, 4, false, true>  same, but lane 0 hands the whole tile to the TMA engine as one 2-D tensor store
-//                       (cp.async.bulk.tensor shared -> global, evict-first): no read-back of the tile, no per-piece stores
-//   <2, 512, 2, true>   two periods per write (whole 32-byte sectors in DRAM), 16 warps per CTA, 2 CTAs/SM: the
-//                       unpadded 2*NSO-double rows of 16 warps fill the CTA's shared memory exactly, so rows are
-//                       column-rotated by (lane/4)%4 instead of padded and moments accumulate in a per-CTA global
-//                       scratch with fire-and-forget reductions (summed by egdst_k_momreduce)
-template <int PB, int BLOCK, int MINB, bool SWZ, bool TMAST>
-__global__ void __launch_bounds__(BLOCK, MINB) egdst_k_simulate(EgdstDev P, EgdstSimArgs S, const EGDST_GRID_CONSTANT EgdstSimHdrs H, const EGDST_GRID_CONSTANT EgdstTensorMap TM) {
+//   tile[warps][32*TS]                PB staged records per agent of the warp's tile
+//   mom[nt][nso][3] + clean[nt]       (mom_smem) per-CTA moment accumulators, flushed once at the end
+// Template parameters:
+//   PHILOX  uniforms from Philox4x32-10 (else: the caller's randstream, egdst_simulator.c:259-261)
+//   OUT     bit 0: write the sims array; bit 1: accumulate moments
+//   HDR     single-vector launch whose per-cell headers and parameter values travel in the kernel arguments
+//   PB      periods per write of the sims array:
+//     1  one record (8*nso bytes) per agent and store pass; rows padded to an odd stride (conflict-free staging and
+//        column walks), 8 warps per CTA, 4 CTAs/SM, moments in shared memory
+//     2  two consecutive periods of an agent are staged side by side and written together (nt even): the output
+//        stream is 1.5e5 concurrent per-agent runs, and DRAM takes runs of 16*nso bytes much better than runs of 8*nso
+//        (tools/micro/wpat.cu).  The unpadded 2*nso-double rows of 16 warps fill two CTAs per SM exactly, so rows are
+//        column-rotated by (lane/4)%4 instead of padded, and moments accumulate in a per-CTA slice of a global scratch
+//        with fire-and-forget reductions (summed by egdst_k_momreduce)
+template <bool PHILOX, int OUT, bool HDR, int PB>
+__global__ void __launch_bounds__(PB == 2 ? EGDST_SIM_WIDE : EGDST_SIM_BLOCK, PB == 2 ? 2 : EGDST_SIM_MINBLOCKS)
+egdst_k_simulate(EgdstDev P, EgdstSimArgs S, const EGDST_GRID_CONSTANT EgdstSimHdrs H) {
     EGDST_DYN_SMEM(double, egdst_sim_smem);
     constexpr int NSO = EGDST_NSIMOUT_MAX;   // the model image fixes nsimout (checked on the host)
     constexpr int W = PB * NSO;              // doubles per staged row (one agent)
-    constexpr int TS = (SWZ || TMAST) ? W : (W | 1);  // padded rows have an odd stride: conflict-free staging and column walks;
-                                                      // TMAST: plain contiguous 16-byte aligned rows, the source of a TMA bulk store
-    constexpr int WPB = BLOCK / 32;
+    constexpr bool SWZ = PB == 2;
+    constexpr int TS = SWZ ? W : (W | 1);
+    constexpr int WPB = (PB == 2 ? EGDST_SIM_WIDE : EGDST_SIM_BLOCK) / 32;
+    constexpr bool SIMS = (OUT & 1) != 0, MOM = (OUT & 2) != 0;
+    // position of column j in the row of the agent staged by lane l: rotated rows spread a column over the banks
+#define EGDST_TILE_POS(l, j) ((l) * TS + (SWZ ? (((j) + (((l) >> 2) & 3) >= W) ? (j) + (((l) >> 2) & 3) - W : (j) + (((l) >> 2) & 3)) : (j)))
     // blockIdx.y walks the parameter vectors of a batched sweep: same agents and shocks under every vector,
     // per-vector output blocks (sims [nvec][nsimout,nt,nsim], moments [nvec][3,nsimout,nt])
     const int ivec = S.ivec + blockIdx.y;
@@ -175,37 +184,35 @@ __global__ void __launch_bounds__(BLOCK, MINB) egdst_k_simulate(EgdstDev P, Egds
 #if EGDST_NCONT > 0
     cx.byval = 1;  // model functions read the exact continuous state from curr->st (egdst_simulator.c:91-92)
 #endif
-    if (S.has_param) {
+    if (HDR) {
 #pragma unroll
         for (int i = 0; i < EGDST_NPARAM; i++) cx.param[i] = S.param[i];
     }
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int nt = P.NT;
-    // position of column j in the row of the agent staged by lane l: rotated rows spread a column over the banks
-#define EGDST_TILE_POS(l, j) ((l) * TS + (SWZ ? (((j) + (((l) >> 2) & 3) >= W) ? (j) + (((l) >> 2) & 3) - W : (j) + (((l) >> 2) & 3)) : (j)))
-    if (S.sims) S.sims += (size_t)blockIdx.y * EGDST_NSIMOUT_MAX * nt * S.nsim;
-    if (S.moments) S.moments += (size_t)blockIdx.y * EGDST_NSIMOUT_MAX * nt * 3;
+    double *sims = SIMS ? S.sims + (size_t)blockIdx.y * NSO * nt * S.nsim : (double *)0;
+    double *gmom = MOM ? S.moments + (size_t)blockIdx.y * NSO * nt * 3 : (double *)0;
     double *tile = egdst_sim_smem + (size_t)w * 32 * TS;
-    // moment accumulators of this CTA: shared memory (mom_smem) or its slice of the global scratch (momscratch)
-    double *mom = S.momscratch ? S.momscratch + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * ((size_t)nt * NSO * 3 + nt)
-                               : egdst_sim_smem + (size_t)WPB * 32 * TS;
-    int *clean_s = reinterpret_cast<int *>(mom + (size_t)nt * NSO * 3);  // [nt] clean tiles per period
+    double *smom = egdst_sim_smem + (size_t)WPB * 32 * TS;                    // [nt][NSO][3] when mom_smem
+    int *clean_s = reinterpret_cast<int *>(smom + (size_t)nt * NSO * 3);      // [nt] clean tiles per period
+    const bool momsm = MOM && PB == 1 && S.mom_smem;
+    // PB == 2: this CTA's slice of the global scratch
+    double *gslice = (MOM && PB == 2) ? S.momscratch + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * ((size_t)nt * NSO * 3 + nt) : (double *)0;
+    int *clean_g = reinterpret_cast<int *>(gslice + (size_t)nt * NSO * 3);
     const double NaN = EGDST_NAN;
     const int ntiles = (S.nsim + 31) / 32;
 #ifndef EGDST_HOSTEMU
     const unsigned long long l2keep = egdst_policy_evict_last();
-    unsigned long long l2first = 0ULL;
-    if (TMAST) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(l2first));
 #else
     const unsigned long long l2keep = 0ULL;
 #endif
-    const EgdstCellHdr *hdr = H.h;
     if (H.tabs_ok) { cx.stm = H.stm; cx.states = H.states; cx.decisions = H.decisions; }
-    if (S.moments && S.mom_smem && !S.momscratch) {
-        for (int i = threadIdx.x; i < nt * NSO * 3; i += blockDim.x) mom[i] = 0.0;
+    if (momsm) {
+        for (int i = threadIdx.x; i < nt * NSO * 3; i += blockDim.x) smom[i] = 0.0;
         for (int i = threadIdx.x; i < nt; i += blockDim.x) clean_s[i] = 0;
         __syncthreads();
     }
+    const size_t rowpitch = (size_t)nt * NSO;  // doubles between the records of consecutive agents
     // persistent: every warp strides over tiles of 32 agents and walks each tile through all periods
     for (int tileidx = blockIdx.x * WPB + w; tileidx < ntiles; tileidx += gridDim.x * WPB) {
         const int isim = tileidx * 32 + lane;
@@ -228,20 +235,28 @@ __global__ void __launch_bounds__(BLOCK, MINB) egdst_k_simulate(EgdstDev P, Egds
         // state, so their integer pipeline work overlaps the table-gather latency of the current period
         unsigned pr0 = 0, pr1 = 0, pr2 = 0, pr3 = 0;
         const unsigned long long gid = (unsigned long long)(S.agent0 + isim);
-        if (!S.randstream && nt > 1)
+        if (PHILOX && nt > 1)
             egdst_philox4x32((unsigned)gid, (unsigned)(gid >> 32), 1u, 0u, (unsigned)S.seed, (unsigned)(S.seed >> 32), pr0, pr1, pr2, pr3);
+        const double *rs = PHILOX ? (const double *)0 : S.randstream + (S.rndtype == 1 ? 0 : (size_t)4 * nt * isim);
+        // cooperative write of the tile: lane = (agent sub-index, 16-byte piece); running pointer over the periods
+        constexpr bool VEC = (W & 1) == 0 && W <= 32;
+        constexpr int SL = W / 2 <= 8 ? 8 : 16, APT = 32 / SL;
+        const int wk = lane % SL, wa0 = lane / SL;
+        const int na = S.nsim - tileidx * 32 < 32 ? S.nsim - tileidx * 32 : 32;
+        const bool vecok = VEC && (((size_t)sims & 15) == 0);
+        double *wdst = SIMS ? sims + (size_t)tileidx * 32 * rowpitch + (vecok ? (size_t)wa0 * rowpitch + 2 * wk : 0) : (double *)0;
         for (int it = 0; it < nt; it++) {
             const unsigned cr0 = pr0, cr1 = pr1, cr2 = pr2;
-            if (!S.randstream && it > 0 && it + 1 < nt)
+            if (PHILOX && it > 0 && it + 1 < nt)
                 egdst_philox4x32((unsigned)gid, (unsigned)(gid >> 32), (unsigned)(it + 1), 0u, (unsigned)S.seed, (unsigned)(S.seed >> 32), pr0, pr1, pr2, pr3);
             if (state == 0 && it > 0) {
                 PeriodVars nx = cur;
                 nx.it = it;
                 nx.savings = cur.savings;
                 double rrr, rrr1, rrr2;
-                if (S.randstream) {
-                    const double *rs = S.randstream + (S.rndtype == 1 ? 0 : (size_t)4 * nt * isim) + (size_t)3 * (it - 1);
-                    rrr = rs[0]; rrr1 = rs[1]; rrr2 = rs[2];
+                if (!PHILOX) {
+                    const double *r3 = rs + (size_t)3 * (it - 1);
+                    rrr = r3[0]; rrr1 = r3[1]; rrr2 = r3[2];
                 } else {
                     rrr = egdst_u01(cr0); rrr1 = egdst_u01(cr1); rrr2 = egdst_u01(cr2);
                 }
@@ -270,12 +285,13 @@ __global__ void __launch_bounds__(BLOCK, MINB) egdst_k_simulate(EgdstDev P, Egds
                         if (!feasible(&cx, &nx)) continue;
                         lastfeas = ist1;
                         double pr;
-                        if (cx.optim_TRPRnoSH == 1) pr = trpr(&cx, &cur, &nx, 0);
-                        else {
-                            mu = mu_param(&cx, &cur, &nx); sigma = sigma_param(&cx, &cur, &nx);
-                            nx.shock = (sigma <= 0) ? egdst_expectation(&cx, &cur, &nx) : egdst_cdfinv(rrr1, mu, sigma);
-                            pr = trpr(&cx, &cur, &nx, 0);
-                        }
+#if EGDST_OPT_TRPRNOSH
+                        pr = trpr(&cx, &cur, &nx, 0);
+#else
+                        mu = mu_param(&cx, &cur, &nx); sigma = sigma_param(&cx, &cur, &nx);
+                        nx.shock = (sigma <= 0) ? egdst_expectation(&cx, &cur, &nx) : egdst_cdfinv(rrr1, mu, sigma);
+                        pr = trpr(&cx, &cur, &nx, 0);
+#endif
                         rrr -= pr;
                         if (rrr <= 0) { chosen = ist1; break; }
                     }
@@ -285,10 +301,11 @@ __global__ void __launch_bounds__(BLOCK, MINB) egdst_k_simulate(EgdstDev P, Egds
 #if EGDST_NCONT > 0
                     trpr_cont(&cx, &cur, &nx);
 #endif
-                    if (cx.optim_TRPRnoSH == 1) {  // shocks for the shock-independent case (egdst_simulator.c:292-298)
-                        mu = mu_param(&cx, &cur, &nx); sigma = sigma_param(&cx, &cur, &nx);
-                        nx.shock = (sigma <= 0) ? egdst_expectation(&cx, &cur, &nx) : egdst_cdfinv(rrr1, mu, sigma);
-                    }
+#if EGDST_OPT_TRPRNOSH
+                    // shocks for the shock-independent case (egdst_simulator.c:292-298)
+                    mu = mu_param(&cx, &cur, &nx); sigma = sigma_param(&cx, &cur, &nx);
+                    nx.shock = (sigma <= 0) ? egdst_expectation(&cx, &cur, &nx) : egdst_cdfinv(rrr1, mu, sigma);
+#endif
                     nx.cash = cashinhand(&cx, &cur, &nx);
                     eqs_sim(&cx, &cur, &nx, eqs);
                     cur = nx;
@@ -359,30 +376,17 @@ __global__ void __launch_bounds__(BLOCK, MINB) egdst_k_simulate(EgdstDev P, Egds
             if (state == 0) {
                 // policy (egdst_simulator.c:145-199)
                 const int cell = egdst_cell(P, ivec, it, cur.ist);
-                const EgdstCellHdr *hc = hdr + it * cx.nst + cur.ist;
-                const int nm = S.hdr_smem ? hc->n : P.mlen[cell];
-                if (nm < 2) { state = 1; }
+                const EgdstCellHdr *hc = H.h + it * cx.nst + cur.ist;
+                const int nm = HDR ? hc->n : P.mlen[cell];
+                EgdstInterval iv;
+                if (!egdst_sim_interval(P, cell, nm, cur.cash, l2keep, iv)) { state = 1; }
                 else {
-                    EgdstInterval iv;
-                    double M1;
-                    if (egdst_cell_has_tab(P, nm)) {
-                        const EgdstInterval *ivl = egdst_cell_ivl(P, cell);
-                        egdst_lookup_tab<true>(P, cell, ivl, cur.cash, nm, iv, l2keep);
-                        M1 = S.hdr_smem ? hc->M1 : ivl[0].g1;
-                    } else {  // oversized cell: plain columns
-                        const int i = egdst_bracket(cur.cash, egdst_colM(P, cell), nm, 0);
-                        const double *Mg = egdst_colM(P, cell), *Cg = egdst_colC(P, cell), *Vg = egdst_colV(P, cell);
-                        iv.g0 = Mg[i]; iv.g1 = Mg[i + 1]; iv.c0 = Cg[i]; iv.c1 = Cg[i + 1]; iv.v0 = Vg[i]; iv.v1 = Vg[i + 1];
-                        M1 = Mg[1];
-                    }
-                    // one division for the weights of both interpolations (the reference divides four times, egdst_lib.c:175).
-                    // The exactly rounded shared-reciprocal form of the solver (egdst_div_by) costs 7 % of this kernel; here the
-                    // difference is in the last bit and no discrete branch of the simulator depends on it.
-                    const double rw = 1.0 / (iv.g1 - iv.g0), wl = (cur.cash - iv.g0) * rw, wr = (iv.g1 - cur.cash) * rw;
+                    double wl, wr;
+                    egdst_sim_weights(iv, cur.cash, wl, wr);
                     c = iv.c1 * wl + iv.c0 * wr;
                     cur.savings = cur.cash - c;
-                    const int nth = S.hdr_smem ? hc->nth : P.thlen[cell];
-                    if (S.hdr_smem && nth <= EGDST_SIM_TH8) {
+                    const int nth = HDR ? hc->nth : P.thlen[cell];
+                    if (HDR && nth <= EGDST_SIM_TH8) {
                         int ith = 0;
                         while (ith < nth && cur.cash >= hc->th[ith]) ith++;
                         cur.id = (int)hc->dd[ith > 0 ? ith - 1 : 0];
@@ -393,26 +397,17 @@ __global__ void __launch_bounds__(BLOCK, MINB) egdst_k_simulate(EgdstDev P, Egds
                         cur.id = (int)dd[ith > 0 ? ith - 1 : 0];
                     }
                     egdst_fill_decision(&cx, &cur);
-                    const double evf = S.hdr_smem ? hc->evf : P.evf[cell];  // == V(row 0)
+                    const double evf = HDR ? hc->evf : P.evf[cell];  // == V(row 0)
+                    const double M1 = HDR ? hc->M1 : egdst_colM(P, cell)[1];
                     uu = utility(&cx, &cur, c); bb = discount(&cx, &cur);  // output columns 9, 10; shared with the exact value below
                     if (cur.cash < M1 && evf > -EGDST_INF) vf = uu + bb * evf;
                     else vf = iv.v1 * wl + iv.v0 * wr;
                 }
             }
 #endif
-            // stage the record of this period
-            // two consecutive periods of an agent are staged side by side (PB = 2 when nt is even): their 2*NSO doubles
-            // are written together, so every 32-byte DRAM sector of the sims array is written whole -- one period alone
-            // (112 B at S2) ends in a half sector, and half-sector write-backs halve the achieved write bandwidth
-            // (tools/micro/wpat.cu: 2.5 TB/s for 112-byte chunks, 4.2 TB/s for 224-byte chunks)
+            // stage the record of this period (PB == 2: odd periods go to the second half of the agent's row)
             const int half = (PB == 2) ? (it & 1) : 0;
             const int hoff = half * NSO;
-#ifndef EGDST_HOSTEMU
-            if (TMAST && half == 0) {  // the TMA engine must be done reading the tile before it is overwritten
-                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                __syncwarp();
-            }
-#endif
 #define EGDST_REC(j) tile[EGDST_TILE_POS(lane, hoff + (j))]
             if (state == 0) {
                 EGDST_REC(0) = cur.cash; EGDST_REC(1) = c; EGDST_REC(2) = cur.savings; EGDST_REC(3) = vf; EGDST_REC(4) = (double)cur.id; EGDST_REC(5) = (double)cur.ist;
@@ -428,70 +423,44 @@ __global__ void __launch_bounds__(BLOCK, MINB) egdst_k_simulate(EgdstDev P, Egds
                 for (int j = 0; j < NSO; j++) EGDST_REC(j) = NaN;
             }
 #undef EGDST_REC
-            const bool clean = __all_sync(EGDST_FULL, state == 0) && it > 0;  // no NaN record in the tile
+            const bool clean = MOM && __all_sync(EGDST_FULL, state == 0) && it > 0;  // no NaN record in the tile
             __syncwarp();
-            if (S.sims && (PB == 1 || half == 1)) {
-                // cooperative write of the tile: PB records per agent, PB*NSO contiguous doubles each
-                const int na = S.nsim - tileidx * 32 < 32 ? S.nsim - tileidx * 32 : 32;
-                const int it0 = it - (PB - 1);
-#ifdef EGDST_SIM_EXP_WRAP
-                double *dst = S.sims + (((size_t)tileidx * 32 * nt + it0) * NSO) % ((size_t)4 << 20);  // experiment: stay inside 32 MB
-#else
-                double *dst = S.sims + ((size_t)tileidx * 32 * nt + it0) * NSO;
-#endif
-                if (TMAST) {
-#ifndef EGDST_HOSTEMU
-                    // ONE tensor store per tile: the TMA engine scatters the 32 staged rows (W doubles each) to their
-                    // slots of the sims array (row pitch nt*NSO doubles), clipping rows beyond nsim; evict-first
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // rows were written through the generic proxy
-                    __syncwarp();
-                    if (lane == 0) {
-                        const unsigned saddr = (unsigned)__cvta_generic_to_shared(tile);
-                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%1, %2}], [%3], %4;"
-                                     :: "l"(reinterpret_cast<unsigned long long>(&TM)), "r"(it0 * NSO), "r"(tileidx * 32), "r"(saddr), "l"(l2first) : "memory");
-                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                    }
-#else
-                    for (int e = lane; e < na * W; e += 32) { const int a = e / W, j = e - a * W; dst[(size_t)a * nt * NSO + j] = tile[a * TS + j]; }
-#endif
-                } else if ((W & 1) == 0 && W <= 32 && (((size_t)S.sims & 15) == 0)) {
-                    // 16-byte pieces, SL slots per agent (W/2 used): agent = (32/SL)*t + lane/SL, piece = lane%SL
-                    constexpr int SL = W / 2 <= 8 ? 8 : 16, APT = 32 / SL;
-                    const int k = lane % SL, a0 = lane / SL;
-                    if (k < W / 2) {
-                        double *d = dst + (size_t)a0 * nt * NSO + 2 * k;
-                        const size_t dstride = (size_t)APT * nt * NSO;
+            if (SIMS && (PB == 1 || half == 1)) {
+                if (vecok) {
+                    // 16-byte pieces, SL slots per agent (W/2 used): agent = APT*t + lane/SL, piece = lane%SL
+                    if (wk < W / 2) {
                         if (na == 32) {
 #pragma unroll
                             for (int t = 0; t < 32 / APT; t++) {
-                                const int a = APT * t + a0;
-                                EGDST_STREAM_STORE2(d + t * dstride, make_double2(tile[EGDST_TILE_POS(a, 2 * k)], tile[EGDST_TILE_POS(a, 2 * k + 1)]));
+                                const int a = APT * t + wa0;
+                                EGDST_STREAM_STORE2(wdst + (size_t)t * APT * rowpitch, make_double2(tile[EGDST_TILE_POS(a, 2 * wk)], tile[EGDST_TILE_POS(a, 2 * wk + 1)]));
                             }
                         } else {
-                            for (int t = 0; APT * t + a0 < na; t++) {
-                                const int a = APT * t + a0;
-                                EGDST_STREAM_STORE2(d + t * dstride, make_double2(tile[EGDST_TILE_POS(a, 2 * k)], tile[EGDST_TILE_POS(a, 2 * k + 1)]));
+                            for (int t = 0; APT * t + wa0 < na; t++) {
+                                const int a = APT * t + wa0;
+                                EGDST_STREAM_STORE2(wdst + (size_t)t * APT * rowpitch, make_double2(tile[EGDST_TILE_POS(a, 2 * wk)], tile[EGDST_TILE_POS(a, 2 * wk + 1)]));
                             }
                         }
                     }
                 } else {
                     for (int e = lane; e < na * W; e += 32) {
                         const int a = e / W, j = e - a * W;
-                        dst[(size_t)a * nt * NSO + j] = tile[EGDST_TILE_POS(a, j)];
+                        wdst[(size_t)a * rowpitch + j] = tile[EGDST_TILE_POS(a, j)];
                     }
                 }
+                wdst += W;
             }
-            if (S.moments) {
+            if (MOM) {
                 // column sums over the tile: lanes split the NSO columns (two half-tiles when 2*NSO <= 32)
                 constexpr int HV = (2 * NSO <= 32) ? 2 : 1;
                 double s1 = 0, s2 = 0, n = 0;
                 if (lane < HV * NSO) {
                     const int j = lane % NSO, h = lane / NSO;
-                    const int a_lo = h * (32 / HV), cj = half * NSO + j;
+                    const int a_lo = h * (32 / HV), cj = hoff + j;
                     if (clean) {
                         // every agent of the tile is alive: sum without NaN tests (warp-uniform branch); a column that
                         // holds a NaN after all (user equations) shows up as a NaN sum and is redone below
-#pragma unroll 8
+#pragma unroll
                         for (int a = 0; a < 32 / HV; a++) { const double x = tile[EGDST_TILE_POS(a_lo + a, cj)]; s1 += x; s2 = fma(x, x, s2); }
                         n = 32 / HV;
                     }
@@ -507,26 +476,35 @@ __global__ void __launch_bounds__(BLOCK, MINB) egdst_k_simulate(EgdstDev P, Egds
                 }
                 // a clean tile adds 32 to the count of every column: one integer atomic per tile instead of NSO
                 // floating-point ones (clean_s[it], folded into the counts at the final flush)
-                const bool cntint = (S.mom_smem || S.momscratch) && clean && __all_sync(EGDST_FULL, lane >= NSO || n == 32.0);
-                if (cntint && lane == 0) atomicAdd(clean_s + it, 1);
-                if (lane < NSO && n > 0) {
-                    double *dstm = (S.mom_smem || S.momscratch) ? mom + ((size_t)it * NSO + lane) * 3 : S.moments + ((size_t)it * NSO + lane) * 3;
-                    atomicAdd(dstm + 0, s1); atomicAdd(dstm + 1, s2);
-                    if (!cntint) atomicAdd(dstm + 2, n);
+                const bool cntint = (momsm || PB == 2) && clean && __all_sync(EGDST_FULL, lane >= NSO || n == 32.0);
+                if (momsm) {
+                    if (cntint && lane == 0) atomicAdd(clean_s + it, 1);
+                    if (lane < NSO && n > 0) {
+                        double *d = smom + ((size_t)it * NSO + lane) * 3;
+                        atomicAdd(d + 0, s1); atomicAdd(d + 1, s2);
+                        if (!cntint) atomicAdd(d + 2, n);
+                    }
+                } else if (PB == 2) {
+                    if (cntint && lane == 0) atomicAdd(clean_g + it, 1);
+                    if (lane < NSO && n > 0) {
+                        double *d = gslice + ((size_t)it * NSO + lane) * 3;
+                        atomicAdd(d + 0, s1); atomicAdd(d + 1, s2);
+                        if (!cntint) atomicAdd(d + 2, n);
+                    }
+                } else if (lane < NSO && n > 0) {
+                    double *d = gmom + ((size_t)it * NSO + lane) * 3;
+                    atomicAdd(d + 0, s1); atomicAdd(d + 1, s2); atomicAdd(d + 2, n);
                 }
             }
             __syncwarp();
         }
     }
-#ifndef EGDST_HOSTEMU
-    if (TMAST && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-#endif
-    if (S.moments && S.mom_smem && !S.momscratch) {
+    if (momsm) {
         __syncthreads();
         for (int i = threadIdx.x; i < nt * NSO * 3; i += blockDim.x) {
-            double v = mom[i];
+            double v = smom[i];
             if (i % 3 == 2) v += 32.0 * clean_s[i / (3 * NSO)];
-            if (v != 0.0) atomicAdd(S.moments + i, v);
+            if (v != 0.0) atomicAdd(gmom + i, v);
         }
     }
 }

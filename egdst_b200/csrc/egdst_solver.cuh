@@ -23,7 +23,7 @@ struct EgdstNext {
     int n1, nth;              // n1 = egdims (rows excluding the a0 row)
     double evf;
     int cell;
-    const EgdstInterval *ivl; // lookup tables of the cell (egdst_tables.cuh)
+    const EgdstRow *ivl;      // row table of the cell (egdst_tables.cuh)
     double M1, Mlast, Clast;  // M[1], M[n1], C[n1]
 };
 
@@ -39,7 +39,7 @@ EGDST_DEV EgdstNext egdst_next_tables(const EgdstDev &P, int ivec, int it1, int 
     t.nth = P.thlen[cell];
     t.evf = P.evf[cell];
     t.cell = cell;
-    t.ivl = egdst_cell_ivl(P, cell);
+    t.ivl = egdst_cell_rows(P, cell);
     t.M1 = t.M[1]; t.Mlast = t.M[t.n1]; t.Clast = t.C[t.n1];
     return t;
 }
@@ -126,12 +126,15 @@ EGDST_DEV void egdst_eval_nodes(const egdst_ctx *cx, const EgdstDev &P, int ivec
             EgdstInterval iv;
             int i;
             if (tab) i = egdst_lookup_tab(P, t.cell, t.ivl, next.cash, t.n1 + 1, iv);
-            else { i = egdst_bracket(next.cash, t.M, t.n1 + 1, 0); iv.g0 = t.M[i]; iv.g1 = t.M[i + 1]; iv.c0 = t.C[i]; iv.c1 = t.C[i + 1]; iv.v0 = t.V[i]; iv.v1 = t.V[i + 1]; }
+            else {
+                i = egdst_bracket(next.cash, t.M, t.n1 + 1, 0); iv.g0 = t.M[i]; iv.g1 = t.M[i + 1]; iv.c0 = t.C[i]; iv.c1 = t.C[i + 1]; iv.v0 = t.V[i]; iv.v1 = t.V[i + 1];
+                iv.y = egdst_div_safe(iv.g1 - iv.g0) ? 1.0 / (iv.g1 - iv.g0) : 0.0;
+            }
             // the reference's quotients are kept bit for bit (two divisions per interpolation, egdst_lib.c:175): next to its
             // instability boundary a plain reciprocal-multiply variant drifted 1e-2 away in C, so the
             // shared-reciprocal form below is the exactly rounded one (egdst_div_by)
             double w = iv.g1 - iv.g0;
-            double y = egdst_div_safe(w) ? 1.0 / w : 0.0;  // shared correctly rounded reciprocal (0: degenerate interval)
+            double y = iv.y;  // shared correctly rounded reciprocal RN(1/w), from the record (0: degenerate interval, plain divisions)
             double c1 = y != 0.0 ? egdst_lerp_y(next.cash, iv.g0, iv.g1, iv.c0, iv.c1, w, y) : egdst_lerp(next.cash, iv.g0, iv.g1, iv.c0, iv.c1);
             if (next.cash > t.Mlast) c1 = MAX(c1, t.Clast);  // constant extrapolation guard (egdst_solver.c:554)
             if (c1 <= 0) {
@@ -150,9 +153,9 @@ EGDST_DEV void egdst_eval_nodes(const egdst_ctx *cx, const EgdstDev &P, int ivec
                 } else {
                     if (i < 1) {  // value table starts at row 1 (row 0 of V is evf(a0), not a value)
                         if (tab) iv = egdst_load_interval(t.ivl + 1);
-                        else { iv.g0 = t.M[1]; iv.g1 = t.M[2]; iv.v0 = t.V[1]; iv.v1 = t.V[2]; }
+                        else { iv.g0 = t.M[1]; iv.g1 = t.M[2]; iv.v0 = t.V[1]; iv.v1 = t.V[2]; iv.y = egdst_div_safe(iv.g1 - iv.g0) ? 1.0 / (iv.g1 - iv.g0) : 0.0; }
                         w = iv.g1 - iv.g0;
-                        y = egdst_div_safe(w) ? 1.0 / w : 0.0;
+                        y = iv.y;
                     }
                     v1 = egdst_linter_extrap_iv(cx, &next, next.cash, iv.g0, iv.g1, iv.v0, iv.v1, t.M1, t.Mlast, w, y);
                 }

@@ -5,11 +5,16 @@
 // lookup cost four 16-byte loads (neighbouring A points / agents with neighbouring cash hit the same lines):
 //   lut [ncell][lutcap+1] EgdstLutEntry  direct index by the leading bits of the IEEE representation of
 //        (x - a0 + 1): key = exponent and the top `mbits` mantissa bits, a piecewise-linear log2 -- the endogenous
-//        grids are (sym-)log spaced (egdst_solver.c:1104-1136), so buckets are evenly filled.  Entry b holds
-//        l = #rows with key < b, the number of rows in the bucket and the abscissa of its first row: with about
-//        half a row per bucket, #rows <= x is l + (m <= x) without touching the grid (crowded buckets bisect).
-//   ivl [ncell][tabcap] EgdstInterval    (M_i, M_i+1, C_i, C_i+1, V_i, V_i+1): everything the interpolations of the
-//        EGM step (egdst_solver.c:552-567, 755-772) and of policy() (egdst_simulator.c:178-197) need, contiguous.
+//        grids are (sym-)log spaced (egdst_solver.c:1104-1136), so buckets are evenly filled.  Entry b (32 bytes)
+//        holds l = #rows with key < b, the number of rows in the bucket and the abscissas of its first three rows
+//        (+inf where there is none): #rows <= x is l + (m0<=x) + (m1<=x) + (m2<=x) without touching the grid, so the
+//        bracket is final after ONE gather; only buckets with more than three rows bisect.
+//   row [ncell][tabcap+1] EgdstRow       (M_i, C_i, V_i, RN(1/(M_i+1 - M_i))), 32 bytes = one sector per row: rows i and
+//        i+1 -- 64 contiguous bytes -- are everything the interpolations of the EGM step (egdst_solver.c:552-567,
+//        755-772) and of policy() (egdst_simulator.c:178-197) need.  The correctly rounded reciprocal of the interval
+//        width is a function of the two abscissas only, so it is computed once per row here instead of once per lookup.
+// The tables of one cell take 32 B per row plus 32 B per index bucket (about one bucket per row): the working set of
+// the simulator -- every period's tables at once -- has to stay L2-resident next to its output stream.
 // This replaces the 14-step bisections of bxsearch (egdst_lib.c:138-165), 2 per quadrature node and agent-period.
 // Cells with more rows than tabcap+1 (possible only when ngridmax >> 2*ngridm is actually used) keep the bisection.
 #pragma once
@@ -27,7 +32,7 @@ EGDST_DEV int egdst_lut_key(double x, double a0, int mbits) {
     return (hi >> (20 - mbits)) - (0x3FF00000 >> (20 - mbits));
 }
 
-EGDST_DEV const EgdstInterval *egdst_cell_ivl(const EgdstDev &P, int cell) { return P.tabIvl + (size_t)cell * P.tabcap; }
+EGDST_DEV const EgdstRow *egdst_cell_rows(const EgdstDev &P, int cell) { return P.tabRow + (size_t)cell * (P.tabcap + 1); }
 EGDST_DEV const EgdstLutEntry *egdst_cell_lut(const EgdstDev &P, int cell) { return P.tabLut + (size_t)cell * (P.lutcap + 1); }
 EGDST_DEV bool egdst_cell_has_tab(const EgdstDev &P, int n) { return n - 1 <= P.tabcap; }
 
@@ -46,15 +51,19 @@ EGDST_DEV double2 egdst_ld16_hint(const void *p, unsigned long long pol) {
 }
 #endif
 
-EGDST_DEV EgdstInterval egdst_load_interval(const EgdstInterval *p) {
+// rows i and i+1 as one interval: four 16-byte loads of 64 contiguous bytes
+EGDST_DEV EgdstInterval egdst_load_interval(const EgdstRow *p) {
+    EgdstInterval iv;
 #ifdef EGDST_HOSTEMU
-    return *p;
+    iv.g0 = p[0].m; iv.c0 = p[0].c; iv.v0 = p[0].v; iv.y = p[0].y; iv.g1 = p[1].m; iv.c1 = p[1].c; iv.v1 = p[1].v;
 #else
-    const double2 *q = reinterpret_cast<const double2 *>(p);  // three 16-byte loads
+    const double2 *q = reinterpret_cast<const double2 *>(p);
     const double2 q0 = q[0], q1 = q[1], q2 = q[2];
-    EgdstInterval iv; iv.g0 = q0.x; iv.g1 = q0.y; iv.c0 = q1.x; iv.c1 = q1.y; iv.v0 = q2.x; iv.v1 = q2.y;
-    return iv;
+    const double v1 = reinterpret_cast<const double *>(p)[6];
+    iv.g0 = q0.x; iv.c0 = q0.y; iv.v0 = q1.x; iv.y = q1.y; iv.g1 = q2.x; iv.c1 = q2.y; iv.v1 = v1;
 #endif
+    iv.pad = 0.0;
+    return iv;
 }
 
 // Start-of-period housekeeping for parameter vector ivec (all threads of one CTA): reset the chained-scan state of
@@ -82,31 +91,28 @@ EGDST_DEV void egdst_cells_body(const EgdstDev &P, int ivec, int it) {
     }
 }
 
-// build the tables of the cells (ivec, it, all ist): grid (nblk, nst, nvec)
-__global__ void egdst_k_tab(EgdstDev P, int it) {
-    const int ivec = blockIdx.z, ist = blockIdx.y;
-    // the last kernel of period `it` also opens period it-1 (saves a launch per period)
-    if (blockIdx.x == 0 && blockIdx.y == 0 && it > 0) egdst_cells_body(P, ivec, it - 1);
-    const int cell = egdst_cell(P, ivec, it, ist);
+// Build the tables of one cell: the share of virtual block vb of nvb (all threads of the CTA, 1-D blocks).
+EGDST_DEV void egdst_tab_cell(const EgdstDev &P, int cell, int vb, int nvb) {
     const int n = P.mlen[cell];
     if (n < 2 || !egdst_cell_has_tab(P, n)) return;
     const double a0 = P.cx.a0;
     const double *M = egdst_colM(P, cell), *C = egdst_colC(P, cell), *V = egdst_colV(P, cell);
-    EgdstInterval *r = P.tabIvl + (size_t)cell * P.tabcap;
-    const int stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
-    for (int i = t0; i + 1 < n; i += stride) {
-        EgdstInterval v; v.g0 = M[i]; v.g1 = M[i + 1]; v.c0 = C[i]; v.c1 = C[i + 1]; v.v0 = V[i]; v.v1 = V[i + 1];
+    EgdstRow *r = P.tabRow + (size_t)cell * (P.tabcap + 1);
+    const int stride = nvb * blockDim.x, t0 = vb * blockDim.x + threadIdx.x;
+    for (int i = t0; i < n; i += stride) {
+        EgdstRow v; v.m = M[i]; v.c = C[i]; v.v = V[i]; v.y = 0.0;
+        if (i + 1 < n) { const double w = M[i + 1] - v.m; v.y = egdst_div_safe(w) ? 1.0 / w : 0.0; }  // shared correctly rounded reciprocal (0: plain divisions)
         r[i] = v;
     }
     // direct index, row-centric (no searches): row r is the first row with key >= b for every bucket b in
-    // (key(r-1), key(r)]; the bucket key(r) also gets the number of rows that share the key
+    // (key(r-1), key(r)]; the bucket key(r) also gets the number of rows that share the key and their abscissas
     EgdstLutEntry *L = P.tabLut + (size_t)cell * (P.lutcap + 1);
     const int kmax = P.lutcap - 1;
     const int lane = threadIdx.x & 31;
-    for (int base = blockIdx.x * blockDim.x; base < n; base += stride) {  // warp-uniform trip count
+    for (int base = vb * blockDim.x; base < n; base += stride) {  // warp-uniform trip count
         const int r = base + threadIdx.x;
         int gap0 = 0, gap1 = 0;
-        EgdstLutEntry e; e.l = r; e.cnt = 0; e.m = 0.0;
+        EgdstLutEntry e; e.l = r; e.cnt = 0; e.m0 = EGDST_INF; e.m1 = EGDST_INF; e.m2 = EGDST_INF;
         if (r < n) {
             const double m = M[r];
             int kr = egdst_lut_key(m, a0, P.mbits); kr = kr < 0 ? 0 : (kr > kmax ? kmax : kr);
@@ -114,10 +120,17 @@ __global__ void egdst_k_tab(EgdstDev P, int it) {
             if (r > 0) { kp = egdst_lut_key(M[r - 1], a0, P.mbits); kp = kp < 0 ? 0 : (kp > kmax ? kmax : kp); }
             if (kr > kp) {
                 int cnt = 1;
-                while (r + cnt < n) { int kn = egdst_lut_key(M[r + cnt], a0, P.mbits); kn = kn < 0 ? 0 : (kn > kmax ? kmax : kn); if (kn != kr) break; cnt++; }
-                e.m = m; e.cnt = cnt;
-                L[kr] = e;
-                e.cnt = 0;
+                EgdstLutEntry f = e;
+                f.m0 = m;
+                while (r + cnt < n) {
+                    const double mn = M[r + cnt];
+                    int kn = egdst_lut_key(mn, a0, P.mbits); kn = kn < 0 ? 0 : (kn > kmax ? kmax : kn);
+                    if (kn != kr) break;
+                    if (cnt == 1) f.m1 = mn; else if (cnt == 2) f.m2 = mn;
+                    cnt++;
+                }
+                f.cnt = cnt;
+                L[kr] = f;
                 gap0 = kp + 1; gap1 = kr;  // empty buckets [gap0, gap1) point at row r too
             }
         }
@@ -128,36 +141,42 @@ __global__ void egdst_k_tab(EgdstDev P, int it) {
             const int src = __ffs(longm) - 1;
             longm &= longm - 1;
             const int b0 = __shfl_sync(EGDST_FULL, gap0, src), b1 = __shfl_sync(EGDST_FULL, gap1, src);
-            EgdstLutEntry f; f.l = __shfl_sync(EGDST_FULL, e.l, src); f.cnt = 0; f.m = __shfl_sync(EGDST_FULL, e.m, src);
+            EgdstLutEntry f; f.l = __shfl_sync(EGDST_FULL, e.l, src); f.cnt = 0; f.m0 = EGDST_INF; f.m1 = EGDST_INF; f.m2 = EGDST_INF;
             for (int bb = b0 + lane; bb < b1; bb += 32) L[bb] = f;
         }
     }
     {   // buckets above the last row's key
         int kl = egdst_lut_key(M[n - 1], a0, P.mbits); kl = kl < 0 ? 0 : (kl > kmax ? kmax : kl);
-        EgdstLutEntry e; e.l = n; e.cnt = 0; e.m = EGDST_INF;
+        EgdstLutEntry e; e.l = n; e.cnt = 0; e.m0 = EGDST_INF; e.m1 = EGDST_INF; e.m2 = EGDST_INF;
         for (int bb = kl + 1 + t0; bb <= P.lutcap; bb += stride) L[bb] = e;
     }
 }
 
-// the simulator's versions: same lookups with the evict_last hint
-EGDST_DEV EgdstInterval egdst_load_interval_keep(const EgdstInterval *p, unsigned long long pol) {
+// build the tables of the cells (ivec, it, all ist): grid (nblk, nst, nvec)
+__global__ void egdst_k_tab(EgdstDev P, int it) {
+    const int ivec = blockIdx.z, ist = blockIdx.y;
+    // the last kernel of period `it` also opens period it-1 (saves a launch per period)
+    if (blockIdx.x == 0 && blockIdx.y == 0 && it > 0) egdst_cells_body(P, ivec, it - 1);
+    egdst_tab_cell(P, egdst_cell(P, ivec, it, ist), blockIdx.x, gridDim.x);
+}
+
+// the simulator's version: the same loads with the evict_last hint
+EGDST_DEV EgdstInterval egdst_load_interval_keep(const EgdstRow *p, unsigned long long pol) {
 #ifdef EGDST_HOSTEMU
-    return *p;
+    return egdst_load_interval(p);
 #else
-    const double2 q0 = egdst_ld16_hint(p, pol), q1 = egdst_ld16_hint((const double2 *)p + 1, pol), q2 = egdst_ld16_hint((const double2 *)p + 2, pol);
-    EgdstInterval iv; iv.g0 = q0.x; iv.g1 = q0.y; iv.c0 = q1.x; iv.c1 = q1.y; iv.v0 = q2.x; iv.v1 = q2.y;
+    const double2 q0 = egdst_ld16_hint(p, pol), q1 = egdst_ld16_hint((const double2 *)p + 1, pol), q2 = egdst_ld16_hint((const double2 *)p + 2, pol),
+                  q3 = egdst_ld16_hint((const double2 *)p + 3, pol);
+    EgdstInterval iv; iv.g0 = q0.x; iv.c0 = q0.y; iv.v0 = q1.x; iv.y = q1.y; iv.g1 = q2.x; iv.c1 = q2.y; iv.v1 = q3.x; iv.pad = 0.0;
     return iv;
 #endif
 }
 
 // Bracket AND interval record of x in a cell that has tables (egdst_cell_has_tab).  Same bracket as
 // egdst_bracket(x, M, n, 0) on a strictly increasing grid: (#rows <= x) - 1 clamped to [0, n-2].  KEEP: load with the
-// evict_last hint `pol`.
-// A bucket that holds two rows (about a quarter of the lookups at two buckets per row) is resolved by fetching the
-// records of both rows at once -- two independent gathers -- instead of a dependent read of the grid column followed
-// by the record: the second row's abscissa is g1 of the first row's record.  Three and more rows bisect as before.
+// evict_last hint `pol`.  Two dependent gathers: the 32-byte index entry, then rows i and i+1 (64 contiguous bytes).
 template <bool KEEP = false>
-EGDST_DEV int egdst_lookup_tab(const EgdstDev &P, int cell, const EgdstInterval *ivl, double x, int n, EgdstInterval &iv,
+EGDST_DEV int egdst_lookup_tab(const EgdstDev &P, int cell, const EgdstRow *ivl, double x, int n, EgdstInterval &iv,
                                unsigned long long pol = 0ULL) {
     int b = egdst_lut_key(x, P.cx.a0, P.mbits);
     b = b < 0 ? 0 : (b > P.lutcap - 1 ? P.lutcap - 1 : b);
@@ -167,29 +186,24 @@ EGDST_DEV int egdst_lookup_tab(const EgdstDev &P, int cell, const EgdstInterval 
 #else
     EgdstLutEntry e;
     if (KEEP) {
-        const double2 raw = egdst_ld16_hint(lut + b, pol);
-        const long long lo = __double_as_longlong(raw.x);
-        e.l = (int)(lo & 0xffffffffLL); e.cnt = (int)(lo >> 32); e.m = raw.y;
+        const double2 r0 = egdst_ld16_hint(lut + b, pol), r1 = egdst_ld16_hint((const double2 *)(lut + b) + 1, pol);
+        const long long lo = __double_as_longlong(r0.x);
+        e.l = (int)(lo & 0xffffffffLL); e.cnt = (int)(lo >> 32); e.m0 = r0.y; e.m1 = r1.x; e.m2 = r1.y;
     } else {
-        const int4 raw = *reinterpret_cast<const int4 *>(lut + b);
-        e.l = raw.x; e.cnt = raw.y; e.m = __hiloint2double(raw.w, raw.z);
+        const int4 r0 = *reinterpret_cast<const int4 *>(lut + b);
+        const double2 r1 = *(reinterpret_cast<const double2 *>(lut + b) + 1);
+        e.l = r0.x; e.cnt = r0.y; e.m0 = __hiloint2double(r0.w, r0.z); e.m1 = r1.x; e.m2 = r1.y;
     }
 #endif
-    const bool in = e.cnt > 0 && e.m <= x;
-    int i = e.l - 1 + (in ? 1 : 0);
-    if (in && e.cnt > 2) {
+    int i = e.l - 1 + (e.m0 <= x ? 1 : 0) + (e.m1 <= x ? 1 : 0) + (e.m2 <= x ? 1 : 0);
+    if (e.cnt > 3 && e.m2 <= x) {  // crowded bucket (double points next to a dense stretch): bisect its remaining rows
         const double *M = egdst_colM(P, cell);
-        int l = e.l + 1, h = e.l + e.cnt;
+        int l = e.l + 3, h = e.l + e.cnt;
         while (l < h) { const int mid = (l + h) >> 1; if (M[mid] <= x) l = mid + 1; else h = mid; }
         i = l - 1;
     }
     i = i > n - 2 ? n - 2 : i;
     i = i < 0 ? 0 : i;
-    const bool two = in && e.cnt == 2 && i + 1 <= n - 2;
-    const int i2 = two ? i + 1 : i;
-    EgdstInterval iv2;
-    if (KEEP) { iv = egdst_load_interval_keep(ivl + i, pol); iv2 = two ? egdst_load_interval_keep(ivl + i2, pol) : iv; }
-    else { iv = egdst_load_interval(ivl + i); iv2 = two ? egdst_load_interval(ivl + i2) : iv; }
-    if (two && x >= iv.g1) { iv = iv2; i = i2; }
+    iv = KEEP ? egdst_load_interval_keep(ivl + i, pol) : egdst_load_interval(ivl + i);
     return i;
 }

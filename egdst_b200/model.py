@@ -457,6 +457,8 @@ class EgdstModel:
         lib = self._capi()
         table = {"utility": 1, "util": 1, "u": 1, "mutility": 2, "mu": 2, "discount": 3, "df": 3,
                  "budget": 4, "b": 4, "mbudget": 5, "mb": 5, "value": 6, "vf": 6}
+        if self._solution is None:  # egdstmodel.m:1182-1184
+            raise RuntimeError("The model needs to be compiled and solved first!")
         if func not in table:
             raise ValueError("Unknown internal model function to call!")
         return lib.call(self, self._solution, table[func], np.atleast_2d(np.asarray(funcargs, dtype=np.float64)))

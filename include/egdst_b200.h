@@ -85,6 +85,10 @@ int egdst_solution_nvec(const egdst_solution *s);
 /* total number of EGM grid points kept over all (it,ist,id) of the last solve (the solve work unit) */
 long long egdst_solution_units(egdst_solution *s);
 void egdst_free_solution(egdst_solution *s);
+/* Frees what the library keeps between calls: the one released solution object it caches for re-use by the next
+ * solve of the same shape, and the calling thread's simulation workspace.  (The reference leaks on error paths and
+ * relies on MATLAB clearing the MEX file, egdst_solver.c:19; a long-lived host calls this when it unloads a model.) */
+void egdst_shutdown(void);
 /* Build a solution object from host M/D cells (the MEX simulator receives model.M, model.D). */
 int egdst_solution_import(const egdst_desc *d, const int *mlen, const int *thlen, const double *Mbuf, const double *Dbuf,
                           egdst_solution **out);
