@@ -209,10 +209,10 @@ def own_arm(a):
         lib.resolve(sol, m)
     torch.cuda.synchronize()
     prof = lib.profile_read()
+    phases = sol.phase_ms()  # in-kernel phase timers of the two profiled solves
     lib.profile_enable(False)
-    ksum = sum(v[0] for v in prof.values()) or 1.0
-    egm_ms, egm_n = prof["egm"]
-    egm_launch_ms = egm_ms / max(egm_n, 1)
+    ksum = sum(phases.values()) or 1.0
+    egm_launch_ms = phases["egm"] / 2 / max(nt - 1, 1)  # the EGM phase of one period (what used to be one launch)
     # algorithmic bytes of one EGM launch: read M,C,V of t+1 (24 B/row), write M,C,V_d per stored point
     egm_bytes = 24.0 * (rows / nt + 1) + 24.0 * (stored / nt)
     solve_alg_bytes = 56.0 * rows  # 56 B per final grid row per period, whole solve
@@ -234,15 +234,16 @@ def own_arm(a):
         "e2e": {"value": units / solve_e2e_s, "unit": "grid-point-periods/s", "ms": solve_e2e_s * 1e3,
                 "h2d_bytes_per_step": int(8 * (2 * m.ny + len(m.param) + 2 * m.nnst + m.nst * m.nnst + m.nd * m.nnd)),
                 "d2h_bytes_per_step": int(Mbuf.nbytes + Dbuf.nbytes + mlen.nbytes + thlen.nbytes)},
-        "roofline": {"bound": "hbm", "kernel": "egdst_k_egm", "achieved": egm_bytes / (egm_launch_ms / 1e3) / 1e9, "peak": hbm_peak,
+        "roofline": {"bound": "hbm", "kernel": "egdst_k_solve_grid, EGM phase of one period", "achieved": egm_bytes / (egm_launch_ms / 1e3) / 1e9, "peak": hbm_peak,
                      "unit": "GB/s", "frac": egm_bytes / (egm_launch_ms / 1e3) / 1e9 / hbm_peak, "peak_source": peak_src,
                      "traffic": committed_traffic("egdst_k_egm", "S1"),
                      "algorithmic_bytes_per_launch": egm_bytes, "launch_ms": egm_launch_ms,
                      "whole_solve_GBs": solve_alg_bytes / (solve_ms / 1e3) / 1e9,
                      "fp64": fp64_side(micro_peaks().get("egm_fp64_flop_per_launch_S1"), egm_launch_ms),
                      "note": "FP64-issue/latency-bound, not HBM-bound: ~200 flop per algorithmic byte (SURVEY 8d)"},
-        "kernel_share": {k: round(v[0] / ksum, 4) for k, v in prof.items() if v[1]},
-        "kernel_ms_per_solve": {k: round(v[0] / 2, 4) for k, v in prof.items() if v[1]},
+        "phase_share": {k: round(v / ksum, 4) for k, v in phases.items() if v},
+        "phase_ms_per_solve": {k: round(v / 2, 4) for k, v in phases.items() if v},
+        "resends_after_seed": sol.resends(),
     }
 
     # ------------------------------------------------------------------ simulation (sharded, weak scaling)

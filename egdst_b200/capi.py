@@ -147,6 +147,18 @@ class Solution:
     def units(self) -> int:
         return int(self.lib.L.egdst_solution_units(self.handle))
 
+    PHASES = ("terminal", "seed", "egm", "resend", "envelope2", "rank", "merge", "tables")
+
+    def phase_ms(self):
+        """{phase: ms} of the solve kernel, accumulated over profiled solves of this object (reading resets)."""
+        ms = (C.c_double * 8)()
+        n = self.lib.L.egdst_solution_phase_ms(self.handle, ms)
+        return {self.PHASES[i]: float(ms[i]) for i in range(max(n, 0))}
+
+    def resends(self) -> int:
+        """Zero-consumption re-sends after the seed stage that the last solve handled (diagnostic)."""
+        return int(self.lib.L.egdst_solution_resends(self.handle))
+
 
 class ModelLibrary:
     """One loaded model image (libegdst_b200_<key>.so)."""
@@ -154,7 +166,7 @@ class ModelLibrary:
     EXPORTS = ["egdst_abi_version", "egdst_model_key", "egdst_model_nparam", "egdst_model_neq", "egdst_last_error",
                "egdst_set_stream", "egdst_launch_count", "egdst_profile_classes", "egdst_profile_class_name",
                "egdst_profile_enable", "egdst_profile_read", "egdst_solve", "egdst_solve_batch", "egdst_resolve", "egdst_solution_sizes",
-               "egdst_solution_export", "egdst_solution_status", "egdst_solution_nvec", "egdst_solution_units",
+               "egdst_solution_export", "egdst_solution_status", "egdst_solution_nvec", "egdst_solution_units", "egdst_solution_resends", "egdst_solution_phase_ms", "egdst_test_envelope2",
                "egdst_free_solution", "egdst_solution_import", "egdst_simulate", "egdst_simulate_philox",
                "egdst_simulate_device", "egdst_sim_moments", "egdst_sim_moments_device", "egdst_call", "egdst_shutdown"]
 
@@ -182,6 +194,9 @@ class ModelLibrary:
         L.egdst_solution_nvec.argtypes = [vp]
         L.egdst_solution_units.argtypes = [vp]
         L.egdst_solution_units.restype = C.c_longlong
+        L.egdst_solution_phase_ms.argtypes = [vp, _dp]
+        L.egdst_solution_resends.argtypes = [vp]
+        L.egdst_solution_resends.restype = C.c_longlong
         L.egdst_free_solution.argtypes = [vp]
         L.egdst_free_solution.restype = None
         L.egdst_shutdown.restype = None
@@ -356,6 +371,19 @@ class ModelLibrary:
             import warnings
             warnings.warn(self.last_error(), EgdstWarning)
         return res
+
+    def test_envelope2(self, model, it: int, idd: int, X, Cc, V, evfa0: float):
+        """Secondary envelope of one decision's EGM points (generation order) by the solve kernel's phases."""
+        d = Desc(model)
+        X, Cc, V = _arr(X), _arr(Cc), _arr(V)
+        cap = int(model.ngridmax) + 8
+        oX, oC, oV = np.zeros(cap), np.zeros(cap), np.zeros(cap)
+        n = C.c_int(0)
+        self.L.egdst_test_envelope2.argtypes = [C.POINTER(EgdstDesc), C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, C.c_int, C.c_double, _dp, _dp, _dp, _ip]
+        rc = self.L.egdst_test_envelope2(C.byref(d.c), it, 0, idd, _ptr(X), _ptr(Cc), _ptr(V), X.size, float(evfa0), _ptr(oX), _ptr(oC), _ptr(oV), C.byref(n))
+        if rc:
+            self._raise(rc)
+        return oX[:n.value].copy(), oC[:n.value].copy(), oV[:n.value].copy()
 
     def shutdown(self):
         """Release the library's cached solution object and this thread's simulation workspace."""

@@ -1,7 +1,7 @@
 // egdst_capi.cu -- host orchestration and the C ABI (include/egdst_b200.h).
 //
 // Replaces the reference's MEX gateways and driver loops:
-//   mexFunction/solver()      egdst_solver.c:143-339   -> egdst_solve / egdst_resolve (period loop of kernel launches)
+//   mexFunction/solver()      egdst_solver.c:143-339   -> egdst_solve / egdst_resolve (one kernel: the period loop runs on the device)
 //   saveoutput/swappointers   egdst_solver.c:917-952,342 -> the device arena (next period reads the cells in place)
 //   parseModel/loadparameters egdst_lib.c:34-62          -> egdst_desc
 // There is no host arithmetic on the data path: even the cdfni transform of the quadrature abscissas
@@ -20,9 +20,8 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #endif
-#include "egdst_envelope.cuh"
+#include "egdst_period.cuh"
 #include "egdst_simulator.cuh"
-#include "egdst_solver.cuh"
 
 #ifndef EGDST_MODEL_KEY
 #define EGDST_MODEL_KEY "unknown"
@@ -32,8 +31,8 @@ static thread_local std::string g_err;
 static thread_local cudaStream_t g_stream = 0;
 
 // ---- launch counter and optional per-kernel-class event timing (bench.py's roofline leg) --------------
-enum { KC_SETUP = 0, KC_TERMINAL, KC_SEED, KC_EGM, KC_COMPACT, KC_ENV2, KC_ENV, KC_TAB, KC_SIM, KC_OTHER, KC_COUNT };
-static const char *const g_kc_names[KC_COUNT] = {"setup", "terminal", "seed", "egm", "compact", "envelope2", "envelope", "tables", "simulate", "other"};
+enum { KC_SETUP = 0, KC_SOLVE, KC_TAB, KC_SIM, KC_OTHER, KC_COUNT };
+static const char *const g_kc_names[KC_COUNT] = {"setup", "solve", "tables", "simulate", "other"};
 static std::atomic<long long> g_launches{0};
 static bool g_prof_on = false;  // profiling is a single-threaded measurement aid (egdst_profile_enable)
 struct ProfRec { int cls; cudaEvent_t a, b; };
@@ -62,11 +61,6 @@ static void prof_collect() {
     }
     g_prof_pending.clear();
 }
-// Period-chain launches.  Programmatic dependent launch (griddepcontrol) was used here for the eager chain and removed:
-// with the successor's CTAs resident while the predecessor still runs, the successor read stale first lines of arrays
-// the predecessor rewrites every period (rawFlag) in 6 of 8 runs of the S1b case -- the eager chain costs 0.5 ms more
-// without it, the graph replay (third solve of a shape onwards) never used it.
-#define PLAUNCH KLAUNCH
 #define KLAUNCH(cls, kernel, grid, block, smem, stream, ...) \
     do { prof_begin(cls, stream); EGDST_LAUNCH(kernel, grid, block, smem, stream, __VA_ARGS__); prof_end(stream); } while (0)
 
@@ -94,7 +88,7 @@ static const char *status_text(int code) {
     case EGDST_ERR_CASHINVERSE: return "Did not manage to invert the intertemporal budget (cashinhand) after performing many-many iterations!";
     case EGDST_ERR_INTERP2PT: return "Error: At least two points are required for interpolation!";
     case EGDST_ERR_ENV2SPACE: return "Not enough space for endogenous grid in envelop2()";
-    case EGDST_ERR_RESEND_LATE: return "Zero-consumption re-send requested after the seed stage of the savings grid (not supported by the parallel grid)";
+    case EGDST_ERR_BARRIER: return "internal error: a phase barrier of the solve kernel timed out";
     case EGDST_ERR_TRPR_INDEX: return "Error in trpr: unknown index of the state variable";
     case EGDST_ERR_TRPR_CASES: return "Error in trpr: unknown combination of current state and decision (the set of cases is not complete)!";
     default: return "unknown error";
@@ -114,12 +108,9 @@ struct egdst_solution {
     size_t pack_cap;
     int *d_moff, *d_toff;
     int neq;
-    // CUDA graph of the period chain (run_solve)
-    cudaGraphExec_t g_exec;
-    EgdstDev g_P;
-    cudaStream_t g_stream;
-    bool g_seen;
-    long long g_nlaunch;
+    unsigned long long *d_phase;  // per-phase device time of profiled solves
+    int grid_ctas;  // CTAs of the solve kernel (one resident wave), 0 = not sized yet
+    bool cta_scope; // sweeps of many small models: one CTA per parameter vector
     size_t bytes;   // device bytes owned (workspace cache policy)
     void *tab_base; size_t tab_bytes;  // lookup tables (one allocation)
     std::vector<double> h_params;  // host copy of the parameter matrix of the last solve (simulator kernel arguments)
@@ -143,9 +134,6 @@ static egdst_solution *g_cached = 0;
 static const size_t EGDST_CACHE_MAX_BYTES = (size_t)2 << 30;
 static void destroy_solution(egdst_solution *s) {
     cudaSetDevice(s->device);
-#ifndef EGDST_HOSTEMU
-    if (s->g_exec) cudaGraphExecDestroy(s->g_exec);
-#endif
     for (void *p : s->owned) cudaFree(p);
     if (s->d_pack) cudaFree(s->d_pack);
     if (s->d_momscratch) cudaFree(s->d_momscratch);
@@ -158,10 +146,6 @@ __global__ void egdst_k_quadrature(const double *qraw, double *q, int ny) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < ny) { q[i] = qraw[i]; q[ny + i] = egdst_cdfni(qraw[ny + i]); }
 }
-
-// mark infeasible (it,ist) cells as empty, detect empty choice sets and reset the chained-scan state: the first
-// period's call; later periods get this from egdst_k_tab of the period before (egdst_tables.cuh)
-__global__ void egdst_k_cells(EgdstDev P, int it) { egdst_cells_body(P, blockIdx.x, it); }
 
 // the descriptor must describe the model this image was generated from: sizes of the generated structures and the
 // optim_* switches, which are functions of the exec strings (compile.m:669-747) and compiled into the kernels
@@ -221,7 +205,7 @@ static int create_solution(const egdst_desc *d, int nvec, egdst_solution **out) 
             const double *stm = s->d_stm, *states = s->d_states, *decisions = s->d_decisions;
             s->P.cx = cx; s->P.cx.stm = stm; s->P.cx.states = states; s->P.cx.decisions = decisions;
             s->P.bparams = 0;
-            cudaMemset(s->P.units, 0, sizeof(unsigned long long) * nvec);
+            cudaMemset(s->P.units, 0, sizeof(unsigned long long) * 2 * nvec);
             *out = s;
             return 0;
         }
@@ -229,7 +213,7 @@ static int create_solution(const egdst_desc *d, int nvec, egdst_solution **out) 
     egdst_solution *s = new egdst_solution();
     s->bytes = 0; memcpy(s->dims, dims, sizeof(dims)); s->dkey[0] = d->mmax; s->dkey[1] = d->a0;
     s->d_momscratch = 0; s->momscratch_cap = 0; s->d_hdr = 0; s->hdr_ivec = -1;
-    s->g_exec = 0; s->g_seen = false; s->g_stream = 0; s->g_nlaunch = 0;
+    s->grid_ctas = 0; s->cta_scope = false;
     s->device = d->device; s->sizes_valid = false; s->d_pack = 0; s->pack_cap = 0; s->neq = d->neq;
     EgdstDev &P = s->P;
     memset(&P, 0, sizeof(P));
@@ -243,9 +227,7 @@ static int create_solution(const egdst_desc *d, int nvec, egdst_solution **out) 
     DA(s->d_bparams, (size_t)nvec * EGDST_NPARAM_); DA(s->d_qraw, 2 * d->ny); DA(s->d_q, 2 * d->ny);
     DA(P.arena, (size_t)s->ncell * 4 * P.rowcap); DA(P.mlen, s->ncell); DA(P.thlen, s->ncell); DA(P.evf, s->ncell);
     DA(P.thD, (size_t)s->ncell * d->nthrhmax); DA(P.thTH, (size_t)s->ncell * d->nthrhmax);
-    DA(P.active, s->nsd); DA(P.seed, (size_t)s->nsd * 8); DA(P.evfa0, s->nsd);
-    DA(P.rawM, (size_t)s->nsd * P.N); DA(P.rawC, (size_t)s->nsd * P.N); DA(P.rawV, (size_t)s->nsd * P.N); DA(P.rawStop, (size_t)s->nsd * P.N);
-    DA(P.rawFlag, (size_t)s->nsd * P.N);
+    DA(P.active, s->nsd); DA(P.seed, (size_t)s->nsd * EGDST_SEEDW); DA(P.evfa0, s->nsd);
     DA(P.ptX, (size_t)s->nsd * P.gcap); DA(P.ptC, (size_t)s->nsd * P.gcap); DA(P.ptV, (size_t)s->nsd * P.gcap);
     DA(P.ptN, s->nsd); DA(P.nfold, s->nsd); DA(P.runStart, (size_t)s->nsd * (P.gcap + 1));
     DA(P.mgX, (size_t)s->nslot * P.envcap); DA(P.mgF, (size_t)s->nslot * P.envcap); DA(P.mgK, (size_t)s->nslot * P.envcap); DA(P.mgA, (size_t)s->nslot * P.envcap);
@@ -272,24 +254,20 @@ static int create_solution(const egdst_desc *d, int nvec, egdst_solution **out) 
         P.tabLut = (EgdstLutEntry *)base; P.tabRow = (EgdstRow *)(base + lutbytes);
         s->tab_base = base; s->tab_bytes = lutbytes + ivlbytes;
     }
-    P.cmpW = (P.N <= 64 * EGDST_CMP_IPT) ? 64 : EGDST_CMP_THREADS;
-    P.cmpIPT = (nvec * d->nst * nd < 148 && P.cmpW == EGDST_CMP_THREADS) ? 2 : EGDST_CMP_IPT;
-    P.chC = (P.N + P.cmpW * P.cmpIPT - 1) / (P.cmpW * P.cmpIPT);
-    // envelope merge: narrow CTAs when the usual union (nd lists of about N points) fits one narrow chunk -- small
-    // models of a batched sweep then keep four times as many jobs resident per SM
-    const bool smalljob = nd * (P.N + 64) <= 64 * EGDST_ENV_IPT;
-    P.envW = smalljob ? 64 : EGDST_ENVW;
-    P.envFuse = smalljob ? 1 : 0;  // one narrow CTA per job also ranks the points (no launch of its own)
-    // envelope merges of one large model: 2 positions per thread instead of 8 -- four times as many CTAs share the
-    // latency of the passes, and the crossing chains of the secondary envelope (~2 per run, ~10^2 runs in the zig-zag
-    // periods, one chain per warp at a time) find four times as many warps
-    P.envIPT = (nvec * d->nst * nd < 148 && !smalljob) ? 2 : EGDST_ENV_IPT;
-    P.chE = (P.envcap + P.envW * P.envIPT - 1) / (P.envW * P.envIPT) + 1;
+    // chained scans: one state word per work item of a job plus the seed's slot (EGM phase: at least 8 grid points per
+    // item), one per chunk of EGDST_BLOCK union positions (envelope merge)
+    P.chC = (P.N - 1 + 7) / 8 + 2;
+    P.chE = (P.envcap + EGDST_BLOCK - 1) / EGDST_BLOCK + 1;
+    // a point of the secondary envelope ranks itself against every run (~10^2 in the zig-zag periods of S1): with few
+    // jobs, 8 threads share the runs of a point
+    P.envA1parts = (nvec * nst * nd < 148) ? 8 : 1;
     DA(P.scanC, (size_t)s->nsd * P.chC); DA(P.tickC, (size_t)2 * s->nsd); DA(P.foldList, (size_t)s->nsd * (P.gcap + 1)); DA(P.foldCnt, s->nsd);
     DA(P.scanE, (size_t)s->nslot * P.chE); DA(P.tickE, (size_t)2 * s->nslot); DA(P.envNact, s->nslot);
-    DA(P.status, 4 * nvec); DA(P.units, nvec); DA(s->d_moff, s->ncell + 1); DA(s->d_toff, s->ncell + 1);
+    DA(P.lateN, s->nsd); DA(P.flags, (size_t)8 * (nvec + 1)); DA(P.bar, 4); DA(s->d_phase, EGDST_NPHASE);
+    cudaMemset(s->d_phase, 0, sizeof(unsigned long long) * EGDST_NPHASE);
+    DA(P.status, 4 * nvec); DA(P.units, 2 * nvec); DA(s->d_moff, s->ncell + 1); DA(s->d_toff, s->ncell + 1);
 #undef DA
-    cudaMemset(P.units, 0, sizeof(unsigned long long) * nvec);
+    cudaMemset(P.units, 0, sizeof(unsigned long long) * 2 * nvec);
     P.cx.stm = s->d_stm; P.cx.states = s->d_states; P.cx.decisions = s->d_decisions;
     P.qw = s->d_q; P.qz = s->d_q + d->ny;
     s->h_mlen.assign(s->ncell, 0); s->h_thlen.assign(s->ncell, 0); s->h_status.assign(4 * nvec, 0);
@@ -299,76 +277,77 @@ static int create_solution(const egdst_desc *d, int nvec, egdst_solution **out) 
 
 static inline int imin(int a, int b) { return a < b ? a : b; }
 
-// one backward-induction pass as a chain of launches on `st` (also what the CUDA graph captures)
-static int launch_periods(egdst_solution *s, cudaStream_t st) {
+// One backward-induction pass = one kernel on `st`.  Scope (egdst_period.cuh): sweeps of many small models run one CTA
+// per parameter vector (every CTA walks its vector through all periods on its own); everything else is a cooperative
+// launch of exactly one resident wave whose CTAs share every phase of every period.
+static int launch_solve(egdst_solution *s, cudaStream_t st) {
     EgdstDev &P = s->P;
+    // test hook: keep the cells of the periods after EGDST_SOLVE_FROM (an imported solution) and solve from there down
+    P.itStart = P.NT - 1;
+    P.itStop = 0;
+    if (getenv("EGDST_SOLVE_FROM")) { const int k = atoi(getenv("EGDST_SOLVE_FROM")); if (k >= 0 && k < P.NT - 1) P.itStart = k; }
+    if (getenv("EGDST_SOLVE_TO")) { const int k = atoi(getenv("EGDST_SOLVE_TO")); if (k >= 0 && k <= P.itStart) P.itStop = k; }
     CK(cudaMemsetAsync(P.status, 0, sizeof(int) * 4 * P.nvec, st));
-    CK(cudaMemsetAsync(P.units, 0, sizeof(unsigned long long) * P.nvec, st));
-    CK(cudaMemsetAsync(P.mlen, 0, sizeof(int) * s->ncell, st));
-    CK(cudaMemsetAsync(P.thlen, 0, sizeof(int) * s->ncell, st));
+    CK(cudaMemsetAsync(P.units, 0, sizeof(unsigned long long) * 2 * P.nvec, st));
+    if (P.itStart == P.NT - 1) {
+        CK(cudaMemsetAsync(P.mlen, 0, sizeof(int) * s->ncell, st));
+        CK(cudaMemsetAsync(P.thlen, 0, sizeof(int) * s->ncell, st));
+    }
+    CK(cudaMemsetAsync(P.bar, 0, sizeof(unsigned) * 4, st));
     const int nst = P.cx.nst, nd = P.cx.nd, nvec = P.nvec, N = P.N, B = EGDST_BLOCK;
     // per-CTA table of quadrature shocks and node probabilities (models whose shocks cannot depend on savings)
     const size_t shbytes = (size_t)2 * nst * P.cx.ny * sizeof(double);
-    const int useTab = (EGDST_SHOCK_INDEP_A && shbytes <= 40 * 1024) ? 1 : 0;
-    const size_t shsmem = useTab ? shbytes : 0;
-    int tabblocks = (P.lutcap + 1 + B - 1) / B;
-    if (nvec * nst * tabblocks > 4096) tabblocks = (4096 + nvec * nst - 1) / (nvec * nst);  // batched sweeps: fewer, looping CTAs per cell
-    const int cellthreads = ((nst + 31) / 32) * 32 < 128 ? 128 : ((nst + 31) / 32) * 32;
-    // warps per CTA that share the quadrature nodes of 32 grid points in the EGM step: with few nodes, the count
-    // that leaves no warp idle in the last round (10 nodes: 5 warps of 2 nodes)
-    int egmparts = EGDST_EGM_SPLIT;
-    if (P.cx.ny < 2 * EGDST_EGM_SPLIT) {
-        int bestwaste = 1 << 30;
-        for (int p = 1; p <= EGDST_EGM_SPLIT; p++) {
-            const int waste = (P.cx.ny + p - 1) / p * p - P.cx.ny;
-            if (waste <= bestwaste) { bestwaste = waste; egmparts = p; }
-        }
-    }
-    // envelope kernels: grids sized for the usual list lengths (a decision keeps at most N points plus the few the
-    // secondary envelope inserts); longer lists, up to the capacity ngridmax, are covered by the kernels' own loops
-    const int envchunk = P.envW * P.envIPT;
-    int envA1 = imin((2 * P.gcap + B - 1) / B, (N + 64 + B - 1) / B + 1);
-    const int envA0 = imin((nd * P.gcap + B - 1) / B, (nd * (N + 64) + B - 1) / B + 1);
-    // a point of the secondary envelope ranks itself against every run (~10^2 in the zig-zag periods of S1): with few
-    // jobs, 8 threads share the runs of a point
-    const bool envA1split = nvec * nst * nd < 148;
-    const dim3 envA1block = envA1split ? dim3(32, 8) : dim3(B, 1);
-    if (envA1split) envA1 = imin((2 * P.gcap + 31) / 32, (N + 64 + 31) / 32 + 1);
-    const int envBC1 = imin(P.chE, (N + 64 + envchunk - 1) / envchunk + 1);
-    const int envBC0 = imin(P.chE, (nd * (N + 64) + envchunk - 1) / envchunk);
-    const bool env_one_cta = getenv("EGDST_ENV_ONECTA") != 0 || P.envFuse;  // test hook / fused rank step: a single CTA per job
-    // CTAs per (ist,id) in the EGM step: one per block of 32 grid points, fewer (looping) when a batched sweep already
-    // fills the machine several times over
-    const int egmblocks = (N - 1 + 31) / 32;
-    int egmgx = egmblocks;
-    while (egmgx > 1 && (long long)nvec * nst * nd * egmgx > 8LL * 148 * 5) egmgx = (egmgx + 1) / 2;
-    if (getenv("EGDST_EGM_PARTS")) { const int p = atoi(getenv("EGDST_EGM_PARTS")); if (p >= 1 && p <= EGDST_EGM_SPLIT) egmparts = p; }
-    // the seed's CTA splits the nst*ny nodes of one savings point over its threads: small models in a batched sweep
-    // get small CTAs (more of the nvec*nst*nd independent seeds resident per SM)
-    int seedthreads = B;
-    if (nvec * nst * nd >= 4 * 148) {
-        seedthreads = ((nst * P.cx.ny + 31) / 32) * 32;
-        seedthreads = seedthreads < 32 ? 32 : (seedthreads > B ? B : seedthreads);
-    }
-    for (int it = P.NT - 1; it >= 0; it--) {
-        if (it == P.NT - 1) {
-            KLAUNCH(KC_SETUP, egdst_k_cells, dim3(nvec), dim3(cellthreads), 0, st, P, it);
-            PLAUNCH(KC_TERMINAL, egdst_k_terminal, dim3((N + B - 1) / B, nst * nd, nvec), dim3(B), 0, st, P, it);
+    const size_t shsmem = (EGDST_SHOCK_INDEP_A && shbytes <= EGDST_SHOCKTAB_BYTES) ? shbytes : 0;
+    if (!s->grid_ctas) {
+        int dev = 0, sms = 1, occ = 1;
+#ifndef EGDST_HOSTEMU
+        CK(cudaGetDevice(&dev));
+        CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        // small models, many of them: a CTA per vector keeps all of a vector's arrays in its SM's L1/L2 neighbourhood
+        // and needs neither launches nor inter-CTA waits
+        static const char *scope_env = getenv("EGDST_SOLVE_SCOPE");  // test hook: "cta" / "grid"
+        s->cta_scope = nvec >= 2 * sms && N <= 4 * B;
+        if (scope_env) s->cta_scope = strcmp(scope_env, "cta") == 0;
+        if (s->cta_scope) {
+            CK(cudaFuncSetAttribute(egdst_k_solve_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shsmem));
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, egdst_k_solve_cta, B, shsmem) != cudaSuccess || occ < 1) occ = 1;
         } else {
-            PLAUNCH(KC_SEED, egdst_k_seed, dim3(nd, nst, nvec), dim3(seedthreads), shsmem, st, P, it, useTab);
-            PLAUNCH(KC_EGM, egdst_k_egm, dim3(egmgx, nst * nd, nvec), dim3(32, egmparts), shsmem, st, P, it, useTab);
-            if (P.cmpIPT == 2) PLAUNCH(KC_COMPACT, egdst_k_compact<2>, dim3(P.chC, nst * nd, nvec), dim3(P.cmpW), 0, st, P, it);
-            else PLAUNCH(KC_COMPACT, egdst_k_compact<EGDST_CMP_IPT>, dim3(P.chC, nst * nd, nvec), dim3(P.cmpW), 0, st, P, it);
-            // secondary envelope (no-op for (ist,id) without folds)
-            if (!P.envFuse) PLAUNCH(KC_ENV2, egdst_k_envA<1>, dim3(env_one_cta ? 1 : envA1, nst * nd, nvec), envA1block, 0, st, P, it);
-            if (P.envIPT == 2) PLAUNCH(KC_ENV2, (egdst_k_envBC<1, 2>), dim3(env_one_cta ? 1 : envBC1, nst * nd, nvec), dim3(P.envW), 0, st, P, it);
-            else PLAUNCH(KC_ENV2, (egdst_k_envBC<1, EGDST_ENV_IPT>), dim3(env_one_cta ? 1 : envBC1, nst * nd, nvec), dim3(P.envW), 0, st, P, it);
+            CK(cudaFuncSetAttribute(egdst_k_solve_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shsmem));
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, egdst_k_solve_grid, B, shsmem) != cudaSuccess || occ < 1) occ = 1;
         }
-        if (!P.envFuse) PLAUNCH(KC_ENV, egdst_k_envA<0>, dim3(env_one_cta ? 1 : envA0, nst, nvec), dim3(B), 0, st, P, it);
-        if (P.envIPT == 2) PLAUNCH(KC_ENV, (egdst_k_envBC<0, 2>), dim3(env_one_cta ? 1 : envBC0, nst, nvec), dim3(P.envW), 0, st, P, it);
-        else PLAUNCH(KC_ENV, (egdst_k_envBC<0, EGDST_ENV_IPT>), dim3(env_one_cta ? 1 : envBC0, nst, nvec), dim3(P.envW), 0, st, P, it);
-        PLAUNCH(KC_TAB, egdst_k_tab, dim3(tabblocks, nst, nvec), dim3(B), 0, st, P, it);
+        (void)dev;
+#else
+        s->cta_scope = getenv("EGDST_SOLVE_SCOPE") && strcmp(getenv("EGDST_SOLVE_SCOPE"), "cta") == 0;
+#endif
+        s->grid_ctas = sms * occ;
+        if (s->cta_scope && s->grid_ctas > nvec) s->grid_ctas = nvec;
+        if (getenv("EGDST_SOLVE_CTAS")) { const int g = atoi(getenv("EGDST_SOLVE_CTAS")); if (g >= 1 && g < s->grid_ctas) s->grid_ctas = g; }  // test hook
     }
+    // grid points per work item of the EGM phase: the items of one period fill the team exactly once (no tail wave);
+    // a CTA of the vector-per-CTA scope takes the whole grid of a decision at a time
+    const int G = s->cta_scope ? 1 : s->grid_ctas;
+    long long jobs = (long long)(s->cta_scope ? 1 : nvec) * nst * nd;
+    int egmP = (int)(((long long)(N - 1) * jobs + G - 1) / G);
+    if (egmP < 8) egmP = 8;
+    if (egmP > B) egmP = B;
+    if (egmP > N - 1 && N - 1 >= 1) egmP = N - 1 < 8 ? 8 : N - 1;
+    if (getenv("EGDST_EGM_P")) { const int p = atoi(getenv("EGDST_EGM_P")); if (p >= 8 && p <= B) egmP = p; }  // test hook
+    P.egmP = egmP;
+    P.phase_ns = g_prof_on ? s->d_phase : 0;  // measurement aid: in-kernel phase timers while profiling is enabled
+    if ((N - 1 + egmP - 1) / egmP + 2 > P.chC) return fail(2, "internal: scan state too small for the EGM items");
+#ifndef EGDST_HOSTEMU
+    prof_begin(KC_SOLVE, st);
+    if (s->cta_scope) {
+        egdst_k_solve_cta<<<s->grid_ctas, B, shsmem, st>>>(P);
+    } else {
+        void *args[] = {(void *)&P};
+        CK(cudaLaunchCooperativeKernel((const void *)egdst_k_solve_grid, dim3(s->grid_ctas), dim3(B), args, shsmem, st));
+    }
+    prof_end(st);
+#else
+    if (s->cta_scope) { KLAUNCH(KC_SOLVE, egdst_k_solve_cta, dim3(s->grid_ctas), dim3(B), shsmem, st, P); }
+    else { KLAUNCH(KC_SOLVE, egdst_k_solve_grid, dim3(1), dim3(B), shsmem, st, P); }
+#endif
     CK(cudaGetLastError());
     return 0;
 }
@@ -401,39 +380,8 @@ static int run_solve(egdst_solution *s, const egdst_desc *d, const double *param
         CK(cudaMemcpyAsync(s->d_qraw, d->quadrature, sizeof(double) * 2 * d->ny, cudaMemcpyHostToDevice, st));
         KLAUNCH(KC_SETUP, egdst_k_quadrature, dim3((d->ny + 127) / 128), dim3(128), 0, st, s->d_qraw, s->d_q, d->ny);
     }
-    // The period chain (~10 launches per period) is replayed as a CUDA graph from the third solve of an unchanged
-    // shape on: the first runs eagerly, the second is captured while it runs.  Everything that varies between
-    // solves of one shape (parameters, quadrature, state tables) lives in device memory, so the kernel arguments
-    // -- the EgdstDev block -- are identical and the instantiated graph stays valid.
-#ifndef EGDST_HOSTEMU
-    static const bool graphs_env_off = getenv("EGDST_NO_GRAPH") != 0;
-    const bool graphs_off = graphs_env_off || st == 0;  // the legacy default stream cannot be captured
-    const bool same = s->g_seen && s->g_stream == st && memcmp(&s->g_P, &P, sizeof(P)) == 0;
-    if (!g_prof_on && !graphs_off && same && s->g_exec) {
-        CK(cudaGraphLaunch(s->g_exec, st));
-        g_launches += s->g_nlaunch;
-    } else if (!g_prof_on && !graphs_off && same) {
-        cudaGraph_t graph = 0;
-        const long long l0 = g_launches;
-        CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-        rc = launch_periods(s, st);
-        cudaError_t e = cudaStreamEndCapture(st, &graph);
-        if (rc || e != cudaSuccess || !graph) { if (graph) cudaGraphDestroy(graph); return rc ? rc : fail(2, std::string("graph capture failed: ") + cudaGetErrorString(e)); }
-        s->g_nlaunch = g_launches - l0;
-        e = cudaGraphInstantiate(&s->g_exec, graph, 0);
-        cudaGraphDestroy(graph);
-        if (e != cudaSuccess) { s->g_exec = 0; return fail(2, std::string("graph instantiation failed: ") + cudaGetErrorString(e)); }
-        CK(cudaGraphLaunch(s->g_exec, st));
-    } else {
-        if (s->g_exec && !same) { cudaGraphExecDestroy(s->g_exec); s->g_exec = 0; }
-        rc = launch_periods(s, st);
-        if (rc) return rc;
-        s->g_P = P; s->g_stream = st; s->g_seen = true;
-    }
-#else
-    rc = launch_periods(s, st);
+    rc = launch_solve(s, st);
     if (rc) return rc;
-#endif
     s->sizes_valid = false;
     s->hdr_ivec = -1;
     CK(cudaGetLastError());
@@ -599,6 +547,81 @@ long long egdst_solution_units(egdst_solution *s) {
     return tot;
 }
 
+long long egdst_solution_resends(egdst_solution *s) {
+    // diagnostic: zero-consumption re-sends requested by grid points after the seed stage (egdst_solver.c:1080-1099)
+    // that the last solve handled, over all vectors
+    if (!s) return -1;
+    if (cudaSetDevice(s->device) != cudaSuccess) return -1;
+    std::vector<unsigned long long> u(s->P.nvec, 0ULL);
+    if (cudaMemcpyAsync(u.data(), s->P.units + s->P.nvec, sizeof(unsigned long long) * s->P.nvec, cudaMemcpyDeviceToHost, g_stream) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(g_stream) != cudaSuccess) return -1;
+    long long tot = 0;
+    for (unsigned long long x : u) tot += (long long)x;
+    return tot;
+}
+
+int egdst_solution_phase_ms(egdst_solution *s, double *ms) {
+    // device time per phase of the solve kernel (terminal, seed, egm, resend, envelope2, rank, merge, tables), accumulated over
+    // the solves of this object that ran while egdst_profile_enable(1) was in effect; reading resets the counters
+    if (!s || !ms) return -1;
+    if (cudaSetDevice(s->device) != cudaSuccess) return -1;
+    unsigned long long ns[EGDST_NPHASE];
+    if (cudaMemcpyAsync(ns, s->d_phase, sizeof(ns), cudaMemcpyDeviceToHost, g_stream) != cudaSuccess) return -1;
+    if (cudaMemsetAsync(s->d_phase, 0, sizeof(ns), g_stream) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(g_stream) != cudaSuccess) return -1;
+    for (int i = 0; i < EGDST_NPHASE; i++) ms[i] = (double)ns[i] * 1e-6;
+    return EGDST_NPHASE;
+}
+
+int egdst_test_envelope2(const egdst_desc *d, int it, int ist, int id, const double *X, const double *Cc, const double *V, int n, double evfa0,
+                         double *outX, double *outC, double *outV, int *nout) {
+    // diagnostic: the secondary upper envelope (envelope2, egdst_solver.c:776-913) of n EGM points of decision id in
+    // generation order, run by the same phases as the solve; the counterpart of the reference harness of the tests
+    if (!d || !X || !Cc || !V || !outX || !outC || !outV || !nout || n < 1) return fail(2, "invalid arguments");
+    if (ist != 0 || id < 0 || id >= d->nd) return fail(2, "egdst_test_envelope2: ist must be 0 and id a decision index");
+    if (n >= d->ngridmax) return fail(2, "egdst_test_envelope2: more points than ngridmax");
+    egdst_solution *s = 0;
+    int rc = create_solution(d, 1, &s);
+    if (rc) return rc;
+    EgdstDev P = s->P;
+    cudaStream_t st = g_stream;
+    cudaError_t ce = cudaSuccess;
+#define EGDST_TRY(call) do { if (ce == cudaSuccess) ce = (call); } while (0)
+    EGDST_TRY(cudaMemcpyAsync(s->d_stm, d->stm, sizeof(double) * 2 * d->nnst, cudaMemcpyHostToDevice, st));
+    EGDST_TRY(cudaMemcpyAsync(s->d_states, d->states, sizeof(double) * d->nst * d->nnst, cudaMemcpyHostToDevice, st));
+    EGDST_TRY(cudaMemcpyAsync(s->d_decisions, d->decisions, sizeof(double) * d->nd * d->nnd, cudaMemcpyHostToDevice, st));
+    // the decision's slot is sd = 0 of the scratch object; its decision index travels in the view (ist = 0 => sd = id):
+    // place the points in the slot of (ist 0, id) so that the analytic segment uses the right decision
+    const size_t off = (size_t)id * P.gcap;
+    EGDST_TRY(cudaMemsetAsync(P.status, 0, sizeof(int) * 4, st));
+    EGDST_TRY(cudaMemcpyAsync(P.ptX + off, X, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    EGDST_TRY(cudaMemcpyAsync(P.ptC + off, Cc, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    EGDST_TRY(cudaMemcpyAsync(P.ptV + off, V, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    EGDST_TRY(cudaMemcpyAsync(P.evfa0 + id, &evfa0, sizeof(double), cudaMemcpyHostToDevice, st));
+    int nres = 0;
+    if (ce == cudaSuccess) {
+        P.bparams = 0;
+        KLAUNCH(KC_OTHER, egdst_k_env2_only, dim3(1), dim3(EGDST_BLOCK), 0, st, P, it, n, id);
+        EGDST_TRY(cudaGetLastError());
+        EGDST_TRY(cudaMemcpyAsync(&nres, P.ptN + id, sizeof(int), cudaMemcpyDeviceToHost, st));
+        EGDST_TRY(cudaStreamSynchronize(st));
+    }
+    if (ce == cudaSuccess && nres > 0) {
+        EGDST_TRY(cudaMemcpyAsync(outX, P.ptX + off, sizeof(double) * nres, cudaMemcpyDeviceToHost, st));
+        EGDST_TRY(cudaMemcpyAsync(outC, P.ptC + off, sizeof(double) * nres, cudaMemcpyDeviceToHost, st));
+        EGDST_TRY(cudaMemcpyAsync(outV, P.ptV + off, sizeof(double) * nres, cudaMemcpyDeviceToHost, st));
+        EGDST_TRY(cudaStreamSynchronize(st));
+    }
+#undef EGDST_TRY
+    if (ce != cudaSuccess) { egdst_free_solution(s); return fail(2, std::string("CUDA error in egdst_test_envelope2: ") + cudaGetErrorString(ce)); }
+    *nout = nres;
+    s->sizes_valid = false;
+    rc = fetch_sizes(s);
+    if (!rc) rc = status_rc(s);
+    egdst_free_solution(s);
+    return rc;
+}
+
 void egdst_free_solution(egdst_solution *s) {
     if (!s) return;
     {
@@ -608,9 +631,6 @@ void egdst_free_solution(egdst_solution *s) {
     destroy_solution(s);
 }
 
-
-// tables of imported cells: the table part of egdst_k_tab only (no period housekeeping)
-__global__ void egdst_k_tabonly(EgdstDev P, int it) { egdst_tab_cell(P, egdst_cell(P, blockIdx.z, it, blockIdx.y), blockIdx.x, gridDim.x); }
 
 int egdst_solution_import(const egdst_desc *d, const int *mlen, const int *thlen, const double *Mbuf, const double *Dbuf, egdst_solution **out) {
     if (!out || !mlen || !thlen || !Mbuf || !Dbuf) return fail(2, "invalid arguments");

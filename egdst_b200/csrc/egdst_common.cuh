@@ -21,11 +21,21 @@
 
 #ifdef __CUDACC__
 #define EGDST_DEV_M __device__ __forceinline__
+#define EGDST_NOINLINE static __device__ __noinline__
 #else
 #define EGDST_DEV_M inline
+#define EGDST_NOINLINE static __attribute__((noinline))
 #endif
 
 #define EGDST_FULL 0xffffffffu
+#define EGDST_SEEDW 12
+#define EGDST_NPHASE 8   /* terminal, seed, egm, resend, envelope2, rank, merge, tables */
+#define EGDST_SHOCKTAB_BYTES (40 * 1024)  /* per-CTA table of quadrature shocks and node probabilities (dynamic shared memory) */
+#ifdef EGDST_HOSTEMU
+#define EGDST_SOLVE_MINB 1
+#else
+#define EGDST_SOLVE_MINB 3   /* CTAs per SM of the solve kernel (register budget 80) */
+#endif
 #define EGDST_MAXCAND 72   /* stage-0 bisection candidates: (mmax-a0)/2^k < TOLERANCE well before 72 halvings */
 #define EGDST_ENV_STACK 24 /* crossing-chain stack (thresholds() recursion depth) */
 #define EGDST_ENV_MARKW 32 /* 32*32 = 1024 functions (envelope2 runs) can be marked */
@@ -53,9 +63,7 @@ struct EgdstDev {
     double *evf;                    // [nvec*NT*nst]
     // per-period workspace, indexed by sd = (ivec*nst+ist)*nd+id
     int *active;                    // 1 if feasible(ist) && inchoiceset(id)
-    double *seed;                   // [nsd*8]: lim1,lim2,lim3,lim3p,k3,A0,-,-
-    double *rawM, *rawC, *rawV, *rawStop;  // [nsd*N]
-    int *rawFlag;                   // [nsd*N]
+    double *seed;                   // [nsd*EGDST_SEEDW]: lim1,lim2,lim3,lim3p,k3,A(prev),nfirst,ncalls,baseA,baseM (egdst_solver.cuh)
     double *evfa0;                  // [nsd]
     double *ptX, *ptC, *ptV;        // [nsd*gcap] per-id point lists
     int *ptN, *nfold, *runStart;    // [nsd], [nsd], [nsd*(gcap+1)]
@@ -64,18 +72,22 @@ struct EgdstDev {
     double *outX, *outC, *outV;            // per-slot output staging, capacity envcap
     int envcap;
     int *status;                    // [nvec*4]: code, it, ist, id of the first error
-    unsigned long long *units;      // [nvec] EGM grid points stored over all (it,ist,id): the solve work unit
+    unsigned long long *units;      // [2*nvec] EGM grid points stored over all (it,ist,id): the solve work unit; then: late re-sends handled
     // chained scans across CTAs (decoupled look-back): state words per chunk, [ticket, done] counters per job;
     // zeroed at the start of every period by egdst_k_cells
     unsigned long long *scanC, *scanE;  // [nsd*chC] compaction, [nslot*chE] envelope merge
     int *tickC, *tickE;                 // [nsd*2], [nslot*2]
     int chC, chE;                       // chunks per job
-    int cmpW, cmpIPT;                   // threads per CTA and raw points per thread of the compaction (chunk = cmpW * cmpIPT)
-    int envW;                           // threads per CTA of the envelope merge (chunk = envW * IPT positions)
-    int envFuse;                        // 1: the envelope merge kernels run the rank step themselves (single-CTA jobs)
-    int envIPT;                        // positions per thread in the envelope merges (8, or 2 for a single large model)
+    int envA1parts;                     // threads that share the runs of one point in the rank step of the secondary envelope (1 or 8)
     int *foldList, *foldCnt;            // [nsd*(gcap+1)] unordered fold positions, [nsd]
     int *envNact;                       // [nslot] active prefix length of the merged union (egdst_k_envA)
+    int *lateN;                         // [nsd] first grid index whose evaluation asked for a zero-consumption re-send in this pass (INT_MAX: none)
+    int *flags;                         // [(1+nvec)*8] per team: [0..2] re-sends pending after EGM pass k%3, [3] folds found in this period
+    unsigned *bar;                      // grid barrier word of the cooperative solve kernel
+    unsigned long long *phase_ns;       // [EGDST_NPHASE] device time per phase of the solve kernel (measurement aid; null = off)
+    int itStop;                         // last period to solve (0; higher: test hook)
+    int itStart;                        // period the backward induction starts from (NT-1; lower: test hook, cells of later periods are given)
+    int egmP;                           // grid points per work item of the EGM phase (<= threads per CTA); slices = threads / egmP
     // per-cell lookup tables (egdst_tables.cuh)
     EgdstRow *tabRow;                   // [ncell*(tabcap+1)]
     EgdstLutEntry *tabLut;              // [ncell*(lutcap+1)]
@@ -99,6 +111,62 @@ EGDST_DEV void egdst_load_ctx(const EgdstDev &P, int ivec, egdst_ctx &cx) {
 EGDST_DEV void egdst_fail(const EgdstDev &P, int ivec, int code, int it, int ist, int id) {
     int *s = P.status + 4 * ivec;
     if (atomicCAS(s, 0, code) == 0) { s[1] = it; s[2] = ist; s[3] = id; }
+}
+
+// ---- teams ------------------------------------------------------------------------------------
+// The backward induction runs as ONE kernel (egdst_period.cuh).  A team is the set of CTAs that cooperate on the
+// periods of a set of parameter vectors [v0, v0+nv):
+//   GRID scope  every CTA of a cooperative launch (one resident wave) works on all vectors; the phases of a period
+//               are separated by a grid-wide barrier                                  -- one large model, few vectors
+//   CTA scope   one CTA owns one vector at a time and walks it through all periods; phases are separated by
+//               __syncthreads()                                                        -- sweeps of many small models
+// Every phase is a loop `for (w = rank; w < nwork; w += size)` over work items, so the same code serves both.
+struct EgdstTeam { int rank, size, v0, nv, slot; };
+
+// Grid-wide barrier of a cooperative launch (all CTAs resident): CTA barrier, one thread arrives on a global word
+// with release/acquire fences around it, CTA barrier (the scheme of cooperative_groups::grid_group::sync; the high
+// bit of the word flips once per generation, so the counter never has to be reset).  The acquire side also
+// invalidates this SM's L1, which is what lets the phases after the barrier read with plain cached loads the arrays
+// that other CTAs rewrote.
+// Returns false when the barrier was abandoned: polls are bounded (a protocol bug or a CTA that died must surface as
+// an error status, never as a hung device); bar[1] is the abort flag every waiting CTA also watches.
+#define EGDST_BARRIER_POLLS (1 << 24)
+EGDST_DEV bool egdst_grid_barrier(unsigned *bar) {
+    __syncthreads();
+#ifndef EGDST_HOSTEMU
+    if (gridDim.x > 1) {
+        __shared__ int s_ok;
+        if (threadIdx.x == 0) {
+            const unsigned nb = (blockIdx.x == 0) ? 0x80000000u - (gridDim.x - 1u) : 1u;
+            __threadfence();
+            const unsigned old = atomicAdd(bar, nb);
+            int polls = 0, ok = 1;
+            while ((((old ^ *((volatile unsigned *)bar)) & 0x80000000u) == 0u)) {
+                if (((++polls) & 1023) == 0 && (polls >= EGDST_BARRIER_POLLS || *((volatile unsigned *)(bar + 1)) != 0u)) { *((volatile unsigned *)(bar + 1)) = 1u; ok = 0; break; }
+            }
+            __threadfence();
+            s_ok = ok;
+        }
+        __syncthreads();
+        return s_ok != 0;
+    }
+#endif
+    return true;
+}
+// work items of a phase: w = vb * njobs + j with j = (ivec - T.v0) * jobs_per_vector + jy; virtual blocks of a job are
+// spread over the CTAs that run at the same time (chained scans wait on lower virtual blocks of the same job only)
+EGDST_DEV void egdst_item(const EgdstTeam &T, int w, int jpv, int &ivec, int &jy, int &vb) {
+    const int njobs = T.nv * jpv;
+    vb = w / njobs;
+    const int j = w - vb * njobs;
+    ivec = T.v0 + j / jpv;
+    jy = j - (j / jpv) * jpv;
+}
+template <bool GRID>
+EGDST_DEV bool egdst_team_sync(const EgdstDev &P) {
+    if (GRID) return egdst_grid_barrier(P.bar);
+    __syncthreads();
+    return true;
 }
 
 // ---- warp / block collectives (shuffle based) -------------------------------------------------

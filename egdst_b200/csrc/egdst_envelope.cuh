@@ -27,6 +27,7 @@
 //         extended by the constant-extrapolation sentinel (1.5*mmax, C_last, V_last) (egdst_solver.c:824-827)
 template <int MODE>
 struct EgdstEnvView {
+    static const int kMode = MODE;
     int F;
     const double *X, *C, *V;  // MODE 0: base of decision 0 (stride gcap); MODE 1: the id's list
     const int *n;             // MODE 0: ptN + sd0 ; MODE 1: runStart
@@ -202,45 +203,52 @@ EGDST_DEV void egdst_env_check_allinf(const EgdstDev &P, int ivec, int it, int i
     if (any && tot == 0) egdst_fail(P, ivec, EGDST_ERR_ALLINF, it, ist, -1);
 }
 
+// Step A as a phase: work item = (job, virtual block of npt points); nvb virtual blocks per job stride over its points.
+// `nparts` threads share the functions of one point and combine rank and argmax through shared memory -- the
+// secondary envelope of a zig-zagging grid has ~10^2 runs, and a point that walks them alone is a chain of ~10^2
+// dependent loads.
 template <int MODE>
-__global__ void egdst_k_envA(EgdstDev P, int it) {
-    // blockDim = (points, parts): `parts` threads share the functions of one point and combine rank and argmax through
-    // shared memory -- the secondary envelope of a zig-zagging grid has ~10^2 runs, and a point that walks them alone
-    // is a chain of ~10^2 dependent loads
+EGDST_DEV void egdst_ph_envA(const EgdstDev &P, int it, const EgdstTeam &T, int nvb) {
     __shared__ double shg[33];
-    __shared__ int s_rank[256], s_best[256];
-    __shared__ double s_bv[256];
-    const int ivec = blockIdx.z;
-    const int lane = threadIdx.x, part = threadIdx.y, nparts = blockDim.y, npt = blockDim.x;
-    int ist, id, slot;
-    EgdstEnvView<MODE> E;
-    if (MODE == 0 && blockIdx.x == 0 && lane == 0 && part == 0) egdst_env_check_allinf(P, ivec, it, blockIdx.y);
-    if (!egdst_env_job<MODE>(P, ivec, blockIdx.y, ist, id, slot, E)) return;
-    egdst_ctx cx; egdst_load_ctx(P, ivec, cx);
-    const int Ptot = E.pstart(E.F - 1) + E.npts(E.F - 1);
-    if (blockIdx.x * npt >= Ptot) return;  // CTA-uniform
-    const double grb = egdst_env_grb_block(E, shg);
-    // the grid is sized for the usual number of points (host: launch_periods) and strides over longer lists
-    for (int base = blockIdx.x * npt; base < Ptot; base += gridDim.x * npt) {
-        const int p = base + lane;
-        const bool valid = p < Ptot;
-        int f = 0, k = 0, rank = 0, best = 0x7fffffff;
-        double x = 0, v = 0, bestv = -EGDST_INF;
-        if (valid) egdst_env_point_partial<MODE>(cx, E, it, ist, p, part, nparts, f, k, x, v, rank, best, bestv);
-        if (nparts > 1) {
-            const int slotx = part * npt + lane;
-            s_rank[slotx] = rank; s_best[slotx] = best; s_bv[slotx] = bestv;
-            __syncthreads();
-            if (part == 0 && valid) {
-                for (int q = 1; q < nparts; q++) {
-                    const int o = q * npt + lane;
-                    rank += s_rank[o];
-                    if (s_bv[o] > bestv || (s_bv[o] == bestv && s_best[o] < best)) { bestv = s_bv[o]; best = s_best[o]; }
+    __shared__ int s_rank[EGDST_BLOCK], s_best[EGDST_BLOCK];
+    __shared__ double s_bv[EGDST_BLOCK];
+    const int nparts = (MODE == 1) ? P.envA1parts : 1, npt = blockDim.x / nparts;
+    const int lane = threadIdx.x % npt, part = threadIdx.x / npt;
+    const int jpv = (MODE == 0) ? P.cx.nst : P.cx.nst * P.cx.nd;
+    const int nwork = T.nv * jpv * nvb;
+    for (int w = T.rank; w < nwork; w += T.size) {
+        int ivec, jy, vb;
+        egdst_item(T, w, jpv, ivec, jy, vb);
+        int ist, id, slot;
+        EgdstEnvView<MODE> E;
+        if (MODE == 0 && vb == 0 && threadIdx.x == 0) egdst_env_check_allinf(P, ivec, it, jy);
+        if (!egdst_env_job<MODE>(P, ivec, jy, ist, id, slot, E)) continue;
+        const int Ptot = E.pstart(E.F - 1) + E.npts(E.F - 1);
+        if (vb * npt >= Ptot) continue;  // CTA-uniform
+        egdst_ctx cx; egdst_load_ctx(P, ivec, cx);
+        __syncthreads();  // scratch of the previous item is free
+        const double grb = egdst_env_grb_block(E, shg);
+        for (int base = vb * npt; base < Ptot; base += nvb * npt) {
+            const int p = base + lane;
+            const bool valid = p < Ptot;
+            int f = 0, k = 0, rank = 0, best = 0x7fffffff;
+            double x = 0, v = 0, bestv = -EGDST_INF;
+            if (valid) egdst_env_point_partial<MODE>(cx, E, it, ist, p, part, nparts, f, k, x, v, rank, best, bestv);
+            if (nparts > 1) {
+                const int slotx = part * npt + lane;
+                s_rank[slotx] = rank; s_best[slotx] = best; s_bv[slotx] = bestv;
+                __syncthreads();
+                if (part == 0 && valid) {
+                    for (int q = 1; q < nparts; q++) {
+                        const int o = q * npt + lane;
+                        rank += s_rank[o];
+                        if (s_bv[o] > bestv || (s_bv[o] == bestv && s_best[o] < best)) { bestv = s_bv[o]; best = s_best[o]; }
+                    }
                 }
             }
+            if (part == 0 && valid) egdst_env_point_commit(P, slot, grb, f, k, x, rank, best);
+            if (nparts > 1 && base + nvb * npt < Ptot) __syncthreads();  // scratch reused by the next stride
         }
-        if (part == 0 && valid) egdst_env_point_commit(P, slot, grb, f, k, x, rank, best);
-        if (nparts > 1 && base + (int)(gridDim.x * npt) < Ptot) __syncthreads();  // scratch reused by the next stride
     }
 }
 
@@ -306,7 +314,17 @@ EGDST_DEV void egdst_env_chain(const egdst_ctx *cx, const View &E, int it, int i
             const double spp = (pf1 - pf0) / (pg1 - pg0), ip = (pf0 * pg1 - pf1 * pg0) / (pg1 - pg0);
             if (pg1 == pg0) { newpoint = pg0; cmax = newpoint * sq + iq; }
             else if (qg1 == qg0) { newpoint = qg0; cmax = newpoint * spp + ip; }
-            else if (sq == spp) { newpoint = (pg0 + pg1 + qg0 + qg1) / 4; cmax = newpoint * sq + iq; }
+            else if (sq == spp) {
+                // Parallel pieces.  Between two consecutive abscissas of the union both functions are single linear
+                // pieces, so the maximum can pass from one to the other only where they coincide: the constant
+                // extrapolations of two runs of a flat stretch (egdst_solver.c:824-827), told apart by the last bit of
+                // an interpolation.  The reference places a double point at the mean of the four end points here
+                // (:1737-1753) -- an abscissa far outside the bracket, which its later qsort moves beyond the unified
+                // grid's bound and so never reaches the solution.  The runs of one decision share the decision, so no
+                // threshold is due either: nothing is emitted, the list stays sorted.
+                if (View::kMode == 1) continue;
+                newpoint = (pg0 + pg1 + qg0 + qg1) / 4; cmax = newpoint * sq + iq;
+            }
             else { newpoint = (ip - iq) / (sq - spp); cmax = newpoint * sq + iq; }
         }
         // is a third, not yet visited function above at the crossing? (egdst_solver.c:1807-1845, mode 1)
@@ -358,17 +376,8 @@ EGDST_DEV void egdst_env_chain(const egdst_ctx *cx, const View &E, int it, int i
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Step B/C: one wide CTA per job walks the union in order, EGDST_ENV_IPT consecutive positions per thread
-// and pass; one block-wide scan per pass places the kept points, the crossing double points and the
-// thresholds (a 2*10^4-point union is five passes).
-// MODE 0 writes the period's solution cell (rows 1.., thresholds, evf, row 0); MODE 1 rewrites the id's list.
-// grid (1, njobs_y, nvec)
-// ---------------------------------------------------------------------------------------------
-#define EGDST_ENV_IPT 8
-
 // one position r of the union: its own contribution (kept point, first threshold) and whether a crossing chain
-// sits on the boundary before it.  The chains themselves are queued and run one per warp (egdst_k_envBC).
+// sits on the boundary before it.  The chains themselves are queued and run one per warp (egdst_ph_envBC).
 struct EgdstEnvPos { double x, v; int f, k, a, aprev; bool newx, chain; };
 template <int MODE>
 EGDST_DEV EgdstEnvPos egdst_env_pos(const EgdstEnvView<MODE> &E, const double *mgX, const int *mgF, const int *mgK, const int *mgA, int r) {
@@ -381,118 +390,94 @@ EGDST_DEV EgdstEnvPos egdst_env_pos(const EgdstEnvView<MODE> &E, const double *m
     return q;
 }
 
-#define EGDST_ENV_CHUNK (EGDST_ENVW * EGDST_ENV_IPT)  /* union positions per chunk at the widest CTA */
-#define EGDST_ENV_QCAP 512                             /* crossing chains queued per CTA */
-// IPT positions per thread: 8, or 2 for the secondary envelope of a single large model, whose crossing chains (one
-// per warp at a time) then spread over four times as many warps.
-// grid (<= chE, njobs_y, nvec), blockDim.x = P.envW: the CTAs of one job take chunks of blockDim.x*IPT union positions
-// by ticket until none is left and are chained by a decoupled look-back scan over (grid points, thresholds) emitted
-// so far; the last CTA to finish writes the cell header (MODE 0) or copies the staged result back over the
-// decision's point list (MODE 1).  Small models in batched sweeps run narrow CTAs (P.envW = 64), one per job.
-// register budget: the 8-positions-per-thread instances serve sweeps of small models, where CTAs per SM count (64
-// registers, 4 x 256 threads); the 2-positions instances serve one large model and keep their registers
-template <int MODE, int IPT>
-__global__ void __launch_bounds__(EGDST_ENVW, IPT == 8 ? 4 : 1) egdst_k_envBC(EgdstDev P, int it) {
-    __shared__ long long sh[40];
-    __shared__ double s_grb[33];
-    __shared__ int s_chunk, s_last, s_qn;
-    __shared__ unsigned long long s_excl;
-    __shared__ int s_qr[EGDST_ENV_QCAP], s_qg[EGDST_ENV_QCAP], s_qt[EGDST_ENV_QCAP], s_qgpos[EGDST_ENV_QCAP], s_qtpos[EGDST_ENV_QCAP];
-    const int ivec = blockIdx.z;
-    int ist, id, slot;
-    EgdstEnvView<MODE> E;
-    if (!egdst_env_job<MODE>(P, ivec, blockIdx.y, ist, id, slot, E)) return;
-    egdst_ctx cx; egdst_load_ctx(P, ivec, cx);
-    const double *mgX = P.mgX + (size_t)slot * P.envcap;
-    const int *mgF = P.mgF + (size_t)slot * P.envcap, *mgK = P.mgK + (size_t)slot * P.envcap, *mgA = P.mgA + (size_t)slot * P.envcap;
-    volatile unsigned long long *st = P.scanE + (size_t)slot * P.chE;
-    double *ox, *oc, *ov, *oa = 0, *oth = 0, *odd = 0;
-    int gcapacity, tcapacity = 0, cell = 0;
-    if (MODE == 0) {
-        cell = egdst_cell(P, ivec, it, ist);
-        ox = egdst_colM(P, cell) + 1; oc = egdst_colC(P, cell) + 1; ov = egdst_colV(P, cell) + 1; oa = egdst_colA(P, cell) + 1;
-        oth = P.thTH + (size_t)cell * cx.nthrhmax; odd = P.thD + (size_t)cell * cx.nthrhmax;
-        gcapacity = P.rowcap - 1; tcapacity = cx.nthrhmax;
-    } else {
-        ox = P.outX + (size_t)slot * P.envcap; oc = P.outC + (size_t)slot * P.envcap; ov = P.outV + (size_t)slot * P.envcap;
-        gcapacity = P.envcap;
-    }
-    // the active positions of the union are the prefix with x<=grb (length recorded by egdst_k_envA)
-    if (P.envFuse) {
-        // small jobs (a single CTA per job, host: launch_periods): the rank step runs here instead of as a launch of
-        // its own; __syncthreads() orders this CTA's global writes before its reads below
-        if (MODE == 0 && threadIdx.x == 0) egdst_env_check_allinf(P, ivec, it, ist);
-        const int Ptot = E.pstart(E.F - 1) + E.npts(E.F - 1);
-        const double grbA = egdst_env_grb_block(E, s_grb);
-        for (int p = threadIdx.x; p < Ptot; p += blockDim.x) {
-            int f, k, rank, best; double x, v, bestv;
-            egdst_env_point_partial<MODE>(cx, E, it, ist, p, 0, 1, f, k, x, v, rank, best, bestv);
-            egdst_env_point_commit(P, slot, grbA, f, k, x, rank, best);
-        }
-        __threadfence();
-        __syncthreads();
-    }
-    const int nact = EGDST_LDCG(P.envNact + slot);
-    const int chunkw = blockDim.x * IPT;
-    const int nch = (nact + chunkw - 1) / chunkw;
-    const double grb = nch > 0 ? egdst_env_grb_block(E, s_grb) : 0.0;  // nch is CTA-uniform
+// Step B/C as a phase.  The union of a job is cut into chunks of blockDim.x positions (one per thread); a work item
+// takes the next chunk of its job by ticket and the chunks are chained by a decoupled look-back scan over (grid
+// points, thresholds) emitted so far.  The rare crossing chains are queued per chunk and run one per warp.  The last
+// item of a job to finish writes the cell header (MODE 0) or copies the staged result back over the decision's point
+// list (MODE 1).  P.chE items per job, most of which find no chunk left.
+// MODE 0 writes the period's solution cell (rows 1.., thresholds, evf, row 0); MODE 1 rewrites the id's list.
+struct EgdstEnvShared {
+    long long sh[40];
+    double grb[33];
+    int chunk, last, qn;
+    unsigned long long excl;
+    int qr[EGDST_BLOCK], qg[EGDST_BLOCK], qt[EGDST_BLOCK], qgpos[EGDST_BLOCK], qtpos[EGDST_BLOCK];
+};
+
+template <int MODE>
+EGDST_DEV void egdst_ph_envBC(const EgdstDev &P, int it, const EgdstTeam &T) {
+    __shared__ EgdstEnvShared Sh;
+    const int jpv = (MODE == 0) ? P.cx.nst : P.cx.nst * P.cx.nd;
+    const int nitems = P.chE;
+    const int nwork = T.nv * jpv * nitems;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    int err = 0, serr = 0;
-    while (true) {
-        __syncthreads();  // the previous chunk's queue and scan scratch are free again
-        if (threadIdx.x == 0) { s_chunk = atomicAdd(P.tickE + 2 * slot, 1); s_qn = 0; }
+    for (int w = T.rank; w < nwork; w += T.size) {
+        int ivec, jy, vb;
+        egdst_item(T, w, jpv, ivec, jy, vb);
+        int ist, id, slot;
+        EgdstEnvView<MODE> E;
+        if (!egdst_env_job<MODE>(P, ivec, jy, ist, id, slot, E)) continue;
+        egdst_ctx cx; egdst_load_ctx(P, ivec, cx);
+        const double *mgX = P.mgX + (size_t)slot * P.envcap;
+        const int *mgF = P.mgF + (size_t)slot * P.envcap, *mgK = P.mgK + (size_t)slot * P.envcap, *mgA = P.mgA + (size_t)slot * P.envcap;
+        volatile unsigned long long *st = P.scanE + (size_t)slot * P.chE;
+        double *ox, *oc, *ov, *oa = 0, *oth = 0, *odd = 0;
+        int gcapacity, tcapacity = 0, cell = 0;
+        if (MODE == 0) {
+            cell = egdst_cell(P, ivec, it, ist);
+            ox = egdst_colM(P, cell) + 1; oc = egdst_colC(P, cell) + 1; ov = egdst_colV(P, cell) + 1; oa = egdst_colA(P, cell) + 1;
+            oth = P.thTH + (size_t)cell * cx.nthrhmax; odd = P.thD + (size_t)cell * cx.nthrhmax;
+            gcapacity = P.rowcap - 1; tcapacity = cx.nthrhmax;
+        } else {
+            ox = P.outX + (size_t)slot * P.envcap; oc = P.outC + (size_t)slot * P.envcap; ov = P.outV + (size_t)slot * P.envcap;
+            gcapacity = P.envcap;
+        }
+        // the active positions of the union are the prefix with x<=grb (length recorded by egdst_ph_envA)
+        const int nact = EGDST_LDCG(P.envNact + slot);
+        const int chunkw = blockDim.x;
+        const int nch = (nact + chunkw - 1) / chunkw;
+        int err = 0, serr = 0;
+        __syncthreads();  // the previous item's queue and scan scratch are free again
+        if (threadIdx.x == 0) { Sh.chunk = atomicAdd(P.tickE + 2 * slot, 1); Sh.qn = 0; }
         __syncthreads();
-        const int chunk = s_chunk;
-        if (chunk >= nch) break;
-        const int r0 = chunk * chunkw + threadIdx.x * IPT;
-        // pass 1: own contribution of every position; crossing chains go to the CTA's queue
-        int ngj[IPT], ntj[IPT], qj[IPT];
-#pragma unroll
-        for (int j = 0; j < IPT; j++) {
-            ngj[j] = 0; ntj[j] = 0; qj[j] = -1;
-            const int r = r0 + j;
+        const int chunk = Sh.chunk;
+        if (chunk < nch) {
+            const double grb = egdst_env_grb_block(E, Sh.grb);
+            const int r = chunk * chunkw + threadIdx.x;
+            // pass 1: own contribution of every position; crossing chains go to the item's queue
+            int ngj = 0, ntj = 0, qj = -1;
+            EgdstEnvPos q; q.x = 0; q.v = 0; q.f = 0; q.k = 0; q.a = 0; q.aprev = 0; q.newx = false; q.chain = false;
             if (r < nact) {
-                const EgdstEnvPos q = egdst_env_pos<MODE>(E, mgX, mgF, mgK, mgA, r);
-                if (r == 0) ntj[j] = 1;  // (a0, argmax at the first point)  egdst_solver.c:1321-1325
-                if (q.newx && (q.a == q.f || q.x == grb)) ngj[j] = 1;
-                if (q.chain) { const int c = atomicAdd(&s_qn, 1); if (c < EGDST_ENV_QCAP) { s_qr[c] = r; qj[j] = c; } else qj[j] = -2; }
+                q = egdst_env_pos<MODE>(E, mgX, mgF, mgK, mgA, r);
+                if (r == 0) ntj = 1;  // (a0, argmax at the first point)  egdst_solver.c:1321-1325
+                if (q.newx && (q.a == q.f || q.x == grb)) ngj = 1;
+                if (q.chain) { const int c = atomicAdd(&Sh.qn, 1); Sh.qr[c] = r; qj = c; }
             }
-        }
-        __syncthreads();
-        const int qn = s_qn < EGDST_ENV_QCAP ? s_qn : EGDST_ENV_QCAP;
-        if (s_qn > EGDST_ENV_QCAP) serr = 2;  // more crossings in one chunk than the queue holds
-        // pass 2: one chain per warp, counting
-        for (int c = warp; c < qn; c += nwarps) {
-            const int r = s_qr[c];
-            const EgdstEnvPos q = egdst_env_pos<MODE>(E, mgX, mgF, mgK, mgA, r);
-            int cg, ct;
-            egdst_env_chain(&cx, E, it, ist, q.x, q.v, q.f, q.k, q.aprev, q.a, false, (double *)0, (double *)0, (double *)0, (double *)0, 0, (double *)0, (double *)0, 0, cg, ct, &err);
-            if (lane == 0) { s_qg[c] = cg; s_qt[c] = ct; }
-        }
-        __syncthreads();
-        int ngs = 0, nts = 0;
-#pragma unroll
-        for (int j = 0; j < IPT; j++) {
-            if (qj[j] >= 0) { ngj[j] += s_qg[qj[j]]; ntj[j] += s_qt[qj[j]]; }
-            ngs += ngj[j]; nts += ntj[j];
-        }
-        long long tot;
-        const long long off = egdst_block_excl_scan64(((long long)nts << 32) | (long long)ngs, sh, &tot);
-        if (threadIdx.x < 32) {
-            const unsigned long long e = egdst_lookback<0>(st, chunk, egdst_scan_pack((int)(tot & 0xffffffffLL), (int)(tot >> 32)), &serr);
-            if (threadIdx.x == 0) s_excl = e;
-        }
-        __syncthreads();
-        int gpos = egdst_scan_lo(s_excl) + (int)(off & 0xffffffffLL), tpos = egdst_scan_hi(s_excl) + (int)(off >> 32);
-        // pass 3: write the kept points; chains get their output offsets
-#pragma unroll
-        for (int j = 0; j < IPT; j++) {
-            const int r = r0 + j;
-            if (r < nact && (ngj[j] | ntj[j])) {
-                const EgdstEnvPos q = egdst_env_pos<MODE>(E, mgX, mgF, mgK, mgA, r);
+            __syncthreads();
+            const int qn = Sh.qn;
+            // pass 2: one chain per warp, counting
+            for (int c = warp; c < qn; c += nwarps) {
+                const int rr = Sh.qr[c];
+                const EgdstEnvPos qq = egdst_env_pos<MODE>(E, mgX, mgF, mgK, mgA, rr);
+                int cg, ct;
+                egdst_env_chain(&cx, E, it, ist, qq.x, qq.v, qq.f, qq.k, qq.aprev, qq.a, false, (double *)0, (double *)0, (double *)0, (double *)0, 0, (double *)0, (double *)0, 0, cg, ct, &err);
+                if (lane == 0) { Sh.qg[c] = cg; Sh.qt[c] = ct; }
+            }
+            __syncthreads();
+            if (qj >= 0) { ngj += Sh.qg[qj]; ntj += Sh.qt[qj]; }
+            long long tot;
+            const long long off = egdst_block_excl_scan64(((long long)ntj << 32) | (long long)ngj, Sh.sh, &tot);
+            if (threadIdx.x < 32) {
+                const unsigned long long e = egdst_lookback<0>(st, chunk, egdst_scan_pack((int)(tot & 0xffffffffLL), (int)(tot >> 32)), &serr);
+                if (threadIdx.x == 0) Sh.excl = e;
+            }
+            __syncthreads();
+            const int gpos = egdst_scan_lo(Sh.excl) + (int)(off & 0xffffffffLL), tpos = egdst_scan_hi(Sh.excl) + (int)(off >> 32);
+            // pass 3: write the kept points; chains get their output offsets
+            if (r < nact && (ngj | ntj)) {
                 int g = gpos, t = tpos;
                 if (r == 0) { if (MODE == 0 && t < tcapacity) { oth[t] = cx.a0; odd[t] = (double)q.a; } t += 1; }
-                if (qj[j] >= 0) { s_qgpos[qj[j]] = g; s_qtpos[qj[j]] = t; g += s_qg[qj[j]]; }
+                if (qj >= 0) { Sh.qgpos[qj] = g; Sh.qtpos[qj] = t; g += Sh.qg[qj]; }
                 if (q.newx && (q.a == q.f || q.x == grb)) {
                     double v = q.v, c;
                     if (q.a == q.f) c = E.c(q.f, q.k);
@@ -505,64 +490,62 @@ __global__ void __launch_bounds__(EGDST_ENVW, IPT == 8 ? 4 : 1) egdst_k_envBC(Eg
                     if (g < gcapacity) { ox[g] = q.x; ov[g] = v; oc[g] = c; if (oa) oa[g] = q.x - c; }
                 }
             }
-            gpos += ngj[j]; tpos += ntj[j];
-        }
-        __syncthreads();
-        // pass 4: one chain per warp, writing
-        for (int c = warp; c < qn; c += nwarps) {
-            const int r = s_qr[c];
-            const EgdstEnvPos q = egdst_env_pos<MODE>(E, mgX, mgF, mgK, mgA, r);
-            const int bg = s_qgpos[c], bt = s_qtpos[c];
-            int cg, ct;
-            egdst_env_chain(&cx, E, it, ist, q.x, q.v, q.f, q.k, q.aprev, q.a, true, ox + bg, ov + bg, oc + bg, oa ? oa + bg : (double *)0, gcapacity - bg,
-                            MODE == 0 ? oth + bt : (double *)0, MODE == 0 ? odd + bt : (double *)0, MODE == 0 ? tcapacity - bt : 0, cg, ct, &err);
-        }
-    }
-    if (err) egdst_fail(P, ivec, err, it, ist, id);
-    if (serr) egdst_fail(P, ivec, serr == 2 ? EGDST_ERR_THRSPACE : EGDST_ERR_ENV2SPACE, it, ist, id);
-    // last CTA of the job: totals and epilogue
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(P.tickE + 2 * slot + 1, 1) == (int)gridDim.x - 1);
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    const unsigned long long totals = nch > 0 ? egdst_scan_inclusive(st, nch - 1) : 0ULL;
-    const int nout = egdst_scan_lo(totals), nth = egdst_scan_hi(totals);
-    if (MODE == 0) {
-        if (threadIdx.x == 0) {
-            if (nout >= cx.ngridmax) egdst_fail(P, ivec, EGDST_ERR_GRIDSPACE, it, ist, -1);
-            if (nth >= cx.nthrhmax) egdst_fail(P, ivec, EGDST_ERR_THRSPACE, it, ist, -1);
-            if (nout == 0 || nth == 0) egdst_fail(P, ivec, EGDST_ERR_ENVELOPE, it, ist, -1);
-            const int n = nout < gcapacity ? nout : gcapacity;
-            const int d0 = nact > 0 ? mgA[0] : 0;
-            const double e = E.evf(d0);  // egdst_solver.c:730
-            P.evf[cell] = e;
-            P.mlen[cell] = n + 1;
-            P.thlen[cell] = nth < tcapacity ? nth : tcapacity;
-            egdst_colM(P, cell)[0] = cx.a0; egdst_colC(P, cell)[0] = 0.0; egdst_colV(P, cell)[0] = e;  // saveoutput :931-941
-            egdst_colA(P, cell)[0] = cx.a0 - 0.0;
-        }
-    } else {
-        const int sd = slot;
-        if (threadIdx.x == 0 && nout >= cx.ngridmax) egdst_fail(P, ivec, EGDST_ERR_ENV2SPACE, it, ist, id);
-        const int n = nout < P.gcap ? nout : P.gcap;
-        double *X = P.ptX + (size_t)sd * P.gcap, *Cc = P.ptC + (size_t)sd * P.gcap, *V = P.ptV + (size_t)sd * P.gcap;
-        __syncthreads();
-        // copy-back by one CTA: batches of independent loads (a plain loop is a chain of n/blockDim L2 round trips)
-        for (int i0 = threadIdx.x; i0 < n; i0 += 8 * blockDim.x) {
-            double bx[8], bc[8], bv[8];
-#pragma unroll
-            for (int u = 0; u < 8; u++) {
-                const int i = i0 + u * blockDim.x;
-                if (i < n) { bx[u] = EGDST_LDCG(ox + i); bc[u] = EGDST_LDCG(oc + i); bv[u] = EGDST_LDCG(ov + i); }
-            }
-#pragma unroll
-            for (int u = 0; u < 8; u++) {
-                const int i = i0 + u * blockDim.x;
-                if (i < n) { X[i] = bx[u]; Cc[i] = bc[u]; V[i] = bv[u]; }
+            __syncthreads();
+            // pass 4: one chain per warp, writing
+            for (int c = warp; c < qn; c += nwarps) {
+                const int rr = Sh.qr[c];
+                const EgdstEnvPos qq = egdst_env_pos<MODE>(E, mgX, mgF, mgK, mgA, rr);
+                const int bg = Sh.qgpos[c], bt = Sh.qtpos[c];
+                int cg, ct;
+                egdst_env_chain(&cx, E, it, ist, qq.x, qq.v, qq.f, qq.k, qq.aprev, qq.a, true, ox + bg, ov + bg, oc + bg, oa ? oa + bg : (double *)0, gcapacity - bg,
+                                MODE == 0 ? oth + bt : (double *)0, MODE == 0 ? odd + bt : (double *)0, MODE == 0 ? tcapacity - bt : 0, cg, ct, &err);
             }
         }
-        if (threadIdx.x == 0) P.ptN[sd] = n;
+        if (err) egdst_fail(P, ivec, err, it, ist, id);
+        if (serr) egdst_fail(P, ivec, EGDST_ERR_ENV2SPACE, it, ist, id);
+        // last item of the job: totals and epilogue
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) Sh.last = (atomicAdd(P.tickE + 2 * slot + 1, 1) == nitems - 1);
+        __syncthreads();
+        if (!Sh.last) continue;
+        __threadfence();
+        const unsigned long long totals = nch > 0 ? egdst_scan_inclusive(st, nch - 1) : 0ULL;
+        const int nout = egdst_scan_lo(totals), nth = egdst_scan_hi(totals);
+        if (MODE == 0) {
+            if (threadIdx.x == 0) {
+                if (nout >= cx.ngridmax) egdst_fail(P, ivec, EGDST_ERR_GRIDSPACE, it, ist, -1);
+                if (nth >= cx.nthrhmax) egdst_fail(P, ivec, EGDST_ERR_THRSPACE, it, ist, -1);
+                if (nout == 0 || nth == 0) egdst_fail(P, ivec, EGDST_ERR_ENVELOPE, it, ist, -1);
+                const int n = nout < gcapacity ? nout : gcapacity;
+                const int d0 = nact > 0 ? EGDST_LDCG(mgA) : 0;
+                const double e = E.evf(d0);  // egdst_solver.c:730
+                P.evf[cell] = e;
+                P.mlen[cell] = n + 1;
+                P.thlen[cell] = nth < tcapacity ? nth : tcapacity;
+                egdst_colM(P, cell)[0] = cx.a0; egdst_colC(P, cell)[0] = 0.0; egdst_colV(P, cell)[0] = e;  // saveoutput :931-941
+                egdst_colA(P, cell)[0] = cx.a0 - 0.0;
+            }
+        } else {
+            const int sd = slot;
+            if (threadIdx.x == 0 && nout >= cx.ngridmax) egdst_fail(P, ivec, EGDST_ERR_ENV2SPACE, it, ist, id);
+            const int n = nout < P.gcap ? nout : P.gcap;
+            double *X = P.ptX + (size_t)sd * P.gcap, *Cc = P.ptC + (size_t)sd * P.gcap, *V = P.ptV + (size_t)sd * P.gcap;
+            // copy-back by one CTA: batches of independent loads (a plain loop is a chain of n/blockDim L2 round trips)
+            for (int i0 = threadIdx.x; i0 < n; i0 += 8 * blockDim.x) {
+                double bx[8], bc[8], bv[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int i = i0 + u * blockDim.x;
+                    if (i < n) { bx[u] = EGDST_LDCG(ox + i); bc[u] = EGDST_LDCG(oc + i); bv[u] = EGDST_LDCG(ov + i); }
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int i = i0 + u * blockDim.x;
+                    if (i < n) { X[i] = bx[u]; Cc[i] = bc[u]; V[i] = bv[u]; }
+                }
+            }
+            if (threadIdx.x == 0) P.ptN[sd] = n;
+        }
     }
 }

@@ -1,0 +1,154 @@
+// egdst_period.cuh -- the backward induction as ONE kernel: solver() and egmbellman() of the reference
+// (egdst_solver.c:258-339, 370-752) with the period loop on the device.
+//
+//   for it = T-t0 .. 0:                                                      egdst_solver.c:288
+//       terminal grid                      | seed -> EGM (+ re-send passes)   :452-475 | :477-665
+//       secondary envelope (only if a decision's grid folded back)            :668, 776-913
+//       primary envelope over decisions, thresholds, cell header              :720-730, 1165-1550
+//       lookup tables of the new cells (read by period it-1 and by the simulator) + housekeeping of period it-1
+//
+// Scope GRID: a cooperative launch of one resident wave, every CTA takes part in every phase, phases separated by a
+// grid barrier (one model or a few vectors).  Scope CTA: every CTA walks its own parameter vector through all periods,
+// phases separated by __syncthreads() (sweeps of many small models: no launches and no inter-CTA waits at all).
+// Period t reads the cells of t+1 where saveoutput left them (the arena), exactly as the reference does (:931-951).
+#pragma once
+
+#include "egdst_envelope.cuh"
+#include "egdst_solver.cuh"
+
+// phase boundary: team barrier, and (measurement aid, GRID scope) the device time since the previous boundary
+#ifndef EGDST_HOSTEMU
+EGDST_DEV unsigned long long egdst_globaltimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#else
+EGDST_DEV unsigned long long egdst_globaltimer() { return 0ULL; }
+#endif
+template <bool GRID>
+EGDST_DEV bool egdst_phase_end(const EgdstDev &P, const EgdstTeam &T, int phase, unsigned long long &t0) {
+    const bool ok = egdst_team_sync<GRID>(P);
+    if (GRID && P.phase_ns && T.rank == 0 && threadIdx.x == 0) {
+        const unsigned long long t = egdst_globaltimer();
+        P.phase_ns[phase] += t - t0;
+        t0 = t;
+    }
+    if (!ok && threadIdx.x == 0) egdst_fail(P, T.v0, EGDST_ERR_BARRIER, -1, -1, -1);
+    return ok;
+}
+#define EGDST_PHASE_END(phase) do { if (!egdst_phase_end<GRID>(P, T, phase, t0)) return; } while (0)
+
+#ifdef EGDST_HOSTEMU
+// debugging aid of the host emulator: the per-decision point lists of one period, before and after the secondary envelope
+static void egdst_debug_dump(const EgdstDev &P, int it, const char *tag) {
+    const char *e = getenv("EGDST_DEBUG_DUMP_IT");
+    if (!e || atoi(e) != it || threadIdx.x != 0) return;
+    for (int sd = 0; sd < P.nvec * P.cx.nst * P.cx.nd; sd++) {
+        char name[256];
+        snprintf(name, sizeof(name), "/tmp/egdst_pt_%s_sd%d.bin", tag, sd);
+        FILE *f = fopen(name, "wb");
+        if (!f) continue;
+        const int n = P.ptN[sd], nf = P.nfold[sd];
+        const double ev = P.evfa0[sd];
+        fwrite(&n, sizeof(int), 1, f); fwrite(&nf, sizeof(int), 1, f); fwrite(&ev, sizeof(double), 1, f);
+        fwrite(P.ptX + (size_t)sd * P.gcap, sizeof(double), n, f);
+        fwrite(P.ptC + (size_t)sd * P.gcap, sizeof(double), n, f);
+        fwrite(P.ptV + (size_t)sd * P.gcap, sizeof(double), n, f);
+        fwrite(P.runStart + (size_t)sd * (P.gcap + 1), sizeof(int), nf + 2, f);
+        fclose(f);
+    }
+}
+#define EGDST_DEBUG_DUMP(tag) egdst_debug_dump(P, it, tag)
+#else
+#define EGDST_DEBUG_DUMP(tag)
+#endif
+
+template <bool GRID>
+EGDST_DEV void egdst_solve_team(const EgdstDev &P, const EgdstTeam &T, double *shsm) {
+    const int N = P.N, B = blockDim.x, nd = P.cx.nd;
+    // virtual blocks per job of the rank step and of the table build: sized for the usual list lengths (a decision
+    // keeps at most N points plus the few the secondary envelope inserts); longer lists are covered by stride loops
+    const int nptA1 = B / P.envA1parts;
+    const int nvbA1 = GRID ? MIN((2 * P.gcap + nptA1 - 1) / nptA1, (N + 64 + nptA1 - 1) / nptA1 + 1) : 1;
+    const int nvbA0 = GRID ? MIN((nd * P.gcap + B - 1) / B, (nd * (N + 64) + B - 1) / B + 1) : 1;
+    int nvbT = GRID ? (P.lutcap + 1 + B - 1) / B : 1;
+    if (GRID && T.nv * P.cx.nst * nvbT > 8 * T.size) nvbT = MAX(1, 8 * T.size / (T.nv * P.cx.nst));
+    unsigned long long t0 = 0ULL;
+    egdst_ph_cells(P, P.itStart, T);
+    if (!egdst_team_sync<GRID>(P)) return;
+    if (GRID && P.phase_ns) t0 = egdst_globaltimer();
+    for (int it = P.itStart; it >= P.itStop; it--) {
+        if (it == P.NT - 1) {
+            egdst_ph_terminal(P, it, T);
+            EGDST_PHASE_END(0);
+        } else {
+            egdst_ph_seed(P, it, T, shsm);
+            EGDST_PHASE_END(1);
+            for (int pass = 0;; pass++) {
+                egdst_ph_egm(P, it, T, pass, shsm);
+                EGDST_PHASE_END(2);
+                if (EGDST_LDCG(P.flags + 8 * T.slot + (pass % 3)) == 0) break;  // no grid asked for a zero-consumption re-send
+                egdst_ph_resend(P, it, T, pass, shsm);
+                EGDST_PHASE_END(3);
+            }
+            EGDST_DEBUG_DUMP("raw");
+            if (EGDST_LDCG(P.flags + 8 * T.slot + 3) != 0) {  // some decision's grid folded back: secondary envelope
+                egdst_ph_envA<1>(P, it, T, nvbA1);
+                EGDST_PHASE_END(4);
+                egdst_ph_envBC<1>(P, it, T);
+                EGDST_PHASE_END(4);
+                EGDST_DEBUG_DUMP("env2");
+            }
+        }
+        egdst_ph_envA<0>(P, it, T, nvbA0);
+        EGDST_PHASE_END(5);
+        egdst_ph_envBC<0>(P, it, T);
+        EGDST_PHASE_END(6);
+        egdst_ph_tab(P, it, T, nvbT);
+        if (it > P.itStop) egdst_ph_cells(P, it - 1, T);
+        EGDST_PHASE_END(7);
+    }
+}
+
+// GRID scope: cooperative launch, gridDim.x = one resident wave
+__global__ void __launch_bounds__(EGDST_BLOCK, EGDST_SOLVE_MINB) egdst_k_solve_grid(EgdstDev P) {
+    EGDST_DYN_SMEM(double, shsm);
+    EgdstTeam T; T.rank = blockIdx.x; T.size = gridDim.x; T.v0 = 0; T.nv = P.nvec; T.slot = 0;
+    egdst_solve_team<true>(P, T, shsm);
+}
+// CTA scope: CTA b solves vectors b, b + gridDim.x, ...
+__global__ void __launch_bounds__(EGDST_BLOCK, EGDST_SOLVE_MINB) egdst_k_solve_cta(EgdstDev P) {
+    EGDST_DYN_SMEM(double, shsm);
+    for (int v = blockIdx.x; v < P.nvec; v += gridDim.x) {
+        EgdstTeam T; T.rank = 0; T.size = 1; T.v0 = v; T.nv = 1; T.slot = 1 + v;
+        egdst_solve_team<false>(P, T, shsm);
+        __syncthreads();
+    }
+}
+
+// Diagnostic entry (egdst_test_envelope2): the secondary envelope of given EGM points of decision id of state 0 (of a
+// scratch solution object), as the period loop runs it: folds (egdst_solver.c:819) -> runs -> rank -> merge.  One CTA.
+__global__ void __launch_bounds__(EGDST_BLOCK, EGDST_SOLVE_MINB) egdst_k_env2_only(EgdstDev P, int it, int n, int id) {
+    EgdstTeam T; T.rank = 0; T.size = 1; T.v0 = 0; T.nv = 1; T.slot = 1;
+    __shared__ int s_nf;
+    egdst_cells_body(P, 0, it);
+    if (threadIdx.x == 0) s_nf = 0;
+    __syncthreads();
+    const int sd = id;  // ist = 0
+    const double *X = P.ptX + (size_t)sd * P.gcap, *V = P.ptV + (size_t)sd * P.gcap;
+    int *runStart = P.runStart + (size_t)sd * (P.gcap + 1), *foldList = P.foldList + (size_t)sd * (P.gcap + 1);
+    for (int p = 1 + threadIdx.x; p < n; p += blockDim.x)
+        if (X[p - 1] > X[p] || V[p - 1] > V[p]) { const int k = atomicAdd(&s_nf, 1); foldList[k] = p; }
+    __syncthreads();
+    const int nf = s_nf;
+    for (int i = threadIdx.x; i < nf; i += blockDim.x) {
+        const int v = foldList[i];
+        int r = 0;
+        for (int j = 0; j < nf; j++) r += foldList[j] < v ? 1 : 0;
+        runStart[r + 1] = v;
+    }
+    if (threadIdx.x == 0) { runStart[0] = 0; runStart[nf + 1] = n; P.ptN[sd] = n; P.nfold[sd] = nf; P.active[sd] = 1; }
+    for (int k = threadIdx.x; k < P.cx.nst * P.cx.nd; k += blockDim.x) if (k != sd) { P.active[k] = 0; P.nfold[k] = 0; P.ptN[k] = 0; }
+    __syncthreads();
+    if (nf == 0) return;
+    egdst_ph_envA<1>(P, it, T, 1);
+    __syncthreads();
+    egdst_ph_envBC<1>(P, it, T);
+}

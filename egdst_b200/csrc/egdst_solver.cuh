@@ -1,17 +1,21 @@
-// egdst_solver.cuh -- backward-induction kernels for one period (all states, all decisions, all
-// parameter vectors of a batch at once).
+// egdst_solver.cuh -- the EGM phases of one backward-induction period (all states, all decisions, all
+// parameter vectors of a team at once).
 //
 // Restates the reference's egmbellman (egdst_solver.c:370-752) in parallel form:
-//   k_terminal   terminal-period closed-form grid                     egdst_solver.c:452-475
-//   k_seed       adraw stage 0/1 + ZEROCONSUMPTION feedback            egdst_solver.c:955-1099, 583-627
-//   k_egm        expectation over (ist1, iy) + Euler inversion         egdst_solver.c:490-665
-//   k_compact    adraw stop rule, drop rules, fold detection           egdst_solver.c:1100-1152, 640-664, 819
-// The upper envelopes are in egdst_envelope.cuh.
+//   egdst_ph_terminal   terminal-period closed-form grid                     egdst_solver.c:452-475
+//   egdst_ph_seed       adraw stage 0/1 + ZEROCONSUMPTION feedback            egdst_solver.c:955-1099, 583-627
+//   egdst_ph_egm        expectation over (ist1, iy) + Euler inversion         egdst_solver.c:490-665
+//                       fused with the adraw stop rule, the drop rules and fold detection
+//                                                                            egdst_solver.c:1100-1152, 640-664, 819
+//   egdst_ph_resend     a zero-consumption re-send after the seed stage      egdst_solver.c:1080-1099
+// The upper envelopes are in egdst_envelope.cuh, the period loop in egdst_period.cuh.
 //
 // Parallel decomposition (hard part 1): the A-grid is sequential in the reference only
 // through (i) the stage-0 bisection, whose candidates mmax, (mmax+a0)/2, ... are known in advance and
 // are evaluated concurrently, (ii) the a0 point and its re-sends (serial, a handful of evaluations),
-// and (iii) the stop rule, which is applied after all N-1 closed-form grid points were evaluated.
+// (iii) the stop rule, which is applied after all N-1 closed-form grid points were evaluated, and (iv) a
+// re-send requested by a later grid point, after which the REST of the grid is a new closed form: the
+// EGM phase keeps the points before it, egdst_ph_resend re-seeds, and the EGM phase runs again from there.
 #pragma once
 
 #include "egdst_tables.cuh"
@@ -53,11 +57,9 @@ struct EgdstAcc {
 };
 #define EGDST_NOBAD 0x7fffffff
 
-// Evaluate nodes q = part, part+nparts, ... of the expectation at end-of-period savings A
-// (egdst_solver.c:494-574).  keep==0 skips the value function (adraw seed phase).
 // Quadrature shocks and node probabilities of one (it, ist, id) for every (ist1, iy): shk/shp [nst*ny].
 // Valid when the model image says they cannot depend on savings (EGDST_SHOCK_INDEP_A, codegen): computed once
-// per CTA instead of once per node (one exp per node saved).  shp == 0 marks nodes the reference skips
+// per work item instead of once per node (one exp per node saved).  shp == 0 marks nodes the reference skips
 // (infeasible ist1, zero transition probability, iy >= niy).
 EGDST_DEV void egdst_fill_shocktab(const egdst_ctx *cx, const EgdstDev &P, const PeriodVars *curr, double *shk, double *shp, int tid, int nthreads) {
     const int ny = cx->ny, nst = cx->nst;
@@ -79,6 +81,97 @@ EGDST_DEV void egdst_fill_shocktab(const egdst_ctx *cx, const EgdstDev &P, const
     }
 }
 
+// One quadrature node of the expectation (egdst_solver.c:547-573), all cases: table-free cells, extrapolation on either
+// side of the grid, the credit-constrained branch of the value function, decision-dependent marginal utility, aborts.
+// Returns false when the evaluation ends at this node (acc.bad* say why).  Kept out of line: the hot loop of
+// egdst_eval_nodes handles the common case itself and must not pay this function's registers.
+EGDST_DEV bool egdst_eval_node(const egdst_ctx *cx, const EgdstDev &P, const EgdstNext &t, bool tab, const PeriodVars *curr, PeriodVars &next,
+                                    int keep, int q, double pr1, EgdstAcc &acc) {
+    acc.checksum += pr1;
+    next.cash = cashinhand(cx, curr, &next);
+    // one bracket lookup serves consumption (rows 0..n1) and value (rows 1..n1): the second bracket of the
+    // reference is max(i,1) of the first (same strictly increasing grid); rows i, i+1 come as one record
+    EgdstInterval iv;
+    int i;
+    if (tab) i = egdst_lookup_tab(P, t.cell, t.ivl, next.cash, t.n1 + 1, iv);
+    else {
+        i = egdst_bracket(next.cash, t.M, t.n1 + 1, 0); iv.g0 = t.M[i]; iv.g1 = t.M[i + 1]; iv.c0 = t.C[i]; iv.c1 = t.C[i + 1]; iv.v0 = t.V[i]; iv.v1 = t.V[i + 1];
+        iv.y = egdst_div_safe(iv.g1 - iv.g0) ? 1.0 / (iv.g1 - iv.g0) : 0.0;
+    }
+    // the reference's quotients are kept bit for bit (two divisions per interpolation, egdst_lib.c:175): next to its
+    // instability boundary a plain reciprocal-multiply variant drifted 1e-2 away in C, so the
+    // shared-reciprocal form below is the exactly rounded one (egdst_div_by)
+    double w = iv.g1 - iv.g0;
+    double y = iv.y;  // shared correctly rounded reciprocal RN(1/w), from the table (0: degenerate interval, plain divisions)
+    double c1 = y != 0.0 ? egdst_lerp_y(next.cash, iv.g0, iv.g1, iv.c0, iv.c1, w, y) : egdst_lerp(next.cash, iv.g0, iv.g1, iv.c0, iv.c1);
+    if (next.cash > t.Mlast) c1 = MAX(c1, t.Clast);  // constant extrapolation guard (egdst_solver.c:554)
+    if (c1 <= 0) {
+        acc.badq = q; acc.badtype = EGDST_PT_C1NEG; acc.badcash = next.cash; acc.badshock = next.shock;
+        return false;
+    }
+    if (!EGDST_OPT_MUNOD || (!EGDST_OPT_UNOD && keep == 1 && next.cash < t.M1))
+        next.id = egdst_optimd(next.cash, t.th, t.dd, t.nth);
+    else
+        next.id = 0;
+    acc.rhs += pr1 * utility_marginal(cx, &next, c1) * cashinhand_marginal(cx, curr, &next);
+    if (keep == 1) {
+        double v1;
+        if (next.cash < t.M1 && t.evf > -EGDST_INF) {
+            v1 = utility(cx, &next, next.cash - cx->a0) + discount(cx, &next) * t.evf;  // egdst_solver.c:763
+        } else {
+            if (i < 1) {  // value table starts at row 1 (row 0 of V is evf(a0), not a value)
+                if (tab) iv = egdst_load_interval(t.ivl + 1);
+                else { iv.g0 = t.M[1]; iv.g1 = t.M[2]; iv.v0 = t.V[1]; iv.v1 = t.V[2]; iv.y = egdst_div_safe(iv.g1 - iv.g0) ? 1.0 / (iv.g1 - iv.g0) : 0.0; }
+                w = iv.g1 - iv.g0;
+                y = iv.y;
+            }
+            v1 = egdst_linter_extrap_iv(cx, &next, next.cash, iv.g0, iv.g1, iv.v0, iv.v1, t.M1, t.Mlast, w, y);
+        }
+        const double term = pr1 * v1;
+        acc.evf += term;
+        if (term == -EGDST_INF) {
+            acc.badq = q; acc.badtype = EGDST_PT_EVFINF; acc.badcash = next.cash; acc.badshock = next.shock;
+            return false;
+        }
+    }
+    return true;
+}
+
+// The common case of a node, straight-line: the cell has tables, cash lies inside the value grid [M[1], M[last]] (no
+// extrapolation, no credit-constrained branch), the bucket of the index resolves the bracket by itself, the interval
+// is safely invertible and its values are finite.  Two nodes are prepared side by side so that their four gathers and
+// their arithmetic overlap; `ok` says whether the straight-line result may be used.
+struct EgdstFastNode { double cash, c1, v1; bool ok; };
+EGDST_DEV void egdst_fast_lookup(const EgdstDev &P, const EgdstNext &t, double cash, int &i, bool &ok) {
+    int b = egdst_lut_key(cash, P.cx.a0, P.mbits);
+    b = b < 0 ? 0 : (b > P.lutcap - 1 ? P.lutcap - 1 : b);
+    const EgdstLutEntry *lut = egdst_cell_lut(P, t.cell) + b;
+#ifdef EGDST_HOSTEMU
+    const EgdstLutEntry e = *lut;
+#else
+    EgdstLutEntry e;
+    const int4 r0 = *reinterpret_cast<const int4 *>(lut);
+    const double2 r1 = *(reinterpret_cast<const double2 *>(lut) + 1);
+    e.l = r0.x; e.cnt = r0.y; e.m0 = __hiloint2double(r0.w, r0.z); e.m1 = r1.x; e.m2 = r1.y;
+#endif
+    i = e.l - 1 + (e.m0 <= cash ? 1 : 0) + (e.m1 <= cash ? 1 : 0) + (e.m2 <= cash ? 1 : 0);
+    ok = !(e.cnt > 3 && e.m2 <= cash) && i >= 1 && i <= t.n1 - 1;  // rows i, i+1 exist and belong to the value grid
+}
+EGDST_DEV void egdst_fast_interp(const EgdstNext &t, int i, double cash, EgdstFastNode &f) {
+    const EgdstInterval iv = egdst_load_interval(t.ivl + i);
+    const double w = iv.g1 - iv.g0, y = iv.y;
+    const double xl = cash - iv.g0, xr = iv.g1 - cash;
+    const double ac1 = iv.c1 * xl, ac0 = iv.c0 * xr, av1 = iv.v1 * xl, av0 = iv.v0 * xr;
+    const double big = 1e290;
+    f.ok = f.ok && y != 0.0 && cash >= iv.g0 && cash <= iv.g1 && fabs(ac1) < big && fabs(ac0) < big && fabs(av1) < big && fabs(av0) < big;
+    f.c1 = egdst_div_by(ac1, w, y) + egdst_div_by(ac0, w, y);
+    f.v1 = egdst_div_by(av1, w, y) + egdst_div_by(av0, w, y);
+}
+
+// Evaluate nodes iy = part, part+nparts, ... (of every ist1) of the expectation at end-of-period savings A
+// (egdst_solver.c:494-574).  keep==0 skips the value function (adraw seed phase).  The optim_* switches are
+// constants of the model image (EGDST_OPT_*).  Nodes are taken in ascending order; with a shock table (shk/shp) and
+// keep==1 -- the EGM phase -- two nodes at a time go through the straight-line path when both qualify.
 EGDST_DEV void egdst_eval_nodes(const egdst_ctx *cx, const EgdstDev &P, int ivec, const PeriodVars *curr, double A, int keep,
                                 int part, int nparts, EgdstAcc &acc, const double *shk = 0, const double *shp = 0) {
     const int ny = cx->ny, nst = cx->nst;
@@ -95,77 +188,72 @@ EGDST_DEV void egdst_eval_nodes(const egdst_ctx *cx, const EgdstDev &P, int ivec
         double pr1pre = 0.0;
         int niy = ny;
         if (!shk) {
-            if (cx->optim_TRPRnoSH == 1) {
-                pr1pre = trpr(cx, curr, &next, 1);
-                if (pr1pre == 0.0) continue;
-            }
+#if EGDST_OPT_TRPRNOSH
+            pr1pre = trpr(cx, curr, &next, 1);
+            if (pr1pre == 0.0) continue;
+#endif
             niy = (sigma_param(cx, curr, &next) <= 0 || ny == 1) ? 1 : ny;
         }
         const EgdstNext t = egdst_next_tables(P, ivec, next.it, ist1);
-        for (int iy = part; iy < niy; iy += nparts) {
+        const bool tab = egdst_cell_has_tab(P, t.n1 + 1);
+        int iy = part;
+#if EGDST_OPT_MUNOD
+        if (shk && tab && keep == 1 && t.n1 >= 3) {
+            for (; iy + nparts < niy; iy += 2 * nparts) {
+                const int qa = ist1 * ny + iy, qb = qa + nparts;
+                if (qa > acc.badq) break;
+                const double pa = shp[qa], pb = shp[qb], sa = shk[qa], sb = shk[qb];
+                EgdstFastNode fa, fb;
+                next.shock = sa; fa.cash = cashinhand(cx, curr, &next);
+                next.shock = sb; fb.cash = cashinhand(cx, curr, &next);
+                int ia, ib;
+                egdst_fast_lookup(P, t, fa.cash, ia, fa.ok);
+                egdst_fast_lookup(P, t, fb.cash, ib, fb.ok);
+                fa.ok = fa.ok && pa != 0.0; fb.ok = fb.ok && pb != 0.0;
+                if (fa.ok && fb.ok) {
+                    egdst_fast_interp(t, ia, fa.cash, fa);
+                    egdst_fast_interp(t, ib, fb.cash, fb);
+                }
+                if (fa.ok && fb.ok && fa.c1 > 0 && fb.c1 > 0) {
+                    // same operations in the same order as the general path, node qa then node qb
+                    next.id = 0;
+                    next.shock = sa; next.cash = fa.cash;
+                    acc.checksum += pa;
+                    acc.rhs += pa * utility_marginal(cx, &next, fa.c1) * cashinhand_marginal(cx, curr, &next);
+                    acc.evf += pa * fa.v1;
+                    next.shock = sb; next.cash = fb.cash;
+                    acc.checksum += pb;
+                    acc.rhs += pb * utility_marginal(cx, &next, fb.c1) * cashinhand_marginal(cx, curr, &next);
+                    acc.evf += pb * fb.v1;
+                    continue;
+                }
+                // general path, one node after the other
+                if (pa != 0.0) { next.shock = sa; if (!egdst_eval_node(cx, P, t, tab, curr, next, keep, qa, pa, acc)) break; }
+                if (pb != 0.0) {
+                    if (qb > acc.badq) break;
+                    next.shock = sb; if (!egdst_eval_node(cx, P, t, tab, curr, next, keep, qb, pb, acc)) break;
+                }
+            }
+            if (acc.badq != EGDST_NOBAD) continue;  // the evaluation ended in (or before) this state: nothing is left for this slice
+        }
+#endif
+        for (; iy < niy; iy += nparts) {
             double pr1;
             if (shk) {
                 pr1 = shp[ist1 * ny + iy];
                 next.shock = shk[ist1 * ny + iy];
             } else if (niy == 1) {
                 next.shock = egdst_expectation(cx, curr, &next);
-                pr1 = (cx->optim_TRPRnoSH != 1) ? trpr(cx, curr, &next, 1) : pr1pre;
+                pr1 = EGDST_OPT_TRPRNOSH ? pr1pre : trpr(cx, curr, &next, 1);
             } else {
                 next.shock = egdst_rescale(cx, curr, &next, P.qz[iy]);
-                pr1 = (cx->optim_TRPRnoSH != 1) ? trpr(cx, curr, &next, 1) : pr1pre;
+                pr1 = EGDST_OPT_TRPRNOSH ? pr1pre : trpr(cx, curr, &next, 1);
                 pr1 *= P.qw[iy];
             }
             if (pr1 == 0.0) continue;
             const int q = ist1 * ny + iy;
             if (q > acc.badq) break;  // the reference would have stopped before this node
-            acc.checksum += pr1;
-            next.cash = cashinhand(cx, curr, &next);
-            // one bracket lookup serves consumption (rows 0..n1) and value (rows 1..n1): the second bracket of the
-            // reference is max(i,1) of the first (same strictly increasing grid); rows i, i+1 come as one record
-            const bool tab = egdst_cell_has_tab(P, t.n1 + 1);
-            EgdstInterval iv;
-            int i;
-            if (tab) i = egdst_lookup_tab(P, t.cell, t.ivl, next.cash, t.n1 + 1, iv);
-            else {
-                i = egdst_bracket(next.cash, t.M, t.n1 + 1, 0); iv.g0 = t.M[i]; iv.g1 = t.M[i + 1]; iv.c0 = t.C[i]; iv.c1 = t.C[i + 1]; iv.v0 = t.V[i]; iv.v1 = t.V[i + 1];
-                iv.y = egdst_div_safe(iv.g1 - iv.g0) ? 1.0 / (iv.g1 - iv.g0) : 0.0;
-            }
-            // the reference's quotients are kept bit for bit (two divisions per interpolation, egdst_lib.c:175): next to its
-            // instability boundary a plain reciprocal-multiply variant drifted 1e-2 away in C, so the
-            // shared-reciprocal form below is the exactly rounded one (egdst_div_by)
-            double w = iv.g1 - iv.g0;
-            double y = iv.y;  // shared correctly rounded reciprocal RN(1/w), from the record (0: degenerate interval, plain divisions)
-            double c1 = y != 0.0 ? egdst_lerp_y(next.cash, iv.g0, iv.g1, iv.c0, iv.c1, w, y) : egdst_lerp(next.cash, iv.g0, iv.g1, iv.c0, iv.c1);
-            if (next.cash > t.Mlast) c1 = MAX(c1, t.Clast);  // constant extrapolation guard (egdst_solver.c:554)
-            if (c1 <= 0) {
-                acc.badq = q; acc.badtype = EGDST_PT_C1NEG; acc.badcash = next.cash; acc.badshock = next.shock;
-                break;
-            }
-            if (cx->optim_MUnoD != 1 || (cx->optim_UnoD != 1 && keep == 1 && next.cash < t.M1))
-                next.id = egdst_optimd(next.cash, t.th, t.dd, t.nth);
-            else
-                next.id = 0;
-            acc.rhs += pr1 * utility_marginal(cx, &next, c1) * cashinhand_marginal(cx, curr, &next);
-            if (keep == 1) {
-                double v1;
-                if (next.cash < t.M1 && t.evf > -EGDST_INF) {
-                    v1 = utility(cx, &next, next.cash - cx->a0) + discount(cx, &next) * t.evf;  // egdst_solver.c:763
-                } else {
-                    if (i < 1) {  // value table starts at row 1 (row 0 of V is evf(a0), not a value)
-                        if (tab) iv = egdst_load_interval(t.ivl + 1);
-                        else { iv.g0 = t.M[1]; iv.g1 = t.M[2]; iv.v0 = t.V[1]; iv.v1 = t.V[2]; iv.y = egdst_div_safe(iv.g1 - iv.g0) ? 1.0 / (iv.g1 - iv.g0) : 0.0; }
-                        w = iv.g1 - iv.g0;
-                        y = iv.y;
-                    }
-                    v1 = egdst_linter_extrap_iv(cx, &next, next.cash, iv.g0, iv.g1, iv.v0, iv.v1, t.M1, t.Mlast, w, y);
-                }
-                const double term = pr1 * v1;
-                acc.evf += term;
-                if (term == -EGDST_INF) {
-                    acc.badq = q; acc.badtype = EGDST_PT_EVFINF; acc.badcash = next.cash; acc.badshock = next.shock;
-                    break;
-                }
-            }
+            if (!egdst_eval_node(cx, P, t, tab, curr, next, keep, q, pr1, acc)) break;
         }
     }
 }
@@ -188,29 +276,34 @@ EGDST_DEV void egdst_warp_combine(EgdstAcc &a) {
 
 // ---------------------------------------------------------------------------------------------
 // terminal period: M_i = trinv(m1 + i (m2-m1)/(N-1)), C = M, V = u(C); evfa0 = -inf   (END2, A0T = 0)
-// grid (ceil(N/B), nst*nd, nvec)
 // ---------------------------------------------------------------------------------------------
-__global__ void egdst_k_terminal(EgdstDev P, int it) {
-    const int ivec = blockIdx.z, ist = blockIdx.y / P.cx.nd, id = blockIdx.y % P.cx.nd;
-    egdst_ctx cx; egdst_load_ctx(P, ivec, cx);
-    const int sd = egdst_sd(P, ivec, ist, id);
-    PeriodVars curr; curr.it = it; curr.ist = ist; curr.id = id; curr.cash = 0; curr.savings = 0; curr.shock = 0;
-    const int act = (feasible(&cx, &curr) == 1) && (inchoiceset(&cx, &curr) == 1);
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) {
-        P.active[sd] = act;
-        P.evfa0[sd] = -EGDST_INF;
-        P.ptN[sd] = act ? P.N : 0;
-        P.nfold[sd] = 0;
-        if (act) atomicAdd(P.units + ivec, (unsigned long long)P.N);
+EGDST_DEV void egdst_ph_terminal(const EgdstDev &P, int it, const EgdstTeam &T) {
+    const int B = blockDim.x, nxb = (P.N + B - 1) / B, jpv = P.cx.nst * P.cx.nd;
+    const int nwork = T.nv * jpv * nxb;
+    for (int w = T.rank; w < nwork; w += T.size) {
+        int ivec, jy, xb;
+        egdst_item(T, w, jpv, ivec, jy, xb);
+        const int ist = jy / P.cx.nd, id = jy % P.cx.nd;
+        egdst_ctx cx; egdst_load_ctx(P, ivec, cx);
+        const int sd = egdst_sd(P, ivec, ist, id);
+        PeriodVars curr; curr.it = it; curr.ist = ist; curr.id = id; curr.cash = 0; curr.savings = 0; curr.shock = 0;
+        const int act = (feasible(&cx, &curr) == 1) && (inchoiceset(&cx, &curr) == 1);
+        const int i = xb * B + threadIdx.x;
+        if (i == 0) {
+            P.active[sd] = act;
+            P.evfa0[sd] = -EGDST_INF;
+            P.ptN[sd] = act ? P.N : 0;
+            P.nfold[sd] = 0;
+            if (act) atomicAdd(P.units + ivec, (unsigned long long)P.N);
+        }
+        if (!act || i >= P.N) continue;
+        const double m1 = tr(&cx, &curr, cx.zeroconsumption - 0.0), m2 = tr(&cx, &curr, cx.mmax - 0.0);
+        const double m = trinv(&cx, &curr, m1 + i * (m2 - m1) / (P.N - 1)) + 0.0;
+        const double c = m - 0.0;
+        P.ptX[(size_t)sd * P.gcap + i] = m;
+        P.ptC[(size_t)sd * P.gcap + i] = c;
+        P.ptV[(size_t)sd * P.gcap + i] = utility(&cx, &curr, c);
     }
-    if (!act || i >= P.N) return;
-    const double m1 = tr(&cx, &curr, cx.zeroconsumption - 0.0), m2 = tr(&cx, &curr, cx.mmax - 0.0);
-    const double m = trinv(&cx, &curr, m1 + i * (m2 - m1) / (P.N - 1)) + 0.0;
-    const double c = m - 0.0;
-    P.ptX[(size_t)sd * P.gcap + i] = m;
-    P.ptC[(size_t)sd * P.gcap + i] = c;
-    P.ptV[(size_t)sd * P.gcap + i] = utility(&cx, &curr, c);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -223,7 +316,7 @@ struct EgdstSeedShared {
     double wr[32], we[32], wc[32], wcash[32], wshock[32];
     int wq[32], wt[32];
     double A, rhs, evf, checksum, badcash, badshock;
-    int ncand, badq, badtype, go, nresend;
+    int ncand, badq, badtype, go, calls;
 };
 
 EGDST_DEV void egdst_block_eval(const egdst_ctx *cx, const EgdstDev &P, int ivec, const PeriodVars *curr, double A, int keep,
@@ -242,29 +335,64 @@ EGDST_DEV void egdst_block_eval(const egdst_ctx *cx, const EgdstDev &P, int ivec
     __syncthreads();
 }
 
-__global__ void egdst_k_seed(EgdstDev P, int it, int useTab) {
-    __shared__ EgdstSeedShared S;
-    EGDST_DYN_SMEM(double, shsm);
-    const int ivec = blockIdx.z, ist = blockIdx.y, id = blockIdx.x;
+// adraw limits from the line through the base point and (A, M) (egdst_solver.c:1032-1076), or, after a zero-consumption
+// re-send, through the base point and (a0, a0) with the re-sent point as the new focal point (:1080-1099)
+struct EgdstLims { double lim1, lim2, lim3, lim2p, lim3p, k3; };
+EGDST_DEV void egdst_lims_first(const egdst_ctx *cx, const PeriodVars *curr, double aM, double lastA, double baseA, double baseM, int N, EgdstLims &L) {
+    const double aa = (aM - baseM) / (lastA - baseA), bb = baseM - aa * baseA;
+    L.lim2p = MIN(cx->mmax, (cx->mmax - bb) / aa);
+    L.lim3p = -bb / aa;
+    if (cx->a0 < 0 && cx->a0 < L.lim3p) L.k3 = MAX(floor(N * (L.lim3p - cx->a0) / (L.lim2p - cx->a0)), 2.0);
+    else { L.lim3p = cx->a0; L.k3 = 1.0; }
+    L.lim1 = tr(cx, curr, L.lim3p - cx->a0); L.lim2 = tr(cx, curr, L.lim2p - L.lim3p); L.lim3 = tr(cx, curr, 0);
+}
+EGDST_DEV void egdst_lims_resend(const egdst_ctx *cx, const PeriodVars *curr, double lastA, double baseA, double baseM, EgdstLims &L) {
+    const double aa = (cx->a0 - baseM) / (cx->a0 - baseA), bb = baseM - aa * baseA;
+    L.lim2p = MIN(cx->mmax, (cx->mmax - bb) / aa);
+    L.lim3p = lastA - cx->zeroconsumption;
+    L.k3 = 1.0;
+    L.lim1 = tr(cx, curr, L.lim3p - cx->a0); L.lim2 = tr(cx, curr, L.lim2p - L.lim3p); L.lim3 = tr(cx, curr, 0);
+}
+// the savings point that replaces one whose evaluation met c1<=0 at node (ist1, shock) (egdst_solver.c:600-616)
+EGDST_DEV double egdst_resend_point(const egdst_ctx *cx, const EgdstDev &P, int ivec, const PeriodVars *curr, int it, double lastA,
+                                    int badq, double badshock, double badcash, int *fail) {
+    PeriodVars next; next.it = it + 1; next.ist = badq / cx->ny; next.id = 0; next.savings = lastA; next.shock = badshock; next.cash = badcash;
+    const EgdstNext t = egdst_next_tables(P, ivec, it + 1, next.ist);
+    const double target = (t.evf > -EGDST_INF) ? cx->a0 : t.M[1];
+    return egdst_cashinhandinverse(cx, curr, next, target, fail) + cx->zeroconsumption;
+}
+
+// publish the state of a (re)seeded savings grid: slot 0 of the job's chained scan holds the inclusive prefix the
+// EGM items start from -- points kept so far, and "the grid stopped" (egdst_solver.c:1100)
+EGDST_DEV void egdst_seed_publish(const EgdstDev &P, int sd, double *seed, const EgdstLims &L, double lastA, int nfirst, int calls,
+                                  double baseA, double baseM, int kept, int stop, int pass) {
+    seed[0] = L.lim1; seed[1] = L.lim2; seed[2] = L.lim3; seed[3] = L.lim3p; seed[4] = L.k3; seed[5] = lastA;
+    seed[6] = (double)nfirst; seed[7] = (double)calls; seed[8] = baseA; seed[9] = baseM; seed[10] = (double)pass;
+    P.scanC[(size_t)sd * P.chC] = EGDST_SCAN_INC | egdst_scan_pack(kept, stop);
+}
+
+EGDST_DEV void egdst_seed_job(const EgdstDev &P, int it, int ivec, int ist, int id, EgdstSeedShared &S, double *shsm, int useTab) {
     egdst_ctx cx; egdst_load_ctx(P, ivec, cx);
     const int sd = egdst_sd(P, ivec, ist, id);
     PeriodVars curr; curr.it = it; curr.ist = ist; curr.id = id; curr.cash = 0; curr.savings = 0; curr.shock = 0;
     const int act = (feasible(&cx, &curr) == 1) && (inchoiceset(&cx, &curr) == 1);
     const int N = P.N;
-    double *rawM = P.rawM + (size_t)sd * N, *rawC = P.rawC + (size_t)sd * N, *rawV = P.rawV + (size_t)sd * N, *rawStop = P.rawStop + (size_t)sd * N;
-    int *rawFlag = P.rawFlag + (size_t)sd * N;
-    double *seed = P.seed + (size_t)sd * 8;
+    double *seed = P.seed + (size_t)sd * EGDST_SEEDW;
+    double *X = P.ptX + (size_t)sd * P.gcap, *Cc = P.ptC + (size_t)sd * P.gcap, *V = P.ptV + (size_t)sd * P.gcap;
+    __syncthreads();  // S and the shock table of the previous job are free
     if (threadIdx.x == 0) {
         P.active[sd] = act;
         P.evfa0[sd] = 0.0;
         P.ptN[sd] = 0;
         P.nfold[sd] = 0;
-        rawFlag[0] = EGDST_PT_NONE;
-        rawStop[0] = EGDST_INF;  // "stop": no grid points unless the seed succeeds
+        P.lateN[sd] = 0x7fffffff;
+        P.scanC[(size_t)sd * P.chC] = EGDST_SCAN_INC | egdst_scan_pack(0, 1);  // "stopped, no points" unless the seed succeeds
+        seed[6] = 1.0; seed[7] = 0.0; seed[10] = 0.0;
         // stage-0 candidates (egdst_solver.c:979-1027): mmax, then halfway to a0 until A-a0<TOLERANCE
         int n = 0; double A = cx.mmax;
         while (n < EGDST_MAXCAND) { S.candA[n++] = A; if (A - cx.a0 < cx.tolerance) break; A = (A + cx.a0) / 2; }
         S.ncand = n;
+        S.go = 0;
     }
     __syncthreads();
     if (!act) return;
@@ -279,8 +407,6 @@ __global__ void egdst_k_seed(EgdstDev P, int it, int useTab) {
     // stage 0 in waves of one candidate per warp: the base point is almost always among the first few
     // candidates (mmax, (mmax+a0)/2, ...), so later waves rarely run
     double baseA = 0, baseM = 0;
-    if (threadIdx.x == 0) S.go = 0;
-    __syncthreads();
     for (int k0 = 0; k0 < S.ncand; k0 += nw) {
         const int kk = k0 + w;
         if (kk < S.ncand) {
@@ -302,22 +428,19 @@ __global__ void egdst_k_seed(EgdstDev P, int it, int useTab) {
             for (int k = k0; k < kend; k++) {
                 if (S.candBad[k] == EGDST_PT_C1NEG) { egdst_fail(P, ivec, EGDST_ERR_NOSAVINGS, it, ist, id); S.go = -1; break; }
                 if (S.candBad[k] == EGDST_PT_CHECKSUM) { egdst_fail(P, ivec, EGDST_ERR_CHECKSUM, it, ist, id); S.go = -1; break; }
-                if (S.candM[k] <= cx.mmax) { baseA = S.candA[k]; baseM = S.candM[k]; S.go = 1; break; }
+                if (S.candM[k] <= cx.mmax) { baseA = S.candA[k]; baseM = S.candM[k]; S.go = 1; S.calls = k + 2; break; }  // adraw calls so far: k+1 guesses + the call that returns a0
                 if (S.candA[k] - cx.a0 < cx.tolerance) { egdst_fail(P, ivec, EGDST_ERR_ADRAW_INIT, it, ist, id); S.go = -1; break; }
             }
             if (kend == S.ncand && S.go == 0) { egdst_fail(P, ivec, EGDST_ERR_ADRAW_INIT, it, ist, id); S.go = -1; }
+            S.A = cx.a0;
         }
         __syncthreads();
         if (S.go != 0) break;
     }
-    if (threadIdx.x == 0) {
-        S.A = cx.a0;
-        S.nresend = S.ncand;  // used as the adraw call counter (loop guard, egdst_solver.c:963)
-    }
-    __syncthreads();
     if (S.go != 1) return;
     // stage 1 (+ re-sends): serial in A, parallel over nodes
-    double lim1 = 0, lim2 = 0, lim3 = 0, lim2p = 0, lim3p = 0, k3 = 0, lastA = cx.a0, aM = 0, evfa0 = 0.0;
+    EgdstLims L; L.lim1 = 0; L.lim2 = 0; L.lim3 = 0; L.lim2p = 0; L.lim3p = 0; L.k3 = 0;
+    double lastA = cx.a0, aM = 0, evfa0 = 0.0;
     int stored = 0;
     while (true) {
         egdst_block_eval(&cx, P, ivec, &curr, S.A, 1, S, shk, shp);
@@ -331,39 +454,25 @@ __global__ void egdst_k_seed(EgdstDev P, int it, int useTab) {
                 aM = S.badcash;
                 if (S.badtype == EGDST_PT_C1NEG) {
                     aM = cx.a0 - 1;
-                    PeriodVars next; next.it = it + 1; next.ist = S.badq / cx.ny; next.id = 0; next.savings = lastA; next.shock = S.badshock; next.cash = S.badcash;
-                    const EgdstNext t = egdst_next_tables(P, ivec, it + 1, next.ist);
-                    const double target = (t.evf > -EGDST_INF) ? cx.a0 : t.M[1];
                     int fail = 0;
-                    lastA = egdst_cashinhandinverse(&cx, &curr, next, target, &fail) + cx.zeroconsumption;
+                    lastA = egdst_resend_point(&cx, P, ivec, &curr, it, lastA, S.badq, S.badshock, S.badcash, &fail);
                     if (fail) { egdst_fail(P, ivec, EGDST_ERR_CASHINVERSE, it, ist, id); fatal = 1; }
                 }
             } else {
                 aM = lastA + utility_marginal_inverse(&cx, &curr, beta * S.rhs);
                 if (isfinite(aM)) {
                     if (fabs(lastA - cx.a0) < cx.tolerance && evfa0 > -EGDST_INF) evfa0 = S.evf;
-                    rawM[0] = aM; rawC[0] = aM - lastA; rawV[0] = utility(&cx, &curr, aM - lastA) + beta * S.evf;
-                    rawFlag[0] = EGDST_PT_OK; stored = 1;
+                    X[0] = aM; Cc[0] = aM - lastA; V[0] = utility(&cx, &curr, aM - lastA) + beta * S.evf;
+                    stored = 1;
                 }
             }
             if (!fatal) {
                 // adraw, ngenerated==1 branch (egdst_solver.c:1032-1099)
-                double aa = (aM - baseM) / (lastA - baseA), bb = baseM - aa * baseA;
-                if (k3 == 0) {
-                    lim2p = MIN(cx.mmax, (cx.mmax - bb) / aa);
-                    lim3p = -bb / aa;
-                    if (cx.a0 < 0 && cx.a0 < lim3p) k3 = MAX(floor(N * (lim3p - cx.a0) / (lim2p - cx.a0)), 2.0);
-                    else { lim3p = cx.a0; k3 = 1.0; }
-                    lim1 = tr(&cx, &curr, lim3p - cx.a0); lim2 = tr(&cx, &curr, lim2p - lim3p); lim3 = tr(&cx, &curr, 0);
-                }
+                if (L.k3 == 0) egdst_lims_first(&cx, &curr, aM, lastA, baseA, baseM, N, L);
                 if (aM <= cx.a0 - 1 + cx.tolerance) {
-                    aa = (cx.a0 - baseM) / (cx.a0 - baseA); bb = baseM - aa * baseA;
-                    lim2p = MIN(cx.mmax, (cx.mmax - bb) / aa);
-                    lim3p = lastA - cx.zeroconsumption;
-                    k3 = 1.0;
-                    lim1 = tr(&cx, &curr, lim3p - cx.a0); lim2 = tr(&cx, &curr, lim2p - lim3p); lim3 = tr(&cx, &curr, 0);
+                    egdst_lims_resend(&cx, &curr, lastA, baseA, baseM, L);
                     resend = 1;
-                    if (++S.nresend + 1 >= cx.ngridmax) { egdst_fail(P, ivec, EGDST_ERR_ADRAW_LOOP, it, ist, id); resend = 0; fatal = 1; }
+                    if (++S.calls >= cx.ngridmax) { egdst_fail(P, ivec, EGDST_ERR_ADRAW_LOOP, it, ist, id); resend = 0; fatal = 1; }
                 }
             }
             S.A = lastA;
@@ -375,14 +484,27 @@ __global__ void egdst_k_seed(EgdstDev P, int it, int useTab) {
     if (threadIdx.x == 0) {
         P.evfa0[sd] = evfa0;
         if (S.go == 0) {
-            seed[0] = lim1; seed[1] = lim2; seed[2] = lim3; seed[3] = lim3p; seed[4] = k3; seed[5] = lastA;
-            rawStop[0] = aM;
-            if (!stored) rawFlag[0] = EGDST_PT_EVFINF;
+            egdst_seed_publish(P, sd, seed, L, lastA, 1, S.calls, baseA, baseM, stored, (aM < cx.mmax) ? 0 : 1, 0);
+            if (stored) atomicAdd(P.units + ivec, 1ULL);
         }
     }
 }
 
-// closed-form A-grid after the seed (egdst_solver.c:1104-1136); n = 1..N-1
+EGDST_DEV int egdst_use_shocktab(const EgdstDev &P) {
+    return (EGDST_SHOCK_INDEP_A && (size_t)2 * P.cx.nst * P.cx.ny * sizeof(double) <= EGDST_SHOCKTAB_BYTES) ? 1 : 0;
+}
+
+EGDST_DEV void egdst_ph_seed(const EgdstDev &P, int it, const EgdstTeam &T, double *shsm) {
+    __shared__ EgdstSeedShared S;
+    const int jpv = P.cx.nst * P.cx.nd, nwork = T.nv * jpv;
+    const int useTab = egdst_use_shocktab(P);
+    for (int w = T.rank; w < nwork; w += T.size) {
+        const int ivec = T.v0 + w / jpv, jy = w % jpv;
+        egdst_seed_job(P, it, ivec, jy / P.cx.nd, jy % P.cx.nd, S, shsm, useTab);
+    }
+}
+
+// closed-form A-grid after the seed (egdst_solver.c:1104-1136); n = nfirst..N-1
 EGDST_DEV double egdst_agrid_target(const egdst_ctx *cx, const PeriodVars *curr, const double *seed, int n, int N) {
     const double lim1 = seed[0], lim2 = seed[1], lim3 = seed[2], lim3p = seed[3], k3 = seed[4];
     if (n < (int)k3 - 1) return -trinv(cx, curr, lim3 + (k3 - 1 - n) * (lim1 - lim3) / (k3 - 1)) + lim3p;
@@ -390,195 +512,48 @@ EGDST_DEV double egdst_agrid_target(const egdst_ctx *cx, const PeriodVars *curr,
 }
 EGDST_DEV double egdst_agrid(const egdst_ctx *cx, const PeriodVars *curr, const double *seed, int n, int N) {
     const double t = egdst_agrid_target(cx, curr, seed, n, N);
-    const double prev = (n == 1) ? seed[5] : egdst_agrid_target(cx, curr, seed, n - 1, N);
+    const double prev = (n == (int)seed[6]) ? seed[5] : egdst_agrid_target(cx, curr, seed, n - 1, N);
     return (t - prev < 0) ? prev + 1e-5 : t;  // astep<0 rule (egdst_solver.c:1120-1133)
 }
 
 // ---------------------------------------------------------------------------------------------
-// EGM step for grid points n=1..N-1.  blockDim = (32, parts <= SPLIT): lanes are 32 consecutive A points (their
-// next-period cash values are neighbours, so the table searches of a warp stay coherent), the `parts`
-// warps of a CTA share the quadrature nodes of the same 32 points and combine through shared memory.
-// The host picks `parts` so that the nodes divide evenly (10 nodes: 5 warps of 2, not 8 warps of 2 and 1).
-// grid (ceil((N-1)/32), nst*nd, nvec)
+// EGM step for grid points n = nfirst..N-1 of every (ist, id): expectation, Euler inversion, and -- in the same
+// work item -- the stop rule, the drop rules and the compaction into the decision's point list.
+//
+// A work item is a run of P.egmP consecutive grid points of one (ist, id); thread t handles point t % egmP and the
+// quadrature nodes t / egmP, t / egmP + slices, ... (slices = threads / egmP): the threads of a warp are consecutive
+// A points (their next-period cash values are neighbours, so the table gathers of a warp stay coherent), the slices
+// combine through shared memory in a fixed order.  The host sizes egmP so that the items of one period fill the
+// team exactly once (no tail wave).
+//
+// The reference generates point n only while every earlier returned M was < mmax (egdst_solver.c:1100) and no
+// earlier point asked for a zero-consumption re-send (:1080); stored points are those with a finite M and no abort
+// (:640-664).  The items of one (ist, id) are chained by a decoupled look-back scan whose state carries (points kept
+// so far, "the grid ended here"); slot 0 of the chain is the seed's own contribution.  Folds (M or V decreasing,
+// :819) inside an item's output are appended to an unordered list; the last item to finish adds the folds on item
+// boundaries, orders the list and publishes the counts.
 // ---------------------------------------------------------------------------------------------
-#ifndef EGDST_EGM_SPLIT
-#ifdef EGDST_HOSTEMU
-#define EGDST_EGM_SPLIT 2
-#else
-#define EGDST_EGM_SPLIT 8
-#endif
-#endif
+struct EgdstEgmShared {
+    double rhs[EGDST_BLOCK], evf[EGDST_BLOCK], chk[EGDST_BLOCK], cash[EGDST_BLOCK];
+    int q[EGDST_BLOCK], t[EGDST_BLOCK];
+    double kx[EGDST_BLOCK], kv[EGDST_BLOCK];  // kept points of the item in output order (fold test between neighbours)
+    int sh[40];
+    int evmin[2];                              // first point of the item that stops the grid / asks for a re-send
+    int last;
+    unsigned long long excl;
+};
 
-#ifndef EGDST_EGM_MINB
-#define EGDST_EGM_MINB 3
-#endif
-__global__ void __launch_bounds__(32 * EGDST_EGM_SPLIT, EGDST_EGM_MINB) egdst_k_egm(EgdstDev P, int it, int useTab) {
-    EGDST_DYN_SMEM(double, shsm);
-    __shared__ double s_rhs[EGDST_EGM_SPLIT][32], s_evf[EGDST_EGM_SPLIT][32], s_chk[EGDST_EGM_SPLIT][32], s_cash[EGDST_EGM_SPLIT][32];
-    __shared__ int s_q[EGDST_EGM_SPLIT][32], s_t[EGDST_EGM_SPLIT][32];
-    const int ivec = blockIdx.z, ist = blockIdx.y / P.cx.nd, id = blockIdx.y % P.cx.nd;
-    const int sd = egdst_sd(P, ivec, ist, id);
-    const int lane = threadIdx.x, part = threadIdx.y, nparts = blockDim.y;
-    const int N = P.N;
-    if (!P.active[sd] || P.rawFlag[(size_t)sd * N] == EGDST_PT_NONE) return;  // uniform per CTA
-    egdst_ctx cx; egdst_load_ctx(P, ivec, cx);
-    PeriodVars curr; curr.it = it; curr.ist = ist; curr.id = id; curr.cash = 0; curr.savings = 0; curr.shock = 0;
-    const double *seed = P.seed + (size_t)sd * 8;
-    const double *shk = 0, *shp = 0;
-    if (useTab) {  // shocks and node probabilities of this (it, ist, id), once per CTA
-        egdst_fill_shocktab(&cx, P, &curr, shsm, shsm + cx.nst * cx.ny, threadIdx.y * 32 + threadIdx.x, 32 * nparts);
-        shk = shsm; shp = shsm + cx.nst * cx.ny;
-        __syncthreads();
-    }
-    // gridDim.x CTAs share the ceil((N-1)/32) blocks of 32 points of this (ist,id): one block each for a single model,
-    // all of them in turn for the short grids of a batched sweep (context and shock table set up once)
-    for (int xb = blockIdx.x; xb * 32 < N - 1; xb += gridDim.x) {
-        const int n = 1 + xb * 32 + lane;
-        double A = 0.0;
-        EgdstAcc a; a.rhs = 0; a.evf = 0; a.checksum = 0; a.badq = EGDST_NOBAD; a.badtype = 0; a.badcash = 0; a.badshock = 0;
-        if (n < N) {
-            A = egdst_agrid(&cx, &curr, seed, n, N);
-            egdst_eval_nodes(&cx, P, ivec, &curr, A, 1, part, nparts, a, shk, shp);
-        }
-        s_rhs[part][lane] = a.rhs; s_evf[part][lane] = a.evf; s_chk[part][lane] = a.checksum;
-        s_q[part][lane] = a.badq; s_t[part][lane] = a.badtype; s_cash[part][lane] = a.badcash;
-        __syncthreads();
-        if (part == 0 && n < N) {
-            double rhs = 0, evf = 0, chk = 0, badcash = 0; int bq = EGDST_NOBAD, bt = 0;
-            for (int k = 0; k < nparts; k++) {
-                rhs += s_rhs[k][lane]; evf += s_evf[k][lane]; chk += s_chk[k][lane];
-                if (s_q[k][lane] < bq) { bq = s_q[k][lane]; bt = s_t[k][lane]; badcash = s_cash[k][lane]; }
-            }
-            const size_t o = (size_t)sd * N + n;
-            if (bq != EGDST_NOBAD) {
-                P.rawFlag[o] = bt;
-                P.rawStop[o] = (bt == EGDST_PT_C1NEG) ? cx.a0 - 1 : badcash;
-            } else if (fabs(chk - 1) > cx.tolerance) {
-                P.rawFlag[o] = EGDST_PT_CHECKSUM; P.rawStop[o] = EGDST_INF;
-            } else {
-                const double beta = discount(&cx, &curr);
-                const double M = A + utility_marginal_inverse(&cx, &curr, beta * rhs);
-                P.rawStop[o] = M;
-                if (!isfinite(M)) P.rawFlag[o] = EGDST_PT_NONFINITE;
-                else {
-                    const double c = M - A;
-                    P.rawM[o] = M; P.rawC[o] = c; P.rawV[o] = utility(&cx, &curr, c) + beta * evf;
-                    P.rawFlag[o] = EGDST_PT_OK;
-                }
-            }
-        }
-        if (xb + (int)gridDim.x < (N - 1 + 31) / 32) __syncthreads();  // the partial sums are reused by the next block
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// stop rule + compaction + fold detection: one CTA per (ist,id,ivec).
-// The reference generates point n only while every earlier returned M was < mmax
-// (egdst_solver.c:1100); stored points are those with a finite M and no abort (:640-664).
-// Folds (M or V decreasing, :819) split the list into runs for the secondary envelope.
-// ---------------------------------------------------------------------------------------------
-#define EGDST_CMP_IPT 8
-#ifdef EGDST_HOSTEMU
-#define EGDST_CMP_THREADS 64
-#else
-#define EGDST_CMP_THREADS 256
-#endif
-// IPT raw points per thread (8; 2 for a single large model: more CTAs share the latency of the passes).
-// grid (chC, nst*nd, nvec), blockDim.x = P.cmpW <= EGDST_CMP_THREADS: the CTAs of one (ist,id) list are chained by a decoupled look-back scan whose state
-// carries (points kept so far, "stop rule fired").  Folds inside a CTA's own output are appended to an unordered
-// list; the last CTA to finish adds the folds on chunk boundaries, orders the list and publishes the counts.
-template <int IPT>
-__global__ void __launch_bounds__(EGDST_CMP_THREADS) egdst_k_compact(EgdstDev P, int it) {
-    __shared__ int sh[40];
-    __shared__ int s_chunk, s_last;
-    __shared__ unsigned long long s_excl;
-    const int ivec = blockIdx.z, ist = blockIdx.y / P.cx.nd, id = blockIdx.y % P.cx.nd;
-    const int sd = egdst_sd(P, ivec, ist, id);
-    if (!P.active[sd]) return;
-    const int N = P.N;
-    const double *rawM = P.rawM + (size_t)sd * N, *rawC = P.rawC + (size_t)sd * N, *rawV = P.rawV + (size_t)sd * N, *rawStop = P.rawStop + (size_t)sd * N;
-    const int *rawFlag = P.rawFlag + (size_t)sd * N;
-    double *X = P.ptX + (size_t)sd * P.gcap, *Cc = P.ptC + (size_t)sd * P.gcap, *V = P.ptV + (size_t)sd * P.gcap;
+EGDST_DEV void egdst_egm_epilogue(const EgdstDev &P, int it, int ivec, int ist, int id, int sd, int nitems, int slot) {
+    // last item of this (ist,id): folds on item boundaries, ordering of the fold list, counts
+    const volatile unsigned long long *st = P.scanC + (size_t)sd * P.chC;
+    const double *X = P.ptX + (size_t)sd * P.gcap, *V = P.ptV + (size_t)sd * P.gcap;
     int *runStart = P.runStart + (size_t)sd * (P.gcap + 1);
     int *foldList = P.foldList + (size_t)sd * (P.gcap + 1);
-    volatile unsigned long long *st = P.scanC + (size_t)sd * P.chC;
-    if (rawFlag[0] == EGDST_PT_NONE) { if (blockIdx.x == 0 && threadIdx.x == 0) { P.ptN[sd] = 0; P.nfold[sd] = 0; } return; }
-    const int chunkw = blockDim.x * IPT;  // raw points per CTA (P.cmpW threads: narrow CTAs for short grids)
-    const int nch = (N + chunkw - 1) / chunkw;      // chunks that hold raw points == gridDim.x
-    if (threadIdx.x == 0) s_chunk = atomicAdd(P.tickC + 2 * sd, 1);
-    __syncthreads();
-    const int chunk = s_chunk;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const unsigned ltmask = (1u << lane) - 1u;
-    int err = 0;
-    if (chunk < nch) {
-        const int wbase = chunk * chunkw + w * (32 * IPT);
-        // the stop rule inside this chunk: first n whose returned M fails "M<mmax" (that point itself is kept)
-        int flag[IPT], mystop = 0x7fffffff;
-#pragma unroll
-        for (int j = 0; j < IPT; j++) {
-            const int n = wbase + j * 32 + lane;
-            flag[j] = EGDST_PT_NONE;
-            if (n < N) {
-                flag[j] = rawFlag[n];
-                if (!(rawStop[n] < P.cx.mmax) && n < mystop) mystop = n;
-            }
-        }
-        const int ls = egdst_block_min(mystop, sh);
-        unsigned bal[IPT];
-        int wtotal = 0, late = 0x7fffffff, badsum = 0;
-#pragma unroll
-        for (int j = 0; j < IPT; j++) {
-            const int n = wbase + j * 32 + lane;
-            const bool in = n < N && n <= ls;
-            if (in && flag[j] == EGDST_PT_C1NEG && n > 0 && n < late) late = n;
-            if (in && flag[j] == EGDST_PT_CHECKSUM) badsum = 1;
-            bal[j] = __ballot_sync(EGDST_FULL, in && flag[j] == EGDST_PT_OK);
-            wtotal += __popc(bal[j]);
-        }
-        int total;
-        int woff = egdst_block_excl_scan(lane == 0 ? wtotal : 0, sh, &total);
-        woff = __shfl_sync(EGDST_FULL, woff, 0);
-        if (w == 0) {
-            const unsigned long long e = egdst_lookback<1>(st, chunk, egdst_scan_pack(total, ls != 0x7fffffff ? 1 : 0), &err);
-            if (lane == 0) s_excl = e;
-        }
-        __syncthreads();
-        const unsigned long long excl = s_excl;
-        if (!egdst_scan_hi(excl)) {  // the grid did not stop in an earlier chunk: this chunk's points count
-            if (late != 0x7fffffff) egdst_fail(P, ivec, EGDST_ERR_RESEND_LATE, it, ist, id);
-            if (badsum) egdst_fail(P, ivec, EGDST_ERR_CHECKSUM, it, ist, id);
-            const int first = egdst_scan_lo(excl);
-            int pos = first + woff;
-#pragma unroll
-            for (int j = 0; j < IPT; j++) {
-                const int n = wbase + j * 32 + lane;
-                if (bal[j] & (1u << lane)) {
-                    const int dst = pos + __popc(bal[j] & ltmask);
-                    if (dst < P.gcap) { X[dst] = rawM[n]; Cc[dst] = rawC[n]; V[dst] = rawV[n]; }
-                }
-                pos += __popc(bal[j]);
-            }
-            __syncthreads();
-            // folds between neighbours that this CTA wrote itself (M or V decreasing, egdst_solver.c:819)
-            const int lim = first + total < P.gcap ? first + total : P.gcap;
-            for (int p = first + 1 + threadIdx.x; p < lim; p += blockDim.x)
-                if (X[p - 1] > X[p] || V[p - 1] > V[p]) { const int k = atomicAdd(P.foldCnt + sd, 1); if (k <= P.gcap) foldList[k] = p; }
-        }
-    }
-    if (err) egdst_fail(P, ivec, EGDST_ERR_ENV2SPACE, it, ist, id);
-    // last CTA of this (ist,id): boundary folds, ordering, counts
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(P.tickC + 2 * sd + 1, 1) == (int)gridDim.x - 1);
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    const unsigned long long tot = egdst_scan_inclusive(st, nch - 1);
+    const unsigned long long tot = egdst_scan_inclusive(st, nitems);
     const int kept = egdst_scan_lo(tot);
     const int nvd = kept < P.gcap ? kept : P.gcap;
-    for (int c = 1 + threadIdx.x; c < nch; c += blockDim.x) {
-        const unsigned long long pe = egdst_scan_inclusive(st, c - 1), pi = egdst_scan_inclusive(st, c);
+    for (int c = threadIdx.x; c < nitems; c += blockDim.x) {
+        const unsigned long long pe = egdst_scan_inclusive(st, c), pi = egdst_scan_inclusive(st, c + 1);  // before / after item c
         const int p = egdst_scan_lo(pe);
         if (!egdst_scan_hi(pe) && egdst_scan_lo(pi) > p && p > 0 && p < nvd)
             if (EGDST_LDCG(X + p - 1) > EGDST_LDCG(X + p) || EGDST_LDCG(V + p - 1) > EGDST_LDCG(V + p)) {
@@ -600,6 +575,242 @@ __global__ void __launch_bounds__(EGDST_CMP_THREADS) egdst_k_compact(EgdstDev P,
         runStart[nf + 1] = nvd;
         P.ptN[sd] = nvd;
         P.nfold[sd] = nf;
-        atomicAdd(P.units + ivec, (unsigned long long)nvd);
+        if (nf > 0) atomicAdd(P.flags + 8 * slot + 3, 1);  // the period needs the secondary envelope
+    }
+}
+
+EGDST_DEV void egdst_ph_egm(const EgdstDev &P, int it, const EgdstTeam &T, int pass, double *shsm) {
+    __shared__ EgdstEgmShared E;
+    const int N = P.N, B = blockDim.x, Pp = P.egmP, nsl = B / Pp;
+    const int jpv = P.cx.nst * P.cx.nd;
+    const int nitems = (N - 1 + Pp - 1) / Pp;  // items per (ist,id): the grid points 1..N-1 (a re-seeded pass covers fewer)
+    const int nwork = T.nv * jpv * nitems;
+    const int useTab = egdst_use_shocktab(P);
+    const int p = threadIdx.x % Pp, s = threadIdx.x / Pp;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned ltmask = (1u << lane) - 1u;
+    int tabsd = -1;  // (ist,id,ivec) whose shock table is in shared memory
+    for (int w = T.rank; w < nwork; w += T.size) {
+        int ivec, jy, item;
+        egdst_item(T, w, jpv, ivec, jy, item);
+        const int ist = jy / P.cx.nd, id = jy % P.cx.nd;
+        const int sd = egdst_sd(P, ivec, ist, id);
+        if (!P.active[sd]) continue;  // uniform per CTA
+        const double *seed = P.seed + (size_t)sd * EGDST_SEEDW;
+        volatile unsigned long long *st = P.scanC + (size_t)sd * P.chC;
+        // a pass after a re-send covers only the grids that were re-seeded for it (the others are complete)
+        if ((int)seed[10] != pass) continue;
+        const int nfirst = (int)seed[6];
+        const int n = nfirst + item * Pp + p;
+        if (nfirst + item * Pp >= N || egdst_scan_hi(egdst_scan_inclusive(st, 0))) {
+            // nothing to evaluate (the grid ended at its seed, or a re-seeded pass starts beyond this item): the item
+            // still takes part in the chain and in the completion count
+            __syncthreads();
+            if (warp == 0) { int err = 0; egdst_lookback<1>(st, item + 1, egdst_scan_pack(0, 0), &err); }
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) E.last = (atomicAdd(P.tickC + 2 * sd + 1, 1) == nitems - 1);
+            __syncthreads();
+            if (E.last) { __threadfence(); egdst_egm_epilogue(P, it, ivec, ist, id, sd, nitems, T.slot); }
+            continue;
+        }
+        egdst_ctx cx; egdst_load_ctx(P, ivec, cx);
+        PeriodVars curr; curr.it = it; curr.ist = ist; curr.id = id; curr.cash = 0; curr.savings = 0; curr.shock = 0;
+        const double *shk = 0, *shp = 0;
+        __syncthreads();  // the previous item's shared scratch is free
+        if (useTab) {  // shocks and node probabilities of this (it, ist, id), once per run of items of the same job
+            if (tabsd != sd) {
+                egdst_fill_shocktab(&cx, P, &curr, shsm, shsm + cx.nst * cx.ny, threadIdx.x, B);
+                tabsd = sd;
+            }
+            shk = shsm; shp = shsm + cx.nst * cx.ny;
+        }
+        if (threadIdx.x == 0) { E.evmin[0] = 0x7fffffff; E.evmin[1] = 0x7fffffff; }
+        __syncthreads();
+        // the loop guard of adraw (egdst_solver.c:963-978): the call that would return point n is call seed[7]+n
+        const bool valid = s < nsl && n < N && (int)seed[7] + n < cx.ngridmax;
+        double A = 0.0;
+        EgdstAcc a; a.rhs = 0; a.evf = 0; a.checksum = 0; a.badq = EGDST_NOBAD; a.badtype = 0; a.badcash = 0; a.badshock = 0;
+        if (valid) {
+            A = egdst_agrid(&cx, &curr, seed, n, N);
+            egdst_eval_nodes(&cx, P, ivec, &curr, A, 1, s, nsl, a, shk, shp);
+        }
+        E.rhs[threadIdx.x] = a.rhs; E.evf[threadIdx.x] = a.evf; E.chk[threadIdx.x] = a.checksum;
+        E.q[threadIdx.x] = a.badq; E.t[threadIdx.x] = a.badtype; E.cash[threadIdx.x] = a.badcash;
+        __syncthreads();
+        // threads 0..Pp-1 own the points of the item, in order
+        int flag = EGDST_PT_NONE;
+        double M = 0, c = 0, v = 0;
+        if (s == 0 && n < N) {
+            if (!valid) {
+                flag = EGDST_PT_NONE;
+                atomicMin(&E.evmin[0], p);  // the grid ends before this point (loop guard)
+                if (n == nfirst || (int)seed[7] + n - 1 < cx.ngridmax) egdst_fail(P, ivec, EGDST_ERR_ADRAW_LOOP, it, ist, id);
+            } else {
+                double rhs = 0, evf = 0, chk = 0, badcash = 0; int bq = EGDST_NOBAD, bt = 0;
+                for (int k = 0; k < nsl; k++) {
+                    const int o = k * Pp + p;
+                    rhs += E.rhs[o]; evf += E.evf[o]; chk += E.chk[o];
+                    if (E.q[o] < bq) { bq = E.q[o]; bt = E.t[o]; badcash = E.cash[o]; }
+                }
+                double stopv;
+                if (bq != EGDST_NOBAD) {
+                    flag = bt;
+                    stopv = (bt == EGDST_PT_C1NEG) ? cx.a0 - 1 : badcash;
+                } else if (fabs(chk - 1) > cx.tolerance) {
+                    flag = EGDST_PT_CHECKSUM; stopv = EGDST_INF;
+                } else {
+                    const double beta = discount(&cx, &curr);
+                    M = A + utility_marginal_inverse(&cx, &curr, beta * rhs);
+                    stopv = M;
+                    if (!isfinite(M)) flag = EGDST_PT_NONFINITE;
+                    else { c = M - A; v = utility(&cx, &curr, c) + beta * evf; flag = EGDST_PT_OK; }
+                }
+                if (flag == EGDST_PT_C1NEG) atomicMin(&E.evmin[1], p);     // asks for a re-send: not kept, ends this pass
+                else if (!(stopv < cx.mmax)) atomicMin(&E.evmin[0], p + 1);  // stop rule: this point is the last one generated
+            }
+        }
+        __syncthreads();
+        // points of the item that the sequential generator would have produced: p < lim
+        const int ls = E.evmin[0], ll = E.evmin[1];
+        const int lim = ll < ls ? ll : ls;
+        const bool in = s == 0 && n < N && p < lim;
+        const bool keep = in && flag == EGDST_PT_OK;
+        const unsigned bal = __ballot_sync(EGDST_FULL, keep);
+        int total;
+        int woff = egdst_block_excl_scan(lane == 0 ? __popc(bal) : 0, E.sh, &total);
+        woff = __shfl_sync(EGDST_FULL, woff, 0);
+        int err = 0;
+        if (warp == 0) {
+            const unsigned long long e = egdst_lookback<1>(st, item + 1, egdst_scan_pack(total, lim != 0x7fffffff ? 1 : 0), &err);
+            if (lane == 0) E.excl = e;
+        }
+        __syncthreads();
+        const unsigned long long excl = E.excl;
+        if (!egdst_scan_hi(excl)) {  // the grid did not end in an earlier item: this item's points count
+            if (in && flag == EGDST_PT_CHECKSUM) egdst_fail(P, ivec, EGDST_ERR_CHECKSUM, it, ist, id);
+            if (in && flag == EGDST_PT_EVFINF) P.evfa0[sd] = -EGDST_INF;  // egdst_solver.c:596 (the point itself is dropped)
+            if (threadIdx.x == 0 && ll < ls) {  // first re-send request of this grid: egdst_ph_resend takes over at that point
+                P.lateN[sd] = nfirst + item * Pp + ll;
+                atomicAdd(P.flags + 8 * T.slot + (pass % 3), 1);
+            }
+            const int first = egdst_scan_lo(excl);
+            double *X = P.ptX + (size_t)sd * P.gcap, *Cc = P.ptC + (size_t)sd * P.gcap, *V = P.ptV + (size_t)sd * P.gcap;
+            if (keep) {
+                const int loc = woff + __popc(bal & ltmask);
+                const int dst = first + loc;
+                if (dst < P.gcap) { X[dst] = M; Cc[dst] = c; V[dst] = v; }
+                E.kx[loc] = M; E.kv[loc] = v;
+            }
+            __syncthreads();
+            // folds between neighbours that this item wrote itself (M or V decreasing, egdst_solver.c:819)
+            if (threadIdx.x >= 1 && threadIdx.x < total && first + threadIdx.x < P.gcap)
+                if (E.kx[threadIdx.x - 1] > E.kx[threadIdx.x] || E.kv[threadIdx.x - 1] > E.kv[threadIdx.x]) {
+                    const int k = atomicAdd(P.foldCnt + sd, 1); if (k <= P.gcap) P.foldList[(size_t)sd * (P.gcap + 1) + k] = first + threadIdx.x;
+                }
+            if (threadIdx.x == 0 && total > 0) atomicAdd(P.units + ivec, (unsigned long long)total);
+        }
+        if (err) egdst_fail(P, ivec, EGDST_ERR_ENV2SPACE, it, ist, id);
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) E.last = (atomicAdd(P.tickC + 2 * sd + 1, 1) == nitems - 1);
+        __syncthreads();
+        if (E.last) { __threadfence(); egdst_egm_epilogue(P, it, ivec, ist, id, sd, nitems, T.slot); }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// A zero-consumption re-send requested by a grid point after the seed stage (egdst_solver.c:583-627, 1080-1099):
+// the reference replaces that point by A = cashinhandinverse(...) + ZEROCONSUMPTION, makes it the new focal point of
+// the grid (k3 = 1, limits from the line through the base point and (a0, a0)) and generates the REST of the grid from
+// there.  One CTA per (ist,id) that asked: re-evaluate the offending point to learn where consumption vanished,
+// re-send (repeatedly if the re-sent point asks again), store the point, publish the new closed form.  The EGM phase
+// then runs again for the grid points after it.
+// ---------------------------------------------------------------------------------------------
+EGDST_DEV void egdst_ph_resend(const EgdstDev &P, int it, const EgdstTeam &T, int pass, double *shsm) {
+    __shared__ EgdstSeedShared S;
+    const int jpv = P.cx.nst * P.cx.nd, nwork = T.nv * jpv;
+    const int useTab = egdst_use_shocktab(P);
+    const int N = P.N;
+    if (T.rank == 0 && threadIdx.x == 0) P.flags[8 * T.slot + ((pass + 1) % 3)] = 0;  // the counter of the next pass
+    for (int w = T.rank; w < nwork; w += T.size) {
+        const int ivec = T.v0 + w / jpv, jy = w % jpv, ist = jy / P.cx.nd, id = jy % P.cx.nd;
+        const int sd = egdst_sd(P, ivec, ist, id);
+        __syncthreads();
+        const int nl = P.lateN[sd];
+        if (!P.active[sd] || nl == 0x7fffffff) continue;  // grids that did not ask are complete
+        egdst_ctx cx; egdst_load_ctx(P, ivec, cx);
+        PeriodVars curr; curr.it = it; curr.ist = ist; curr.id = id; curr.cash = 0; curr.savings = 0; curr.shock = 0;
+        double *seed = P.seed + (size_t)sd * EGDST_SEEDW;
+        double *X = P.ptX + (size_t)sd * P.gcap, *Cc = P.ptC + (size_t)sd * P.gcap, *V = P.ptV + (size_t)sd * P.gcap;
+        const int nitems = (N - 1 + P.egmP - 1) / P.egmP;
+        const double beta = discount(&cx, &curr);
+        const double *shk = 0, *shp = 0;
+        if (useTab) {
+            egdst_fill_shocktab(&cx, P, &curr, shsm, shsm + cx.nst * cx.ny, threadIdx.x, blockDim.x);
+            shk = shsm; shp = shsm + cx.nst * cx.ny;
+        }
+        int kept = egdst_scan_lo(egdst_scan_inclusive(P.scanC + (size_t)sd * P.chC, nitems));  // points before the offending one
+        if (kept > P.gcap) kept = P.gcap;
+        const double baseA = seed[8], baseM = seed[9];
+        if (threadIdx.x == 0) { S.A = egdst_agrid(&cx, &curr, seed, nl, N); S.calls = (int)seed[7]; S.go = 1; }
+#ifdef EGDST_HOSTEMU
+        if (threadIdx.x == 0 && getenv("EGDST_DEBUG_RESEND")) printf("re-send after the seed stage: it=%d ist=%d id=%d at grid point %d (A=%.12g), %d points kept before it\n", it, ist, id, nl, S.A, kept);
+#endif
+        __syncthreads();
+        EgdstLims L; L.lim1 = seed[0]; L.lim2 = seed[1]; L.lim3 = seed[2]; L.lim3p = seed[3]; L.k3 = seed[4]; L.lim2p = 0;
+        double lastA = 0, aM = 0;
+        int stored = 0;
+        while (true) {
+            egdst_block_eval(&cx, P, ivec, &curr, S.A, 1, S, shk, shp);
+            if (threadIdx.x == 0) {
+                lastA = S.A;
+                int resend = 0, fatal = 0;
+                stored = 0;
+                if (S.badq == EGDST_NOBAD && fabs(S.checksum - 1) > cx.tolerance) {
+                    egdst_fail(P, ivec, EGDST_ERR_CHECKSUM, it, ist, id); fatal = 1;
+                } else if (S.badq != EGDST_NOBAD) {
+                    aM = S.badcash;
+                    if (S.badtype == EGDST_PT_C1NEG) {
+                        aM = cx.a0 - 1;
+                        int fail = 0;
+                        lastA = egdst_resend_point(&cx, P, ivec, &curr, it, lastA, S.badq, S.badshock, S.badcash, &fail);
+                        if (fail) { egdst_fail(P, ivec, EGDST_ERR_CASHINVERSE, it, ist, id); fatal = 1; }
+                    }
+                } else {
+                    aM = lastA + utility_marginal_inverse(&cx, &curr, beta * S.rhs);
+                    if (isfinite(aM) && kept < P.gcap) {
+                        X[kept] = aM; Cc[kept] = aM - lastA; V[kept] = utility(&cx, &curr, aM - lastA) + beta * S.evf;
+                        stored = 1;
+                    }
+                }
+                if (!fatal && aM <= cx.a0 - 1 + cx.tolerance) {
+                    egdst_lims_resend(&cx, &curr, lastA, baseA, baseM, L);
+                    resend = 1;
+                    if (++S.calls >= cx.ngridmax) { egdst_fail(P, ivec, EGDST_ERR_ADRAW_LOOP, it, ist, id); resend = 0; fatal = 1; }
+                }
+                S.A = lastA;
+                S.go = fatal ? -1 : resend;
+            }
+            __syncthreads();
+            if (S.go != 1) break;
+        }
+        if (threadIdx.x == 0) {
+            P.evfa0[sd] = -EGDST_INF;  // egdst_solver.c:596
+            atomicAdd(P.units + P.nvec + ivec, 1ULL);  // diagnostic: re-sends after the seed stage handled in this solve
+            if (stored) {
+                if (kept > 0 && (X[kept - 1] > X[kept] || V[kept - 1] > V[kept])) {
+                    const int k = atomicAdd(P.foldCnt + sd, 1); if (k <= P.gcap) P.foldList[(size_t)sd * (P.gcap + 1) + k] = kept;
+                }
+                kept += 1;
+                atomicAdd(P.units + ivec, 1ULL);
+            }
+            // the grid goes on after the re-sent point (which took the place of point nl) unless it ended there
+            const int stop = (S.go == -1 || !(aM < cx.mmax)) ? 1 : 0;
+            egdst_seed_publish(P, sd, seed, L, lastA, nl + 1, S.calls, baseA, baseM, kept, stop, pass + 1);
+            for (int c = 1; c < P.chC; c++) P.scanC[(size_t)sd * P.chC + c] = 0ULL;
+            P.tickC[2 * sd + 1] = 0;
+            P.lateN[sd] = 0x7fffffff;
+        }
     }
 }

@@ -72,7 +72,7 @@ EGDST_DEV void egdst_cells_body(const EgdstDev &P, int ivec, int it) {
     const int nsdv = P.cx.nst * P.cx.nd, sd0 = ivec * nsdv;
     for (int i = threadIdx.x; i < nsdv * P.chC; i += blockDim.x) P.scanC[(size_t)sd0 * P.chC + i] = 0ULL;
     for (int i = threadIdx.x; i < nsdv * 2; i += blockDim.x) P.tickC[2 * sd0 + i] = 0;
-    for (int i = threadIdx.x; i < nsdv; i += blockDim.x) P.foldCnt[sd0 + i] = 0;
+    for (int i = threadIdx.x; i < nsdv; i += blockDim.x) { P.foldCnt[sd0 + i] = 0; P.lateN[sd0 + i] = 0x7fffffff; }
     for (int i = threadIdx.x; i < nsdv * P.chE; i += blockDim.x) P.scanE[(size_t)sd0 * P.chE + i] = 0ULL;          // secondary slots
     for (int i = threadIdx.x; i < nsdv * 2; i += blockDim.x) P.tickE[2 * sd0 + i] = 0;
     for (int i = threadIdx.x; i < nsdv; i += blockDim.x) P.envNact[sd0 + i] = 0;
@@ -89,6 +89,11 @@ EGDST_DEV void egdst_cells_body(const EgdstDev &P, int ivec, int it) {
         for (curr.id = 0; curr.id < cx.nd; curr.id++) any |= (inchoiceset(&cx, &curr) == 1);
         if (!any) { P.mlen[cell] = 0; P.thlen[cell] = 0; egdst_fail(P, ivec, EGDST_ERR_EMPTYCHOICE, it, ist, -1); }
     }
+}
+// the same for every vector of a team, plus the team's period flags
+EGDST_DEV void egdst_ph_cells(const EgdstDev &P, int it, const EgdstTeam &T) {
+    for (int v = T.rank; v < T.nv; v += T.size) egdst_cells_body(P, T.v0 + v, it);
+    if (T.rank == 0 && threadIdx.x < 8) P.flags[8 * T.slot + threadIdx.x] = 0;
 }
 
 // Build the tables of one cell: the share of virtual block vb of nvb (all threads of the CTA, 1-D blocks).
@@ -152,13 +157,16 @@ EGDST_DEV void egdst_tab_cell(const EgdstDev &P, int cell, int vb, int nvb) {
     }
 }
 
-// build the tables of the cells (ivec, it, all ist): grid (nblk, nst, nvec)
-__global__ void egdst_k_tab(EgdstDev P, int it) {
-    const int ivec = blockIdx.z, ist = blockIdx.y;
-    // the last kernel of period `it` also opens period it-1 (saves a launch per period)
-    if (blockIdx.x == 0 && blockIdx.y == 0 && it > 0) egdst_cells_body(P, ivec, it - 1);
-    egdst_tab_cell(P, egdst_cell(P, ivec, it, ist), blockIdx.x, gridDim.x);
+// tables of the cells (ivec, it, all ist) of a team: nvb virtual blocks per cell
+EGDST_DEV void egdst_ph_tab(const EgdstDev &P, int it, const EgdstTeam &T, int nvb) {
+    const int jpv = P.cx.nst, nwork = T.nv * jpv * nvb;
+    for (int w = T.rank; w < nwork; w += T.size) {
+        const int njobs = T.nv * jpv, vb = w / njobs, j = w - vb * njobs;
+        egdst_tab_cell(P, egdst_cell(P, T.v0 + j / jpv, it, j % jpv), vb, nvb);
+    }
 }
+// tables of imported cells (egdst_solution_import): grid (nblk, nst, 1)
+__global__ void egdst_k_tabonly(EgdstDev P, int it) { egdst_tab_cell(P, egdst_cell(P, blockIdx.z, it, blockIdx.y), blockIdx.x, gridDim.x); }
 
 // the simulator's version: the same loads with the evict_last hint
 EGDST_DEV EgdstInterval egdst_load_interval_keep(const EgdstRow *p, unsigned long long pol) {

@@ -57,8 +57,8 @@ int egdst_model_neq(void);
 const char *egdst_last_error(void);  /* per-thread message of the last non-zero return */
 void egdst_set_stream(void *cuda_stream);
 /* measurement aids: number of kernels launched by this library so far; optional CUDA-event timing of
- * every launch, accumulated per kernel class (setup, terminal, seed, egm, compact, envelope2, envelope,
- * simulate, other).  Profiling adds two event records per launch -- never enable it in a timed region. */
+ * every launch, accumulated per kernel class (setup, solve, tables, simulate, other).  Profiling adds two event
+ * records per launch and switches the solve kernel's phase timers on -- never enable it in a timed region. */
 long long egdst_launch_count(void);
 int egdst_profile_classes(void);
 const char *egdst_profile_class_name(int cls);
@@ -84,6 +84,18 @@ int egdst_solution_status(egdst_solution *s, int ivec, int *it, int *ist, int *i
 int egdst_solution_nvec(const egdst_solution *s);
 /* total number of EGM grid points kept over all (it,ist,id) of the last solve (the solve work unit) */
 long long egdst_solution_units(egdst_solution *s);
+/* diagnostic: how many zero-consumption re-sends requested by grid points AFTER the seed stage of the savings grid
+ * (egdst_solver.c:1080-1099) the last solve went through */
+long long egdst_solution_resends(egdst_solution *s);
+/* measurement aid: device time in ms per phase of the solve kernel -- terminal, seed, egm, resend, envelope2, rank,
+ * merge, tables (8 entries) -- accumulated over this object's solves while egdst_profile_enable(1) was in effect;
+ * reading resets the counters.  Returns the number of entries. */
+int egdst_solution_phase_ms(egdst_solution *s, double *ms);
+/* diagnostic: the secondary upper envelope (envelope2, egdst_solver.c:776-913) of n EGM points (M, C, V_d) of decision
+ * id (state 0, period it) in generation order, run by the solve kernel's own phases.  out*: room for ngridmax
+ * doubles each; *nout receives the number of points kept.  The tests compare it with the reference's envelope2. */
+int egdst_test_envelope2(const egdst_desc *d, int it, int ist, int id, const double *X, const double *C, const double *V, int n,
+                         double evfa0, double *outX, double *outC, double *outV, int *nout);
 void egdst_free_solution(egdst_solution *s);
 /* Frees what the library keeps between calls: the one released solution object it caches for re-use by the next
  * solve of the same shape, and the calling thread's simulation workspace.  (The reference leaks on error paths and

@@ -64,7 +64,7 @@ enum {
     EGDST_ERR_CASHINVERSE = 12, /* egdst_lib.c:293 */
     EGDST_ERR_INTERP2PT = 13,   /* egdst_lib.c:171 */
     EGDST_ERR_ENV2SPACE = 14,   /* egdst_solver.c:824,839,877 */
-    EGDST_ERR_RESEND_LATE = 15  /* c1<=0 signalled after the seed stage: reported, the parallel grid does not re-send there */
+    EGDST_ERR_BARRIER = 103     /* internal: a phase barrier of the solve kernel was abandoned (hard error, no result) */
 };
 
 typedef struct curr_variables {

@@ -85,6 +85,32 @@ def build(model, variant: str = "base", force: bool = False) -> Optional[str]:
     return path
 
 
+def build_harness(model, force: bool = False) -> Optional[str]:
+    """oracle/_ref/<key>_env/libegdst_refenv.so: the reference's envelope2()/envelop() callable on given points
+    (oracle/shim/envharness.c includes the unmodified egdst_solver.c from /root/reference)."""
+    model.prepare()
+    outdir = os.path.join(OUTROOT, codegen.model_key(model) + "_env")
+    path = os.path.join(outdir, "libegdst_refenv.so")
+    if os.path.isfile(path) and not force:
+        return path
+    if not reference_available():
+        return None
+    os.makedirs(outdir, exist_ok=True)
+    c_src, h_src = codegen.emit_refspec(model)
+    with open(os.path.join(outdir, "modelspec.c"), "w") as f:
+        f.write(c_src)
+    with open(os.path.join(outdir, "modelspec.h"), "w") as f:
+        f.write(h_src)
+    flags = list(BASE_FLAGS) + ["-DDISTRIB=%d" % (1 if model.shock["type"] == "lognormal" else 2)]
+    for k, v in model.cflags.items():
+        flags.append("-D%s=%s" % (k, v))
+    inc = ["-I" + outdir, "-I" + os.path.join(HERE, "shim"), "-I" + REFSRC]
+    srcs = [os.path.join(REFSRC, "egdst_lib.c"), os.path.join(outdir, "modelspec.c"),
+            os.path.join(HERE, "shim", "mexshim.c"), os.path.join(HERE, "shim", "envharness.c")]
+    subprocess.run(["gcc"] + flags + inc + ["-shared", "-Wl,-Bsymbolic", "-o", path] + srcs + ["-lm"], check=True)
+    return path
+
+
 class _MX(C.Structure):
     pass
 
@@ -253,3 +279,57 @@ class Reference:
         self.lib.shim_free(plhs[0])
         self.lib.shim_free(obj)
         return res
+
+
+class EnvelopeHarness(Reference):
+    """The reference's static envelope routines on given points (differential tests of the envelope kernels)."""
+
+    def __init__(self, model):
+        path = build_harness(model)
+        if path is None:
+            raise FileNotFoundError("oracle/_ref envelope harness is not built and /root/reference is absent")
+        super().__init__(model, libpath=path)
+        L = self.lib
+        dp = C.POINTER(C.c_double)
+        L.ref_envelope2.restype = C.c_int
+        L.ref_envelope2.argtypes = [_PMX, C.c_int, C.c_int, C.c_int, dp, C.c_int, C.c_double, C.c_char_p, C.c_int]
+        L.ref_envelop.restype = C.c_int
+        L.ref_envelop.argtypes = [_PMX, C.c_int, C.c_int, C.c_int, C.c_int, dp, dp, dp, dp, dp, dp, dp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_char_p, C.c_int]
+
+    def envelope2(self, it, ist, idd, X, Cc, V, evfa0):
+        """Secondary envelope of one decision's EGM points (in generation order).  Returns (X, C, V) of the kept points."""
+        m = self.model
+        n = len(X)
+        buf = np.zeros(4 * (m.ngridmax + n + 16))
+        buf[0:4 * n:4] = X; buf[1:4 * n:4] = Cc; buf[2:4 * n:4] = V; buf[3:4 * n:4] = idd
+        obj = self._model_object()
+        err = C.create_string_buffer(400)
+        k = self.lib.ref_envelope2(obj, it, ist, idd, buf.ctypes.data_as(C.POINTER(C.c_double)), n, float(evfa0), err, 400)
+        self.lib.shim_free(obj)
+        if k < 0:
+            raise RefError("reference envelope2: " + err.value.decode(errors="replace"))
+        return buf[0:4 * k:4].copy(), buf[1:4 * k:4].copy(), buf[2:4 * k:4].copy()
+
+    def envelop(self, it, ist, funcs, evfa0):
+        """Primary envelope over functions [(X, C, V), ...] (index = position).  Returns (grid, V, C, thresholds, indices)."""
+        m = self.model
+        quads = []
+        for j, (X, Cc, V) in enumerate(funcs):
+            for x, c, v in zip(X, Cc, V):
+                quads += [x, c, v, float(j)]
+        g = np.array(quads, dtype=np.float64)
+        dim0 = g.size // 4
+        ev = np.array(evfa0, dtype=np.float64)
+        og, of, of2 = np.zeros(m.ngridmax + 8), np.zeros(m.ngridmax + 8), np.zeros(m.ngridmax + 8)
+        oth, oix = np.zeros(m.nthrhmax + 8), np.zeros(m.nthrhmax + 8)
+        n, mm = C.c_int(0), C.c_int(0)
+        dp = C.POINTER(C.c_double)
+        obj = self._model_object()
+        err = C.create_string_buffer(400)
+        rc = self.lib.ref_envelop(obj, it, ist, len(funcs), dim0, g.ctypes.data_as(dp), ev.ctypes.data_as(dp), og.ctypes.data_as(dp),
+                                  of.ctypes.data_as(dp), of2.ctypes.data_as(dp), oth.ctypes.data_as(dp), oix.ctypes.data_as(dp),
+                                  C.byref(n), C.byref(mm), err, 400)
+        self.lib.shim_free(obj)
+        if rc < 0:
+            raise RefError("reference envelop: " + err.value.decode(errors="replace"))
+        return og[:n.value].copy(), of[:n.value].copy(), of2[:n.value].copy(), oth[:mm.value].copy(), oix[:mm.value].copy()

@@ -3,7 +3,7 @@
 Row counts may differ by a row or two where a discrete branch (fold test, stop rule, tie) flips on
 the last ulp (hard part 3), so policies and values are compared as *functions*: both
 solutions' C(M), V(M) are interpolated on a common probe grid over the overlap of their M ranges,
-excluding +-excl neighbourhoods of thresholds (where C jumps); error = |d| / max(1, |f|).
+excluding +-excl = 1e-9 neighbourhoods of thresholds and double points (where C jumps); error = |d| / max(1, |f|).
 Thresholds, evf(a0) (row 0 of V) and the decision sequence are compared directly.
 """
 import numpy as np
@@ -14,7 +14,7 @@ def _interp(M, F, x):
     return np.interp(x, M[1:, 0], F)
 
 
-def cell_errors(Ma, Da, Mb, Db, nprobe=50001, excl=1e-7):
+def cell_errors(Ma, Da, Mb, Db, nprobe=50001, excl=1e-9):
     lo = max(Ma[1, 0], Mb[1, 0])
     hi = min(Ma[-1, 0], Mb[-1, 0])
     out = {"range_lo": abs(Ma[1, 0] - Mb[1, 0]), "range_hi": abs(Ma[-1, 0] - Mb[-1, 0])}

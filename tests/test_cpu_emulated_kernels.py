@@ -1,5 +1,5 @@
 """The CUDA kernels' logic without a GPU: tools/hostemu compiles the same .cu sources with g++ (one std::thread per
-CUDA thread, CTAs in ticket order) and the C ABI is driven exactly as on the device.  Small models only -- this is a
+CUDA thread, a team of one CTA) and the C ABI is driven exactly as on the device.  Small models only -- this is a
 logic check (chained scans, ticket loops, envelope chains, lookup tables, continuous-state branch), not the product
 path: the emulator lives under tools/ and is never loaded by egdst_b200."""
 import os
@@ -57,10 +57,11 @@ def test_emulated_kernels_match_reference(make, kw):
     assert np.allclose(mom[0], np.where(alive, s2, 0.0).sum(axis=0).T, rtol=1e-12, atol=1e-9)
 
 
-def test_emulated_envelope_with_a_single_striding_cta(monkeypatch):
-    """EGDST_ENV_ONECTA: every envelope job runs with one CTA, so the stride loop of the rank kernel and the ticket
-    loop of the merge kernel take several chunks each."""
-    monkeypatch.setenv("EGDST_ENV_ONECTA", "1")
+def test_emulated_phases_with_a_single_striding_cta(monkeypatch):
+    """A team of one CTA (the emulator's only shape) on a grid of 700 points: every phase of the solve kernel strides
+    over many work items -- EGM items chained by the look-back scan (EGDST_EGM_P: 24 points per item), several
+    rank blocks and merge chunks per envelope job."""
+    monkeypatch.setenv("EGDST_EGM_P", "24")
     m = examples.retirement2(T=3, ngridm=700, ngridmax=1500, ny=2, nthrhmax=700)
     if not ref_available(m):
         pytest.skip("oracle/_ref not built and /root/reference absent")
@@ -92,3 +93,22 @@ def test_emulated_table_free_path_for_oversized_cells(monkeypatch):
     rs = rng.random(4 * nsim * m.nt)
     se = goldens.sims_errors(lib.simulate(m, sol, init, rs, 0), orc.simulate(Mr, Dr, init, rs, 0))
     assert se["nan_mismatch"] == 0 and se["discrete_mismatch"] == 0 and se["max"] < 1e-9, se
+
+
+def test_emulated_cta_scope_matches_grid_scope(monkeypatch):
+    """The vector-per-CTA scope of the solve kernel (sweeps of small models) runs the same phases separated by CTA
+    barriers: a batched solve in that scope equals the single solves of its vectors."""
+    m = examples.deaton2(T=8, ngridm=40, ngridmax=200, ny=4)
+    lib = _emulated(m)
+    params = np.array([[0.01, 0.9], [0.04, 1.5], [0.025, 1.2]])
+    monkeypatch.setenv("EGDST_SOLVE_SCOPE", "cta")
+    batch = lib.solve_batch(m, params)
+    monkeypatch.setenv("EGDST_SOLVE_SCOPE", "grid")
+    for v in range(params.shape[0]):
+        assert batch.status(v)[0] == 0
+        mv = examples.deaton2(T=8, ngridm=40, ngridmax=200, ny=4, interest=float(params[v, 0]), income=float(params[v, 1]))
+        mv.prepare()
+        one = lib.solve(mv)
+        Mb, Db = batch.cells(v)
+        e = solution_errors(Mb, Db, one.M, one.D)
+        assert e["C"] < 1e-12 and e["V"] < 1e-12 and e["rowdiff"] == 0, (v, e)

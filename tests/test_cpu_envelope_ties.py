@@ -1,0 +1,102 @@
+"""Exact ties in the upper envelope: the kernels' secondary envelope (run under the host emulator) against the
+reference's own envelope2() called on the same points (oracle/shim/envharness.c includes the unmodified
+egdst_solver.c).  The solver's documented divergence from the reference in ties -- which of several coincident
+functions' points is kept, and no double point where two constant extrapolations coincide -- is pinned here: the
+envelopes agree as functions, and where no tie is involved they agree bit for bit."""
+import os
+import shutil
+import sys
+
+import numpy as np
+import pytest
+
+from egdst_b200 import capi, examples
+from oracle import ref
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(os.path.dirname(HERE), "tools", "hostemu"))
+
+pytestmark = pytest.mark.skipif(shutil.which("g++") is None or not ref.reference_available(),
+                                reason="needs g++ and /root/reference (the reference's envelope routines are compiled from there)")
+
+
+def _model():
+    m = examples.retirement(T=40, ngridm=1000, ngridmax=2000, nthrhmax=1000, ny=10)
+    m.prepare()
+    return m
+
+
+_LIB = {}
+
+
+def _emulated(m):
+    from build import build  # tools/hostemu/build.py
+    if "lib" not in _LIB:
+        _LIB["lib"] = capi.ModelLibrary(build(m))
+    return _LIB["lib"]
+
+
+def _function_space_gap(Xa, Va, Ca, Xb, Vb, Cb, hi):
+    lo = max(Xa.min(), Xb.min())
+    x = np.linspace(lo, hi, 200001)
+    # stay 1e-9 away from double points (C jumps there)
+    for X in (Xa, Xb):
+        for xd in X[:-1][np.diff(X) < 1e-9]:
+            x = x[np.abs(x - xd) > 1e-9]
+    return (float(np.max(np.abs(np.interp(x, Xa, Va) - np.interp(x, Xb, Vb)))),
+            float(np.max(np.abs(np.interp(x, Xa, Ca) - np.interp(x, Xb, Cb)))))
+
+
+def test_secondary_envelope_without_ties_is_bit_identical_to_the_reference():
+    g = np.load(os.path.join(HERE, "golden", "tie_env2.npz"))
+    m = _model()
+    X, C, V = _emulated(m).test_envelope2(m, 7, 0, g["ref_X"], g["ref_C"], g["ref_V"], float(g["evfa0"]))
+    Xr, Cr, Vr = ref.EnvelopeHarness(m).envelope2(7, 0, 0, g["ref_X"], g["ref_C"], g["ref_V"], float(g["evfa0"]))
+    assert len(X) == len(Xr) and len(X) < len(g["ref_X"])
+    assert np.array_equal(X, Xr) and np.array_equal(C, Cr) and np.array_equal(V, Vr)
+
+
+def test_coincident_constant_extrapolations_tie():
+    """pert_*: two runs of a flat stretch whose constant extrapolations coincide.  The reference puts a double point at
+    the mean of the four end points of the two pieces (egdst_solver.c:1737-1753) -- far outside the bracket, so its
+    list is no longer sorted; the later qsort of the primary envelope moves those points beyond the unified grid.  The
+    kernels emit nothing there: the list stays sorted and the envelope is the same function."""
+    g = np.load(os.path.join(HERE, "golden", "tie_env2.npz"))
+    m = _model()
+    X, C, V = _emulated(m).test_envelope2(m, 7, 0, g["pert_X"], g["pert_C"], g["pert_V"], float(g["evfa0"]))
+    Xr, Cr, Vr = ref.EnvelopeHarness(m).envelope2(7, 0, 0, g["pert_X"], g["pert_C"], g["pert_V"], float(g["evfa0"]))
+    assert np.all(np.diff(X) > 0), "the kernels' list must stay strictly increasing"
+    assert not np.all(np.diff(Xr) >= 0), "the reference's list is expected to hold its out-of-bracket double point"
+    stray = Xr > 10.0  # the reference's mean-of-end-points double point (the sentinel abscissa is 1.5*mmax = 15)
+    assert 1 <= stray.sum() <= 4
+    order = np.argsort(Xr[~stray], kind="stable")
+    dv, dc = _function_space_gap(X, V, C, Xr[~stray][order], Vr[~stray][order], Cr[~stray][order], hi=min(X.max(), 9.0))
+    assert dv < 1e-12 and dc < 1e-12, (dv, dc)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_synthetic_folds_with_exact_ties(seed):
+    """Random zig-zag lists with engineered ties: repeated values inside a run (flat stretches), a point of one run
+    lying exactly on another run's piece, equal abscissas in different runs."""
+    rng = np.random.default_rng(100 + seed)
+    m = _model()
+    n1, n2, n3 = 40, 30, 50
+    x1 = np.sort(rng.uniform(-4.0, 6.0, n1)); v1 = np.log(x1 + 6.0)
+    v1[25:32] = v1[25]                                   # flat stretch with bit-identical values
+    x2 = np.sort(rng.uniform(x1[30], 8.0, n2)); v2 = np.log(x2 + 5.5) - 0.01
+    x2[5] = x1[35]                                       # equal abscissa in two runs
+    x3 = np.sort(rng.uniform(x2[10], 9.5, n3)); v3 = np.log(x3 + 5.8) - 0.005
+    k = 20                                               # a point of run 3 exactly on the flat extension of run 1
+    v3[k] = v1[-1]
+    v3 = np.maximum.accumulate(v3)
+    X = np.concatenate([x1, x2, x3]); V = np.concatenate([v1, v2, v3])
+    C = 0.5 + 0.01 * np.arange(X.size)                   # any second function riding along
+    assert X[n1] < X[n1 - 1] and X[n1 + n2] < X[n1 + n2 - 1]  # two fold-backs
+    evfa0 = -1.0
+    Xo, Co, Vo = _emulated(m).test_envelope2(m, 5, 0, X, C, V, evfa0)
+    Xr, Cr, Vr = ref.EnvelopeHarness(m).envelope2(5, 0, 0, X, C, V, evfa0)
+    assert np.all(np.diff(Xo) > 0)
+    keep = Xr < 14.0
+    order = np.argsort(Xr[keep], kind="stable")
+    dv, _ = _function_space_gap(Xo, Vo, Co, Xr[keep][order], Vr[keep][order], Cr[keep][order], hi=min(Xo.max(), Xr[keep].max()))
+    assert dv < 1e-12, dv

@@ -1,6 +1,7 @@
 """Host-side logic that needs no GPU: code generation rules, quadrature, state enumeration, optim_* inference,
 model (de)serialisation, and the oracle (compiled reference) against the committed golden vectors."""
 import json
+import os
 
 import numpy as np
 import pytest
@@ -140,3 +141,60 @@ def test_continuous_state_spec_motion_rule_and_generated_code():
     # round trip through plain data
     again = EgdstModel.from_dict(json.loads(json.dumps(hc.to_dict())))
     assert codegen.emit_devspec(again) == src and again.s[0]["grid"] == hc.s[0]["grid"]
+
+
+# What MATLAB's jsonencode(struct(model)) writes for egdst_examples/model_retirement2.m (hand-written here: neither
+# MATLAB nor Octave exist in this image).  jsonencode turns struct arrays into lists of objects, 1x1 struct arrays
+# into a single object, cell arrays into lists, empty struct arrays into [], numeric scalars into numbers and logicals
+# into true/false; the class stores the trpr matrix [1] as a cell of strings (egdstmodel.m:985-999).
+MATLAB_RETIREMENT2_JSON = r'''
+{"label":"retire2","t0":1,"T":25,
+ "s":{"index":1,"name":"Singleton state","type":"double","discrete":true,"continuous":false,
+      "values":{"value":0,"description":"dummy state"},"gridlimits":[],"gridpoints":[],"grid":[]},
+ "d":{"index":1,"name":"Labour supply","type":"double","discrete":true,"continuous":false,
+      "values":[{"value":0,"description":"retire"},{"value":1,"description":"work"}],"gridlimits":[],"gridpoints":[],"grid":[]},
+ "mmax":10,"ngridm":100,"ngridmax":1000,"nthrhmax":10,"ny":10,"a0":-5,
+ "discount":"1/(1+interest)","survival":"1.0",
+ "u":{"utility":"log(consumption)+duw*(id==0)","marginal":"1/consumption","marginalinverse":"1/mutility","extrap":"log(x)"},
+ "transform":{"direct":"log(x+1)","inverse":"exp(x)-1"},
+ "budget":{"cashinhand":"savings+wage_income*(id!=0)","marginal":"1+interest"},
+ "shock":{"type":"lognormal","mu":"-0.5*sigma*sigma","sigma":"0.25"},
+ "trpr":{"varindex":1,"cases":{"condition":"true","prob":[["1.0000000000"]]}},
+ "choiceset":{"defaultallow":true,"rules":[]},
+ "feasible":{"defaultfeasible":true,"rules":[]},
+ "eq":{"ref":"wage_income","type":"next","expression":"wage*shock","description":"Realized wage income"},
+ "coef":[],
+ "param":[{"ref":"duw","description":"disutility of work","value":0.5},
+          {"ref":"interest","description":"return on savings","value":0.045},
+          {"ref":"wage","description":"wage (times multiplicator shock)","value":1.05}],
+ "cflags":{"TOLERANCE":"1e-10","ZEROCONSUMPTION":"1e-10","DOUBLEPOINT_DELTA":"1e-10","VERBOSE":0},
+ "quiet":false,"needtocompile":true,"dir":"tmp_retire2","id":"abc123",
+ "optim":{"optim_UasD":true,"optim_MUnoD":true,"optim_UnoD":false,"optim_TRPRnoSH":true},
+ "init":[1,0],"nst":1,"nd":2,"nnst":1,"nnd":1,"stm":[1,1],"states":0,"decisions":[0,1]}
+'''
+
+
+def test_build_cli_reads_a_matlab_shaped_dump(tmp_path, capsys):
+    """matlab/compile_b200.m writes jsonencode(struct(model)) and runs `python -m egdst_b200.build_cli` on it
+    (the replacement of compile.m:754-819): the dump of model_retirement2.m must give the model image of the
+    transcribed example, with the switches compile.m:669-747 infers."""
+    from egdst_b200 import build, build_cli
+    d = json.loads(MATLAB_RETIREMENT2_JSON)
+    m = EgdstModel.from_dict(d)
+    ref_m = examples.retirement2()
+    assert codegen.model_key(m) == codegen.model_key(ref_m)
+    assert codegen.emit_devspec(m) == codegen.emit_devspec(ref_m)
+    assert codegen.emit_refspec(m) == codegen.emit_refspec(ref_m)
+    m.prepare()
+    assert {k: bool(v) for k, v in m.optim.items()} == d["optim"]
+    assert (m.t0, m.T, m.ngridm, m.ngridmax, m.nthrhmax, m.ny, m.a0, m.mmax) == (1, 25, 100, 1000, 10, 10, -5, 10)
+    assert list(m.param_vector()) == [0.5, 0.045, 1.05] and m.cflags["VERBOSE"] == "0"
+    # the command compile_b200.m runs (the image of this key is built by __graft_entry__.build(); nothing to compile here)
+    if not os.path.isfile(build.library_path(ref_m)):
+        pytest.skip("model image not built")
+    jf = tmp_path / "model.json"
+    jf.write_text(MATLAB_RETIREMENT2_JSON)
+    assert build_cli.main([str(jf), "--out", str(tmp_path)]) == 0
+    info = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    assert info["key"] == codegen.model_key(ref_m) and os.path.isfile(info["library"])
+    assert {k: bool(v) for k, v in info["optim"].items()} == d["optim"]

@@ -74,19 +74,13 @@ def test_s5_retirement1_2000_points(s1):
     assert e["C"] < TOL and e["V"] < TOL and e["TH"] < TOL and e["Dseq"], e
 
 
-def test_s1b_shipped_parameters_under_noise_floor():
-    """Shipped interest=0.045 at T=40 sits next to the reference's own instability (SURVEY 0, fact 7): parity is
-    asserted only in the cells where two differently rounded builds of the reference agree with each other."""
-    m = examples.retirement(T=40, ngridm=2000, ngridmax=4000, nthrhmax=2000, ny=20)
+def _s1b_check(m, require_all_agreeing):
+    """Parity under the oracle noise floor: every period on which two
+    differently rounded builds of the reference agree with each other must match the base build to 1e-9."""
     m.compile()
     m.solve()
-    # In the unstable early periods (the last ones solved) a rounding-level difference decides whether next-period
-    # consumption turns non-positive far up the savings grid; the reference then re-sends grid points one by one, the
-    # parallel grid reports it (EGDST_ERR_RESEND_LATE) and stops.  Either outcome is accepted there; every period the
-    # two reference builds agree on must have been solved before that.
     st = m._solution.status()
-    assert st[0] in (0, 15), st
-    first_solved = st[1] + 1 if st[0] else 0
+    assert st[0] == 0, st  # a re-send after the seed stage is handled (egdst_solver.c:1080-1099), never reported
     base = ref.Reference(m)
     Mb, Db = base.solve()
     noise = ref.Reference(m, variant="noise")
@@ -95,11 +89,26 @@ def test_s1b_shipped_parameters_under_noise_floor():
     for it in range(m.nt):
         en = cell_errors(Mn[0][it], Dn[0][it], Mb[0][it], Db[0][it])
         if max(en["C"], en["V"]) < 1e-11 and en["nth"][0] == en["nth"][1]:
-            assert it >= first_solved, (it, st)
             eg = cell_errors(m.M[0][it], m.D[0][it], Mb[0][it], Db[0][it])
             assert eg["C"] < TOL and eg["V"] < TOL, (it, eg, en)
             checked += 1
-    assert checked >= m.nt // 2
+    assert checked >= require_all_agreeing, (checked, m.nt)
+    return checked
+
+
+def test_s1b_shipped_parameters_under_noise_floor():
+    """Shipped interest=0.045 at T=40 sits next to the reference's own instability (SURVEY 0, fact 7): parity is
+    asserted in every cell where two differently rounded builds of the reference agree with each other."""
+    m = examples.retirement(T=40, ngridm=2000, ngridmax=4000, nthrhmax=2000, ny=20)
+    _s1b_check(m, m.nt // 2)
+
+
+def test_s1b_at_baseline_size_under_noise_floor():
+    """S1b as BASELINE.md section 4 defines it: retirement2 with the shipped parameters (interest=0.045) at
+    ngridm=10000, ny=100, T=40 -- the largest size the reference completes with its own parameters."""
+    m = examples.retirement(T=40, ngridm=10000, ngridmax=20000, nthrhmax=10000, ny=100)
+    checked = _s1b_check(m, m.nt // 2)
+    print("S1b at BASELINE size: %d of %d periods under the noise floor checked, %d re-sends after the seed stage" % (checked, m.nt, m._solution.resends()))
 
 
 def test_philox_results_do_not_depend_on_sharding(s1):

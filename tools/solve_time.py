@@ -29,3 +29,7 @@ prof = lib.profile_read(); lib.profile_enable(False)
 for k, (t_ms, n) in prof.items():
     if n:
         print("  %-10s %8.3f ms/solve  %6.1f us/launch  (%d launches/solve)" % (k, t_ms / 3, t_ms / n * 1e3, n // 3))
+ph = sol.phase_ms()
+for k, v in ph.items():
+    print("  phase %-10s %8.3f ms/solve  %6.1f us/period" % (k, v / 3, v / 3 / max(m.nt - 1, 1) * 1e3))
+print("  resends handled:", sol.resends())
