@@ -248,16 +248,17 @@ static int create_solution(const egdst_desc *d, int nvec, egdst_solution **out) 
     }
     {   // one allocation for both tables: a single L2 access-policy window can then keep them resident (sim_launch)
         const size_t lutbytes = ((sizeof(EgdstLutEntry) * (size_t)s->ncell * (P.lutcap + 1) + 255) / 256) * 256;
-        const size_t ivlbytes = sizeof(EgdstRow) * (size_t)s->ncell * (P.tabcap + 1);
+        const size_t ivlbytes = ((sizeof(EgdstRow) * (size_t)s->ncell * (P.tabcap + 1) + 255) / 256) * 256;
+        const size_t topbytes = sizeof(EgdstCellTop) * (size_t)s->ncell;
         unsigned char *base = 0;
-        DA(base, lutbytes + ivlbytes);
-        P.tabLut = (EgdstLutEntry *)base; P.tabRow = (EgdstRow *)(base + lutbytes);
-        s->tab_base = base; s->tab_bytes = lutbytes + ivlbytes;
+        DA(base, lutbytes + ivlbytes + topbytes);
+        P.tabLut = (EgdstLutEntry *)base; P.tabRow = (EgdstRow *)(base + lutbytes); P.tabTop = (EgdstCellTop *)(base + lutbytes + ivlbytes);
+        s->tab_base = base; s->tab_bytes = lutbytes + ivlbytes + topbytes;
     }
     // chained scans: one state word per work item of a job plus the seed's slot (EGM phase: at least 8 grid points per
     // item), one per chunk of EGDST_BLOCK union positions (envelope merge)
     P.chC = (P.N - 1 + 7) / 8 + 2;
-    P.chE = (P.envcap + EGDST_BLOCK - 1) / EGDST_BLOCK + 1;
+    P.chE = (P.envcap + EGDST_CTA_BLOCK - 1) / EGDST_CTA_BLOCK + 1;  // allocation: the narrowest CTA; launch_solve sets the value of the scope
     // a point of the secondary envelope ranks itself against every run (~10^2 in the zig-zag periods of S1): with few
     // jobs, 8 threads share the runs of a point
     P.envA1parts = (nvec * nst * nd < 148) ? 8 : 1;
@@ -294,7 +295,8 @@ static int launch_solve(egdst_solution *s, cudaStream_t st) {
         CK(cudaMemsetAsync(P.thlen, 0, sizeof(int) * s->ncell, st));
     }
     CK(cudaMemsetAsync(P.bar, 0, sizeof(unsigned) * 4, st));
-    const int nst = P.cx.nst, nd = P.cx.nd, nvec = P.nvec, N = P.N, B = EGDST_BLOCK;
+    const int nst = P.cx.nst, nd = P.cx.nd, nvec = P.nvec, N = P.N;
+    int B = EGDST_BLOCK;
     // per-CTA table of quadrature shocks and node probabilities (models whose shocks cannot depend on savings)
     const size_t shbytes = (size_t)2 * nst * P.cx.ny * sizeof(double);
     const size_t shsmem = (EGDST_SHOCK_INDEP_A && shbytes <= EGDST_SHOCKTAB_BYTES) ? shbytes : 0;
@@ -310,7 +312,7 @@ static int launch_solve(egdst_solution *s, cudaStream_t st) {
         if (scope_env) s->cta_scope = strcmp(scope_env, "cta") == 0;
         if (s->cta_scope) {
             CK(cudaFuncSetAttribute(egdst_k_solve_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shsmem));
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, egdst_k_solve_cta, B, shsmem) != cudaSuccess || occ < 1) occ = 1;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, egdst_k_solve_cta, EGDST_CTA_BLOCK, shsmem) != cudaSuccess || occ < 1) occ = 1;
         } else {
             CK(cudaFuncSetAttribute(egdst_k_solve_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shsmem));
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, egdst_k_solve_grid, B, shsmem) != cudaSuccess || occ < 1) occ = 1;
@@ -323,6 +325,8 @@ static int launch_solve(egdst_solution *s, cudaStream_t st) {
         if (s->cta_scope && s->grid_ctas > nvec) s->grid_ctas = nvec;
         if (getenv("EGDST_SOLVE_CTAS")) { const int g = atoi(getenv("EGDST_SOLVE_CTAS")); if (g >= 1 && g < s->grid_ctas) s->grid_ctas = g; }  // test hook
     }
+    if (s->cta_scope) B = EGDST_CTA_BLOCK;
+    P.chE = (P.envcap + B - 1) / B + 1;
     // grid points per work item of the EGM phase: the items of one period fill the team exactly once (no tail wave);
     // a CTA of the vector-per-CTA scope takes the whole grid of a decision at a time
     const int G = s->cta_scope ? 1 : s->grid_ctas;

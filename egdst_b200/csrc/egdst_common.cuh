@@ -29,12 +29,16 @@
 
 #define EGDST_FULL 0xffffffffu
 #define EGDST_SEEDW 12
-#define EGDST_NPHASE 8   /* terminal, seed, egm, resend, envelope2, rank, merge, tables */
+#define EGDST_NPHASE 16  /* terminal, seed, egm, resend, envelope2, rank, merge, tables; then the steps of the last EGM work item */
 #define EGDST_SHOCKTAB_BYTES (40 * 1024)  /* per-CTA table of quadrature shocks and node probabilities (dynamic shared memory) */
 #ifdef EGDST_HOSTEMU
 #define EGDST_SOLVE_MINB 1
+#define EGDST_CTA_BLOCK 32
+#define EGDST_CTA_MINB 1
 #else
 #define EGDST_SOLVE_MINB 3   /* CTAs per SM of the solve kernel (register budget 80) */
+#define EGDST_CTA_BLOCK 64   /* threads per CTA in the vector-per-CTA scope */
+#define EGDST_CTA_MINB 12
 #endif
 #define EGDST_MAXCAND 72   /* stage-0 bisection candidates: (mmax-a0)/2^k < TOLERANCE well before 72 halvings */
 #define EGDST_ENV_STACK 24 /* crossing-chain stack (thresholds() recursion depth) */
@@ -47,6 +51,9 @@ enum { EGDST_PT_OK = 0, EGDST_PT_C1NEG = 1, EGDST_PT_EVFINF = 2, EGDST_PT_CHECKS
 struct EgdstLutEntry { int l, cnt; double m0, m1, m2; };                 // first row of the bucket, rows in it, their abscissas (+inf: none)
 struct EgdstRow { double m, c, v, y; };                                   // row i of (M, C, V); y = RN(1/(M[i+1]-M[i])), 0 when not safely invertible / last row
 struct EgdstInterval { double g0, g1, c0, c1, v0, v1, y, pad; };        // rows i, i+1 as the interpolations use them (two consecutive EgdstRow)
+// the last interval of a cell and its image under the extrapolation transform tr(x - a0) (egdst_lib.c:179-206): what a
+// lookup above the grid needs, without touching the tables; yt = RN(1/(t1-t0)), 0 when not safely invertible
+struct EgdstCellTop { double g0, g1, c0, c1, v0, v1, y, t0, t1, yt; };
 
 // Everything a kernel needs.  Leading dimension of every array is the parameter-vector index `ivec`
 // (batched solves; nvec=1 for a single model).
@@ -90,6 +97,7 @@ struct EgdstDev {
     int egmP;                           // grid points per work item of the EGM phase (<= threads per CTA); slices = threads / egmP
     // per-cell lookup tables (egdst_tables.cuh)
     EgdstRow *tabRow;                   // [ncell*(tabcap+1)]
+    EgdstCellTop *tabTop;               // [ncell]
     EgdstLutEntry *tabLut;              // [ncell*(lutcap+1)]
     int tabcap, lutcap, mbits;
 };
@@ -239,26 +247,46 @@ EGDST_DEV unsigned long long egdst_scan_combine(unsigned long long earlier, unsi
     return egdst_scan_pack(egdst_scan_lo(earlier) + egdst_scan_lo(later), egdst_scan_hi(earlier) + egdst_scan_hi(later));
 }
 // Called by all 32 lanes of one warp.  Publishes this chunk's aggregate, returns the exclusive prefix over the
-// earlier chunks and publishes the inclusive prefix.
+// earlier chunks and publishes the inclusive prefix.  The chunks of a phase finish at about the same time, so a chunk
+// usually has to walk back over many aggregates before it meets an inclusive prefix: the state words of the next
+// EGDST_SCAN_NW windows of 32 predecessors are requested together (independent loads, one round trip to L2), then
+// resolved nearest first.
+#define EGDST_SCAN_NW 8
 template <int KIND>
 EGDST_DEV unsigned long long egdst_lookback(volatile unsigned long long *st, int chunk, unsigned long long agg, int *err) {
     const int lane = threadIdx.x & 31;
     if (lane == 0 && chunk > 0) st[chunk] = EGDST_SCAN_AGG | agg;
     unsigned long long excl = 0ULL;
-    for (int base = chunk - 1; base >= 0; base -= 32) {
-        const int idx = base - lane;
-        unsigned long long w = EGDST_SCAN_INC;  // positions before chunk 0: inclusive prefix = identity
-        if (idx >= 0) {
-            int polls = 0;
-            do { w = st[idx]; } while ((w >> 62) == 0ULL && ++polls < EGDST_SCAN_POLLS);
-            if ((w >> 62) == 0ULL) { *err = 1; w = EGDST_SCAN_INC; }
+    bool done = false;
+    for (int base = chunk - 1; base >= 0 && !done; base -= 32 * EGDST_SCAN_NW) {
+        unsigned long long wv[EGDST_SCAN_NW];
+#pragma unroll
+        for (int r = 0; r < EGDST_SCAN_NW; r++) {
+            const int idx = base - 32 * r - lane;
+            wv[r] = idx >= 0 ? st[idx] : EGDST_SCAN_INC;  // positions before chunk 0: inclusive prefix = identity
         }
-        const unsigned incmask = __ballot_sync(EGDST_FULL, (w >> 62) == 2ULL);
-        const int cut = incmask ? __ffs(incmask) - 1 : 31;  // nearest predecessor that already knows its prefix
-        unsigned long long acc = __shfl_sync(EGDST_FULL, w, cut) & EGDST_SCAN_MASK;
-        for (int l = cut - 1; l >= 0; l--) acc = egdst_scan_combine<KIND>(acc, __shfl_sync(EGDST_FULL, w, l) & EGDST_SCAN_MASK);
-        excl = egdst_scan_combine<KIND>(acc, excl);
-        if (incmask) break;
+#pragma unroll
+        for (int r = 0; r < EGDST_SCAN_NW; r++) {
+            if (done || base - 32 * r < 0) break;  // warp-uniform
+            const int idx = base - 32 * r - lane;
+            unsigned long long w = wv[r];
+            if (idx >= 0 && (w >> 62) == 0ULL) {
+                int polls = 0;
+                do { w = st[idx]; } while ((w >> 62) == 0ULL && ++polls < EGDST_SCAN_POLLS);
+                if ((w >> 62) == 0ULL) { *err = 1; w = EGDST_SCAN_INC; }
+            }
+            const unsigned incmask = __ballot_sync(EGDST_FULL, (w >> 62) == 2ULL);
+            const int cut = incmask ? __ffs(incmask) - 1 : 31;  // nearest predecessor that already knows its prefix
+            // ordered reduction over lanes cut..0 (far to near; the combine is associative): lanes beyond `cut` are the identity
+            unsigned long long acc = lane <= cut ? (w & EGDST_SCAN_MASK) : 0ULL;
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long far = __shfl_down_sync(EGDST_FULL, acc, o);
+                if (lane + o < 32) acc = egdst_scan_combine<KIND>(far, acc);
+            }
+            acc = __shfl_sync(EGDST_FULL, acc, 0);
+            excl = egdst_scan_combine<KIND>(acc, excl);
+            if (incmask) done = true;
+        }
     }
     if (lane == 0) st[chunk] = EGDST_SCAN_INC | egdst_scan_combine<KIND>(excl, agg);
     return excl;

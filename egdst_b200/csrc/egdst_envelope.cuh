@@ -207,11 +207,11 @@ EGDST_DEV void egdst_env_check_allinf(const EgdstDev &P, int ivec, int it, int i
 // `nparts` threads share the functions of one point and combine rank and argmax through shared memory -- the
 // secondary envelope of a zig-zagging grid has ~10^2 runs, and a point that walks them alone is a chain of ~10^2
 // dependent loads.
-template <int MODE>
+template <int MODE, int BS>
 EGDST_DEV void egdst_ph_envA(const EgdstDev &P, int it, const EgdstTeam &T, int nvb) {
     __shared__ double shg[33];
-    __shared__ int s_rank[EGDST_BLOCK], s_best[EGDST_BLOCK];
-    __shared__ double s_bv[EGDST_BLOCK];
+    __shared__ int s_rank[BS], s_best[BS];
+    __shared__ double s_bv[BS];
     const int nparts = (MODE == 1) ? P.envA1parts : 1, npt = blockDim.x / nparts;
     const int lane = threadIdx.x % npt, part = threadIdx.x / npt;
     const int jpv = (MODE == 0) ? P.cx.nst : P.cx.nst * P.cx.nd;
@@ -275,7 +275,7 @@ EGDST_DEV double egdst_env_brsolve(const egdst_ctx *cx, const View &E, int it, i
 }
 
 template <class View>
-EGDST_DEV void egdst_env_chain(const egdst_ctx *cx, const View &E, int it, int ist, double xr, double vr, int fr, int kr,
+EGDST_DEV void egdst_env_chain(const egdst_ctx *cx, const View &E, int it, int ist, double xl, double xr, double vr, int fr, int kr,
                                int pri0, int nwi0, bool write, double *gx, double *gv, double *gc, double *ga, int gleft,
                                double *tth, double *tdd, int tleft, int &ng, int &nt, int *err) {
     unsigned marks[EGDST_ENV_MARKW];
@@ -326,6 +326,10 @@ EGDST_DEV void egdst_env_chain(const egdst_ctx *cx, const View &E, int it, int i
                 newpoint = (pg0 + pg1 + qg0 + qg1) / 4; cmax = newpoint * sq + iq;
             }
             else { newpoint = (ip - iq) / (sq - spp); cmax = newpoint * sq + iq; }
+            // The same tie with slopes that differ in the last bit: the "intersection" of two all but coincident pieces
+            // lands anywhere.  A crossing that belongs to this boundary lies between the two abscissas of the union that
+            // enclose it; anything else is the tie again and is not emitted (secondary envelope, as above).
+            if (View::kMode == 1 && !(newpoint >= xl && newpoint <= xr)) continue;
         }
         // is a third, not yet visited function above at the crossing? (egdst_solver.c:1807-1845, mode 1)
         // The candidates are split over the lanes of the warp (the secondary envelope can have ~10^2 runs);
@@ -390,25 +394,26 @@ EGDST_DEV EgdstEnvPos egdst_env_pos(const EgdstEnvView<MODE> &E, const double *m
     return q;
 }
 
-// Step B/C as a phase.  The union of a job is cut into chunks of blockDim.x positions (one per thread); a work item
-// takes the next chunk of its job by ticket and the chunks are chained by a decoupled look-back scan over (grid
-// points, thresholds) emitted so far.  The rare crossing chains are queued per chunk and run one per warp.  The last
-// item of a job to finish writes the cell header (MODE 0) or copies the staged result back over the decision's point
-// list (MODE 1).  P.chE items per job, most of which find no chunk left.
+// Step B/C as a phase.  The union of a job is cut into chunks of blockDim.x positions (one per thread); the nvb work
+// items of a job take chunks by ticket until none is left, and the chunks are chained by a decoupled look-back scan
+// over (grid points, thresholds) emitted so far.  The rare crossing chains are queued per chunk and run one per warp.
+// The last item of a job to finish writes the cell header (MODE 0) or copies the staged result back over the
+// decision's point list (MODE 1).
 // MODE 0 writes the period's solution cell (rows 1.., thresholds, evf, row 0); MODE 1 rewrites the id's list.
+template <int BS>
 struct EgdstEnvShared {
     long long sh[40];
     double grb[33];
     int chunk, last, qn;
     unsigned long long excl;
-    int qr[EGDST_BLOCK], qg[EGDST_BLOCK], qt[EGDST_BLOCK], qgpos[EGDST_BLOCK], qtpos[EGDST_BLOCK];
+    int qr[BS], qg[BS], qt[BS], qgpos[BS], qtpos[BS];
 };
 
-template <int MODE>
-EGDST_DEV void egdst_ph_envBC(const EgdstDev &P, int it, const EgdstTeam &T) {
-    __shared__ EgdstEnvShared Sh;
+template <int MODE, int BS>
+EGDST_DEV void egdst_ph_envBC(const EgdstDev &P, int it, const EgdstTeam &T, int nvb) {
+    __shared__ EgdstEnvShared<BS> Sh;
     const int jpv = (MODE == 0) ? P.cx.nst : P.cx.nst * P.cx.nd;
-    const int nitems = P.chE;
+    const int nitems = nvb;
     const int nwork = T.nv * jpv * nitems;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     for (int w = T.rank; w < nwork; w += T.size) {
@@ -437,12 +442,13 @@ EGDST_DEV void egdst_ph_envBC(const EgdstDev &P, int it, const EgdstTeam &T) {
         const int chunkw = blockDim.x;
         const int nch = (nact + chunkw - 1) / chunkw;
         int err = 0, serr = 0;
-        __syncthreads();  // the previous item's queue and scan scratch are free again
-        if (threadIdx.x == 0) { Sh.chunk = atomicAdd(P.tickE + 2 * slot, 1); Sh.qn = 0; }
-        __syncthreads();
-        const int chunk = Sh.chunk;
-        if (chunk < nch) {
-            const double grb = egdst_env_grb_block(E, Sh.grb);
+        const double grb = nch > 0 ? egdst_env_grb_block(E, Sh.grb) : 0.0;  // nch is CTA-uniform
+        while (true) {
+            __syncthreads();  // the previous chunk's queue and scan scratch are free again
+            if (threadIdx.x == 0) { Sh.chunk = atomicAdd(P.tickE + 2 * slot, 1); Sh.qn = 0; }
+            __syncthreads();
+            const int chunk = Sh.chunk;
+            if (chunk >= nch) break;
             const int r = chunk * chunkw + threadIdx.x;
             // pass 1: own contribution of every position; crossing chains go to the item's queue
             int ngj = 0, ntj = 0, qj = -1;
@@ -460,7 +466,7 @@ EGDST_DEV void egdst_ph_envBC(const EgdstDev &P, int it, const EgdstTeam &T) {
                 const int rr = Sh.qr[c];
                 const EgdstEnvPos qq = egdst_env_pos<MODE>(E, mgX, mgF, mgK, mgA, rr);
                 int cg, ct;
-                egdst_env_chain(&cx, E, it, ist, qq.x, qq.v, qq.f, qq.k, qq.aprev, qq.a, false, (double *)0, (double *)0, (double *)0, (double *)0, 0, (double *)0, (double *)0, 0, cg, ct, &err);
+                egdst_env_chain(&cx, E, it, ist, mgX[rr - 1], qq.x, qq.v, qq.f, qq.k, qq.aprev, qq.a, false, (double *)0, (double *)0, (double *)0, (double *)0, 0, (double *)0, (double *)0, 0, cg, ct, &err);
                 if (lane == 0) { Sh.qg[c] = cg; Sh.qt[c] = ct; }
             }
             __syncthreads();
@@ -497,7 +503,7 @@ EGDST_DEV void egdst_ph_envBC(const EgdstDev &P, int it, const EgdstTeam &T) {
                 const EgdstEnvPos qq = egdst_env_pos<MODE>(E, mgX, mgF, mgK, mgA, rr);
                 const int bg = Sh.qgpos[c], bt = Sh.qtpos[c];
                 int cg, ct;
-                egdst_env_chain(&cx, E, it, ist, qq.x, qq.v, qq.f, qq.k, qq.aprev, qq.a, true, ox + bg, ov + bg, oc + bg, oa ? oa + bg : (double *)0, gcapacity - bg,
+                egdst_env_chain(&cx, E, it, ist, mgX[rr - 1], qq.x, qq.v, qq.f, qq.k, qq.aprev, qq.a, true, ox + bg, ov + bg, oc + bg, oa ? oa + bg : (double *)0, gcapacity - bg,
                                 MODE == 0 ? oth + bt : (double *)0, MODE == 0 ? odd + bt : (double *)0, MODE == 0 ? tcapacity - bt : 0, cg, ct, &err);
             }
         }

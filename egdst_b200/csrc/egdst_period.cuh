@@ -25,7 +25,7 @@ EGDST_DEV unsigned long long egdst_globaltimer() { return 0ULL; }
 template <bool GRID>
 EGDST_DEV bool egdst_phase_end(const EgdstDev &P, const EgdstTeam &T, int phase, unsigned long long &t0) {
     const bool ok = egdst_team_sync<GRID>(P);
-    if (GRID && P.phase_ns && T.rank == 0 && threadIdx.x == 0) {
+    if (P.phase_ns && T.rank == 0 && threadIdx.x == 0 && (GRID || T.v0 == 0)) {  // CTA scope: the CTA of vector 0 reports
         const unsigned long long t = egdst_globaltimer();
         P.phase_ns[phase] += t - t0;
         t0 = t;
@@ -60,7 +60,7 @@ static void egdst_debug_dump(const EgdstDev &P, int it, const char *tag) {
 #define EGDST_DEBUG_DUMP(tag)
 #endif
 
-template <bool GRID>
+template <bool GRID, int BS>
 EGDST_DEV void egdst_solve_team(const EgdstDev &P, const EgdstTeam &T, double *shsm) {
     const int N = P.N, B = blockDim.x, nd = P.cx.nd;
     // virtual blocks per job of the rank step and of the table build: sized for the usual list lengths (a decision
@@ -68,12 +68,15 @@ EGDST_DEV void egdst_solve_team(const EgdstDev &P, const EgdstTeam &T, double *s
     const int nptA1 = B / P.envA1parts;
     const int nvbA1 = GRID ? MIN((2 * P.gcap + nptA1 - 1) / nptA1, (N + 64 + nptA1 - 1) / nptA1 + 1) : 1;
     const int nvbA0 = GRID ? MIN((nd * P.gcap + B - 1) / B, (nd * (N + 64) + B - 1) / B + 1) : 1;
+    // work items of the merge: enough to take the usual number of chunks at once; they loop over tickets for more
+    const int nvbM1 = GRID ? MIN(P.chE, (N + 64 + B - 1) / B + 1) : 1;
+    const int nvbM0 = GRID ? MIN(P.chE, (nd * (N + 64) + B - 1) / B + 1) : 1;
     int nvbT = GRID ? (P.lutcap + 1 + B - 1) / B : 1;
     if (GRID && T.nv * P.cx.nst * nvbT > 8 * T.size) nvbT = MAX(1, 8 * T.size / (T.nv * P.cx.nst));
     unsigned long long t0 = 0ULL;
     egdst_ph_cells(P, P.itStart, T);
     if (!egdst_team_sync<GRID>(P)) return;
-    if (GRID && P.phase_ns) t0 = egdst_globaltimer();
+    if (P.phase_ns) t0 = egdst_globaltimer();
     for (int it = P.itStart; it >= P.itStop; it--) {
         if (it == P.NT - 1) {
             egdst_ph_terminal(P, it, T);
@@ -82,7 +85,7 @@ EGDST_DEV void egdst_solve_team(const EgdstDev &P, const EgdstTeam &T, double *s
             egdst_ph_seed(P, it, T, shsm);
             EGDST_PHASE_END(1);
             for (int pass = 0;; pass++) {
-                egdst_ph_egm(P, it, T, pass, shsm);
+                egdst_ph_egm<BS>(P, it, T, pass, shsm);
                 EGDST_PHASE_END(2);
                 if (EGDST_LDCG(P.flags + 8 * T.slot + (pass % 3)) == 0) break;  // no grid asked for a zero-consumption re-send
                 egdst_ph_resend(P, it, T, pass, shsm);
@@ -90,16 +93,16 @@ EGDST_DEV void egdst_solve_team(const EgdstDev &P, const EgdstTeam &T, double *s
             }
             EGDST_DEBUG_DUMP("raw");
             if (EGDST_LDCG(P.flags + 8 * T.slot + 3) != 0) {  // some decision's grid folded back: secondary envelope
-                egdst_ph_envA<1>(P, it, T, nvbA1);
+                egdst_ph_envA<1, BS>(P, it, T, nvbA1);
                 EGDST_PHASE_END(4);
-                egdst_ph_envBC<1>(P, it, T);
+                egdst_ph_envBC<1, BS>(P, it, T, nvbM1);
                 EGDST_PHASE_END(4);
                 EGDST_DEBUG_DUMP("env2");
             }
         }
-        egdst_ph_envA<0>(P, it, T, nvbA0);
+        egdst_ph_envA<0, BS>(P, it, T, nvbA0);
         EGDST_PHASE_END(5);
-        egdst_ph_envBC<0>(P, it, T);
+        egdst_ph_envBC<0, BS>(P, it, T, nvbM0);
         EGDST_PHASE_END(6);
         egdst_ph_tab(P, it, T, nvbT);
         if (it > P.itStop) egdst_ph_cells(P, it - 1, T);
@@ -111,14 +114,16 @@ EGDST_DEV void egdst_solve_team(const EgdstDev &P, const EgdstTeam &T, double *s
 __global__ void __launch_bounds__(EGDST_BLOCK, EGDST_SOLVE_MINB) egdst_k_solve_grid(EgdstDev P) {
     EGDST_DYN_SMEM(double, shsm);
     EgdstTeam T; T.rank = blockIdx.x; T.size = gridDim.x; T.v0 = 0; T.nv = P.nvec; T.slot = 0;
-    egdst_solve_team<true>(P, T, shsm);
+    egdst_solve_team<true, EGDST_BLOCK>(P, T, shsm);
 }
-// CTA scope: CTA b solves vectors b, b + gridDim.x, ...
-__global__ void __launch_bounds__(EGDST_BLOCK, EGDST_SOLVE_MINB) egdst_k_solve_cta(EgdstDev P) {
+// CTA scope: CTA b solves vectors b, b + gridDim.x, ...  Narrow CTAs (EGDST_CTA_BLOCK threads): the jobs of a small
+// model occupy a few dozen threads, and what hides the latency of its dependent phases is the number of vectors in
+// flight per SM.
+__global__ void __launch_bounds__(EGDST_CTA_BLOCK, EGDST_CTA_MINB) egdst_k_solve_cta(EgdstDev P) {
     EGDST_DYN_SMEM(double, shsm);
     for (int v = blockIdx.x; v < P.nvec; v += gridDim.x) {
         EgdstTeam T; T.rank = 0; T.size = 1; T.v0 = v; T.nv = 1; T.slot = 1 + v;
-        egdst_solve_team<false>(P, T, shsm);
+        egdst_solve_team<false, EGDST_CTA_BLOCK>(P, T, shsm);
         __syncthreads();
     }
 }
@@ -148,7 +153,7 @@ __global__ void __launch_bounds__(EGDST_BLOCK, EGDST_SOLVE_MINB) egdst_k_env2_on
     for (int k = threadIdx.x; k < P.cx.nst * P.cx.nd; k += blockDim.x) if (k != sd) { P.active[k] = 0; P.nfold[k] = 0; P.ptN[k] = 0; }
     __syncthreads();
     if (nf == 0) return;
-    egdst_ph_envA<1>(P, it, T, 1);
+    egdst_ph_envA<1, EGDST_BLOCK>(P, it, T, 1);
     __syncthreads();
-    egdst_ph_envBC<1>(P, it, T);
+    egdst_ph_envBC<1, EGDST_BLOCK>(P, it, T, 1);
 }

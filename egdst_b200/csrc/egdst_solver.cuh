@@ -137,12 +137,18 @@ EGDST_DEV bool egdst_eval_node(const egdst_ctx *cx, const EgdstDev &P, const Egd
     return true;
 }
 
-// The common case of a node, straight-line: the cell has tables, cash lies inside the value grid [M[1], M[last]] (no
-// extrapolation, no credit-constrained branch), the bucket of the index resolves the bracket by itself, the interval
-// is safely invertible and its values are finite.  Two nodes are prepared side by side so that their four gathers and
-// their arithmetic overlap; `ok` says whether the straight-line result may be used.
+// The common cases of a node, straight-line.  The cell has tables and either
+//   (interior) cash lies inside the value grid [M[1], M[last]] (no extrapolation, no credit-constrained branch), the
+//              bucket of the index resolves the bracket by itself, the interval is safely invertible, or
+//   (above)    cash lies above the grid: the last interval extrapolates consumption linearly (with the constant guard of
+//              egdst_solver.c:554) and the value in the metric of the transform (egdst_lib.c:179-206); everything about
+//              that interval, including its image under the transform, comes with the cell (EgdstCellTop) -- no gather.
+// Values must be finite.  Two nodes are prepared side by side so that their gathers and their arithmetic overlap;
+// `ok` says whether the straight-line result may be used.  The operations and their order are those of the general
+// path (egdst_eval_node), so the results are the same bits.
 struct EgdstFastNode { double cash, c1, v1; bool ok; };
-EGDST_DEV void egdst_fast_lookup(const EgdstDev &P, const EgdstNext &t, double cash, int &i, bool &ok) {
+EGDST_DEV void egdst_fast_lookup(const EgdstDev &P, const EgdstNext &t, const EgdstCellTop &top, double cash, int &i, bool &ok) {
+    if (cash > top.g1) { i = -1; ok = top.y != 0.0 && top.yt != 0.0 && cash > P.cx.a0; return; }
     int b = egdst_lut_key(cash, P.cx.a0, P.mbits);
     b = b < 0 ? 0 : (b > P.lutcap - 1 ? P.lutcap - 1 : b);
     const EgdstLutEntry *lut = egdst_cell_lut(P, t.cell) + b;
@@ -155,14 +161,31 @@ EGDST_DEV void egdst_fast_lookup(const EgdstDev &P, const EgdstNext &t, double c
     e.l = r0.x; e.cnt = r0.y; e.m0 = __hiloint2double(r0.w, r0.z); e.m1 = r1.x; e.m2 = r1.y;
 #endif
     i = e.l - 1 + (e.m0 <= cash ? 1 : 0) + (e.m1 <= cash ? 1 : 0) + (e.m2 <= cash ? 1 : 0);
-    ok = !(e.cnt > 3 && e.m2 <= cash) && i >= 1 && i <= t.n1 - 1;  // rows i, i+1 exist and belong to the value grid
+    if (e.cnt > 3 && e.m2 <= cash) {  // crowded bucket (the grid is dense around its focal point): bisect its remaining rows
+        int l = e.l + 3, h = e.l + e.cnt;
+        while (l < h) { const int mid = (l + h) >> 1; if (t.M[mid] <= cash) l = mid + 1; else h = mid; }
+        i = l - 1;
+    }
+    ok = i >= 1 && i <= t.n1 - 1;  // rows i, i+1 exist and belong to the value grid
 }
-EGDST_DEV void egdst_fast_interp(const EgdstNext &t, int i, double cash, EgdstFastNode &f) {
+EGDST_DEV void egdst_fast_interp(const egdst_ctx *cx, const PeriodVars *next, const EgdstNext &t, const EgdstCellTop &top, int i, double cash, EgdstFastNode &f) {
+    const double big = 1e290;
+    if (i < 0) {  // above the grid
+        const double w = top.g1 - top.g0, y = top.y;
+        const double ac1 = top.c1 * (cash - top.g0), ac0 = top.c0 * (top.g1 - cash);
+        const double tx = tr(cx, next, cash - cx->a0);
+        const double wt = top.t1 - top.t0;
+        const double av1 = top.v1 * (tx - top.t0), av0 = top.v0 * (top.t1 - tx);
+        f.ok = f.ok && fabs(ac1) < big && fabs(ac0) < big && fabs(av1) < big && fabs(av0) < big && fabs(top.v0) < big && fabs(top.v1) < big;
+        const double c = egdst_div_by(ac1, w, y) + egdst_div_by(ac0, w, y);
+        f.c1 = MAX(c, top.c1);
+        f.v1 = egdst_div_by(av1, wt, top.yt) + egdst_div_by(av0, wt, top.yt);
+        return;
+    }
     const EgdstInterval iv = egdst_load_interval(t.ivl + i);
     const double w = iv.g1 - iv.g0, y = iv.y;
     const double xl = cash - iv.g0, xr = iv.g1 - cash;
     const double ac1 = iv.c1 * xl, ac0 = iv.c0 * xr, av1 = iv.v1 * xl, av0 = iv.v0 * xr;
-    const double big = 1e290;
     f.ok = f.ok && y != 0.0 && cash >= iv.g0 && cash <= iv.g1 && fabs(ac1) < big && fabs(ac0) < big && fabs(av1) < big && fabs(av0) < big;
     f.c1 = egdst_div_by(ac1, w, y) + egdst_div_by(ac0, w, y);
     f.v1 = egdst_div_by(av1, w, y) + egdst_div_by(av0, w, y);
@@ -199,6 +222,7 @@ EGDST_DEV void egdst_eval_nodes(const egdst_ctx *cx, const EgdstDev &P, int ivec
         int iy = part;
 #if EGDST_OPT_MUNOD
         if (shk && tab && keep == 1 && t.n1 >= 3) {
+            const EgdstCellTop top = P.tabTop[t.cell];
             for (; iy + nparts < niy; iy += 2 * nparts) {
                 const int qa = ist1 * ny + iy, qb = qa + nparts;
                 if (qa > acc.badq) break;
@@ -207,12 +231,13 @@ EGDST_DEV void egdst_eval_nodes(const egdst_ctx *cx, const EgdstDev &P, int ivec
                 next.shock = sa; fa.cash = cashinhand(cx, curr, &next);
                 next.shock = sb; fb.cash = cashinhand(cx, curr, &next);
                 int ia, ib;
-                egdst_fast_lookup(P, t, fa.cash, ia, fa.ok);
-                egdst_fast_lookup(P, t, fb.cash, ib, fb.ok);
+                egdst_fast_lookup(P, t, top, fa.cash, ia, fa.ok);
+                egdst_fast_lookup(P, t, top, fb.cash, ib, fb.ok);
                 fa.ok = fa.ok && pa != 0.0; fb.ok = fb.ok && pb != 0.0;
                 if (fa.ok && fb.ok) {
-                    egdst_fast_interp(t, ia, fa.cash, fa);
-                    egdst_fast_interp(t, ib, fb.cash, fb);
+                    next.id = 0;
+                    next.shock = sa; next.cash = fa.cash; egdst_fast_interp(cx, &next, t, top, ia, fa.cash, fa);
+                    next.shock = sb; next.cash = fb.cash; egdst_fast_interp(cx, &next, t, top, ib, fb.cash, fb);
                 }
                 if (fa.ok && fb.ok && fa.c1 > 0 && fb.c1 > 0) {
                     // same operations in the same order as the general path, node qa then node qb
@@ -227,6 +252,10 @@ EGDST_DEV void egdst_eval_nodes(const egdst_ctx *cx, const EgdstDev &P, int ivec
                     acc.evf += pb * fb.v1;
                     continue;
                 }
+#ifdef EGDST_HOSTEMU
+                if (getenv("EGDST_DEBUG_SLOW") && curr->it == atoi(getenv("EGDST_DEBUG_SLOW")))
+                    printf("slow it=%d id=%d A=%.6f qa=%d cash=%.9f/%.9f ok=%d/%d ia=%d ib=%d c1=%.3g/%.3g n1=%d top=%.9f\n", curr->it, curr->id, A, qa, fa.cash, fb.cash, (int)fa.ok, (int)fb.ok, ia, ib, fa.c1, fb.c1, t.n1, top.g1);
+#endif
                 // general path, one node after the other
                 if (pa != 0.0) { next.shock = sa; if (!egdst_eval_node(cx, P, t, tab, curr, next, keep, qa, pa, acc)) break; }
                 if (pb != 0.0) {
@@ -533,10 +562,11 @@ EGDST_DEV double egdst_agrid(const egdst_ctx *cx, const PeriodVars *curr, const 
 // :819) inside an item's output are appended to an unordered list; the last item to finish adds the folds on item
 // boundaries, orders the list and publishes the counts.
 // ---------------------------------------------------------------------------------------------
+template <int BS>
 struct EgdstEgmShared {
-    double rhs[EGDST_BLOCK], evf[EGDST_BLOCK], chk[EGDST_BLOCK], cash[EGDST_BLOCK];
-    int q[EGDST_BLOCK], t[EGDST_BLOCK];
-    double kx[EGDST_BLOCK], kv[EGDST_BLOCK];  // kept points of the item in output order (fold test between neighbours)
+    double rhs[BS], evf[BS], chk[BS], cash[BS];
+    int q[BS], t[BS];
+    double kx[BS], kv[BS];  // kept points of the item in output order (fold test between neighbours)
     int sh[40];
     int evmin[2];                              // first point of the item that stops the grid / asks for a re-send
     int last;
@@ -579,8 +609,20 @@ EGDST_DEV void egdst_egm_epilogue(const EgdstDev &P, int it, int ivec, int ist, 
     }
 }
 
+#ifndef EGDST_HOSTEMU
+#define EGDST_EGM_TIC(k) do { if (tic && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_)); P.phase_ns[8 + (k)] += t_ - tprev; tprev = t_; } } while (0)
+#else
+#define EGDST_EGM_TIC(k)
+#endif
+template <int BS>
 EGDST_DEV void egdst_ph_egm(const EgdstDev &P, int it, const EgdstTeam &T, int pass, double *shsm) {
-    __shared__ EgdstEgmShared E;
+    __shared__ EgdstEgmShared<BS> E;
+    // measurement aid: the steps of the team's last work item (the longest look-back), from the start of the phase
+    unsigned long long tprev = 0ULL;
+    bool tic = false;
+#ifndef EGDST_HOSTEMU
+    if (P.phase_ns && threadIdx.x == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tprev));
+#endif
     const int N = P.N, B = blockDim.x, Pp = P.egmP, nsl = B / Pp;
     const int jpv = P.cx.nst * P.cx.nd;
     const int nitems = (N - 1 + Pp - 1) / Pp;  // items per (ist,id): the grid points 1..N-1 (a re-seeded pass covers fewer)
@@ -595,6 +637,7 @@ EGDST_DEV void egdst_ph_egm(const EgdstDev &P, int it, const EgdstTeam &T, int p
         egdst_item(T, w, jpv, ivec, jy, item);
         const int ist = jy / P.cx.nd, id = jy % P.cx.nd;
         const int sd = egdst_sd(P, ivec, ist, id);
+        tic = P.phase_ns != 0 && w == nwork - 1;
         if (!P.active[sd]) continue;  // uniform per CTA
         const double *seed = P.seed + (size_t)sd * EGDST_SEEDW;
         volatile unsigned long long *st = P.scanC + (size_t)sd * P.chC;
@@ -627,6 +670,11 @@ EGDST_DEV void egdst_ph_egm(const EgdstDev &P, int it, const EgdstTeam &T, int p
         }
         if (threadIdx.x == 0) { E.evmin[0] = 0x7fffffff; E.evmin[1] = 0x7fffffff; }
         __syncthreads();
+        EGDST_EGM_TIC(0);  // set-up: context, shock table
+#ifndef EGDST_HOSTEMU
+        unsigned long long tstart = 0ULL;
+        if (P.phase_ns && threadIdx.x == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tstart));
+#endif
         // the loop guard of adraw (egdst_solver.c:963-978): the call that would return point n is call seed[7]+n
         const bool valid = s < nsl && n < N && (int)seed[7] + n < cx.ngridmax;
         double A = 0.0;
@@ -638,6 +686,13 @@ EGDST_DEV void egdst_ph_egm(const EgdstDev &P, int it, const EgdstTeam &T, int p
         E.rhs[threadIdx.x] = a.rhs; E.evf[threadIdx.x] = a.evf; E.chk[threadIdx.x] = a.checksum;
         E.q[threadIdx.x] = a.badq; E.t[threadIdx.x] = a.badtype; E.cash[threadIdx.x] = a.badcash;
         __syncthreads();
+        EGDST_EGM_TIC(1);  // node loop
+#ifndef EGDST_HOSTEMU
+        if (P.phase_ns && threadIdx.x == 0 && it == P.NT / 2) {  // measurement aid: the slowest node loop of the middle period and its item
+            unsigned long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_));
+            atomicMax(P.phase_ns + 14, ((t_ - tstart) << 20) | (unsigned long long)w);
+        }
+#endif
         // threads 0..Pp-1 own the points of the item, in order
         int flag = EGDST_PT_NONE;
         double M = 0, c = 0, v = 0;
@@ -681,11 +736,13 @@ EGDST_DEV void egdst_ph_egm(const EgdstDev &P, int it, const EgdstTeam &T, int p
         int woff = egdst_block_excl_scan(lane == 0 ? __popc(bal) : 0, E.sh, &total);
         woff = __shfl_sync(EGDST_FULL, woff, 0);
         int err = 0;
+        EGDST_EGM_TIC(2);  // combine, Euler inversion, stop rule, block scan
         if (warp == 0) {
             const unsigned long long e = egdst_lookback<1>(st, item + 1, egdst_scan_pack(total, lim != 0x7fffffff ? 1 : 0), &err);
             if (lane == 0) E.excl = e;
         }
         __syncthreads();
+        EGDST_EGM_TIC(3);  // look-back
         const unsigned long long excl = E.excl;
         if (!egdst_scan_hi(excl)) {  // the grid did not end in an earlier item: this item's points count
             if (in && flag == EGDST_PT_CHECKSUM) egdst_fail(P, ivec, EGDST_ERR_CHECKSUM, it, ist, id);
@@ -715,7 +772,9 @@ EGDST_DEV void egdst_ph_egm(const EgdstDev &P, int it, const EgdstTeam &T, int p
         __syncthreads();
         if (threadIdx.x == 0) E.last = (atomicAdd(P.tickC + 2 * sd + 1, 1) == nitems - 1);
         __syncthreads();
+        EGDST_EGM_TIC(4);  // writes, folds, completion count
         if (E.last) { __threadfence(); egdst_egm_epilogue(P, it, ivec, ist, id, sd, nitems, T.slot); }
+        EGDST_EGM_TIC(5);  // epilogue (if this item finished last)
     }
 }
 

@@ -104,6 +104,19 @@ EGDST_DEV void egdst_tab_cell(const EgdstDev &P, int cell, int vb, int nvb) {
     const double *M = egdst_colM(P, cell), *C = egdst_colC(P, cell), *V = egdst_colV(P, cell);
     EgdstRow *r = P.tabRow + (size_t)cell * (P.tabcap + 1);
     const int stride = nvb * blockDim.x, t0 = vb * blockDim.x + threadIdx.x;
+    if (t0 == 0) {  // the cell's last interval and its image under the extrapolation transform
+        EgdstCellTop T; T.g0 = M[n - 2]; T.g1 = M[n - 1]; T.c0 = C[n - 2]; T.c1 = C[n - 1]; T.v0 = V[n - 2]; T.v1 = V[n - 1];
+        const double w = T.g1 - T.g0;
+        T.y = egdst_div_safe(w) ? 1.0 / w : 0.0;
+        const int ist = cell % P.cx.nst, it = (cell / P.cx.nst) % P.NT, ivec = cell / (P.cx.nst * P.NT);
+        egdst_ctx cx; egdst_load_ctx(P, ivec, cx);
+        PeriodVars prd; prd.it = it; prd.ist = ist; prd.id = 0; prd.cash = 0; prd.savings = 0; prd.shock = 0;
+        egdst_fill_state(&cx, &prd);
+        T.t0 = tr(&cx, &prd, T.g0 - a0); T.t1 = tr(&cx, &prd, T.g1 - a0);
+        const double wt = T.t1 - T.t0;
+        T.yt = egdst_div_safe(wt) ? 1.0 / wt : 0.0;
+        P.tabTop[cell] = T;
+    }
     for (int i = t0; i < n; i += stride) {
         EgdstRow v; v.m = M[i]; v.c = C[i]; v.v = V[i]; v.y = 0.0;
         if (i + 1 < n) { const double w = M[i + 1] - v.m; v.y = egdst_div_safe(w) ? 1.0 / w : 0.0; }  // shared correctly rounded reciprocal (0: plain divisions)

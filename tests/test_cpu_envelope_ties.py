@@ -74,6 +74,31 @@ def test_coincident_constant_extrapolations_tie():
     assert dv < 1e-12 and dc < 1e-12, (dv, dc)
 
 
+def test_all_but_coincident_constant_extrapolations_tie():
+    """pert2_*: the same flat stretch split one point later, with the two constant extrapolations one ulp apart: their
+    "intersection" (a quotient of two rounding errors) lies far outside the boundary it belongs to.  The reference
+    emits it (its list is unsorted again); the kernels do not."""
+    g = np.load(os.path.join(HERE, "golden", "tie_env2.npz"))
+    m = _model()
+    X, C, V = _emulated(m).test_envelope2(m, 7, 0, g["pert2_X"], g["pert2_C"], g["pert2_V"], float(g["evfa0"]))
+    Xr, Cr, Vr = ref.EnvelopeHarness(m).envelope2(7, 0, 0, g["pert2_X"], g["pert2_C"], g["pert2_V"], float(g["evfa0"]))
+    assert np.all(np.diff(X) > 0) and np.isfinite(C).all() and np.isfinite(V).all()
+    assert not np.all(np.diff(Xr) >= 0)
+    # drop the reference's stray double point(s): abscissas that break the order of its list
+    keep = np.ones(Xr.size, bool)
+    run_max = -np.inf
+    for i in range(Xr.size):
+        if Xr[i] < run_max:  # everything between the stray point and here was out of order
+            j = i - 1
+            while j >= 0 and Xr[j] > Xr[i]:
+                keep[j] = False
+                j -= 1
+        run_max = max(run_max, Xr[i]) if keep[i] else run_max
+    assert 1 <= (~keep).sum() <= 4
+    dv, dc = _function_space_gap(X, V, C, Xr[keep], Vr[keep], Cr[keep], hi=min(X.max(), 9.0))
+    assert dv < 1e-12 and dc < 1e-12, (dv, dc)
+
+
 @pytest.mark.parametrize("seed", range(6))
 def test_synthetic_folds_with_exact_ties(seed):
     """Random zig-zag lists with engineered ties: repeated values inside a run (flat stretches), a point of one run

@@ -28,6 +28,7 @@ units = nvec * m.nt * m.nst * m.nd * m.ngridm
 print("batched solve: %.2f ms for %d vectors = %.1f us/vector, %.3e grid-point-periods/s" % (ms, nvec, ms * 1e3 / nvec, units / ms * 1e3))
 lib.profile_enable(True); lib.resolve(sol, m, params); torch.cuda.synchronize(); prof = lib.profile_read(); lib.profile_enable(False)
 print("  ", {k: round(v[0], 2) for k, v in prof.items() if v[1]})
+print("   phases of vector 0 (ms):", {k: round(v, 3) for k, v in sol.phase_ms().items()})
 init = np.column_stack([np.ones(nsim), np.full(nsim, 0.25)])
 mom = lib.sim_moments(m, sol, init, 7)
 t = time.perf_counter()
