@@ -296,6 +296,36 @@ def own_arm(a):
         sim_units = int(alive)  # agents that died or were skipped write no record
     sim_bytes = 8.0 * nso * nt * nsim + 16.0 * nsim  # per launch: sims records out + init in (8*nsimout B per unit)
 
+    # ------------------------------------------------------------------ strong scaling: BASELINE config[3] as stated,
+    # 10M agents IN TOTAL split over the ranks (the primary line above is weak scaling: 10M agents per GPU)
+    from egdst_b200.distributed import shard_range
+    ns_total = a.strong_nsim
+    slo, shi = shard_range(ns_total, rank, world)
+    ns = shi - slo
+    d_init_s = torch.empty(2 * ns, dtype=torch.float64, device=dev)
+    d_init_s[:ns] = 1.0
+    d_init_s[ns:] = d_init[nsim:nsim + ns] if ns <= nsim else m.a0 + 0.5 * (m.mmax - m.a0) * torch.rand(ns, dtype=torch.float64, device=dev, generator=g)
+
+    def strong_step():
+        d_mom.zero_()
+        lib.simulate_device(m, sol, d_init_s.data_ptr(), ns, slo, SEED_SHOCKS, d_sims.data_ptr(), d_mom.data_ptr(), desc=desc)
+        if world > 1:
+            dist.all_reduce(d_mom)
+
+    for _ in range(a.warmup):
+        strong_step()
+    barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for _ in range(a.steps):
+        strong_step()
+    s1.record()
+    barrier()
+    strong_ms = max_over_ranks(s0.elapsed_time(s1) / a.steps)
+    strong = {"metric": SIM_METRIC, "value": ns_total * nt / (strong_ms / 1e3), "unit": "agent-periods/s", "ms_per_step": strong_ms, "scaling": "strong",
+              "config": {"workload": "S2 as BASELINE config[3] states it: %d agents in total, sharded over %d GPU(s), moments all-reduced" % (ns_total, world),
+                         "agents_per_gpu": ns}}
+
     # e2e: the host-buffer C-ABI call a MEX gateway makes -- init from pinned host memory, full sims array back to host
     ne = min(a.e2e_nsim, nsim)
     h_init = torch.empty(2 * ne, dtype=torch.float64).pin_memory()
@@ -319,7 +349,10 @@ def own_arm(a):
     e2e_s = max_over_ranks((time.perf_counter() - t0) / a.e2e_steps)
     e2e = {"value": world * ne * nt / e2e_s, "unit": "agent-periods/s", "h2d_bytes_per_step": int(16 * ne),
            "d2h_bytes_per_step": int(8 * nso * nt * ne), "agents_per_gpu": ne, "ms": e2e_s * 1e3,
-           "api": "egdst_simulate_philox (host init in, host sims out; pinned buffers)"}
+           "api": "egdst_simulate_philox (host init in, host sims out; pinned buffers)",
+           "sample": "1/%d of the headline workload: %d of %d agents per GPU (the leg is bound by the device-to-host copy of the path array, so its rate does not depend on the agent count)" % (max(nsim // max(ne, 1), 1), ne, nsim),
+           "d2h_GBs_aggregate": world * 8.0 * nso * nt * ne / e2e_s / 1e9,
+           "limiter": "device-to-host copy of the [nsimout, nt, nsim] path array (PCIe / host memory): all GPUs of the box drain into the same host"}
 
     # the moments-only entry point (no path array crosses PCIe): what an estimation loop calls
     h_mom = torch.zeros(3 * nso * nt, dtype=torch.float64).pin_memory()
@@ -345,6 +378,12 @@ def own_arm(a):
                            "h2d_bytes_per_step": int(16 * nm_agents), "d2h_bytes_per_step": int(8 * 3 * nso * nt),
                            "api": "egdst_simulate_philox(sims=NULL, moments): host init in, [3,nsimout,nt] moments out"}
 
+    # ------------------------------------------------------------------ BASELINE config[4]: the batched estimation sweep
+    batch = None
+    if not a.no_batch:
+        lib.set_stream(stream.cuda_stream)
+        batch = measure_batch(a, rank, world, dev, with_cpu=(world == 1 and not a.no_cpu))
+
     # cpu baseline: the unmodified reference C on one host core (it is single-threaded), rank 0 at N=1 only
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu:
@@ -369,6 +408,8 @@ def own_arm(a):
                          "fp64": fp64_side((micro_peaks().get("sim_fp64_flop_per_launch_nsim10M") or 0) * nsim / 1e7 or None, kern_ms)},
             "cpu_baseline": cpu,
             "solve": solve_obj,
+            "strong": strong,
+            "batch": batch,
         }
         emit(line)
     if world > 1:
@@ -376,26 +417,19 @@ def own_arm(a):
 
 
 # =====================================================================================================
-# optional workload: BASELINE config[4], the batched estimation sweep (S3)
+# BASELINE config[4], the batched estimation sweep (S3): part of the default line ("batch" object) and a workload of its own
 # =====================================================================================================
-def batch_arm(a):
+def measure_batch(a, rank, world, dev, with_cpu):
     """4096 deaton2 parameter vectors, block-partitioned over the ranks (strong scaling): one batched solve, one
     batched moments-only simulation of 1024 agents under every vector, one all-reduce that assembles the moment
-    table [nvec, 3, nsimout, nt] on every rank.  A step = the whole sweep."""
+    table [nvec, 3, nsimout, nt] on every rank.  A step = the whole sweep.  Returns the result object on rank 0."""
     import torch
     import torch.distributed as dist
     from egdst_b200 import capi, examples
     from egdst_b200.distributed import shard_range
-    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=dev)
-    m = examples.deaton2(); m.device = local; m.compile()
+    m = examples.deaton2(); m.device = dev.index; m.compile()
     lib = m._capi()
-    stream = torch.cuda.Stream(); torch.cuda.set_stream(stream); lib.set_stream(stream.cuda_stream)
+    lib.set_stream(torch.cuda.current_stream().cuda_stream)
     nvec, nsim = a.batch_nvec, a.batch_nsim
     rng = np.random.default_rng(4096)
     params = np.column_stack([rng.uniform(0.0, 0.05, nvec), rng.uniform(0.75, 1.75, nvec)])
@@ -433,17 +467,72 @@ def batch_arm(a):
     ms = e0.elapsed_time(e1) / a.steps
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+    # split of one step on this rank (events around the two calls, outside the timed region)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    ev[0].record(); lib.resolve(sol, m, mine); ev[1].record()
+    lib.sim_moments_device(m, sol, d_init.data_ptr(), nsim, 0, 7, table.data_ptr() + 8 * lo * nmom, desc=desc); ev[2].record()
+    torch.cuda.synchronize()
     bad = sum(1 for v in range(hi - lo) if sol.status(v)[0])
+    if rank != 0:
+        return None
+    units = nvec * nominal_units(m)
+    out = {"metric": "parameter vectors/s (batched solve + simulated moments)", "value": nvec / (ms / 1e3), "unit": "vectors/s", "n_gpus": world,
+           "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "S3: %d deaton2 parameter vectors (interest~U[0,.05], income~U[.75,1.75], default_rng(4096)), %d agents each, moments all-reduced" % (nvec, nsim),
+                      "parallelism": "parameter vectors sharded, dp%d" % world},
+           "gpu_launches": int(lib.launch_count() - l0), "solve_units_per_s": units / (ms / 1e3), "agent_periods_per_s": nvec * nsim * nt / (ms / 1e3),
+           "ms_solve_rank0": ev[0].elapsed_time(ev[1]), "ms_moments_rank0": ev[1].elapsed_time(ev[2]),
+           "vectors_with_error_status_on_rank0": bad}
+    if with_cpu:
+        out["cpu_baseline"] = batch_cpu_baseline(params, nsim, a)
+    return out
+
+
+def _batch_worker(job):
+    from egdst_b200 import examples
+    from tests.oracles import oracle_for
+    interest, income, nsim, seed = job
+    mi = examples.deaton2(interest=float(interest), income=float(income))
+    o = oracle_for(mi)
+    Mr, Dr = o.solve()
+    s = o.seconds
+    init = np.column_stack([np.ones(nsim), np.full(nsim, 0.25)])
+    rs = np.random.default_rng(seed).random(4 * nsim * mi.nt)
+    o.simulate(Mr, Dr, init, rs, 0)
+    return s + o.seconds
+
+
+def batch_cpu_baseline(params, nsim, a):
+    """The reference C on every host core: `cores` independent single-threaded reference
+    processes, each solving and simulating its share of a bounded sample of the sweep's vectors."""
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    nv = max(cores, min(a.batch_cpu_nvec, params.shape[0]))
+    jobs = [(params[i, 0], params[i, 1], nsim, i) for i in range(nv)]
+    ctx = mp.get_context("fork")
+    t0 = time.perf_counter()
+    with ctx.Pool(cores) as pool:
+        gate = pool.map(_batch_worker, jobs)
+    wall = time.perf_counter() - t0
+    return {"value": nv / wall, "unit": "vectors/s", "cores": cores, "kind": "reference",
+            "sample": "%d of the sweep's vectors, solved and simulated (%d agents) by %d reference processes; wall %.2f s, gateway time per vector %.2f ms" % (nv, nsim, cores, wall, 1e3 * float(np.mean(gate)))}
+
+
+def batch_arm(a):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
+        dist.init_process_group("nccl", device_id=dev)
+    stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
+    out = measure_batch(a, rank, world, dev, with_cpu=(world == 1 and not a.no_cpu))
     if rank == 0:
-        units = nvec * nominal_units(m)
-        emit({
-            "metric": "parameter vectors/s (batched solve + simulated moments)", "value": nvec / (ms / 1e3), "unit": "vectors/s", "n_gpus": world,
-            "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "S3: %d deaton2 parameter vectors (interest~U[0,.05], income~U[.75,1.75], default_rng(4096)), %d agents each, moments all-reduced" % (nvec, nsim),
-                       "parallelism": "parameter vectors sharded, dp%d" % world},
-            "gpu_launches": int(lib.launch_count() - l0), "solve_units_per_s": units / (ms / 1e3), "agent_periods_per_s": nvec * nsim * nt / (ms / 1e3),
-            "vectors_with_error_status_on_rank0": bad})
+        out["vs_baseline"] = None
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -568,6 +657,9 @@ def main():
     ap.add_argument("--workload", default="s1s2", choices=["s1s2", "batch"], help="s1s2: BASELINE config[3] (default); batch: config[4] sweep")
     ap.add_argument("--batch-nvec", type=int, default=4096)
     ap.add_argument("--batch-nsim", type=int, default=1024)
+    ap.add_argument("--batch-cpu-nvec", type=int, default=4096, help="vectors of the sweep the CPU baseline solves and simulates (all host cores)")
+    ap.add_argument("--strong-nsim", type=int, default=10_000_000, help="agents IN TOTAL of the strong-scaling object")
+    ap.add_argument("--no-batch", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-cpu-solve", action="store_true")
     a = ap.parse_args()

@@ -110,7 +110,9 @@ struct egdst_solution {
     int neq;
     unsigned long long *d_phase;  // per-phase device time of profiled solves
     int grid_ctas;  // CTAs of the solve kernel (one resident wave), 0 = not sized yet
-    bool cta_scope; // sweeps of many small models: one CTA per parameter vector
+    bool cta_scope; // sweeps of many small models: one CTA (or warp) per parameter vector
+    int warp_groups; // > 0: WARP scope with this many warps (vectors) per CTA
+    int chC_alloc;  // scan windows per job the allocation provides
     size_t bytes;   // device bytes owned (workspace cache policy)
     void *tab_base; size_t tab_bytes;  // lookup tables (one allocation)
     std::vector<double> h_params;  // host copy of the parameter matrix of the last solve (simulator kernel arguments)
@@ -213,7 +215,7 @@ static int create_solution(const egdst_desc *d, int nvec, egdst_solution **out) 
     egdst_solution *s = new egdst_solution();
     s->bytes = 0; memcpy(s->dims, dims, sizeof(dims)); s->dkey[0] = d->mmax; s->dkey[1] = d->a0;
     s->d_momscratch = 0; s->momscratch_cap = 0; s->d_hdr = 0; s->hdr_ivec = -1;
-    s->grid_ctas = 0; s->cta_scope = false;
+    s->grid_ctas = 0; s->cta_scope = false; s->warp_groups = 0;
     s->device = d->device; s->sizes_valid = false; s->d_pack = 0; s->pack_cap = 0; s->neq = d->neq;
     EgdstDev &P = s->P;
     memset(&P, 0, sizeof(P));
@@ -258,7 +260,8 @@ static int create_solution(const egdst_desc *d, int nvec, egdst_solution **out) 
     // chained scans: one state word per work item of a job plus the seed's slot (EGM phase: at least 8 grid points per
     // item), one per chunk of EGDST_BLOCK union positions (envelope merge)
     P.chC = (P.N - 1 + 7) / 8 + 2;
-    P.chE = (P.envcap + EGDST_CTA_BLOCK - 1) / EGDST_CTA_BLOCK + 1;  // allocation: the narrowest CTA; launch_solve sets the value of the scope
+    s->chC_alloc = P.chC;
+    P.chE = (P.envcap + 31) / 32 + 1;  // allocation: the narrowest group (a warp); launch_solve sets the value of the scope
     // a point of the secondary envelope ranks itself against every run (~10^2 in the zig-zag periods of S1): with few
     // jobs, 8 threads share the runs of a point
     P.envA1parts = (nvec * nst * nd < 148) ? 8 : 1;
@@ -297,59 +300,108 @@ static int launch_solve(egdst_solution *s, cudaStream_t st) {
     CK(cudaMemsetAsync(P.bar, 0, sizeof(unsigned) * 4, st));
     const int nst = P.cx.nst, nd = P.cx.nd, nvec = P.nvec, N = P.N;
     int B = EGDST_BLOCK;
+    P.priSync0 = nvec * nst * nd;
     // per-CTA table of quadrature shocks and node probabilities (models whose shocks cannot depend on savings)
     const size_t shbytes = (size_t)2 * nst * P.cx.ny * sizeof(double);
-    const size_t shsmem = (EGDST_SHOCK_INDEP_A && shbytes <= EGDST_SHOCKTAB_BYTES) ? shbytes : 0;
-    if (!s->grid_ctas) {
-        int dev = 0, sms = 1, occ = 1;
+    const size_t shtab = (EGDST_SHOCK_INDEP_A && shbytes <= EGDST_SHOCKTAB_BYTES) ? shbytes : 0;
+    size_t shsmem = 0;  // dynamic shared memory: phase scratch + shock table (+ the per-vector state of the CTA and WARP scopes)
+    int syncOff = -1, groupBytes = 0;
+    int dev = 0, sms = 1, occ = 1;
+    const bool first = !s->grid_ctas;
+    if (first) {
+        // small models, many of them: a CTA (or warp) per vector keeps all of a vector's arrays in its SM's L1/L2
+        // neighbourhood and needs neither launches nor inter-CTA waits
+        const char *scope_env = getenv("EGDST_SOLVE_SCOPE");  // test hook: "grid" / "cta" / "warp"
 #ifndef EGDST_HOSTEMU
         CK(cudaGetDevice(&dev));
         CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        // small models, many of them: a CTA per vector keeps all of a vector's arrays in its SM's L1/L2 neighbourhood
-        // and needs neither launches nor inter-CTA waits
-        static const char *scope_env = getenv("EGDST_SOLVE_SCOPE");  // test hook: "cta" / "grid"
         s->cta_scope = nvec >= 2 * sms && N <= 4 * B;
-        if (scope_env) s->cta_scope = strcmp(scope_env, "cta") == 0;
-        if (s->cta_scope) {
+        s->warp_groups = s->cta_scope && nvec >= 8 * sms ? EGDST_WARP_GROUPS : 0;
+#else
+        s->cta_scope = false; s->warp_groups = 0;
+#endif
+        if (scope_env) { s->cta_scope = strcmp(scope_env, "grid") != 0; s->warp_groups = strcmp(scope_env, "warp") == 0 ? EGDST_WARP_GROUPS : 0; }
+    }
+    for (bool again = true; again;) {
+        again = false;
+        B = s->cta_scope ? (s->warp_groups ? 32 : EGDST_CTA_BLOCK) : EGDST_BLOCK;
+        P.chE = (P.envcap + B - 1) / B + 1;
+        P.chC = s->chC_alloc;
+        if (!s->cta_scope) { shsmem = EgdstScratch<EGDST_BLOCK>::bytes + shtab; break; }
+        // a CTA takes the whole grid of a decision at a time: few scan windows, and the vector's small state fits shared memory
+        int p = B < N - 1 ? B : (N - 1 < 8 ? 8 : N - 1);
+        if (getenv("EGDST_EGM_P")) { const int q = atoi(getenv("EGDST_EGM_P")); if (q >= 8 && q <= B) p = q; }  // test hook
+        P.egmP = p;
+        const int need = (N - 1 + p - 1) / p + 2;
+        if (need < P.chC) P.chC = need;
+        const size_t sb = egdst_cta_sync_bytes(P);
+        if (s->warp_groups) {
+            syncOff = (int)((EgdstScratch<32>::bytes + shtab + 15) / 16 * 16);
+            groupBytes = (int)((syncOff + sb + 127) / 128 * 128);
+            if (first) {
+                // as many warps per CTA as shared memory allows, and no more than spreads the vectors over all SMs
+                int g = (int)((200 * 1024) / groupBytes);
+                if (g > EGDST_WARP_GROUPS) g = EGDST_WARP_GROUPS;
+                const int even = (nvec + sms - 1) / sms;
+                if (even < g) g = even;
+                if (getenv("EGDST_WARP_G")) { const int q = atoi(getenv("EGDST_WARP_G")); if (q >= 1 && q <= g) g = q; }  // test hook
+                if (g < 4 && !getenv("EGDST_WARP_G")) { s->warp_groups = 0; again = true; continue; }  // too few warps per SM to hide anything: CTA scope
+                s->warp_groups = g;
+            }
+            shsmem = (size_t)groupBytes * s->warp_groups;
+        } else {
+            shsmem = EgdstScratch<EGDST_CTA_BLOCK>::bytes + shtab;
+            static const char *nosm = getenv("EGDST_CTA_SYNC_GLOBAL");  // measurement hook
+            syncOff = -1;
+            if (sb <= 6144 && !nosm) { syncOff = (int)((shsmem + 15) / 16 * 16); shsmem = syncOff + sb; }
+        }
+    }
+    if (first) {
+#ifndef EGDST_HOSTEMU
+        if (s->warp_groups) {
+            CK(cudaFuncSetAttribute(egdst_k_solve_warps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shsmem));
+            occ = 1;
+        } else if (s->cta_scope) {
             CK(cudaFuncSetAttribute(egdst_k_solve_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shsmem));
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, egdst_k_solve_cta, EGDST_CTA_BLOCK, shsmem) != cudaSuccess || occ < 1) occ = 1;
         } else {
             CK(cudaFuncSetAttribute(egdst_k_solve_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shsmem));
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, egdst_k_solve_grid, B, shsmem) != cudaSuccess || occ < 1) occ = 1;
         }
-        (void)dev;
-#else
-        s->cta_scope = getenv("EGDST_SOLVE_SCOPE") && strcmp(getenv("EGDST_SOLVE_SCOPE"), "cta") == 0;
 #endif
         s->grid_ctas = sms * occ;
-        if (s->cta_scope && s->grid_ctas > nvec) s->grid_ctas = nvec;
+        const int owners = s->warp_groups ? (nvec + s->warp_groups - 1) / s->warp_groups : nvec;
+        if (s->cta_scope && s->grid_ctas > owners) s->grid_ctas = owners;
         if (getenv("EGDST_SOLVE_CTAS")) { const int g = atoi(getenv("EGDST_SOLVE_CTAS")); if (g >= 1 && g < s->grid_ctas) s->grid_ctas = g; }  // test hook
     }
-    if (s->cta_scope) B = EGDST_CTA_BLOCK;
-    P.chE = (P.envcap + B - 1) / B + 1;
-    // grid points per work item of the EGM phase: the items of one period fill the team exactly once (no tail wave);
-    // a CTA of the vector-per-CTA scope takes the whole grid of a decision at a time
-    const int G = s->cta_scope ? 1 : s->grid_ctas;
-    long long jobs = (long long)(s->cta_scope ? 1 : nvec) * nst * nd;
-    int egmP = (int)(((long long)(N - 1) * jobs + G - 1) / G);
-    if (egmP < 8) egmP = 8;
-    if (egmP > B) egmP = B;
-    if (egmP > N - 1 && N - 1 >= 1) egmP = N - 1 < 8 ? 8 : N - 1;
-    if (getenv("EGDST_EGM_P")) { const int p = atoi(getenv("EGDST_EGM_P")); if (p >= 8 && p <= B) egmP = p; }  // test hook
-    P.egmP = egmP;
+    (void)dev;
+    if (!s->cta_scope) {
+        // grid points per work item of the EGM phase: the items of one period fill the grid exactly once (no tail wave)
+        const int G = s->grid_ctas;
+        long long jobs = (long long)nvec * nst * nd;
+        int egmP = (int)(((long long)(N - 1) * jobs + G - 1) / G);
+        if (egmP < 8) egmP = 8;
+        if (egmP > B) egmP = B;
+        if (egmP > N - 1 && N - 1 >= 1) egmP = N - 1 < 8 ? 8 : N - 1;
+        if (getenv("EGDST_EGM_P")) { const int p = atoi(getenv("EGDST_EGM_P")); if (p >= 8 && p <= B) egmP = p; }  // test hook
+        P.egmP = egmP;
+    }
     P.phase_ns = g_prof_on ? s->d_phase : 0;  // measurement aid: in-kernel phase timers while profiling is enabled
-    if ((N - 1 + egmP - 1) / egmP + 2 > P.chC) return fail(2, "internal: scan state too small for the EGM items");
+    if ((N - 1 + P.egmP - 1) / P.egmP + 2 > P.chC) return fail(2, "internal: scan state too small for the EGM items");
 #ifndef EGDST_HOSTEMU
     prof_begin(KC_SOLVE, st);
-    if (s->cta_scope) {
-        egdst_k_solve_cta<<<s->grid_ctas, B, shsmem, st>>>(P);
+    if (s->warp_groups) {
+        egdst_k_solve_warps<<<s->grid_ctas, dim3(32, s->warp_groups), shsmem, st>>>(P, syncOff, groupBytes);
+    } else if (s->cta_scope) {
+        egdst_k_solve_cta<<<s->grid_ctas, B, shsmem, st>>>(P, syncOff);
     } else {
         void *args[] = {(void *)&P};
         CK(cudaLaunchCooperativeKernel((const void *)egdst_k_solve_grid, dim3(s->grid_ctas), dim3(B), args, shsmem, st));
     }
     prof_end(st);
 #else
-    if (s->cta_scope) { KLAUNCH(KC_SOLVE, egdst_k_solve_cta, dim3(s->grid_ctas), dim3(B), shsmem, st, P); }
+    if (s->warp_groups) { KLAUNCH(KC_SOLVE, egdst_k_solve_warps, dim3(s->grid_ctas), dim3(32, s->warp_groups), shsmem, st, P, syncOff, groupBytes); }
+    else if (s->cta_scope) { KLAUNCH(KC_SOLVE, egdst_k_solve_cta, dim3(s->grid_ctas), dim3(B), shsmem, st, P, syncOff); }
     else { KLAUNCH(KC_SOLVE, egdst_k_solve_grid, dim3(1), dim3(B), shsmem, st, P); }
 #endif
     CK(cudaGetLastError());
@@ -605,7 +657,7 @@ int egdst_test_envelope2(const egdst_desc *d, int it, int ist, int id, const dou
     int nres = 0;
     if (ce == cudaSuccess) {
         P.bparams = 0;
-        KLAUNCH(KC_OTHER, egdst_k_env2_only, dim3(1), dim3(EGDST_BLOCK), 0, st, P, it, n, id);
+        KLAUNCH(KC_OTHER, egdst_k_env2_only, dim3(1), dim3(EGDST_BLOCK), EgdstScratch<EGDST_BLOCK>::bytes, st, P, it, n, id);
         EGDST_TRY(cudaGetLastError());
         EGDST_TRY(cudaMemcpyAsync(&nres, P.ptN + id, sizeof(int), cudaMemcpyDeviceToHost, st));
         EGDST_TRY(cudaStreamSynchronize(st));

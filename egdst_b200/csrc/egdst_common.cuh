@@ -37,8 +37,12 @@
 #define EGDST_CTA_MINB 1
 #else
 #define EGDST_SOLVE_MINB 3   /* CTAs per SM of the solve kernel (register budget 80) */
+#ifndef EGDST_CTA_BLOCK
 #define EGDST_CTA_BLOCK 64   /* threads per CTA in the vector-per-CTA scope */
-#define EGDST_CTA_MINB 12
+#endif
+#ifndef EGDST_CTA_MINB
+#define EGDST_CTA_MINB 16
+#endif
 #endif
 #define EGDST_MAXCAND 72   /* stage-0 bisection candidates: (mmax-a0)/2^k < TOLERANCE well before 72 halvings */
 #define EGDST_ENV_STACK 24 /* crossing-chain stack (thresholds() recursion depth) */
@@ -92,6 +96,7 @@ struct EgdstDev {
     int *flags;                         // [(1+nvec)*8] per team: [0..2] re-sends pending after EGM pass k%3, [3] folds found in this period
     unsigned *bar;                      // grid barrier word of the cooperative solve kernel
     unsigned long long *phase_ns;       // [EGDST_NPHASE] device time per phase of the solve kernel (measurement aid; null = off)
+    int priSync0;                       // index of the first primary-envelope job in the synchronisation arrays (scanE, tickE, envNact): nvec*nst*nd
     int itStop;                         // last period to solve (0; higher: test hook)
     int itStart;                        // period the backward induction starts from (NT-1; lower: test hook, cells of later periods are given)
     int egmP;                           // grid points per work item of the EGM phase (<= threads per CTA); slices = threads / egmP
@@ -127,9 +132,18 @@ EGDST_DEV void egdst_fail(const EgdstDev &P, int ivec, int code, int it, int ist
 //   GRID scope  every CTA of a cooperative launch (one resident wave) works on all vectors; the phases of a period
 //               are separated by a grid-wide barrier                                  -- one large model, few vectors
 //   CTA scope   one CTA owns one vector at a time and walks it through all periods; phases are separated by
-//               __syncthreads()                                                        -- sweeps of many small models
-// Every phase is a loop `for (w = rank; w < nwork; w += size)` over work items, so the same code serves both.
+//               egdst_cta_sync()                                                        -- sweeps of many small models
+//   WARP scope  the CTA scope with a warp in the role of the CTA: the 32-thread "CTAs" of up to 32 vectors form one
+//               real CTA (blockDim = (32, groups)) and start every phase together, so that all warps of an SM run
+//               the same stretch of code at the same time (instruction-cache locality; egdst_period.cuh)
+// Every phase is a loop `for (w = rank; w < nwork; w += size)` over work items, so the same code serves all of them.
 struct EgdstTeam { int rank, size, v0, nv, slot; };
+
+// barrier of the threads that work on one item: the CTA, or the warp where blockDim.y > 1 (WARP scope).  The phases
+// only ever use threadIdx.x / blockDim.x, which is the thread's rank within that group in either case.
+EGDST_DEV void egdst_cta_sync() {
+    if (blockDim.y == 1) __syncthreads(); else __syncwarp();
+}
 
 // Grid-wide barrier of a cooperative launch (all CTAs resident): CTA barrier, one thread arrives on a global word
 // with release/acquire fences around it, CTA barrier (the scheme of cooperative_groups::grid_group::sync; the high
@@ -140,7 +154,7 @@ struct EgdstTeam { int rank, size, v0, nv, slot; };
 // an error status, never as a hung device); bar[1] is the abort flag every waiting CTA also watches.
 #define EGDST_BARRIER_POLLS (1 << 24)
 EGDST_DEV bool egdst_grid_barrier(unsigned *bar) {
-    __syncthreads();
+    egdst_cta_sync();
 #ifndef EGDST_HOSTEMU
     if (gridDim.x > 1) {
         __shared__ int s_ok;
@@ -155,7 +169,7 @@ EGDST_DEV bool egdst_grid_barrier(unsigned *bar) {
             __threadfence();
             s_ok = ok;
         }
-        __syncthreads();
+        egdst_cta_sync();
         return s_ok != 0;
     }
 #endif
@@ -173,7 +187,7 @@ EGDST_DEV void egdst_item(const EgdstTeam &T, int w, int jpv, int &ivec, int &jy
 template <bool GRID>
 EGDST_DEV bool egdst_team_sync(const EgdstDev &P) {
     if (GRID) return egdst_grid_barrier(P.bar);
-    __syncthreads();
+    egdst_cta_sync();
     return true;
 }
 
@@ -199,27 +213,27 @@ EGDST_DEV long long egdst_block_excl_scan64(long long v, long long *sh, long lon
     int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
     long long inc = egdst_warp_incl_scan64(v, lane);
     if (lane == 31) sh[w] = inc;
-    __syncthreads();
+    egdst_cta_sync();
     if (w == 0) {
         long long s = lane < nw ? sh[lane] : 0;
         long long si = egdst_warp_incl_scan64(s, lane);
         if (lane < nw) sh[lane] = si - s;
         if (lane == nw - 1) sh[nw] = si;
     }
-    __syncthreads();
+    egdst_cta_sync();
     long long res = inc - v + sh[w];
     *total = sh[nw];
-    __syncthreads();
+    egdst_cta_sync();
     return res;
 }
 EGDST_DEV int egdst_block_min(int v, int *sh) {  // sh: 32 ints; every thread gets the block minimum
     int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
     v = egdst_warp_min(v);
     if (lane == 0) sh[w] = v;
-    __syncthreads();
+    egdst_cta_sync();
     int r = sh[0];
     for (int k = 1; k < nw; k++) r = sh[k] < r ? sh[k] : r;
-    __syncthreads();
+    egdst_cta_sync();
     return r;
 }
 
@@ -294,21 +308,21 @@ EGDST_DEV unsigned long long egdst_lookback(volatile unsigned long long *st, int
 EGDST_DEV unsigned long long egdst_scan_inclusive(const volatile unsigned long long *st, int chunk) { return st[chunk] & EGDST_SCAN_MASK; }
 
 // exclusive block scan of one int per thread; returns the exclusive prefix, *total gets the block sum.
-// `sh` must hold blockDim.x/32+1 ints.  Contains two __syncthreads().
+// `sh` must hold blockDim.x/32+1 ints.  Contains two egdst_cta_sync().
 EGDST_DEV int egdst_block_excl_scan(int v, int *sh, int *total) {
     int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
     int inc = egdst_warp_incl_scan(v, lane);
     if (lane == 31) sh[w] = inc;
-    __syncthreads();
+    egdst_cta_sync();
     if (w == 0) {
         int s = lane < nw ? sh[lane] : 0;
         int si = egdst_warp_incl_scan(s, lane);
         if (lane < nw) sh[lane] = si - s;
         if (lane == nw - 1) sh[nw] = si;
     }
-    __syncthreads();
+    egdst_cta_sync();
     int res = inc - v + sh[w];
     *total = sh[nw];
-    __syncthreads();
+    egdst_cta_sync();
     return res;
 }

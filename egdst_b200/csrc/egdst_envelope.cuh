@@ -126,7 +126,9 @@ EGDST_DEV double egdst_env_value2(const egdst_ctx *cx, const View &E, int g, int
 // grid (ceil(maxP/B), njobs_y, nvec)
 // ---------------------------------------------------------------------------------------------
 template <int MODE>
-EGDST_DEV bool egdst_env_job(const EgdstDev &P, int ivec, int jy, int &ist, int &id, int &slot, EgdstEnvView<MODE> &E) {
+EGDST_DEV bool egdst_env_job(const EgdstDev &P, int ivec, int jy, int &ist, int &id, int &slot, int &sslot, EgdstEnvView<MODE> &E) {
+    // slot: the job's index in the data arrays (mg*, out*); sslot: its index in the synchronisation arrays (scanE, tickE,
+    // envNact), which the vector-per-CTA scope keeps in shared memory
     if (MODE == 0) {
         ist = jy; id = 0;
         const int sd0 = egdst_sd(P, ivec, ist, 0);
@@ -136,6 +138,7 @@ EGDST_DEV bool egdst_env_job(const EgdstDev &P, int ivec, int jy, int &ist, int 
         E.F = P.cx.nd; E.X = P.ptX + (size_t)sd0 * P.gcap; E.C = P.ptC + (size_t)sd0 * P.gcap; E.V = P.ptV + (size_t)sd0 * P.gcap;
         E.n = P.ptN + sd0; E.evfa0 = P.evfa0 + sd0; E.gcap = P.gcap; E.id = 0; E.sentinel = 0;
         slot = P.nvec * P.cx.nst * P.cx.nd + ivec * P.cx.nst + ist;
+        sslot = P.priSync0 + ivec * P.cx.nst + ist;
         return true;
     } else {
         ist = jy / P.cx.nd; id = jy % P.cx.nd;
@@ -144,12 +147,13 @@ EGDST_DEV bool egdst_env_job(const EgdstDev &P, int ivec, int jy, int &ist, int 
         E.F = P.nfold[sd] + 1; E.X = P.ptX + (size_t)sd * P.gcap; E.C = P.ptC + (size_t)sd * P.gcap; E.V = P.ptV + (size_t)sd * P.gcap;
         E.n = P.runStart + (size_t)sd * (P.gcap + 1); E.evfa0 = P.evfa0 + sd; E.gcap = P.gcap; E.id = id; E.sentinel = 1.5 * P.cx.mmax;
         slot = sd;
+        sslot = sd;
         return true;
     }
 }
 
 // unified grid bound = min over functions of the last abscissa (egdst_solver.c:1266-1271), computed once per CTA
-// (the secondary envelope can have ~10^2 functions).  sh: 33 doubles.  Contains two __syncthreads().
+// (the secondary envelope can have ~10^2 functions).  sh: 33 doubles.  Contains two egdst_cta_sync().
 template <class View>
 EGDST_DEV double egdst_env_grb_block(const View &E, double *sh) {
     double g = EGDST_INF;
@@ -157,10 +161,10 @@ EGDST_DEV double egdst_env_grb_block(const View &E, double *sh) {
     for (int o = 16; o > 0; o >>= 1) { const double w = __shfl_xor_sync(EGDST_FULL, g, o); if (w < g) g = w; }
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
     if (lane == 0) sh[w] = g;
-    __syncthreads();
+    egdst_cta_sync();
     double r = sh[0];
     for (int k = 1; k < nw; k++) if (sh[k] < r) r = sh[k];
-    __syncthreads();
+    egdst_cta_sync();
     return r;
 }
 
@@ -189,11 +193,11 @@ EGDST_DEV void egdst_env_point_partial(const egdst_ctx &cx, const EgdstEnvView<M
     }
 }
 // record the point at its position of the union; the active positions are the prefix with x <= grb
-EGDST_DEV void egdst_env_point_commit(const EgdstDev &P, int slot, double grb, int f, int k, double x, int rank, int best) {
+EGDST_DEV void egdst_env_point_commit(const EgdstDev &P, int slot, int sslot, double grb, int f, int k, double x, int rank, int best) {
     if (best == 0x7fffffff) best = f;  // every value -inf (cannot happen: the own value is finite or the maximum)
     const size_t o = (size_t)slot * P.envcap + rank;
     P.mgX[o] = x; P.mgF[o] = f; P.mgK[o] = k; P.mgA[o] = best;
-    if (x <= grb) atomicMax(P.envNact + slot, rank + 1);
+    if (x <= grb) atomicMax(P.envNact + sslot, rank + 1);
 }
 // "all choices produced empty grids" (egdst_solver.c:704-710), checked where the per-decision lists are final
 EGDST_DEV void egdst_env_check_allinf(const EgdstDev &P, int ivec, int it, int ist) {
@@ -207,11 +211,14 @@ EGDST_DEV void egdst_env_check_allinf(const EgdstDev &P, int ivec, int it, int i
 // `nparts` threads share the functions of one point and combine rank and argmax through shared memory -- the
 // secondary envelope of a zig-zagging grid has ~10^2 runs, and a point that walks them alone is a chain of ~10^2
 // dependent loads.
+template <int BS>
+struct EgdstRankShared { double shg[33]; double bv[BS]; int rank[BS], best[BS]; };
+
 template <int MODE, int BS>
-EGDST_DEV void egdst_ph_envA(const EgdstDev &P, int it, const EgdstTeam &T, int nvb) {
-    __shared__ double shg[33];
-    __shared__ int s_rank[BS], s_best[BS];
-    __shared__ double s_bv[BS];
+EGDST_DEV void egdst_ph_envA(const EgdstDev &P, int it, const EgdstTeam &T, int nvb, void *scratch) {
+    EgdstRankShared<BS> &R = *reinterpret_cast<EgdstRankShared<BS> *>(scratch);
+    double *shg = R.shg, *s_bv = R.bv;
+    int *s_rank = R.rank, *s_best = R.best;
     const int nparts = (MODE == 1) ? P.envA1parts : 1, npt = blockDim.x / nparts;
     const int lane = threadIdx.x % npt, part = threadIdx.x / npt;
     const int jpv = (MODE == 0) ? P.cx.nst : P.cx.nst * P.cx.nd;
@@ -219,14 +226,14 @@ EGDST_DEV void egdst_ph_envA(const EgdstDev &P, int it, const EgdstTeam &T, int 
     for (int w = T.rank; w < nwork; w += T.size) {
         int ivec, jy, vb;
         egdst_item(T, w, jpv, ivec, jy, vb);
-        int ist, id, slot;
+        int ist, id, slot, sslot;
         EgdstEnvView<MODE> E;
         if (MODE == 0 && vb == 0 && threadIdx.x == 0) egdst_env_check_allinf(P, ivec, it, jy);
-        if (!egdst_env_job<MODE>(P, ivec, jy, ist, id, slot, E)) continue;
+        if (!egdst_env_job<MODE>(P, ivec, jy, ist, id, slot, sslot, E)) continue;
         const int Ptot = E.pstart(E.F - 1) + E.npts(E.F - 1);
         if (vb * npt >= Ptot) continue;  // CTA-uniform
         egdst_ctx cx; egdst_load_ctx(P, ivec, cx);
-        __syncthreads();  // scratch of the previous item is free
+        egdst_cta_sync();  // scratch of the previous item is free
         const double grb = egdst_env_grb_block(E, shg);
         for (int base = vb * npt; base < Ptot; base += nvb * npt) {
             const int p = base + lane;
@@ -237,7 +244,7 @@ EGDST_DEV void egdst_ph_envA(const EgdstDev &P, int it, const EgdstTeam &T, int 
             if (nparts > 1) {
                 const int slotx = part * npt + lane;
                 s_rank[slotx] = rank; s_best[slotx] = best; s_bv[slotx] = bestv;
-                __syncthreads();
+                egdst_cta_sync();
                 if (part == 0 && valid) {
                     for (int q = 1; q < nparts; q++) {
                         const int o = q * npt + lane;
@@ -246,8 +253,8 @@ EGDST_DEV void egdst_ph_envA(const EgdstDev &P, int it, const EgdstTeam &T, int 
                     }
                 }
             }
-            if (part == 0 && valid) egdst_env_point_commit(P, slot, grb, f, k, x, rank, best);
-            if (nparts > 1 && base + nvb * npt < Ptot) __syncthreads();  // scratch reused by the next stride
+            if (part == 0 && valid) egdst_env_point_commit(P, slot, sslot, grb, f, k, x, rank, best);
+            if (nparts > 1 && base + nvb * npt < Ptot) egdst_cta_sync();  // scratch reused by the next stride
         }
     }
 }
@@ -410,8 +417,8 @@ struct EgdstEnvShared {
 };
 
 template <int MODE, int BS>
-EGDST_DEV void egdst_ph_envBC(const EgdstDev &P, int it, const EgdstTeam &T, int nvb) {
-    __shared__ EgdstEnvShared<BS> Sh;
+EGDST_DEV void egdst_ph_envBC(const EgdstDev &P, int it, const EgdstTeam &T, int nvb, void *scratch) {
+    EgdstEnvShared<BS> &Sh = *reinterpret_cast<EgdstEnvShared<BS> *>(scratch);
     const int jpv = (MODE == 0) ? P.cx.nst : P.cx.nst * P.cx.nd;
     const int nitems = nvb;
     const int nwork = T.nv * jpv * nitems;
@@ -419,13 +426,13 @@ EGDST_DEV void egdst_ph_envBC(const EgdstDev &P, int it, const EgdstTeam &T, int
     for (int w = T.rank; w < nwork; w += T.size) {
         int ivec, jy, vb;
         egdst_item(T, w, jpv, ivec, jy, vb);
-        int ist, id, slot;
+        int ist, id, slot, sslot;
         EgdstEnvView<MODE> E;
-        if (!egdst_env_job<MODE>(P, ivec, jy, ist, id, slot, E)) continue;
+        if (!egdst_env_job<MODE>(P, ivec, jy, ist, id, slot, sslot, E)) continue;
         egdst_ctx cx; egdst_load_ctx(P, ivec, cx);
         const double *mgX = P.mgX + (size_t)slot * P.envcap;
         const int *mgF = P.mgF + (size_t)slot * P.envcap, *mgK = P.mgK + (size_t)slot * P.envcap, *mgA = P.mgA + (size_t)slot * P.envcap;
-        volatile unsigned long long *st = P.scanE + (size_t)slot * P.chE;
+        volatile unsigned long long *st = P.scanE + (size_t)sslot * P.chE;
         double *ox, *oc, *ov, *oa = 0, *oth = 0, *odd = 0;
         int gcapacity, tcapacity = 0, cell = 0;
         if (MODE == 0) {
@@ -438,15 +445,15 @@ EGDST_DEV void egdst_ph_envBC(const EgdstDev &P, int it, const EgdstTeam &T, int
             gcapacity = P.envcap;
         }
         // the active positions of the union are the prefix with x<=grb (length recorded by egdst_ph_envA)
-        const int nact = EGDST_LDCG(P.envNact + slot);
+        const int nact = *((volatile int *)(P.envNact + sslot));
         const int chunkw = blockDim.x;
         const int nch = (nact + chunkw - 1) / chunkw;
         int err = 0, serr = 0;
         const double grb = nch > 0 ? egdst_env_grb_block(E, Sh.grb) : 0.0;  // nch is CTA-uniform
         while (true) {
-            __syncthreads();  // the previous chunk's queue and scan scratch are free again
-            if (threadIdx.x == 0) { Sh.chunk = atomicAdd(P.tickE + 2 * slot, 1); Sh.qn = 0; }
-            __syncthreads();
+            egdst_cta_sync();  // the previous chunk's queue and scan scratch are free again
+            if (threadIdx.x == 0) { Sh.chunk = atomicAdd(P.tickE + 2 * sslot, 1); Sh.qn = 0; }
+            egdst_cta_sync();
             const int chunk = Sh.chunk;
             if (chunk >= nch) break;
             const int r = chunk * chunkw + threadIdx.x;
@@ -459,7 +466,7 @@ EGDST_DEV void egdst_ph_envBC(const EgdstDev &P, int it, const EgdstTeam &T, int
                 if (q.newx && (q.a == q.f || q.x == grb)) ngj = 1;
                 if (q.chain) { const int c = atomicAdd(&Sh.qn, 1); Sh.qr[c] = r; qj = c; }
             }
-            __syncthreads();
+            egdst_cta_sync();
             const int qn = Sh.qn;
             // pass 2: one chain per warp, counting
             for (int c = warp; c < qn; c += nwarps) {
@@ -469,7 +476,7 @@ EGDST_DEV void egdst_ph_envBC(const EgdstDev &P, int it, const EgdstTeam &T, int
                 egdst_env_chain(&cx, E, it, ist, mgX[rr - 1], qq.x, qq.v, qq.f, qq.k, qq.aprev, qq.a, false, (double *)0, (double *)0, (double *)0, (double *)0, 0, (double *)0, (double *)0, 0, cg, ct, &err);
                 if (lane == 0) { Sh.qg[c] = cg; Sh.qt[c] = ct; }
             }
-            __syncthreads();
+            egdst_cta_sync();
             if (qj >= 0) { ngj += Sh.qg[qj]; ntj += Sh.qt[qj]; }
             long long tot;
             const long long off = egdst_block_excl_scan64(((long long)ntj << 32) | (long long)ngj, Sh.sh, &tot);
@@ -477,7 +484,7 @@ EGDST_DEV void egdst_ph_envBC(const EgdstDev &P, int it, const EgdstTeam &T, int
                 const unsigned long long e = egdst_lookback<0>(st, chunk, egdst_scan_pack((int)(tot & 0xffffffffLL), (int)(tot >> 32)), &serr);
                 if (threadIdx.x == 0) Sh.excl = e;
             }
-            __syncthreads();
+            egdst_cta_sync();
             const int gpos = egdst_scan_lo(Sh.excl) + (int)(off & 0xffffffffLL), tpos = egdst_scan_hi(Sh.excl) + (int)(off >> 32);
             // pass 3: write the kept points; chains get their output offsets
             if (r < nact && (ngj | ntj)) {
@@ -496,7 +503,7 @@ EGDST_DEV void egdst_ph_envBC(const EgdstDev &P, int it, const EgdstTeam &T, int
                     if (g < gcapacity) { ox[g] = q.x; ov[g] = v; oc[g] = c; if (oa) oa[g] = q.x - c; }
                 }
             }
-            __syncthreads();
+            egdst_cta_sync();
             // pass 4: one chain per warp, writing
             for (int c = warp; c < qn; c += nwarps) {
                 const int rr = Sh.qr[c];
@@ -511,9 +518,9 @@ EGDST_DEV void egdst_ph_envBC(const EgdstDev &P, int it, const EgdstTeam &T, int
         if (serr) egdst_fail(P, ivec, EGDST_ERR_ENV2SPACE, it, ist, id);
         // last item of the job: totals and epilogue
         __threadfence();
-        __syncthreads();
-        if (threadIdx.x == 0) Sh.last = (atomicAdd(P.tickE + 2 * slot + 1, 1) == nitems - 1);
-        __syncthreads();
+        egdst_cta_sync();
+        if (threadIdx.x == 0) Sh.last = (atomicAdd(P.tickE + 2 * sslot + 1, 1) == nitems - 1);
+        egdst_cta_sync();
         if (!Sh.last) continue;
         __threadfence();
         const unsigned long long totals = nch > 0 ? egdst_scan_inclusive(st, nch - 1) : 0ULL;

@@ -355,13 +355,13 @@ EGDST_DEV void egdst_block_eval(const egdst_ctx *cx, const EgdstDev &P, int ivec
     egdst_warp_combine(a);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
     if (lane == 0) { S.wr[w] = a.rhs; S.we[w] = a.evf; S.wc[w] = a.checksum; S.wq[w] = a.badq; S.wt[w] = a.badtype; S.wcash[w] = a.badcash; S.wshock[w] = a.badshock; }
-    __syncthreads();
+    egdst_cta_sync();
     if (threadIdx.x == 0) {
         double r = 0, e = 0, c = 0; int bq = EGDST_NOBAD, bw = 0;
         for (int k = 0; k < nw; k++) { r += S.wr[k]; e += S.we[k]; c += S.wc[k]; if (S.wq[k] < bq) { bq = S.wq[k]; bw = k; } }
         S.rhs = r; S.evf = e; S.checksum = c; S.badq = bq; S.badtype = S.wt[bw]; S.badcash = S.wcash[bw]; S.badshock = S.wshock[bw];
     }
-    __syncthreads();
+    egdst_cta_sync();
 }
 
 // adraw limits from the line through the base point and (A, M) (egdst_solver.c:1032-1076), or, after a zero-consumption
@@ -408,7 +408,7 @@ EGDST_DEV void egdst_seed_job(const EgdstDev &P, int it, int ivec, int ist, int 
     const int N = P.N;
     double *seed = P.seed + (size_t)sd * EGDST_SEEDW;
     double *X = P.ptX + (size_t)sd * P.gcap, *Cc = P.ptC + (size_t)sd * P.gcap, *V = P.ptV + (size_t)sd * P.gcap;
-    __syncthreads();  // S and the shock table of the previous job are free
+    egdst_cta_sync();  // S and the shock table of the previous job are free
     if (threadIdx.x == 0) {
         P.active[sd] = act;
         P.evfa0[sd] = 0.0;
@@ -423,7 +423,7 @@ EGDST_DEV void egdst_seed_job(const EgdstDev &P, int it, int ivec, int ist, int 
         S.ncand = n;
         S.go = 0;
     }
-    __syncthreads();
+    egdst_cta_sync();
     if (!act) return;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const double beta = discount(&cx, &curr);
@@ -431,7 +431,7 @@ EGDST_DEV void egdst_seed_job(const EgdstDev &P, int it, int ivec, int ist, int 
     if (useTab) {  // shocks and node probabilities of this (it, ist, id), once per CTA
         egdst_fill_shocktab(&cx, P, &curr, shsm, shsm + cx.nst * cx.ny, threadIdx.x, blockDim.x);
         shk = shsm; shp = shsm + cx.nst * cx.ny;
-        __syncthreads();
+        egdst_cta_sync();
     }
     // stage 0 in waves of one candidate per warp: the base point is almost always among the first few
     // candidates (mmax, (mmax+a0)/2, ...), so later waves rarely run
@@ -450,7 +450,7 @@ EGDST_DEV void egdst_seed_job(const EgdstDev &P, int it, int ivec, int ist, int 
                 S.candM[kk] = S.candA[kk] + utility_marginal_inverse(&cx, &curr, beta * a.rhs);
             }
         }
-        __syncthreads();
+        egdst_cta_sync();
         // thread 0: first candidate with M<=mmax is the base point (sequential semantics of adraw stage 0)
         if (threadIdx.x == 0) {
             const int kend = k0 + nw < S.ncand ? k0 + nw : S.ncand;
@@ -463,7 +463,7 @@ EGDST_DEV void egdst_seed_job(const EgdstDev &P, int it, int ivec, int ist, int 
             if (kend == S.ncand && S.go == 0) { egdst_fail(P, ivec, EGDST_ERR_ADRAW_INIT, it, ist, id); S.go = -1; }
             S.A = cx.a0;
         }
-        __syncthreads();
+        egdst_cta_sync();
         if (S.go != 0) break;
     }
     if (S.go != 1) return;
@@ -507,7 +507,7 @@ EGDST_DEV void egdst_seed_job(const EgdstDev &P, int it, int ivec, int ist, int 
             S.A = lastA;
             S.go = fatal ? -1 : resend;
         }
-        __syncthreads();
+        egdst_cta_sync();
         if (S.go != 1) break;
     }
     if (threadIdx.x == 0) {
@@ -523,8 +523,8 @@ EGDST_DEV int egdst_use_shocktab(const EgdstDev &P) {
     return (EGDST_SHOCK_INDEP_A && (size_t)2 * P.cx.nst * P.cx.ny * sizeof(double) <= EGDST_SHOCKTAB_BYTES) ? 1 : 0;
 }
 
-EGDST_DEV void egdst_ph_seed(const EgdstDev &P, int it, const EgdstTeam &T, double *shsm) {
-    __shared__ EgdstSeedShared S;
+EGDST_DEV void egdst_ph_seed(const EgdstDev &P, int it, const EgdstTeam &T, void *scratch, double *shsm) {
+    EgdstSeedShared &S = *reinterpret_cast<EgdstSeedShared *>(scratch);
     const int jpv = P.cx.nst * P.cx.nd, nwork = T.nv * jpv;
     const int useTab = egdst_use_shocktab(P);
     for (int w = T.rank; w < nwork; w += T.size) {
@@ -590,7 +590,7 @@ EGDST_DEV void egdst_egm_epilogue(const EgdstDev &P, int it, int ivec, int ist, 
                 const int k = atomicAdd(P.foldCnt + sd, 1); if (k <= P.gcap) foldList[k] = p;
             }
     }
-    __syncthreads();
+    egdst_cta_sync();
     int nf = *((volatile int *)(P.foldCnt + sd));
     if (nf > P.gcap - 1) nf = P.gcap - 1;
     for (int i = threadIdx.x; i < nf; i += blockDim.x) {  // rank sort (folds are rare)
@@ -615,8 +615,8 @@ EGDST_DEV void egdst_egm_epilogue(const EgdstDev &P, int it, int ivec, int ist, 
 #define EGDST_EGM_TIC(k)
 #endif
 template <int BS>
-EGDST_DEV void egdst_ph_egm(const EgdstDev &P, int it, const EgdstTeam &T, int pass, double *shsm) {
-    __shared__ EgdstEgmShared<BS> E;
+EGDST_DEV void egdst_ph_egm(const EgdstDev &P, int it, const EgdstTeam &T, int pass, void *scratch, double *shsm) {
+    EgdstEgmShared<BS> &E = *reinterpret_cast<EgdstEgmShared<BS> *>(scratch);
     // measurement aid: the steps of the team's last work item (the longest look-back), from the start of the phase
     unsigned long long tprev = 0ULL;
     bool tic = false;
@@ -648,19 +648,19 @@ EGDST_DEV void egdst_ph_egm(const EgdstDev &P, int it, const EgdstTeam &T, int p
         if (nfirst + item * Pp >= N || egdst_scan_hi(egdst_scan_inclusive(st, 0))) {
             // nothing to evaluate (the grid ended at its seed, or a re-seeded pass starts beyond this item): the item
             // still takes part in the chain and in the completion count
-            __syncthreads();
+            egdst_cta_sync();
             if (warp == 0) { int err = 0; egdst_lookback<1>(st, item + 1, egdst_scan_pack(0, 0), &err); }
             __threadfence();
-            __syncthreads();
+            egdst_cta_sync();
             if (threadIdx.x == 0) E.last = (atomicAdd(P.tickC + 2 * sd + 1, 1) == nitems - 1);
-            __syncthreads();
+            egdst_cta_sync();
             if (E.last) { __threadfence(); egdst_egm_epilogue(P, it, ivec, ist, id, sd, nitems, T.slot); }
             continue;
         }
         egdst_ctx cx; egdst_load_ctx(P, ivec, cx);
         PeriodVars curr; curr.it = it; curr.ist = ist; curr.id = id; curr.cash = 0; curr.savings = 0; curr.shock = 0;
         const double *shk = 0, *shp = 0;
-        __syncthreads();  // the previous item's shared scratch is free
+        egdst_cta_sync();  // the previous item's shared scratch is free
         if (useTab) {  // shocks and node probabilities of this (it, ist, id), once per run of items of the same job
             if (tabsd != sd) {
                 egdst_fill_shocktab(&cx, P, &curr, shsm, shsm + cx.nst * cx.ny, threadIdx.x, B);
@@ -669,7 +669,7 @@ EGDST_DEV void egdst_ph_egm(const EgdstDev &P, int it, const EgdstTeam &T, int p
             shk = shsm; shp = shsm + cx.nst * cx.ny;
         }
         if (threadIdx.x == 0) { E.evmin[0] = 0x7fffffff; E.evmin[1] = 0x7fffffff; }
-        __syncthreads();
+        egdst_cta_sync();
         EGDST_EGM_TIC(0);  // set-up: context, shock table
 #ifndef EGDST_HOSTEMU
         unsigned long long tstart = 0ULL;
@@ -685,7 +685,7 @@ EGDST_DEV void egdst_ph_egm(const EgdstDev &P, int it, const EgdstTeam &T, int p
         }
         E.rhs[threadIdx.x] = a.rhs; E.evf[threadIdx.x] = a.evf; E.chk[threadIdx.x] = a.checksum;
         E.q[threadIdx.x] = a.badq; E.t[threadIdx.x] = a.badtype; E.cash[threadIdx.x] = a.badcash;
-        __syncthreads();
+        egdst_cta_sync();
         EGDST_EGM_TIC(1);  // node loop
 #ifndef EGDST_HOSTEMU
         if (P.phase_ns && threadIdx.x == 0 && it == P.NT / 2) {  // measurement aid: the slowest node loop of the middle period and its item
@@ -725,7 +725,7 @@ EGDST_DEV void egdst_ph_egm(const EgdstDev &P, int it, const EgdstTeam &T, int p
                 else if (!(stopv < cx.mmax)) atomicMin(&E.evmin[0], p + 1);  // stop rule: this point is the last one generated
             }
         }
-        __syncthreads();
+        egdst_cta_sync();
         // points of the item that the sequential generator would have produced: p < lim
         const int ls = E.evmin[0], ll = E.evmin[1];
         const int lim = ll < ls ? ll : ls;
@@ -741,7 +741,7 @@ EGDST_DEV void egdst_ph_egm(const EgdstDev &P, int it, const EgdstTeam &T, int p
             const unsigned long long e = egdst_lookback<1>(st, item + 1, egdst_scan_pack(total, lim != 0x7fffffff ? 1 : 0), &err);
             if (lane == 0) E.excl = e;
         }
-        __syncthreads();
+        egdst_cta_sync();
         EGDST_EGM_TIC(3);  // look-back
         const unsigned long long excl = E.excl;
         if (!egdst_scan_hi(excl)) {  // the grid did not end in an earlier item: this item's points count
@@ -759,7 +759,7 @@ EGDST_DEV void egdst_ph_egm(const EgdstDev &P, int it, const EgdstTeam &T, int p
                 if (dst < P.gcap) { X[dst] = M; Cc[dst] = c; V[dst] = v; }
                 E.kx[loc] = M; E.kv[loc] = v;
             }
-            __syncthreads();
+            egdst_cta_sync();
             // folds between neighbours that this item wrote itself (M or V decreasing, egdst_solver.c:819)
             if (threadIdx.x >= 1 && threadIdx.x < total && first + threadIdx.x < P.gcap)
                 if (E.kx[threadIdx.x - 1] > E.kx[threadIdx.x] || E.kv[threadIdx.x - 1] > E.kv[threadIdx.x]) {
@@ -769,9 +769,9 @@ EGDST_DEV void egdst_ph_egm(const EgdstDev &P, int it, const EgdstTeam &T, int p
         }
         if (err) egdst_fail(P, ivec, EGDST_ERR_ENV2SPACE, it, ist, id);
         __threadfence();
-        __syncthreads();
+        egdst_cta_sync();
         if (threadIdx.x == 0) E.last = (atomicAdd(P.tickC + 2 * sd + 1, 1) == nitems - 1);
-        __syncthreads();
+        egdst_cta_sync();
         EGDST_EGM_TIC(4);  // writes, folds, completion count
         if (E.last) { __threadfence(); egdst_egm_epilogue(P, it, ivec, ist, id, sd, nitems, T.slot); }
         EGDST_EGM_TIC(5);  // epilogue (if this item finished last)
@@ -786,8 +786,8 @@ EGDST_DEV void egdst_ph_egm(const EgdstDev &P, int it, const EgdstTeam &T, int p
 // re-send (repeatedly if the re-sent point asks again), store the point, publish the new closed form.  The EGM phase
 // then runs again for the grid points after it.
 // ---------------------------------------------------------------------------------------------
-EGDST_DEV void egdst_ph_resend(const EgdstDev &P, int it, const EgdstTeam &T, int pass, double *shsm) {
-    __shared__ EgdstSeedShared S;
+EGDST_DEV void egdst_ph_resend(const EgdstDev &P, int it, const EgdstTeam &T, int pass, void *scratch, double *shsm) {
+    EgdstSeedShared &S = *reinterpret_cast<EgdstSeedShared *>(scratch);
     const int jpv = P.cx.nst * P.cx.nd, nwork = T.nv * jpv;
     const int useTab = egdst_use_shocktab(P);
     const int N = P.N;
@@ -795,7 +795,7 @@ EGDST_DEV void egdst_ph_resend(const EgdstDev &P, int it, const EgdstTeam &T, in
     for (int w = T.rank; w < nwork; w += T.size) {
         const int ivec = T.v0 + w / jpv, jy = w % jpv, ist = jy / P.cx.nd, id = jy % P.cx.nd;
         const int sd = egdst_sd(P, ivec, ist, id);
-        __syncthreads();
+        egdst_cta_sync();
         const int nl = P.lateN[sd];
         if (!P.active[sd] || nl == 0x7fffffff) continue;  // grids that did not ask are complete
         egdst_ctx cx; egdst_load_ctx(P, ivec, cx);
@@ -816,7 +816,7 @@ EGDST_DEV void egdst_ph_resend(const EgdstDev &P, int it, const EgdstTeam &T, in
 #ifdef EGDST_HOSTEMU
         if (threadIdx.x == 0 && getenv("EGDST_DEBUG_RESEND")) printf("re-send after the seed stage: it=%d ist=%d id=%d at grid point %d (A=%.12g), %d points kept before it\n", it, ist, id, nl, S.A, kept);
 #endif
-        __syncthreads();
+        egdst_cta_sync();
         EgdstLims L; L.lim1 = seed[0]; L.lim2 = seed[1]; L.lim3 = seed[2]; L.lim3p = seed[3]; L.k3 = seed[4]; L.lim2p = 0;
         double lastA = 0, aM = 0;
         int stored = 0;
@@ -851,7 +851,7 @@ EGDST_DEV void egdst_ph_resend(const EgdstDev &P, int it, const EgdstTeam &T, in
                 S.A = lastA;
                 S.go = fatal ? -1 : resend;
             }
-            __syncthreads();
+            egdst_cta_sync();
             if (S.go != 1) break;
         }
         if (threadIdx.x == 0) {

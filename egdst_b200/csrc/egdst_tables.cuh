@@ -76,7 +76,7 @@ EGDST_DEV void egdst_cells_body(const EgdstDev &P, int ivec, int it) {
     for (int i = threadIdx.x; i < nsdv * P.chE; i += blockDim.x) P.scanE[(size_t)sd0 * P.chE + i] = 0ULL;          // secondary slots
     for (int i = threadIdx.x; i < nsdv * 2; i += blockDim.x) P.tickE[2 * sd0 + i] = 0;
     for (int i = threadIdx.x; i < nsdv; i += blockDim.x) P.envNact[sd0 + i] = 0;
-    const int ps0 = P.nvec * nsdv + ivec * P.cx.nst;                                                                // primary slots
+    const int ps0 = P.priSync0 + ivec * P.cx.nst;                                                                  // primary jobs
     for (int i = threadIdx.x; i < P.cx.nst * P.chE; i += blockDim.x) P.scanE[(size_t)ps0 * P.chE + i] = 0ULL;
     for (int i = threadIdx.x; i < P.cx.nst * 2; i += blockDim.x) P.tickE[2 * ps0 + i] = 0;
     for (int i = threadIdx.x; i < P.cx.nst; i += blockDim.x) P.envNact[ps0 + i] = 0;

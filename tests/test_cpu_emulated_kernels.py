@@ -112,3 +112,39 @@ def test_emulated_cta_scope_matches_grid_scope(monkeypatch):
         Mb, Db = batch.cells(v)
         e = solution_errors(Mb, Db, one.M, one.D)
         assert e["C"] < 1e-12 and e["V"] < 1e-12 and e["rowdiff"] == 0, (v, e)
+
+
+def test_emulated_warp_scope_matches_grid_scope(monkeypatch):
+    """The WARP scope (a warp per vector, the warps of a CTA starting every phase together): 6 vectors on CTAs of 4
+    warps -- a second round with two idle warps -- and a model with two decisions (secondary envelope, primary
+    envelope over decisions) next to the one-decision sweep model."""
+    monkeypatch.setenv("EGDST_WARP_G", "4")
+    m = examples.deaton2(T=8, ngridm=40, ngridmax=200, ny=4)
+    lib = _emulated(m)
+    rng = np.random.default_rng(6)
+    params = np.column_stack([rng.uniform(0.0, 0.05, 6), rng.uniform(0.75, 1.75, 6)])
+    monkeypatch.setenv("EGDST_SOLVE_SCOPE", "warp")
+    batch = lib.solve_batch(m, params)
+    monkeypatch.setenv("EGDST_SOLVE_SCOPE", "grid")
+    for v in range(params.shape[0]):
+        assert batch.status(v)[0] == 0
+        mv = examples.deaton2(T=8, ngridm=40, ngridmax=200, ny=4, interest=float(params[v, 0]), income=float(params[v, 1]))
+        mv.prepare()
+        one = lib.solve(mv)
+        Mb, Db = batch.cells(v)
+        e = solution_errors(Mb, Db, one.M, one.D)
+        assert e["C"] < 1e-12 and e["V"] < 1e-12 and e["rowdiff"] == 0, (v, e)
+    r = examples.retirement2(ngridm=60, ngridmax=300, T=6, ny=3)
+    r.prepare()
+    rl = _emulated(r)
+    pv = np.array([list(r.param_vector())] * 3)
+    monkeypatch.setenv("EGDST_SOLVE_SCOPE", "warp")
+    monkeypatch.setenv("EGDST_WARP_G", "3")
+    rb = rl.solve_batch(r, pv)
+    monkeypatch.setenv("EGDST_SOLVE_SCOPE", "grid")
+    one = rl.solve(r)
+    for v in range(3):
+        assert rb.status(v)[0] == 0
+        Mb, Db = rb.cells(v)
+        e = solution_errors(Mb, Db, one.M, one.D)
+        assert e["C"] < 1e-12 and e["V"] < 1e-12 and e["TH"] < 1e-12 and e["rowdiff"] == 0, (v, e)

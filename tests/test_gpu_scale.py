@@ -183,9 +183,9 @@ def test_batched_solve_matches_individual_solves_and_reference():
 
 
 def test_large_sweep_launch_shapes_match_reference():
-    """A sweep that fills the machine switches to narrow seed CTAs and EGM CTAs that loop over the point blocks
-    (launch_periods): the partition of the node sums changes, so batch and single solves agree to rounding, not bit
-    for bit; both are held to the reference."""
+    """A sweep that fills the machine is solved in the WARP scope of the solve kernel (a warp per vector, launch_solve):
+    the partition of the node sums changes, so batch and single solves agree to rounding, not bit for bit; both are
+    held to the reference."""
     m = examples.deaton2()
     m.compile()
     lib = m._capi()
@@ -445,11 +445,11 @@ def test_random_large_grids_match_reference():
     assert random_probe.main(300, 12, ("retirement_large",)) == 0
 
 
-@pytest.mark.parametrize("nvec,ngridm", [(100, 100), (200, 100), (700, 100), (1600, 100), (200, 500), (640, 500)])
+@pytest.mark.parametrize("nvec,ngridm", [(100, 100), (200, 100), (700, 100), (1600, 100), (3000, 100), (200, 500), (640, 500)])
 def test_sweep_sizes_across_launch_shape_switches(nvec, ngridm):
-    """Sweeps on either side of the thresholds at which launch_periods changes shapes (148 and 592 jobs for the seed and
-    envelope kernels, 5920 CTAs for the looping EGM step, 448/512 grid points for the narrow and fused envelope and
-    compaction CTAs): first, middle and last vector of each sweep against the reference."""
+    """Sweeps on either side of the thresholds at which launch_solve changes scope (GRID below 2 vectors per SM, CTA
+    up to 8 per SM, WARP above; 3000 vectors leave idle warps in the last CTA): first, middle and last vector of each
+    sweep against the reference."""
     m = examples.deaton2(ngridm=ngridm, ngridmax=2 * ngridm + 50)
     m.compile()
     lib = m._capi()
@@ -543,3 +543,24 @@ def test_table_free_path_for_oversized_cells(monkeypatch):
     from tests.goldens import sims_errors
     se = sims_errors(m.sims, orc.simulate(Mr, Dr, init, rs, 0))
     assert se["nan_mismatch"] == 0 and se["discrete_mismatch"] == 0 and se["max"] < TOL, se
+
+
+def test_warp_scope_on_a_model_with_discrete_choices(monkeypatch):
+    """The WARP scope forced on retirement2 (two decisions: secondary envelope per decision, primary envelope with
+    thresholds) -- every vector of the sweep equals the single GRID-scope solve and the reference."""
+    m = examples.retirement2(ngridm=200, ngridmax=600)
+    m.compile()
+    lib = m._capi()
+    Mr, Dr = oracle_for(m).solve()
+    nvec = 40
+    pv = np.array([list(m.param_vector())] * nvec)
+    monkeypatch.setenv("EGDST_SOLVE_SCOPE", "warp")
+    monkeypatch.setenv("EGDST_WARP_G", "6")
+    sol = lib.solve_batch(m, pv)
+    monkeypatch.delenv("EGDST_SOLVE_SCOPE")
+    assert sol.warning is None, sol.warning
+    for v in (0, 5, 17, 39):
+        assert sol.status(v)[0] == 0
+        Mb, Db = sol.cells(v)
+        e = solution_errors(Mb, Db, Mr, Dr)
+        assert e["C"] < TOL and e["V"] < TOL and e["TH"] < TOL and e["Dseq"] and e["rowdiff"] == 0, (v, e)
