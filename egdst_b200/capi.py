@@ -13,7 +13,7 @@ import numpy as np
 
 from .quadrature import model_quadrature
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
 
@@ -27,7 +27,7 @@ class EgdstDesc(C.Structure):
         ("optim_UasD", C.c_int), ("optim_MUnoD", C.c_int), ("optim_UnoD", C.c_int), ("optim_TRPRnoSH", C.c_int),
         ("tolerance", C.c_double), ("zeroconsumption", C.c_double), ("doublepoint_delta", C.c_double),
         ("stm", _dp), ("states", _dp), ("decisions", _dp), ("params", _dp), ("nparam", C.c_int),
-        ("quadrature", _dp), ("neq", C.c_int), ("device", C.c_int),
+        ("quadrature", _dp), ("neq", C.c_int), ("device", C.c_int), ("sigma_eps", C.c_double),
     ]
 
 
@@ -75,6 +75,7 @@ class Desc:
         d.quadrature = _ptr(self.quadrature)
         d.neq = len(m.eq)
         d.device = int(m.device if device is None else device)
+        d.sigma_eps = float(getattr(m, "sigma_eps", 0.0) or 0.0)
         self.c = d
 
 
@@ -139,6 +140,21 @@ class Solution:
     def D(self):
         return self.cells(0)[1]
 
+    def choice_cell(self, it: int, ist: int, id: int, ivec: int = 0):
+        """Smoothing mode (model.sigma_eps > 0) only: the choice-specific cell of decision ``id`` as an (rows x 4) array
+        (M, C, A, V; row 0 = a0, 0, a0, evf_d(a0)), or None where the decision is not available."""
+        n = C.c_int(0)
+        rc = self.lib.L.egdst_solution_choice_cell(self.handle, ivec, it, ist, id, None, 0, C.byref(n))
+        if rc:
+            self.lib._raise(rc)
+        if n.value == 0:
+            return None
+        buf = np.empty(4 * n.value, dtype=np.float64)
+        rc = self.lib.L.egdst_solution_choice_cell(self.handle, ivec, it, ist, id, buf.ctypes.data_as(_dp), n.value, C.byref(n))
+        if rc:
+            self.lib._raise(rc)
+        return buf.reshape(4, n.value).T.copy()
+
     def status(self, ivec: int = 0):
         it, ist, idd = C.c_int(0), C.c_int(0), C.c_int(0)
         code = self.lib.L.egdst_solution_status(self.handle, ivec, C.byref(it), C.byref(ist), C.byref(idd))
@@ -167,7 +183,7 @@ class ModelLibrary:
     EXPORTS = ["egdst_abi_version", "egdst_model_key", "egdst_model_nparam", "egdst_model_neq", "egdst_last_error",
                "egdst_set_stream", "egdst_launch_count", "egdst_profile_classes", "egdst_profile_class_name",
                "egdst_profile_enable", "egdst_profile_read", "egdst_solve", "egdst_solve_batch", "egdst_resolve", "egdst_solution_sizes",
-               "egdst_solution_export", "egdst_solution_status", "egdst_solution_nvec", "egdst_solution_units", "egdst_solution_resends", "egdst_solution_phase_ms", "egdst_test_envelope2",
+               "egdst_solution_export", "egdst_solution_choice_cell", "egdst_solution_status", "egdst_solution_nvec", "egdst_solution_units", "egdst_solution_resends", "egdst_solution_phase_ms", "egdst_test_envelope2",
                "egdst_free_solution", "egdst_solution_import", "egdst_simulate", "egdst_simulate_philox",
                "egdst_simulate_device", "egdst_sim_moments", "egdst_sim_moments_device", "egdst_call", "egdst_shutdown"]
 
@@ -191,6 +207,7 @@ class ModelLibrary:
         L.egdst_resolve.argtypes = [vp, C.POINTER(EgdstDesc), _dp]
         L.egdst_solution_sizes.argtypes = [vp, _ip, _ip]
         L.egdst_solution_export.argtypes = [vp, _dp, _dp]
+        L.egdst_solution_choice_cell.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_int, _ip]
         L.egdst_solution_status.argtypes = [vp, C.c_int, _ip, _ip, _ip]
         L.egdst_solution_nvec.argtypes = [vp]
         L.egdst_solution_units.argtypes = [vp]

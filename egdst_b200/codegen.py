@@ -362,6 +362,10 @@ def emit_devspec(model) -> str:
     opt = infer_optim(model)
     L += ["#define EGDST_OPT_%s %d" % (k[len("optim_"):].upper(), 1 if opt[k] else 0)
           for k in ("optim_UasD", "optim_MUnoD", "optim_UnoD", "optim_TRPRnoSH")]
+    if float(getattr(model, "sigma_eps", 0.0) or 0.0) > 0.0:
+        # taste-shock smoothing (an extension without a reference counterpart) is compiled into its own image, so that the
+        # reference-parity images carry none of its code; the VALUE of sigma_eps stays a run-time property
+        L += ["#define EGDST_SMOOTHING 1"]
     L += ['#include "egdst_modelctx.h"', ""]
     if cont:
         # grids of the continuous states (the reference loads them from model.s(i).grid at run time, compile.m:239-247;

@@ -102,6 +102,8 @@ struct egdst_solution {
     double *d_qraw;             // quadrature as passed (weights, abscissas)
     double *d_stm, *d_states, *d_decisions, *d_bparams, *d_q;
     int nsd, ncell, nslot;
+    EgdstDev *d_self; // copy of P in global memory (smoothing mode)
+    int ncell_all;  // ncell, plus the ncell*nd choice-specific cells of the smoothing mode
     std::vector<int> h_mlen, h_thlen, h_status;
     bool sizes_valid;
     double *d_pack;  // export staging
@@ -160,6 +162,8 @@ static int check_image(const egdst_desc *d) {
         (d->optim_UnoD != 0) != (EGDST_OPT_UNOD != 0) || (d->optim_TRPRnoSH != 0) != (EGDST_OPT_TRPRNOSH != 0))
         return fail(2, "optim_* switches of the descriptor do not match the compiled model image");
     if (EGDST_NPARAM > 0 && !d->params) return fail(2, "parameter values missing");
+    if ((d->sigma_eps > 0.0) != (EGDST_SMOOTHING != 0))
+        return fail(2, "taste-shock smoothing (sigma_eps > 0) is a property of the compiled model image: set it before compiling the model");
     return 0;
 }
 
@@ -192,7 +196,10 @@ static int create_solution(const egdst_desc *d, int nvec, egdst_solution **out) 
     int rc = fill_ctx(d, &cx);
     if (rc) return rc;
     if ((rc = check_device(d->device))) return rc;
-    const int dims[12] = {d->device, nvec, d->T - d->t0 + 1, d->nst, d->nd, d->ngridm, d->ngridmax, d->nthrhmax, d->ny, d->nnst, d->nnd, 0};
+    const bool smooth = d->sigma_eps > 0.0;  // taste-shock smoothing: choice-specific cells next to the solution cells
+    if (smooth && d->nd > EGDST_SMOOTH_MAXND) return fail(2, "sigma_eps > 0 supports at most 8 decisions");
+    if (d->sigma_eps < 0.0 || d->sigma_eps != d->sigma_eps) return fail(2, "sigma_eps must be >= 0");
+    const int dims[12] = {d->device, nvec, d->T - d->t0 + 1, d->nst, d->nd, d->ngridm, d->ngridmax, d->nthrhmax, d->ny, d->nnst, d->nnd, smooth ? 1 : 0};
     {
         std::lock_guard<std::mutex> lk(g_cache_mu);
         if (g_cached && memcmp(g_cached->dims, dims, sizeof(dims)) == 0 && g_cached->dkey[0] == d->mmax && g_cached->dkey[1] == d->a0) {
@@ -207,6 +214,7 @@ static int create_solution(const egdst_desc *d, int nvec, egdst_solution **out) 
             const double *stm = s->d_stm, *states = s->d_states, *decisions = s->d_decisions;
             s->P.cx = cx; s->P.cx.stm = stm; s->P.cx.states = states; s->P.cx.decisions = decisions;
             s->P.bparams = 0;
+            s->P.sigmaEps = d->sigma_eps;
             cudaMemset(s->P.units, 0, sizeof(unsigned long long) * 2 * nvec);
             *out = s;
             return 0;
@@ -223,11 +231,13 @@ static int create_solution(const egdst_desc *d, int nvec, egdst_solution **out) 
     P.NT = d->T - d->t0 + 1; P.nvec = nvec; P.rowcap = d->ngridmax + 2; P.gcap = d->ngridmax; P.N = d->ngridm;
     const int nst = d->nst, nd = d->nd;
     s->ncell = nvec * P.NT * nst; s->nsd = nvec * nst * nd; s->nslot = s->nsd + nvec * nst;
+    s->ncell_all = smooth ? s->ncell * (1 + nd) : s->ncell;
+    P.ncellMain = s->ncell; P.sigmaEps = d->sigma_eps;
     P.envcap = (nd > 2 ? nd : 2) * P.gcap + 2;
 #define DA(ptr, n) do { cudaError_t e_ = dalloc(s, &(ptr), (size_t)(n)); if (e_ != cudaSuccess) { destroy_solution(s); return fail(2, std::string("cudaMalloc failed: ") + cudaGetErrorString(e_)); } } while (0)
     DA(s->d_stm, 2 * d->nnst); DA(s->d_states, nst * d->nnst); DA(s->d_decisions, nd * d->nnd);
     DA(s->d_bparams, (size_t)nvec * EGDST_NPARAM_); DA(s->d_qraw, 2 * d->ny); DA(s->d_q, 2 * d->ny);
-    DA(P.arena, (size_t)s->ncell * 4 * P.rowcap); DA(P.mlen, s->ncell); DA(P.thlen, s->ncell); DA(P.evf, s->ncell);
+    DA(P.arena, (size_t)s->ncell_all * 4 * P.rowcap); DA(P.mlen, s->ncell_all); DA(P.thlen, s->ncell); DA(P.evf, s->ncell_all);
     DA(P.thD, (size_t)s->ncell * d->nthrhmax); DA(P.thTH, (size_t)s->ncell * d->nthrhmax);
     DA(P.active, s->nsd); DA(P.seed, (size_t)s->nsd * EGDST_SEEDW); DA(P.evfa0, s->nsd);
     DA(P.ptX, (size_t)s->nsd * P.gcap); DA(P.ptC, (size_t)s->nsd * P.gcap); DA(P.ptV, (size_t)s->nsd * P.gcap);
@@ -249,9 +259,9 @@ static int create_solution(const egdst_desc *d, int nvec, egdst_solution **out) 
         P.lutcap = (int)(octaves * (double)(1 << mbits)) + 2;
     }
     {   // one allocation for both tables: a single L2 access-policy window can then keep them resident (sim_launch)
-        const size_t lutbytes = ((sizeof(EgdstLutEntry) * (size_t)s->ncell * (P.lutcap + 1) + 255) / 256) * 256;
-        const size_t ivlbytes = ((sizeof(EgdstRow) * (size_t)s->ncell * (P.tabcap + 1) + 255) / 256) * 256;
-        const size_t topbytes = sizeof(EgdstCellTop) * (size_t)s->ncell;
+        const size_t lutbytes = ((sizeof(EgdstLutEntry) * (size_t)s->ncell_all * (P.lutcap + 1) + 255) / 256) * 256;
+        const size_t ivlbytes = ((sizeof(EgdstRow) * (size_t)s->ncell_all * (P.tabcap + 1) + 255) / 256) * 256;
+        const size_t topbytes = sizeof(EgdstCellTop) * (size_t)s->ncell_all;
         unsigned char *base = 0;
         DA(base, lutbytes + ivlbytes + topbytes);
         P.tabLut = (EgdstLutEntry *)base; P.tabRow = (EgdstRow *)(base + lutbytes); P.tabTop = (EgdstCellTop *)(base + lutbytes + ivlbytes);
@@ -269,7 +279,7 @@ static int create_solution(const egdst_desc *d, int nvec, egdst_solution **out) 
     DA(P.scanE, (size_t)s->nslot * P.chE); DA(P.tickE, (size_t)2 * s->nslot); DA(P.envNact, s->nslot);
     DA(P.lateN, s->nsd); DA(P.flags, (size_t)8 * (nvec + 1)); DA(P.bar, 4); DA(s->d_phase, EGDST_NPHASE);
     cudaMemset(s->d_phase, 0, sizeof(unsigned long long) * EGDST_NPHASE);
-    DA(P.status, 4 * nvec); DA(P.units, 2 * nvec); DA(s->d_moff, s->ncell + 1); DA(s->d_toff, s->ncell + 1);
+    DA(s->d_self, 1); DA(P.status, 4 * nvec); DA(P.units, 2 * nvec); DA(s->d_moff, s->ncell + 1); DA(s->d_toff, s->ncell + 1);
 #undef DA
     cudaMemset(P.units, 0, sizeof(unsigned long long) * 2 * nvec);
     P.cx.stm = s->d_stm; P.cx.states = s->d_states; P.cx.decisions = s->d_decisions;
@@ -294,7 +304,7 @@ static int launch_solve(egdst_solution *s, cudaStream_t st) {
     CK(cudaMemsetAsync(P.status, 0, sizeof(int) * 4 * P.nvec, st));
     CK(cudaMemsetAsync(P.units, 0, sizeof(unsigned long long) * 2 * P.nvec, st));
     if (P.itStart == P.NT - 1) {
-        CK(cudaMemsetAsync(P.mlen, 0, sizeof(int) * s->ncell, st));
+        CK(cudaMemsetAsync(P.mlen, 0, sizeof(int) * s->ncell_all, st));
         CK(cudaMemsetAsync(P.thlen, 0, sizeof(int) * s->ncell, st));
     }
     CK(cudaMemsetAsync(P.bar, 0, sizeof(unsigned) * 4, st));
@@ -386,8 +396,10 @@ static int launch_solve(egdst_solution *s, cudaStream_t st) {
         if (getenv("EGDST_EGM_P")) { const int p = atoi(getenv("EGDST_EGM_P")); if (p >= 8 && p <= B) egmP = p; }  // test hook
         P.egmP = egmP;
     }
+    P.self = s->d_self;
     P.phase_ns = g_prof_on ? s->d_phase : 0;  // measurement aid: in-kernel phase timers while profiling is enabled
     if ((N - 1 + P.egmP - 1) / P.egmP + 2 > P.chC) return fail(2, "internal: scan state too small for the EGM items");
+    if (EGDST_SMOOTHING) CK(cudaMemcpyAsync(s->d_self, &P, sizeof(EgdstDev), cudaMemcpyHostToDevice, st));  // read by egdst_smooth_node
 #ifndef EGDST_HOSTEMU
     prof_begin(KC_SOLVE, st);
     if (s->warp_groups) {
@@ -421,6 +433,8 @@ static int run_solve(egdst_solution *s, const egdst_desc *d, const double *param
     CK(cudaSetDevice(s->device));
     cx.stm = s->d_stm; cx.states = s->d_states; cx.decisions = s->d_decisions;
     P.cx = cx;
+    if ((d->sigma_eps > 0.0) != (s->ncell_all > s->ncell)) return fail(2, "egdst_resolve: sigma_eps switches the smoothing mode on or off; solve anew");
+    P.sigmaEps = d->sigma_eps;
     cudaStream_t st = g_stream;
     CK(cudaMemcpyAsync(s->d_stm, d->stm, sizeof(double) * 2 * d->nnst, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(s->d_states, d->states, sizeof(double) * d->nst * d->nnst, cudaMemcpyHostToDevice, st));
@@ -574,6 +588,25 @@ int egdst_solution_export(egdst_solution *s, double *Mbuf, double *Dbuf) {
     CK(cudaMemcpyAsync(Mbuf, s->d_pack, sizeof(double) * nm, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(Dbuf, s->d_pack + nm, sizeof(double) * nd2, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int egdst_solution_choice_cell(egdst_solution *s, int ivec, int it, int ist, int id, double *M, int cap, int *rows) {
+    if (!s || !rows) return fail(2, "invalid arguments");
+    if (s->ncell_all == s->ncell) return fail(2, "the solution was computed without taste-shock smoothing (sigma_eps = 0): no choice-specific cells");
+    const EgdstDev &P = s->P;
+    if (ivec < 0 || ivec >= P.nvec || it < 0 || it >= P.NT || ist < 0 || ist >= P.cx.nst || id < 0 || id >= P.cx.nd) return fail(2, "cell index out of range");
+    CK(cudaSetDevice(s->device));
+    const int dcell = P.ncellMain + ((ivec * P.NT + it) * P.cx.nst + ist) * P.cx.nd + id;
+    int n = 0;
+    CK(cudaMemcpyAsync(&n, P.mlen + dcell, sizeof(int), cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    *rows = n;
+    if (!M || n == 0) return 0;
+    if (cap < n) return fail(2, "buffer too small for the cell");
+    for (int c = 0; c < 4; c++)
+        CK(cudaMemcpyAsync(M + (size_t)c * n, P.arena + ((size_t)dcell * 4 + c) * P.rowcap, sizeof(double) * n, cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
     return 0;
 }
 

@@ -36,13 +36,20 @@
 #define EGDST_CTA_BLOCK 32
 #define EGDST_CTA_MINB 1
 #else
+#ifndef EGDST_SOLVE_MINB
 #define EGDST_SOLVE_MINB 3   /* CTAs per SM of the solve kernel (register budget 80) */
+#endif
 #ifndef EGDST_CTA_BLOCK
 #define EGDST_CTA_BLOCK 64   /* threads per CTA in the vector-per-CTA scope */
 #endif
 #ifndef EGDST_CTA_MINB
 #define EGDST_CTA_MINB 16
 #endif
+#endif
+// taste-shock smoothing (extension; egdst_solver.cuh): a property of the model image (codegen emits 1 for models with sigma_eps > 0),
+// so that the reference-parity images carry none of its code
+#ifndef EGDST_SMOOTHING
+#define EGDST_SMOOTHING 0
 #endif
 #define EGDST_MAXCAND 72   /* stage-0 bisection candidates: (mmax-a0)/2^k < TOLERANCE well before 72 halvings */
 #define EGDST_ENV_STACK 24 /* crossing-chain stack (thresholds() recursion depth) */
@@ -96,6 +103,9 @@ struct EgdstDev {
     int *flags;                         // [(1+nvec)*8] per team: [0..2] re-sends pending after EGM pass k%3, [3] folds found in this period
     unsigned *bar;                      // grid barrier word of the cooperative solve kernel
     unsigned long long *phase_ns;       // [EGDST_NPHASE] device time per phase of the solve kernel (measurement aid; null = off)
+    const struct EgdstDev *self;        // this block, in global memory (read by out-of-line device functions)
+    double sigmaEps;                    // > 0: taste-shock smoothing (extension): scale of the extreme-value choice shocks
+    int ncellMain;                      // nvec*NT*nst: the decision cells of the smoothing mode follow the solution cells in every per-cell array
     int priSync0;                       // index of the first primary-envelope job in the synchronisation arrays (scanE, tickE, envNact): nvec*nst*nd
     int itStop;                         // last period to solve (0; higher: test hook)
     int itStart;                        // period the backward induction starts from (NT-1; lower: test hook, cells of later periods are given)
@@ -108,6 +118,7 @@ struct EgdstDev {
 };
 
 EGDST_DEV int egdst_cell(const EgdstDev &P, int ivec, int it, int ist) { return (ivec * P.NT + it) * P.cx.nst + ist; }
+EGDST_DEV int egdst_dcell(const EgdstDev &P, int cell, int id) { return P.ncellMain + cell * P.cx.nd + id; }  // choice-specific tables (smoothing mode)
 EGDST_DEV int egdst_sd(const EgdstDev &P, int ivec, int ist, int id) { return (ivec * P.cx.nst + ist) * P.cx.nd + id; }
 EGDST_DEV double *egdst_colM(const EgdstDev &P, int cell) { return P.arena + (size_t)cell * 4 * P.rowcap; }
 EGDST_DEV double *egdst_colC(const EgdstDev &P, int cell) { return P.arena + ((size_t)cell * 4 + 1) * P.rowcap; }
@@ -142,7 +153,11 @@ struct EgdstTeam { int rank, size, v0, nv, slot; };
 // barrier of the threads that work on one item: the CTA, or the warp where blockDim.y > 1 (WARP scope).  The phases
 // only ever use threadIdx.x / blockDim.x, which is the thread's rank within that group in either case.
 EGDST_DEV void egdst_cta_sync() {
+#ifdef EGDST_NO_WARP_SCOPE
+    __syncthreads();
+#else
     if (blockDim.y == 1) __syncthreads(); else __syncwarp();
+#endif
 }
 
 // Grid-wide barrier of a cooperative launch (all CTAs resident): CTA barrier, one thread arrives on a global word

@@ -104,13 +104,13 @@ EGDST_DEV void egdst_solve_team(const EgdstDev &P, const EgdstTeam &T, void *scr
             for (int pass = 0; live; pass++) {
                 egdst_ph_egm<BS>(P, it, T, pass, scratch, shsm);
                 EGDST_PHASE_END(2);
-                if (*((volatile int *)(P.flags + 8 * T.slot + (pass % 3))) == 0) break;  // no grid asked for a zero-consumption re-send
+                if ((GRID ? EGDST_LDCG(P.flags + 8 * T.slot + (pass % 3)) : *((volatile int *)(P.flags + 8 * T.slot + (pass % 3)))) == 0) break;  // no grid asked for a zero-consumption re-send
                 egdst_ph_resend(P, it, T, pass, scratch, shsm);
                 EGDST_PHASE_END(3);
             }
             EGDST_DEBUG_DUMP("raw");
             EGDST_LOCKSTEP(2);
-            if (live && *((volatile int *)(P.flags + 8 * T.slot + 3)) != 0) {  // some decision's grid folded back: secondary envelope
+            if (live && (GRID ? EGDST_LDCG(P.flags + 8 * T.slot + 3) : *((volatile int *)(P.flags + 8 * T.slot + 3))) != 0) {  // some decision's grid folded back: secondary envelope
                 egdst_ph_envA<1, BS>(P, it, T, nvbA1, scratch);
                 EGDST_PHASE_END(4);
                 egdst_ph_envBC<1, BS>(P, it, T, nvbM1, scratch);
@@ -119,6 +119,7 @@ EGDST_DEV void egdst_solve_team(const EgdstDev &P, const EgdstTeam &T, void *scr
             }
         }
         EGDST_LOCKSTEP(3);
+        if (EGDST_SMOOTHING && live) egdst_ph_dsave(P, it, T);  // smoothing mode: keep the choice-specific tables (read by period it-1)
         if (live) egdst_ph_envA<0, BS>(P, it, T, nvbA0, scratch);
         EGDST_PHASE_END(5);
         EGDST_LOCKSTEP(4);

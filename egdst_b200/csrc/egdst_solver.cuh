@@ -137,6 +137,124 @@ EGDST_DEV bool egdst_eval_node(const egdst_ctx *cx, const EgdstDev &P, const Egd
     return true;
 }
 
+// ---- taste-shock smoothing (opt-in extension, P.sigmaEps > 0; the reference has no such mode) --------------------
+// With additive extreme-value taste shocks of scale sigma on the discrete choice (DC-EGM, Iskhakov, Jorgensen, Rust and
+// Schjerning 2017), next period's choice is probabilistic: the expectation uses the choice-specific policies c_d(M'),
+// v_d(M') -- kept per decision in the decision cells (egdst_ph_dsave) instead of being discarded after the primary
+// envelope (egdst_solver.c:720-730) -- through
+//     EV(M')  = sigma * log sum_d exp(v_d(M')/sigma)          P_d(M') = exp(v_d/sigma) / sum_d' exp(v_d'/sigma)
+//     rhs    += pr * sum_d P_d u'_d(c_d(M')) * dM'/dA          evf += pr * EV(M')
+// As sigma -> 0 this is the hard max of the reference.  Each decision's table is read exactly as the reference reads
+// the merged cell: bracket + linear interpolation of consumption with the constant-extrapolation guard, the
+// credit-constrained branch below the first endogenous point, transformed extrapolation of the value above the grid.
+#define EGDST_SMOOTH_MAXND 8
+#if EGDST_SMOOTHING
+EGDST_DEV EgdstNext egdst_choice_tables(const EgdstDev &P, int dcell) {
+    EgdstNext t;
+    t.M = egdst_colM(P, dcell); t.C = egdst_colC(P, dcell); t.V = egdst_colV(P, dcell);
+    t.n1 = P.mlen[dcell] - 1;
+    t.th = 0; t.dd = 0; t.nth = 0;
+    t.evf = P.evf[dcell];
+    t.cell = dcell;
+    t.ivl = egdst_cell_rows(P, dcell);
+    t.M1 = t.n1 >= 1 ? t.M[1] : 0.0; t.Mlast = t.n1 >= 1 ? t.M[t.n1] : 0.0; t.Clast = t.n1 >= 1 ? t.C[t.n1] : 0.0;
+    return t;
+}
+// Out of line, with scalar arguments and the kernel-argument block read from its copy in global memory (P.self): the
+// reference-parity kernels must not pay registers, local memory or instruction-cache space for this mode (a by-reference
+// call would pin the caller's context structs to local memory).
+struct EgdstSmoothOut { double mu, ev; int bad; };  // bad: 0, EGDST_PT_C1NEG or EGDST_PT_EVFINF
+EGDST_NOINLINE EgdstSmoothOut egdst_smooth_node(const EgdstDev *Pg, int ivec, int it1, int ist1, double savings, double shock, double cash, int keep) {
+    const EgdstDev &P = *Pg;
+    EgdstSmoothOut o; o.mu = 0.0; o.ev = 0.0; o.bad = 0;
+    egdst_ctx cxs; egdst_load_ctx(P, ivec, cxs);
+    const egdst_ctx *cx = &cxs;
+    PeriodVars next; next.it = it1; next.ist = ist1; next.id = 0; next.savings = savings; next.shock = shock; next.cash = cash;
+    const int nd = cx->nd;
+    const int cell1 = egdst_cell(P, ivec, it1, ist1);
+    double vd[EGDST_SMOOTH_MAXND], md[EGDST_SMOOTH_MAXND], vl[EGDST_SMOOTH_MAXND];
+    double vmax = -EGDST_INF;
+    int nav = 0;
+    bool above = false;
+    const int nm = P.mlen[cell1];
+    const double g0m = nm >= 3 ? egdst_colM(P, cell1)[nm - 2] : -EGDST_INF;  // second-to-last abscissa of the merged cell
+    for (int d1 = 0; d1 < nd; d1++) {
+        vd[d1] = -EGDST_INF; md[d1] = 0.0; vl[d1] = -EGDST_INF;
+        const int dcell = egdst_dcell(P, cell1, d1);
+        if (P.mlen[dcell] < 3) continue;  // decision not available in (it+1, ist1)
+        const EgdstNext t = egdst_choice_tables(P, dcell);
+        vl[d1] = t.V[t.n1];
+        above = above || cash > t.Mlast;
+        const bool tab = egdst_cell_has_tab(P, t.n1 + 1);
+        EgdstInterval iv;
+        int i;
+        if (tab) i = egdst_lookup_tab(P, t.cell, t.ivl, cash, t.n1 + 1, iv);
+        else {
+            i = egdst_bracket(cash, t.M, t.n1 + 1, 0); iv.g0 = t.M[i]; iv.g1 = t.M[i + 1]; iv.c0 = t.C[i]; iv.c1 = t.C[i + 1]; iv.v0 = t.V[i]; iv.v1 = t.V[i + 1];
+            iv.y = egdst_div_safe(iv.g1 - iv.g0) ? 1.0 / (iv.g1 - iv.g0) : 0.0;
+        }
+        double w = iv.g1 - iv.g0, y = iv.y;
+        double c1 = y != 0.0 ? egdst_lerp_y(cash, iv.g0, iv.g1, iv.c0, iv.c1, w, y) : egdst_lerp(cash, iv.g0, iv.g1, iv.c0, iv.c1);
+        if (cash > t.Mlast) c1 = MAX(c1, t.Clast);
+        if (c1 <= 0) { o.bad = EGDST_PT_C1NEG; return o; }
+        next.id = d1;
+        md[d1] = utility_marginal(cx, &next, c1);
+        double v1;
+        if (cash < t.M1 && t.evf > -EGDST_INF) {
+            v1 = utility(cx, &next, cash - cx->a0) + discount(cx, &next) * t.evf;
+        } else {
+            if (i < 1) {
+                if (tab) iv = egdst_load_interval(t.ivl + 1);
+                else { iv.g0 = t.M[1]; iv.g1 = t.M[2]; iv.v0 = t.V[1]; iv.v1 = t.V[2]; iv.y = egdst_div_safe(iv.g1 - iv.g0) ? 1.0 / (iv.g1 - iv.g0) : 0.0; }
+                w = iv.g1 - iv.g0; y = iv.y;
+            }
+            v1 = egdst_linter_extrap_iv(cx, &next, cash, iv.g0, iv.g1, iv.v0, iv.v1, t.M1, t.Mlast, w, y);
+            if (cash > t.Mlast && g0m > t.M1 && g0m < t.Mlast) {
+                // above the grid the value is extrapolated in the metric of the transform (egdst_lib.c:179-206), which depends on
+                // the chord it continues: the reference continues the last interval of the MERGED cell, so every decision's value
+                // is continued from that abscissa (g0m) -- the limit sigma -> 0 is then the reference's extrapolation exactly
+                EgdstInterval jv;
+                if (tab) egdst_lookup_tab(P, t.cell, t.ivl, g0m, t.n1 + 1, jv);
+                else { const int j = egdst_bracket(g0m, t.M, t.n1 + 1, 0); jv.g0 = t.M[j]; jv.g1 = t.M[j + 1]; jv.v0 = t.V[j]; jv.v1 = t.V[j + 1]; }
+                const double vg = egdst_lerp(g0m, jv.g0, jv.g1, jv.v0, jv.v1);
+                v1 = egdst_linter_extrap_iv(cx, &next, cash, g0m, t.Mlast, vg, t.V[t.n1], t.M1, t.Mlast, t.Mlast - g0m, 0.0);
+            }
+        }
+        vd[d1] = v1;
+        if (v1 > vmax) vmax = v1;
+        nav++;
+    }
+    if (nav == 0 || (keep == 1 && !(vmax > -EGDST_INF))) { o.bad = EGDST_PT_EVFINF; return o; }  // the reference's evf = -inf abort (egdst_solver.c:596)
+    const double sig = P.sigmaEps;
+    // Above the unified grid (all choice-specific tables end at its bound, egdst_ph_dsave) the choice probabilities are
+    // held at their values at the bound, and the logsum moves with the probability-weighted extrapolated values: the
+    // reference holds the argmax of the bound there (it extrapolates the last interval of the merged cell), so this is
+    // its limit as sigma -> 0; extrapolated choice-specific values are not compared with each other.
+    double wmax = vmax;
+    if (above) { wmax = -EGDST_INF; for (int d1 = 0; d1 < nd; d1++) if (vd[d1] > -EGDST_INF && vl[d1] > wmax) wmax = vl[d1]; }
+    double ssum = 0.0, mu = 0.0, dv = 0.0;
+    if (wmax > -EGDST_INF) {
+        for (int d1 = 0; d1 < nd; d1++) {
+            if (!(vd[d1] > -EGDST_INF)) continue;
+            const double wv = above ? vl[d1] : vd[d1];
+            if (!(wv > -EGDST_INF)) continue;
+            const double e = exp((wv - wmax) / sig);
+            ssum += e; mu += e * md[d1];
+            if (above) dv += e * (vd[d1] - vl[d1]);
+        }
+    }
+    if (!(ssum > 0.0)) {  // keep == 0 with every value at -inf: the available decisions weigh equally
+        for (int d1 = 0; d1 < nd; d1++) if (md[d1] != 0.0) { ssum += 1.0; mu += md[d1]; }
+        o.mu = mu / ssum; o.ev = -EGDST_INF;
+        return o;
+    }
+    o.mu = mu / ssum;
+    o.ev = wmax + sig * log(ssum) + dv / ssum;
+    return o;
+}
+
+#endif  // EGDST_SMOOTHING
+
 // The common cases of a node, straight-line.  The cell has tables and either
 //   (interior) cash lies inside the value grid [M[1], M[last]] (no extrapolation, no credit-constrained branch), the
 //              bucket of the index resolves the bracket by itself, the interval is safely invertible, or
@@ -221,7 +339,7 @@ EGDST_DEV void egdst_eval_nodes(const egdst_ctx *cx, const EgdstDev &P, int ivec
         const bool tab = egdst_cell_has_tab(P, t.n1 + 1);
         int iy = part;
 #if EGDST_OPT_MUNOD
-        if (shk && tab && keep == 1 && t.n1 >= 3) {
+        if (!EGDST_SMOOTHING && shk && tab && keep == 1 && t.n1 >= 3) {
             const EgdstCellTop top = P.tabTop[t.cell];
             for (; iy + nparts < niy; iy += 2 * nparts) {
                 const int qa = ist1 * ny + iy, qb = qa + nparts;
@@ -282,6 +400,21 @@ EGDST_DEV void egdst_eval_nodes(const egdst_ctx *cx, const EgdstDev &P, int ivec
             if (pr1 == 0.0) continue;
             const int q = ist1 * ny + iy;
             if (q > acc.badq) break;  // the reference would have stopped before this node
+#if EGDST_SMOOTHING
+            {  // taste-shock smoothing (extension): logsum and choice probabilities over the choice-specific tables
+                acc.checksum += pr1;
+                next.cash = cashinhand(cx, curr, &next);
+                const EgdstSmoothOut o = egdst_smooth_node(P.self, ivec, next.it, ist1, next.savings, next.shock, next.cash, keep);
+                if (o.bad) { acc.badq = q; acc.badtype = o.bad; acc.badcash = next.cash; acc.badshock = next.shock; break; }
+                acc.rhs += pr1 * o.mu * cashinhand_marginal(cx, curr, &next);
+                if (keep == 1) {
+                    const double term = pr1 * o.ev;
+                    acc.evf += term;
+                    if (term == -EGDST_INF) { acc.badq = q; acc.badtype = EGDST_PT_EVFINF; acc.badcash = next.cash; acc.badshock = next.shock; break; }
+                }
+                continue;
+            }
+#endif
             if (!egdst_eval_node(cx, P, t, tab, curr, next, keep, q, pr1, acc)) break;
         }
     }

@@ -108,7 +108,8 @@ EGDST_DEV void egdst_tab_cell(const EgdstDev &P, int cell, int vb, int nvb) {
         EgdstCellTop T; T.g0 = M[n - 2]; T.g1 = M[n - 1]; T.c0 = C[n - 2]; T.c1 = C[n - 1]; T.v0 = V[n - 2]; T.v1 = V[n - 1];
         const double w = T.g1 - T.g0;
         T.y = egdst_div_safe(w) ? 1.0 / w : 0.0;
-        const int ist = cell % P.cx.nst, it = (cell / P.cx.nst) % P.NT, ivec = cell / (P.cx.nst * P.NT);
+        const int mc = cell < P.ncellMain ? cell : (cell - P.ncellMain) / P.cx.nd;  // decision cells (smoothing mode) follow the solution cells
+        const int ist = mc % P.cx.nst, it = (mc / P.cx.nst) % P.NT, ivec = mc / (P.cx.nst * P.NT);
         egdst_ctx cx; egdst_load_ctx(P, ivec, cx);
         PeriodVars prd; prd.it = it; prd.ist = ist; prd.id = 0; prd.cash = 0; prd.savings = 0; prd.shock = 0;
         egdst_fill_state(&cx, &prd);
@@ -176,6 +177,51 @@ EGDST_DEV void egdst_ph_tab(const EgdstDev &P, int it, const EgdstTeam &T, int n
     for (int w = T.rank; w < nwork; w += T.size) {
         const int njobs = T.nv * jpv, vb = w / njobs, j = w - vb * njobs;
         egdst_tab_cell(P, egdst_cell(P, T.v0 + j / jpv, it, j % jpv), vb, nvb);
+    }
+    if (EGDST_SMOOTHING) {  // smoothing mode: the choice-specific tables of the period
+        const int nd = P.cx.nd, jpd = jpv * nd, nworkd = T.nv * jpd * nvb;
+        for (int w = T.rank; w < nworkd; w += T.size) {
+            const int njobs = T.nv * jpd, vb = w / njobs, j = w - vb * njobs, r = j % jpd;
+            egdst_tab_cell(P, egdst_dcell(P, egdst_cell(P, T.v0 + j / jpd, it, r / nd), r % nd), vb, nvb);
+        }
+    }
+}
+// smoothing mode: each decision's point list (after its secondary envelope) becomes a cell of its own, in the layout
+// of the solution cells (row 0 = a0, 0, a0, evf_d(a0)); an unavailable decision has 0 rows.  Like the reference's
+// envelop(), which ends the unified grid at the smallest of the decisions' last abscissae (egdst_solver.c:1266-1271)
+// and keeps the interpolated values there, a list that reaches further is cut at that bound: sigma_eps -> 0 then
+// reproduces the reference's cells also where next period's cash lands above the unified grid.
+EGDST_DEV void egdst_ph_dsave(const EgdstDev &P, int it, const EgdstTeam &T) {
+    const int nd = P.cx.nd, jpd = P.cx.nst * nd, nwork = T.nv * jpd;
+    for (int w = T.rank; w < nwork; w += T.size) {
+        const int ivec = T.v0 + w / jpd, r = w % jpd, ist = r / nd, id = r % nd;
+        const int sd = egdst_sd(P, ivec, ist, id), dcell = egdst_dcell(P, egdst_cell(P, ivec, it, ist), id);
+        int n = P.active[sd] ? P.ptN[sd] : 0;
+        if (n > P.rowcap - 2) n = P.rowcap - 2;
+        const double *X = P.ptX + (size_t)sd * P.gcap, *Cc = P.ptC + (size_t)sd * P.gcap, *V = P.ptV + (size_t)sd * P.gcap;
+        double grb = EGDST_INF;
+        for (int f = 0; f < nd; f++) {
+            const int sf = egdst_sd(P, ivec, ist, f), nf = P.active[sf] ? P.ptN[sf] : 0;
+            if (nf > 0) { const double xl = P.ptX[(size_t)sf * P.gcap + nf - 1]; if (xl < grb) grb = xl; }
+        }
+        // rows with x <= grb: the list is sorted, every thread bisects for itself (no exchange needed)
+        int keep = 0;
+        { int l = 0, h = n; while (l < h) { const int mid = (l + h) >> 1; if (X[mid] <= grb) l = mid + 1; else h = mid; } keep = l; }
+        double *oM = egdst_colM(P, dcell), *oC = egdst_colC(P, dcell), *oA = egdst_colA(P, dcell), *oV = egdst_colV(P, dcell);
+        for (int i = threadIdx.x; i < keep; i += blockDim.x) { const double x = X[i], c = Cc[i]; oM[1 + i] = x; oC[1 + i] = c; oA[1 + i] = x - c; oV[1 + i] = V[i]; }
+        if (threadIdx.x == 0) {
+            int rows = keep;
+            if (keep > 0 && keep < n && X[keep - 1] < grb) {  // the values at the bound, interpolated on the interval that straddles it
+                const double x0 = X[keep - 1], x1 = X[keep];
+                const double c = egdst_lerp(grb, x0, x1, Cc[keep - 1], Cc[keep]), v = egdst_lerp(grb, x0, x1, V[keep - 1], V[keep]);
+                oM[1 + keep] = grb; oC[1 + keep] = c; oA[1 + keep] = grb - c; oV[1 + keep] = v;
+                rows = keep + 1;
+            }
+            const double e = P.evfa0[sd], a0 = P.cx.a0;
+            oM[0] = a0; oC[0] = 0.0; oA[0] = a0; oV[0] = e;
+            P.evf[dcell] = e;
+            P.mlen[dcell] = rows > 0 ? rows + 1 : 0;
+        }
     }
 }
 // tables of imported cells (egdst_solution_import): grid (nblk, nst, 1)

@@ -304,6 +304,26 @@ def humancapital2(**kw) -> EgdstModel:
     return humancapital(health=True, **kw)
 
 
+def retirement2_smooth(sigma_eps=0.2, **kw) -> EgdstModel:
+    """retirement2 with extreme-value taste shocks of scale ``sigma_eps`` on the labour-supply choice -- the opt-in
+    smoothing mode (an extension: the reference has a hard max only)."""
+    m = retirement(**kw)
+    m.sigma_eps = sigma_eps
+    return m
+
+
+def retirement_two_period(sigma_eps=0.5, ngridm=2000) -> EgdstModel:
+    """Closed-form case of the smoothing mode (tests/smoothing_checks.py): periods t=1,2, no income risk, zero interest
+    (discount 1), a0 = 0."""
+    m = retirement(label="retire_kat", sigma="0", T=2, ngridm=ngridm, ngridmax=2 * ngridm, nthrhmax=50, ny=1, interest=0.0,
+                   mmax=10, a0=0.0, duw=0.5, wage=1.05)
+    m.sigma_eps = sigma_eps
+    return m
+
+
+# images of the smoothing mode (compiled with EGDST_SMOOTHING, codegen.emit_devspec)
+SMOOTH = {"retirement2_smooth": retirement2_smooth, "retirement_two_period": retirement_two_period}
+
 EXTRA = {"deaton_normal": deaton_normal, "humancapital": humancapital, "humancapital2": humancapital2,
          "retirement_mortal": retirement_mortal, "retirement_jobloss": retirement_jobloss}
 

@@ -54,6 +54,7 @@ class EgdstModel:
         d["nthrhmax"] = 100
         d["ny"] = 1
         d["a0"] = 0.0
+        d["sigma_eps"] = 0.0  # EXTENSION (no reference counterpart): scale of extreme-value taste shocks on the discrete choice; 0 = the reference's hard max
         d["discount"] = ""
         d["survival"] = "1.0"
         d["u"] = {"utility": None, "marginal": None, "marginalinverse": None, "extrap": None}
@@ -467,7 +468,7 @@ class EgdstModel:
         return 11 + self.nnst + self.nnd + len(self.eq)
 
     # ------------------------------------------------------------------ (de)serialisation of the public properties
-    _SCALARS = ("label", "t0", "T", "mmax", "ngridm", "ngridmax", "nthrhmax", "ny", "a0", "discount", "survival")
+    _SCALARS = ("label", "t0", "T", "mmax", "ngridm", "ngridmax", "nthrhmax", "ny", "a0", "discount", "survival", "sigma_eps")
 
     def to_dict(self) -> Dict[str, Any]:
         """The public properties as plain data, in the shape ``jsonencode(struct(model))`` gives in MATLAB."""
@@ -498,6 +499,7 @@ class EgdstModel:
         m.ngridmax = d.get("ngridmax", 100)
         m.ngridm = d.get("ngridm", 10)
         m.nthrhmax, m.ny, m.a0 = d.get("nthrhmax", 100), d.get("ny", 1), d.get("a0", 0.0)
+        m.sigma_eps = float(d.get("sigma_eps", 0.0) or 0.0)
         for kind in ("s", "d"):
             for v in lst(d.get(kind)):
                 if v.get("gridpoints"):

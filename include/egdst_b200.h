@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define EGDST_ABI_VERSION 1
+#define EGDST_ABI_VERSION 2
 
 /* The model object flattened to a POD: exactly the properties the reference reads across the MEX
  * boundary (egdst_lib.c:37-55, compile.m:472, egdst_solver.c:162) plus the -D flags of compile.m:757-777. */
@@ -45,6 +45,9 @@ typedef struct egdst_desc {
     const double *quadrature; /* [2*ny] weights then abscissas in (0,1), as model.quadrature (may be NULL if ny==1) */
     int neq;                  /* numel(model.eq)                                 */
     int device;               /* CUDA device ordinal                             */
+    double sigma_eps;         /* EXTENSION (no reference counterpart; 0 = off = the reference's hard max): scale of additive
+                               * extreme-value taste shocks on the discrete choice.  > 0: the expectation uses the logsum and the
+                               * choice probabilities of the choice-specific value functions (egdst_solution_choice_cell)   */
 } egdst_desc;
 
 typedef struct egdst_solution egdst_solution;
@@ -79,6 +82,10 @@ int egdst_solution_sizes(egdst_solution *s, int *mlen, int *thlen);
  * D cell = thlen x 2 column-major (decision index, threshold) -- the layouts of saveoutput,
  * egdst_solver.c:917-951.  Mbuf holds 4*sum(mlen) doubles, Dbuf 2*sum(thlen). */
 int egdst_solution_export(egdst_solution *s, double *Mbuf, double *Dbuf);
+/* EXTENSION, smoothing mode only (desc.sigma_eps > 0): the choice-specific cell of decision id in (it, ist) -- what the
+ * reference discards after envelop() (egdst_solver.c:720-730).  rows x 4 column-major (M,C,A,V; row 0 = a0,0,a0,
+ * evf_d(a0)); *rows = 0: decision not available.  M may be NULL to query the row count. */
+int egdst_solution_choice_cell(egdst_solution *s, int ivec, int it, int ist, int id, double *M, int cap, int *rows);
 /* status of the last (re)solve of vector ivec: returns the code, fills it/ist/id of the first failure */
 int egdst_solution_status(egdst_solution *s, int ivec, int *it, int *ist, int *id);
 int egdst_solution_nvec(const egdst_solution *s);
