@@ -326,17 +326,23 @@ EGDST_DEV void egdst_env_chain(const egdst_ctx *cx, const View &E, int it, int i
                 // pieces, so the maximum can pass from one to the other only where they coincide: the constant
                 // extrapolations of two runs of a flat stretch (egdst_solver.c:824-827), told apart by the last bit of
                 // an interpolation.  The reference places a double point at the mean of the four end points here
-                // (:1737-1753) -- an abscissa far outside the bracket, which its later qsort moves beyond the unified
-                // grid's bound and so never reaches the solution.  The runs of one decision share the decision, so no
-                // threshold is due either: nothing is emitted, the list stays sorted.
+                // (:1737-1753) -- an abscissa far outside the bracket.  Here nothing is emitted for EXACTLY parallel pieces of
+                // the secondary envelope: a deliberate difference from the reference, seen only in constructed ties
+                // (tests/golden/tie_env2.npz, where the reference's own list comes out unsorted); DESIGN.md section 5.
                 if (View::kMode == 1) continue;
                 newpoint = (pg0 + pg1 + qg0 + qg1) / 4; cmax = newpoint * sq + iq;
             }
             else { newpoint = (ip - iq) / (sq - spp); cmax = newpoint * sq + iq; }
-            // The same tie with slopes that differ in the last bit: the "intersection" of two all but coincident pieces
-            // lands anywhere.  A crossing that belongs to this boundary lies between the two abscissas of the union that
-            // enclose it; anything else is the tie again and is not emitted (secondary envelope, as above).
-            if (View::kMode == 1 && !(newpoint >= xl && newpoint <= xr)) continue;
+            // With slopes that differ only in the last bit the "intersection" of two all but coincident pieces lands anywhere,
+            // usually far outside the bracket of the boundary it belongs to.  The reference emits it regardless (envelope2
+            // copies back every point of envelop(), egdst_solver.c:888-895) and its list comes out UNSORTED.  What happens
+            // next depends on the model: with several decisions the primary envelope qsorts the merged quadruples, and in
+            // every case observed (S1b at BASELINE size, periods 8-6) the stray pair does not reach the solution cell; with
+            // a single decision nothing re-sorts and it does (examples.deaton_meanstest, period 1, a row with C = -inf).
+            // The rank step of the primary envelope here relies on sorted per-decision lists, so: a single decision emits
+            // the pair like the reference; several decisions drop it.  This is an EMPIRICAL rule pinned by those two cases,
+            // not an equivalence -- DESIGN.md section 5 states the gap.
+            if (View::kMode == 1 && cx->nd > 1 && !(newpoint >= xl && newpoint <= xr)) continue;
         }
         // is a third, not yet visited function above at the crossing? (egdst_solver.c:1807-1845, mode 1)
         // The candidates are split over the lanes of the warp (the secondary envelope can have ~10^2 runs);

@@ -55,6 +55,19 @@ def deaton(label="deaton1", a0=0.0, sigma="0", mu="0", mmax=50, ny=2, T=25, ngri
     return m
 
 
+def deaton_meanstest(penalty=4.0, cut=2.0, **kw) -> EgdstModel:
+    """Deaton model whose cash-in-hand drops by ``penalty`` once savings exceed ``cut`` (a means test).  Not shipped by the
+    reference: next period's cash is then non-monotone in savings, which is what makes the zero-consumption signal fire
+    AFTER the seed stage of the savings grid (egdst_solver.c:1080-1099) and the grid fold back with one decision."""
+    args = dict(label="deaton_mt", a0=0.0, sigma="0.25", mu="-0.5*sigma*sigma", mmax=20, ny=5, T=6, ngridm=80, ngridmax=400)
+    args.update(kw)
+    label = args.pop("label")
+    m = deaton(label, **args)
+    m.budget = ("cashinhand", "savings*(1+interest)+income_level-%r*(savings>%r)" % (float(penalty), float(cut)))
+    m.nthrhmax = 200
+    return m
+
+
 def deaton1(**kw) -> EgdstModel:
     return deaton("deaton1", **kw)
 
@@ -324,7 +337,7 @@ def retirement_two_period(sigma_eps=0.5, ngridm=2000) -> EgdstModel:
 # images of the smoothing mode (compiled with EGDST_SMOOTHING, codegen.emit_devspec)
 SMOOTH = {"retirement2_smooth": retirement2_smooth, "retirement_two_period": retirement_two_period}
 
-EXTRA = {"deaton_normal": deaton_normal, "humancapital": humancapital, "humancapital2": humancapital2,
+EXTRA = {"deaton_normal": deaton_normal, "deaton_meanstest": deaton_meanstest, "humancapital": humancapital, "humancapital2": humancapital2,
          "retirement_mortal": retirement_mortal, "retirement_jobloss": retirement_jobloss}
 
 ALL = {

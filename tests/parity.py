@@ -14,6 +14,20 @@ def _interp(M, F, x):
     return np.interp(x, M[1:, 0], F)
 
 
+def _gap(a, b):
+    """max |a-b| / max(1,|b|) over the probes.  Probes where both sides are the SAME infinity or both NaN agree (the
+    reference writes C = -inf rows in places, e.g. the second half of a double point on an analytic segment); a probe
+    where only one side is non-finite, or the infinities differ, is a mismatch (inf) -- never silently skipped."""
+    if a.size == 0:
+        return 0.0
+    fa, fb = np.isfinite(a), np.isfinite(b)
+    same_nonfinite = (~fa & ~fb) & ((a == b) | (np.isnan(a) & np.isnan(b)))
+    if np.any((~fa | ~fb) & ~same_nonfinite):
+        return float("inf")
+    both = fa & fb
+    return float(np.max(np.abs(a[both] - b[both]) / np.maximum(1.0, np.abs(b[both])))) if both.any() else 0.0
+
+
 def cell_errors(Ma, Da, Mb, Db, nprobe=50001, excl=1e-9):
     lo = max(Ma[1, 0], Mb[1, 0])
     hi = min(Ma[-1, 0], Mb[-1, 0])
@@ -30,9 +44,8 @@ def cell_errors(Ma, Da, Mb, Db, nprobe=50001, excl=1e-9):
     x = x[mask]
     ca, cb = _interp(Ma, Ma[1:, 1], x), _interp(Mb, Mb[1:, 1], x)
     va, vb = _interp(Ma, Ma[1:, 3], x), _interp(Mb, Mb[1:, 3], x)
-    fin = np.isfinite(va) & np.isfinite(vb)
-    out["C"] = float(np.max(np.abs(ca - cb) / np.maximum(1.0, np.abs(cb)))) if x.size else 0.0
-    out["V"] = float(np.max(np.abs(va[fin] - vb[fin]) / np.maximum(1.0, np.abs(vb[fin])))) if fin.any() else 0.0
+    out["C"] = _gap(ca, cb)
+    out["V"] = _gap(va, vb)
     ea, eb = Ma[0, 3], Mb[0, 3]
     out["evf"] = 0.0 if (ea == eb or (np.isinf(ea) and np.isinf(eb) and ea == eb)) else float(abs(ea - eb) / max(1.0, abs(eb)))
     out["nth"] = (Da.shape[0], Db.shape[0])

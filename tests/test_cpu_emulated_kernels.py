@@ -148,3 +148,25 @@ def test_emulated_warp_scope_matches_grid_scope(monkeypatch):
         Mb, Db = rb.cells(v)
         e = solution_errors(Mb, Db, one.M, one.D)
         assert e["C"] < 1e-12 and e["V"] < 1e-12 and e["TH"] < 1e-12 and e["rowdiff"] == 0, (v, e)
+
+
+def test_emulated_late_zero_consumption_resends_match_reference():
+    """egdst_solver.c:1080-1099: a zero-consumption signal AFTER the seed stage rebuilds the rest of the savings grid.
+    The means-tested budget of examples.deaton_meanstest fires it in three of six periods (26 re-sends); its grids also
+    fold back with a single decision, and in period 1 the reference's envelope2 keeps a double point (M, M+1e-10) whose
+    second consumption is -inf (a crossing outside its bracket, on an analytic segment) -- with one decision no primary
+    envelope re-sorts the list, so the pair reaches the solution cell and the next period reads it.  All six periods
+    must equal the reference row for row."""
+    m = examples.deaton_meanstest()
+    if not ref_available(m):
+        pytest.skip("oracle/_ref not built and /root/reference absent")
+    Mr, Dr = oracle_for(m).solve()
+    lib = _emulated(m)
+    sol = lib.solve(m)
+    assert sol.status(0)[0] == 0, sol.status(0)
+    assert sol.resends() >= 20, sol.resends()
+    from tests.parity import cell_errors
+    for it in range(m.nt - 1, -1, -1):
+        e = cell_errors(sol.M[0][it], sol.D[0][it], Mr[0][it], Dr[0][it])
+        assert e["C"] < 1e-9 and e["V"] < 1e-9 and e["rows"][0] == e["rows"][1], (it, e)
+    assert np.isneginf(Mr[0][1][:, 1]).sum() == 1 and np.isneginf(sol.M[0][1][:, 1]).sum() == 1  # the -inf row is there, on both sides

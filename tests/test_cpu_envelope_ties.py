@@ -74,28 +74,40 @@ def test_coincident_constant_extrapolations_tie():
     assert dv < 1e-12 and dc < 1e-12, (dv, dc)
 
 
+def _drop_out_of_order(X):
+    """mask of the points left after removing stray double points: abscissas that break the order of the list"""
+    keep = np.ones(X.size, bool)
+    run_max = -np.inf
+    for i in range(X.size):
+        if X[i] < run_max:  # everything between the stray point and here was out of order
+            j = i - 1
+            while j >= 0 and X[j] > X[i]:
+                keep[j] = False
+                j -= 1
+        run_max = max(run_max, X[i]) if keep[i] else run_max
+    return keep
+
+
 def test_all_but_coincident_constant_extrapolations_tie():
     """pert2_*: the same flat stretch split one point later, with the two constant extrapolations one ulp apart: their
     "intersection" (a quotient of two rounding errors) lies far outside the boundary it belongs to.  The reference
-    emits it (its list is unsorted again); the kernels do not."""
+    emits such points (its list comes out unsorted) and so do the kernels -- a crossing outside its bracket is kept,
+    which is what makes examples.deaton_meanstest match the reference row for row.  This is a constructed tie, not a
+    bit-parity case: the reference emits a few more stray points than the kernels (972 vs 967 rows; exactly parallel
+    pieces emit nothing here), so the lists are compared as functions after the out-of-order points of BOTH are
+    dropped."""
     g = np.load(os.path.join(HERE, "golden", "tie_env2.npz"))
     m = _model()
     X, C, V = _emulated(m).test_envelope2(m, 7, 0, g["pert2_X"], g["pert2_C"], g["pert2_V"], float(g["evfa0"]))
     Xr, Cr, Vr = ref.EnvelopeHarness(m).envelope2(7, 0, 0, g["pert2_X"], g["pert2_C"], g["pert2_V"], float(g["evfa0"]))
-    assert np.all(np.diff(X) > 0) and np.isfinite(C).all() and np.isfinite(V).all()
     assert not np.all(np.diff(Xr) >= 0)
-    # drop the reference's stray double point(s): abscissas that break the order of its list
-    keep = np.ones(Xr.size, bool)
-    run_max = -np.inf
-    for i in range(Xr.size):
-        if Xr[i] < run_max:  # everything between the stray point and here was out of order
-            j = i - 1
-            while j >= 0 and Xr[j] > Xr[i]:
-                keep[j] = False
-                j -= 1
-        run_max = max(run_max, Xr[i]) if keep[i] else run_max
-    assert 1 <= (~keep).sum() <= 4
-    dv, dc = _function_space_gap(X, V, C, Xr[keep], Vr[keep], Cr[keep], hi=min(X.max(), 9.0))
+    keep, keepr = _drop_out_of_order(X), _drop_out_of_order(Xr)
+    assert (~keep).sum() <= 4 and 1 <= (~keepr).sum() <= 4
+    assert np.all(np.diff(X[keep]) > 0) and np.isfinite(V[keep]).all()
+    assert np.isfinite(C[keep]).all() and np.isfinite(Cr[keepr]).all()
+    # the stray pair of the kernels is one of the reference's stray pairs
+    assert all(np.min(np.abs(Xr[~keepr] - x)) < 1e-12 for x in X[~keep])
+    dv, dc = _function_space_gap(X[keep], V[keep], C[keep], Xr[keepr], Vr[keepr], Cr[keepr], hi=min(X[keep].max(), 9.0))
     assert dv < 1e-12 and dc < 1e-12, (dv, dc)
 
 

@@ -564,3 +564,22 @@ def test_warp_scope_on_a_model_with_discrete_choices(monkeypatch):
         Mb, Db = sol.cells(v)
         e = solution_errors(Mb, Db, Mr, Dr)
         assert e["C"] < TOL and e["V"] < TOL and e["TH"] < TOL and e["Dseq"] and e["rowdiff"] == 0, (v, e)
+
+
+def test_late_zero_consumption_resends_match_reference():
+    """The re-send AFTER the seed stage of the savings grid (egdst_solver.c:1080-1099) on the GPU: the means-tested
+    Deaton model fires it in three of its six periods (26 re-sends) and folds its grid with a single decision, so the
+    secondary envelope's double point with C = -inf (reference, period 1) reaches the solution cell.  Every period
+    equals the reference row for row.  (The model is constructed for this path and is fragile in the reference itself:
+    other grid sizes and horizons make the reference abort with its own errors, so this one configuration and the
+    periods of S1b above the noise floor -- ~500 re-sends at BASELINE size -- are the parity evidence for the path.)"""
+    m = examples.deaton_meanstest()
+    Mr, Dr = oracle_for(m).solve()
+    m.compile()
+    sol = m._capi().solve(m)
+    assert sol.status(0)[0] == 0, sol.status(0)
+    assert sol.resends() >= 20, sol.resends()
+    for it in range(m.nt - 1, -1, -1):
+        e = cell_errors(sol.M[0][it], sol.D[0][it], Mr[0][it], Dr[0][it])
+        assert e["C"] < TOL and e["V"] < TOL and e["rows"][0] == e["rows"][1], (it, e)
+    assert np.isneginf(sol.M[0][1][:, 1]).sum() == 1 and np.isneginf(Mr[0][1][:, 1]).sum() == 1
