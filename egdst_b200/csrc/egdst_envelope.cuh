@@ -197,7 +197,13 @@ EGDST_DEV void egdst_env_point_commit(const EgdstDev &P, int slot, int sslot, do
     if (best == 0x7fffffff) best = f;  // every value -inf (cannot happen: the own value is finite or the maximum)
     const size_t o = (size_t)slot * P.envcap + rank;
     P.mgX[o] = x; P.mgF[o] = f; P.mgK[o] = k; P.mgA[o] = best;
-    if (x <= grb) atomicMax(P.envNact + sslot, rank + 1);
+}
+// length of the active prefix of the union = 1 + the largest rank of a point with x <= grb.  One atomic per warp, not per
+// point: at S1 the rank step of a period would otherwise send 2*10^4 atomics to one word (they serialise in L2).
+// Called by all threads of the item (cand = 0 for threads without a point).
+EGDST_DEV void egdst_env_active_prefix(const EgdstDev &P, int sslot, int cand) {
+    for (int o = 16; o > 0; o >>= 1) { const int w = __shfl_xor_sync(EGDST_FULL, cand, o); cand = w > cand ? w : cand; }
+    if ((threadIdx.x & 31) == 0 && cand > 0) atomicMax(P.envNact + sslot, cand);
 }
 // "all choices produced empty grids" (egdst_solver.c:704-710), checked where the per-decision lists are final
 EGDST_DEV void egdst_env_check_allinf(const EgdstDev &P, int ivec, int it, int ist) {
@@ -254,6 +260,7 @@ EGDST_DEV void egdst_ph_envA(const EgdstDev &P, int it, const EgdstTeam &T, int 
                 }
             }
             if (part == 0 && valid) egdst_env_point_commit(P, slot, sslot, grb, f, k, x, rank, best);
+            egdst_env_active_prefix(P, sslot, (part == 0 && valid && x <= grb) ? rank + 1 : 0);
             if (nparts > 1 && base + nvb * npt < Ptot) egdst_cta_sync();  // scratch reused by the next stride
         }
     }
