@@ -165,7 +165,7 @@ def own_arm(a):
     m.device = local
     m.compile()
     lib = m._capi()
-    stream = torch.cuda.Stream()  # a capturable (non-legacy) stream: the solve replays as a CUDA graph
+    stream = torch.cuda.Stream()  # the library launches on this stream; torch events on it time the kernels
     torch.cuda.set_stream(stream)
     lib.set_stream(stream.cuda_stream)
     desc = capi.Desc(m)

@@ -206,9 +206,9 @@ def test_large_sweep_launch_shapes_match_reference():
         assert e["C"] < TOL and e["V"] < TOL and e["Dseq"] and e["rowdiff"] == 0, (i, e)
 
 
-def test_resolve_and_graph_replay_track_parameter_changes():
-    """egdst_resolve re-runs the period chain into the same object; from the third call on it is replayed as a CUDA
-    graph with the parameters read from device memory -- results must equal fresh solves for every parameter set."""
+def test_resolve_tracks_parameter_changes():
+    """egdst_resolve re-runs the solve kernel into the same object (no allocation, no host synchronisation) with the
+    parameters read from device memory -- results must equal fresh solves for every parameter set."""
     import torch
     m = examples.deaton2()
     m.compile()
@@ -219,7 +219,7 @@ def test_resolve_and_graph_replay_track_parameter_changes():
         sol = lib.solve(m, strict=True)
         for k, (interest, income) in enumerate([(0.01, 1.25), (0.03, 1.0), (0.045, 1.6), (0.02, 0.8), (0.01, 1.25)]):
             m.setparam("interest", interest, "income", income)
-            lib.resolve(sol, m)                       # k=0 eager, k=1 captured, k>=2 replayed
+            lib.resolve(sol, m)
             stream.synchronize()
             assert sol.status()[0] == 0
             fresh = examples.deaton2(interest=interest, income=income)
@@ -243,9 +243,9 @@ def test_resolve_and_graph_replay_track_parameter_changes():
 
 
 def test_repeated_solves_are_bit_identical(s1):
-    """Run-to-run determinism of the whole chain (eager launches, graph capture, graph replays): no floating-point
-    atomics, ticket-ordered scans -- every export of the same model is the same bytes.  (A programmatic-dependent-
-    launch version of the eager chain failed exactly this kind of check on the S1b case and was removed.)"""
+    """Run-to-run determinism of the solve kernel: no floating-point atomics, ticket-ordered chained scans, the integer
+    atomics only select maxima or positions of unordered lists that are rank-sorted afterwards -- every export of the
+    same model is the same bytes."""
     import torch
     lib = s1._capi()
     stream = torch.cuda.Stream()
