@@ -170,3 +170,56 @@ def test_emulated_late_zero_consumption_resends_match_reference():
         e = cell_errors(sol.M[0][it], sol.D[0][it], Mr[0][it], Dr[0][it])
         assert e["C"] < 1e-9 and e["V"] < 1e-9 and e["rows"][0] == e["rows"][1], (it, e)
     assert np.isneginf(Mr[0][1][:, 1]).sum() == 1 and np.isneginf(sol.M[0][1][:, 1]).sum() == 1  # the -inf row is there, on both sides
+
+
+def test_emulated_reused_solution_object_carries_nothing_over():
+    """the library keeps one released solution object for re-use by the next solve of the same
+    shape.  Solve A, free, solve B (other parameter values), free, import A's cells, simulate -- the MEX simulator's
+    flow -- must give A's paths, not paths under B's parameters."""
+    kw = dict(T=6, ngridm=40, ngridmax=200, ny=4)
+    a = examples.deaton2(income=1.25, **kw)
+    b = examples.deaton2(income=3.0, **kw)
+    lib = _emulated(a)
+    b.prepare()
+    sa = lib.solve(a)
+    Ma, Da = sa.M, sa.D
+    rng = np.random.default_rng(11)
+    nsim = 24
+    init = np.column_stack([np.ones(nsim), a.a0 + 0.5 * (a.mmax - a.a0) * rng.random(nsim)])
+    rs = rng.random(4 * nsim * a.nt)
+    live = lib.simulate(a, sa, init, rs, 0)
+    del sa                      # released: kept for re-use
+    sb = lib.solve(b)           # same shape: the cached object, now solved under income=3.0
+    assert sb.status(0)[0] == 0
+    del sb
+    imported = lib.import_solution(a, Ma, Da)   # the cached object again
+    again = lib.simulate(a, imported, init, rs, 0)
+    se = goldens.sims_errors(again, live)
+    assert se["nan_mismatch"] == 0 and se["discrete_mismatch"] == 0 and se["max"] < 1e-12, se
+
+
+def test_emulated_call_and_simulate_use_the_parameters_of_the_call():
+    """the reference reloads the parameters on every MEX call (egdst_call.c:29-30,
+    egdst_simulator.c:59-60), so setparam after a solve changes what call() and sim() compute without a new solve."""
+    m = examples.deaton2(T=6, ngridm=40, ngridmax=200, ny=4, interest=0.01)
+    lib = _emulated(m)
+    sol = lib.solve(m)
+    args = np.array([[1.0, 1.0]])
+    assert lib.call(m, sol, 3, args)[0] == pytest.approx(1 / 1.01, abs=1e-15)
+    rng = np.random.default_rng(12)
+    nsim = 16
+    init = np.column_stack([np.ones(nsim), m.a0 + 0.5 * (m.mmax - m.a0) * rng.random(nsim)])
+    rs = rng.random(4 * nsim * m.nt)
+    before = lib.simulate(m, sol, init, rs, 0)
+    m.setparam("interest", 0.10)
+    assert lib.call(m, sol, 3, args)[0] == pytest.approx(1 / 1.10, abs=1e-15)     # discount = 1/(1+interest), new value
+    after = lib.simulate(m, sol, init, rs, 0)
+    # the policy tables are those of the old solve, the budget between periods uses the new interest rate: the reference's
+    # own simulator, given the same tables and the new parameters, is the checker
+    if ref_available(m):
+        Mr, Dr = sol.M, sol.D
+        theirs = oracle_for(m).simulate(Mr, Dr, init, rs, 0)
+        se = goldens.sims_errors(after, theirs)
+        assert se["nan_mismatch"] == 0 and se["discrete_mismatch"] == 0 and se["max"] < 1e-9, se
+    both = np.isfinite(after) & np.isfinite(before)
+    assert np.max(np.abs(after[both] - before[both])) > 1e-3
