@@ -223,3 +223,56 @@ def test_emulated_call_and_simulate_use_the_parameters_of_the_call():
         assert se["nan_mismatch"] == 0 and se["discrete_mismatch"] == 0 and se["max"] < 1e-9, se
     both = np.isfinite(after) & np.isfinite(before)
     assert np.max(np.abs(after[both] - before[both])) > 1e-3
+
+
+def test_emulated_means_tested_family_agreement_is_partial_and_tracked():
+    """KNOWN PARITY GAP, tracked as a number.  Random run-time configurations of examples.deaton_meanstest (seed 1, 40
+    draws; the reference completes without a warning on 19 of them) exercise re-sends after the seed stage, folds with
+    a single decision and -- the unsolved part -- flat stretches where runs of the secondary envelope have EXACTLY equal
+    values.  There the reference's sequential sweep switches between equal-valued runs (or does not) by its processing
+    order and emits, or omits, a double point whose consumption is -inf; the parallel restatement decides such ties by
+    "lower index wins" and differs.  Observed at the end of round 2: 10 configurations equal the reference row for row
+    and to 1e-9, 1 more to 1e-9 with a different row count; 6 carry a -inf row or extra rows on one side only (one of them
+    1.3 apart in C around such a row); in 2 the -inf row feeds the next period's seed and this implementation ends in a
+    soft error the reference does not raise.
+    The assertion is a ratchet: the number of exact matches must not go down."""
+    import warnings
+    base = examples.deaton_meanstest()
+    if not ref_available(base):
+        pytest.skip("oracle/_ref not built and /root/reference absent")
+    lib = _emulated(base)
+    from tests.parity import cell_errors
+    from oracle.ref import RefError
+    rng = np.random.default_rng(1)
+    valid = exact = close = 0
+    report = []
+    for trial in range(40):
+        kw = dict(T=int(rng.integers(3, 9)), ngridm=int(rng.integers(40, 200)), ny=int(rng.integers(2, 8)), mmax=float(rng.uniform(12, 30)),
+                  interest=float(rng.uniform(0.0, 0.04)), income=float(rng.uniform(0.9, 1.6)))
+        kw["ngridmax"] = 5 * kw["ngridm"]
+        m = examples.deaton_meanstest(**kw)
+        m.prepare()
+        try:
+            Mr, Dr = oracle_for(m).solve()
+        except RefError:
+            continue  # the reference itself aborts or warns: not a parity case
+        valid += 1
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            sol = lib.solve(m)
+        worst, rows_equal = float("inf"), False
+        if sol.status(0)[0] == 0:
+            worst, rows_equal = 0.0, True
+            for it in range(m.nt):
+                e = cell_errors(sol.M[0][it], sol.D[0][it], Mr[0][it], Dr[0][it])
+                worst = max(worst, e["C"], e["V"])
+                rows_equal = rows_equal and e["rows"][0] == e["rows"][1]
+        if worst < 1e-9 and rows_equal:
+            exact += 1
+        elif worst < 1e-9:
+            close += 1
+        else:
+            report.append((trial, sol.status(0)[0], worst))
+    print("means-tested family: %d valid draws, %d exact, %d more within 1e-9, %d differ: %s" % (valid, exact, close, len(report), report))
+    assert valid >= 15
+    assert exact >= 10, (valid, exact, close, report)
