@@ -237,6 +237,7 @@ static int create_solution(const egdst_desc *d, int nvec, egdst_solution **out) 
 #define DA(ptr, n) do { cudaError_t e_ = dalloc(s, &(ptr), (size_t)(n)); if (e_ != cudaSuccess) { destroy_solution(s); return fail(2, std::string("cudaMalloc failed: ") + cudaGetErrorString(e_)); } } while (0)
     DA(s->d_stm, 2 * d->nnst); DA(s->d_states, nst * d->nnst); DA(s->d_decisions, nd * d->nnd);
     DA(s->d_bparams, (size_t)nvec * EGDST_NPARAM_); DA(s->d_qraw, 2 * d->ny); DA(s->d_q, 2 * d->ny);
+    DA(P.tabOk, s->ncell_all);
     DA(P.arena, (size_t)s->ncell_all * 4 * P.rowcap); DA(P.mlen, s->ncell_all); DA(P.thlen, s->ncell); DA(P.evf, s->ncell_all);
     DA(P.thD, (size_t)s->ncell * d->nthrhmax); DA(P.thTH, (size_t)s->ncell * d->nthrhmax);
     DA(P.active, s->nsd); DA(P.seed, (size_t)s->nsd * EGDST_SEEDW); DA(P.evfa0, s->nsd);
@@ -308,6 +309,7 @@ static int launch_solve(egdst_solution *s, cudaStream_t st) {
         CK(cudaMemsetAsync(P.thlen, 0, sizeof(int) * s->ncell, st));
     }
     CK(cudaMemsetAsync(P.bar, 0, sizeof(unsigned) * 4, st));
+    if (P.itStart == P.NT - 1) CK(cudaMemsetAsync(P.tabOk, 1, sizeof(int) * s->ncell_all, st));  // non-zero: usable; cleared by the table build of a cell whose grid steps back
     const int nst = P.cx.nst, nd = P.cx.nd, nvec = P.nvec, N = P.N;
     int B = EGDST_BLOCK;
     P.priSync0 = nvec * nst * nd;
@@ -753,6 +755,7 @@ int egdst_solution_import(const egdst_desc *d, const int *mlen, const int *thlen
     EGDST_TRY(cudaMemcpyAsync(s->d_states, d->states, sizeof(double) * d->nst * d->nnst, cudaMemcpyHostToDevice, st));
     EGDST_TRY(cudaMemcpyAsync(s->d_decisions, d->decisions, sizeof(double) * d->nd * d->nnd, cudaMemcpyHostToDevice, st));
     EGDST_TRY(cudaMemsetAsync(s->P.status, 0, sizeof(int) * 4, st));
+    EGDST_TRY(cudaMemsetAsync(s->P.tabOk, 1, sizeof(int) * s->ncell_all, st));  // imported cells: usable unless egdst_k_tabonly finds a grid that steps back
     if (ce == cudaSuccess) {
         KLAUNCH(KC_OTHER, egdst_k_unpack, dim3(s->ncell), dim3(EGDST_BLOCK), 0, st, s->P, s->d_moff, s->d_toff, s->d_pack, s->d_pack + nm, s->ncell);
         const int tb = (s->P.lutcap + 1 + EGDST_BLOCK - 1) / EGDST_BLOCK;

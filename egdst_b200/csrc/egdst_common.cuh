@@ -115,6 +115,7 @@ struct EgdstDev {
     EgdstCellTop *tabTop;               // [ncell]
     EgdstLutEntry *tabLut;              // [ncell*(lutcap+1)]
     int tabcap, lutcap, mbits;
+    int *tabOk;                         // [ncell] != 0: the cell's grid is increasing, its tables may be used (egdst_tables.cuh)
 };
 
 EGDST_DEV int egdst_cell(const EgdstDev &P, int ivec, int it, int ist) { return (ivec * P.NT + it) * P.cx.nst + ist; }

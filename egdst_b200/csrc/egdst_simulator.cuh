@@ -63,6 +63,7 @@ EGDST_DEV double egdst_u01(unsigned x) { return ((double)x + 0.5) * (1.0 / 42949
 // agent-period; they travel instead as a by-value kernel argument (constant bank, up to EGDST_SIM_MAXHDR cells).
 #define EGDST_SIM_TH8 4
 #define EGDST_SIM_MAXHDR 128
+#define EGDST_HDR_NOTAB 0x40000000  /* flag in EgdstCellHdr::n */
 struct EgdstCellHdr { int n, nth; double evf, M1; double th[EGDST_SIM_TH8], dd[EGDST_SIM_TH8]; };
 #define EGDST_SIM_MAXTAB 96
 struct EgdstSimHdrs {
@@ -80,6 +81,7 @@ __global__ void egdst_k_simhdr(EgdstDev P, int ivec, EgdstCellHdr *out) {
     EgdstCellHdr h;
     h.n = P.mlen[cell]; h.nth = P.thlen[cell]; h.evf = P.evf[cell];
     h.M1 = h.n > 1 ? egdst_colM(P, cell)[1] : 0.0;
+    if (P.tabOk[cell] == 0) h.n |= EGDST_HDR_NOTAB;  // the cell's grid steps back: bisection, not the direct index (egdst_cell_has_tab)
     for (int k = 0; k < EGDST_SIM_TH8; k++) {
         h.th[k] = k < h.nth ? P.thTH[(size_t)cell * P.cx.nthrhmax + k] : EGDST_INF;
         h.dd[k] = k < h.nth ? P.thD[(size_t)cell * P.cx.nthrhmax + k] : 0.0;
@@ -105,9 +107,9 @@ struct EgdstSimArgs {
 };
 
 // One cell's policy at `cash` (egdst_simulator.c:145-199): interval record and M[1]; false if the cell holds no solution.
-EGDST_DEV bool egdst_sim_interval(const EgdstDev &P, int cell, int nm, double cash, unsigned long long l2keep, EgdstInterval &iv) {
+EGDST_DEV bool egdst_sim_interval(const EgdstDev &P, int cell, int nm, bool tabok, double cash, unsigned long long l2keep, EgdstInterval &iv) {
     if (nm < 2) return false;
-    if (egdst_cell_has_tab(P, nm)) {
+    if (tabok && egdst_cell_fits_tab(P, nm)) {
         egdst_lookup_tab<true>(P, cell, egdst_cell_rows(P, cell), cash, nm, iv, l2keep);
     } else {  // oversized cell: plain columns
         const double *Mg = egdst_colM(P, cell), *Cg = egdst_colC(P, cell), *Vg = egdst_colV(P, cell);
@@ -131,7 +133,7 @@ EGDST_DEV bool egdst_sim_policy_cell(const EgdstDev &P, const egdst_ctx &cx, int
                                      double &c, double &vf) {
     const int nm = P.mlen[cell];
     EgdstInterval iv;
-    if (!egdst_sim_interval(P, cell, nm, pv.cash, l2keep, iv)) return false;
+    if (!egdst_sim_interval(P, cell, nm, P.tabOk[cell] != 0, pv.cash, l2keep, iv)) return false;
     const double M1 = egdst_colM(P, cell)[1];
     double wl, wr;
     egdst_sim_weights(iv, pv.cash, wl, wr);
@@ -377,9 +379,11 @@ egdst_k_simulate(EgdstDev P, EgdstSimArgs S, const EGDST_GRID_CONSTANT EgdstSimH
                 // policy (egdst_simulator.c:145-199)
                 const int cell = egdst_cell(P, ivec, it, cur.ist);
                 const EgdstCellHdr *hc = H.h + it * cx.nst + cur.ist;
-                const int nm = HDR ? hc->n : P.mlen[cell];
+                const int nmraw = HDR ? hc->n : P.mlen[cell];
+                const int nm = HDR ? (nmraw & ~EGDST_HDR_NOTAB) : nmraw;
+                const bool tabok = HDR ? (nmraw & EGDST_HDR_NOTAB) == 0 : P.tabOk[cell] != 0;
                 EgdstInterval iv;
-                if (!egdst_sim_interval(P, cell, nm, cur.cash, l2keep, iv)) { state = 1; }
+                if (!egdst_sim_interval(P, cell, nm, tabok, cur.cash, l2keep, iv)) { state = 1; }
                 else {
                     double wl, wr;
                     egdst_sim_weights(iv, cur.cash, wl, wr);

@@ -185,7 +185,7 @@ EGDST_NOINLINE EgdstSmoothOut egdst_smooth_node(const EgdstDev *Pg, int ivec, in
         const EgdstNext t = egdst_choice_tables(P, dcell);
         vl[d1] = t.V[t.n1];
         above = above || cash > t.Mlast;
-        const bool tab = egdst_cell_has_tab(P, t.n1 + 1);
+        const bool tab = egdst_cell_has_tab(P, t.cell, t.n1 + 1);
         EgdstInterval iv;
         int i;
         if (tab) i = egdst_lookup_tab(P, t.cell, t.ivl, cash, t.n1 + 1, iv);
@@ -336,7 +336,7 @@ EGDST_DEV void egdst_eval_nodes(const egdst_ctx *cx, const EgdstDev &P, int ivec
             niy = (sigma_param(cx, curr, &next) <= 0 || ny == 1) ? 1 : ny;
         }
         const EgdstNext t = egdst_next_tables(P, ivec, next.it, ist1);
-        const bool tab = egdst_cell_has_tab(P, t.n1 + 1);
+        const bool tab = egdst_cell_has_tab(P, t.cell, t.n1 + 1);
         int iy = part;
 #if EGDST_OPT_MUNOD
         if (!EGDST_SMOOTHING && shk && tab && keep == 1 && t.n1 >= 3) {

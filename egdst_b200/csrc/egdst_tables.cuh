@@ -34,7 +34,12 @@ EGDST_DEV int egdst_lut_key(double x, double a0, int mbits) {
 
 EGDST_DEV const EgdstRow *egdst_cell_rows(const EgdstDev &P, int cell) { return P.tabRow + (size_t)cell * (P.tabcap + 1); }
 EGDST_DEV const EgdstLutEntry *egdst_cell_lut(const EgdstDev &P, int cell) { return P.tabLut + (size_t)cell * (P.lutcap + 1); }
-EGDST_DEV bool egdst_cell_has_tab(const EgdstDev &P, int n) { return n - 1 <= P.tabcap; }
+// A cell has usable tables when it fits them and its grid is increasing.  The reference's bisection (bxsearch,
+// egdst_lib.c:138-165; restated by egdst_bracket) is defined on ANY array, and degenerate models do produce cells whose
+// grid steps back (e.g. a row below a0 after a re-send, examples.deaton_meanstest): there the direct index, which counts
+// rows below x, and the bisection, which follows its own path, disagree -- such cells take the bisection.
+EGDST_DEV bool egdst_cell_fits_tab(const EgdstDev &P, int n) { return n - 1 <= P.tabcap; }
+EGDST_DEV bool egdst_cell_has_tab(const EgdstDev &P, int cell, int n) { return n - 1 <= P.tabcap && P.tabOk[cell] != 0; }
 
 // L2 eviction-priority hints (PTX createpolicy / ld.global.L2::cache_hint): the simulator streams tens of GB of
 // output through L2; table lines loaded with evict_last survive that stream, the output is written evict_first.
@@ -81,6 +86,11 @@ EGDST_DEV void egdst_cells_body(const EgdstDev &P, int ivec, int it) {
     for (int i = threadIdx.x; i < P.cx.nst * 2; i += blockDim.x) P.tickE[2 * ps0 + i] = 0;
     for (int i = threadIdx.x; i < P.cx.nst; i += blockDim.x) P.envNact[ps0 + i] = 0;
     for (int ist = threadIdx.x; ist < P.cx.nst; ist += blockDim.x) {
+        {   // the tables of the period's cells (and, in the smoothing mode, choice-specific cells) are usable unless their build says otherwise
+            const int c0 = egdst_cell(P, ivec, it, ist);
+            P.tabOk[c0] = 1;
+            if (EGDST_SMOOTHING) for (int d_ = 0; d_ < P.cx.nd; d_++) P.tabOk[egdst_dcell(P, c0, d_)] = 1;
+        }
         egdst_ctx cx; egdst_load_ctx(P, ivec, cx);
         PeriodVars curr; curr.it = it; curr.ist = ist; curr.id = 0; curr.cash = 0; curr.savings = 0; curr.shock = 0;
         const int cell = egdst_cell(P, ivec, it, ist);
@@ -99,7 +109,7 @@ EGDST_DEV void egdst_ph_cells(const EgdstDev &P, int it, const EgdstTeam &T) {
 // Build the tables of one cell: the share of virtual block vb of nvb (all threads of the CTA, 1-D blocks).
 EGDST_DEV void egdst_tab_cell(const EgdstDev &P, int cell, int vb, int nvb) {
     const int n = P.mlen[cell];
-    if (n < 2 || !egdst_cell_has_tab(P, n)) return;
+    if (n < 2 || !egdst_cell_fits_tab(P, n)) return;
     const double a0 = P.cx.a0;
     const double *M = egdst_colM(P, cell), *C = egdst_colC(P, cell), *V = egdst_colV(P, cell);
     EgdstRow *r = P.tabRow + (size_t)cell * (P.tabcap + 1);
@@ -120,6 +130,7 @@ EGDST_DEV void egdst_tab_cell(const EgdstDev &P, int cell, int vb, int nvb) {
     }
     for (int i = t0; i < n; i += stride) {
         EgdstRow v; v.m = M[i]; v.c = C[i]; v.v = V[i]; v.y = 0.0;
+        if (i + 1 < n && M[i + 1] < v.m) atomicMin(P.tabOk + cell, 0);  // the grid steps back: no tables for this cell
         if (i + 1 < n) { const double w = M[i + 1] - v.m; v.y = egdst_div_safe(w) ? 1.0 / w : 0.0; }  // shared correctly rounded reciprocal (0: plain divisions)
         r[i] = v;
     }
