@@ -484,6 +484,16 @@ struct EgdstSeedShared {
 EGDST_DEV void egdst_block_eval(const egdst_ctx *cx, const EgdstDev &P, int ivec, const PeriodVars *curr, double A, int keep,
                                 EgdstSeedShared &S, const double *shk, const double *shp) {
     EgdstAcc a;
+#ifdef EGDST_HOSTEMU
+    // diagnostic of the host emulator (EGDST_SEED_SERIAL=1): thread 0 sums all nodes in the reference's order.  The
+    // partitioned sum below differs from the reference's sequential one in the last bit now and then; on degenerate models
+    // that bit decides a run split periods later.
+    static const bool serial = getenv("EGDST_SEED_SERIAL") && atoi(getenv("EGDST_SEED_SERIAL")) != 0;
+    if (serial) {
+        if (threadIdx.x == 0) egdst_eval_nodes(cx, P, ivec, curr, A, keep, 0, 1, a, shk, shp);
+        else { a.rhs = 0; a.evf = 0; a.checksum = 0; a.badq = EGDST_NOBAD; a.badtype = 0; a.badcash = 0; a.badshock = 0; }
+    } else
+#endif
     egdst_eval_nodes(cx, P, ivec, curr, A, keep, threadIdx.x, blockDim.x, a, shk, shp);
     egdst_warp_combine(a);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
