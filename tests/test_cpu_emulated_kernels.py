@@ -231,10 +231,15 @@ def test_emulated_means_tested_family_agreement_is_partial_and_tracked():
     a single decision and -- the unsolved part -- flat stretches where runs of the secondary envelope have EXACTLY equal
     values.  There the reference's sequential sweep switches between equal-valued runs (or does not) by its processing
     order and emits, or omits, a double point whose consumption is -inf; the parallel restatement decides such ties by
-    "lower index wins" and differs.  Observed at the end of round 2: 10 configurations equal the reference row for row
-    and to 1e-9, 1 more to 1e-9 with a different row count; 6 carry a -inf row or extra rows on one side only (one of them
-    1.3 apart in C around such a row); in 2 the -inf row feeds the next period's seed and this implementation ends in a
-    soft error the reference does not raise.
+    "lower index wins" and differs -- that was the working hypothesis; tracing one case bit by bit against the reference's
+    captured point lists showed instead (1) cells whose grid steps back need the reference's
+    bisection (fixed), (2) the seed point's node sum is partitioned over threads where the reference's is sequential, and
+    (3) the value at an envelope crossing is x*slope + intercept here and (x*(f1-f0))/(g1-g0) + intercept in the reference:
+    last-bit differences that a run split amplifies.  (3) in the reference's form makes the emulator bit-identical and
+    this count 12, but two of 108 fresh GPU draws of the multi-state families then miss 1e-9 (by exactly 2^-24 at a double
+    point) where all pass with the slope form, so it is NOT adopted.  Observed at the end of round 2: 10 configurations
+    equal the reference row for row and to 1e-9, 1 more to 1e-9 with a different row count, 6 carry a -inf row or extra
+    rows on one side only, in 2 this implementation ends in a soft error the reference does not raise.
     The assertion is a ratchet: the number of exact matches must not go down."""
     import warnings
     base = examples.deaton_meanstest()
